@@ -1,0 +1,984 @@
+// libseqa_cuda.so -- the C ABI of include/seqa_cuda.h: host-side batching / planning / sharding and the
+// launches of the sm_100a kernels in seqa_packed.cuh (short linear-gap pairs, 2 pairs per thread, s16x2),
+// seqa_wavefront.cuh (generic int32 warp wavefront, every full-matrix algorithm, any length) and
+// seqa_linspace.cuh (Hirschberg / Myers-Miller recursion on the GPU).  No CPU fallback exists here: with no
+// CUDA device every compute entry point fails with SEQA_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "seqa_common.cuh"
+#include "seqa_util.cuh"
+#include "seqa_wavefront.cuh"
+#include "seqa_packed.cuh"
+#include "seqa_linspace.cuh"
+#include "../../include/seqa_cuda.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(SEQA_ERR_CUDA, "%s -> %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define CKS(call)                \
+    do {                         \
+        int s_ = (call);         \
+        if (s_ != SEQA_OK) return s_; \
+    } while (0)
+
+template <class T> struct DBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap) return SEQA_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(SEQA_ERR_NOMEM, "device allocation of %zu bytes failed", n * sizeof(T));
+        }
+        cap = n;
+        return SEQA_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int GEN_R = 4;          // rows per lane of the generic wavefront
+constexpr int PK_R = 16;          // rows per register strip of the packed kernel
+constexpr uint32_t PK_MAX_LEN = 320; // longest side the thread-per-pair kernel takes (shared-memory column)
+
+struct Chunk {
+    uint32_t lo, hi;       // range of jobs / list entries
+    uint64_t scratch_bytes;
+};
+
+} // namespace
+
+struct seqa_ctx;
+namespace {
+// linear-space algorithms (seqa_linspace_host.inl)
+int ls_plan(LsState &ls, const std::vector<uint32_t> &len1, const std::vector<uint32_t> &len2,
+            const std::vector<uint32_t> &idx, bool myers_miller, int sms);
+int ls_run(seqa_ctx *c, bool want_ops);
+void ls_release(LsState &ls);
+} // namespace
+
+struct seqa_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    bool own_stream = false;
+    int sms = 0;
+    size_t smem_optin = 0;
+
+    seqa_params prm{};
+    DevScoring sc{};
+    Borders bd{};
+    uint64_t n = 0, cells = 0, slots_total = 0, bases_len = 0;
+    std::vector<uint32_t> hlen1, hlen2;
+
+    DBuf<uint8_t> bases;
+    DBuf<uint64_t> off1, off2;
+    DBuf<uint32_t> len1, len2;
+
+    DBuf<int32_t> score;
+    DBuf<uint32_t> start_i, start_j, end_i, end_j, ops_len, slot_start;
+    DBuf<uint64_t> slot_off, ops_off;
+    DBuf<uint8_t> slots, dense;
+    DBuf<uint64_t> tile_sum, total;
+    DBuf<int> flags; // [0] packed path met a non-ACGT base
+
+    // packed plan
+    std::vector<uint32_t> perm;
+    std::vector<PkWarpJob> jobs;
+    std::vector<Chunk> pk_chunks;
+    uint32_t pk_max_nw = 0;
+    DBuf<uint32_t> d_perm;
+    DBuf<PkWarpJob> d_jobs;
+    // generic plan
+    std::vector<uint32_t> gidx;
+    std::vector<uint64_t> gdir_off;
+    std::vector<Chunk> g_chunks;
+    uint32_t g_max_n = 0;
+    DBuf<uint32_t> d_gidx;
+    DBuf<uint64_t> d_gdir_off;
+    DBuf<int> bound;
+    // linear-space plan
+    std::vector<uint32_t> lidx;
+    LsState ls;
+
+    DBuf<uint8_t> scratch; // trace / direction matrices (+ profiles) of one chunk
+    bool generic_rerun = false;
+
+    uint64_t launches = 0;
+    std::vector<cudaEvent_t> ev; // pairs of events around the DP fill launches of the last run
+    size_t ev_used = 0;
+    const char *last_kernel = "none";
+    bool ran = false;
+};
+
+namespace {
+
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                               \
+    do {                                                                        \
+        (ctx)->launches++;                                                      \
+        SEQA_LAUNCH(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__);       \
+    } while (0)
+
+int validate_params(const seqa_params *p)
+{
+    if (!p) return fail(SEQA_ERR_INVALID, "params is NULL");
+    if (p->algo < SEQA_NW || p->algo > SEQA_MYERS_MILLER) return fail(SEQA_ERR_INVALID, "bad algo %d", p->algo);
+    const bool affine = p->algo == SEQA_GLOBAL_GOTOH || p->algo == SEQA_LOCAL_GOTOH || p->algo == SEQA_MYERS_MILLER;
+    if (p->match <= 0) return fail(SEQA_ERR_UNSUPPORTED, "match must be > 0");
+    if (p->allow_mismatch && p->mismatch >= 0) return fail(SEQA_ERR_UNSUPPORTED, "mismatch must be < 0");
+    if (affine) {
+        if (p->gap_open > 0 || p->gap_extend >= 0)
+            return fail(SEQA_ERR_UNSUPPORTED, "need gap_open <= 0 and gap_extend < 0");
+    } else if (p->gap >= 0)
+        return fail(SEQA_ERR_UNSUPPORTED, "gap must be < 0");
+    const int64_t lim = 1 << 20;
+    if (std::abs((int64_t)p->match) > lim || std::abs((int64_t)p->gap) > lim || std::abs((int64_t)p->gap_open) > lim ||
+        std::abs((int64_t)p->gap_extend) > lim || (p->allow_mismatch && std::abs((int64_t)p->mismatch) > lim))
+        return fail(SEQA_ERR_UNSUPPORTED, "scoring magnitudes above 2^20 are not supported");
+    return SEQA_OK;
+}
+
+void set_scoring(seqa_ctx *c)
+{
+    const seqa_params &p = c->prm;
+    c->sc.gap = p.gap;
+    c->sc.go = p.gap_open;
+    c->sc.ge = p.gap_extend;
+    c->sc.match = p.match;
+    c->sc.mismatch = p.mismatch;
+    c->sc.allow = p.allow_mismatch ? 1 : 0;
+    Borders b{};
+    switch (p.algo) {
+    case SEQA_NW: // include/SANeedlemanWunsch.h:59-62
+        b.hcolB = p.gap;
+        b.hrowB = p.gap;
+        break;
+    case SEQA_GLOBAL_GOTOH: // include/SAGlobalGotoh.h:75-88
+        b.hcolA = b.hrowA = p.gap_open;
+        b.hcolB = b.hrowB = p.gap_extend;
+        b.ixA = b.iyA = SEQA_GOTOH_NEG;
+        break;
+    case SEQA_LOCAL_GOTOH: // include/SALocalGotoh.h:77-90
+        b.ixA = b.iyA = SEQA_GOTOH_NEG;
+        break;
+    default: break; // SW: zeros (include/SASmithWaterman.h:68-77); linear-space algorithms set their own
+    }
+    c->bd = b;
+}
+
+// Can the s16x2 thread-per-pair kernel take (M,N) under the current scoring?  See seqa_packed.cuh.
+bool packed_scoring_ok(const seqa_params &p)
+{
+    if (p.algo != SEQA_NW && p.algo != SEQA_SW) return false;
+    if (p.flags & SEQA_FLAG_FORCE_GENERIC) return false;
+    const int g = -p.gap, m = p.match, x = p.allow_mismatch ? -p.mismatch : 0;
+    if (m > 100 || g > 50 || x > 100) return false;
+    if (m + x + 2 * g > 120) return false; // neighbouring cells must differ by < 128
+    return true;
+}
+bool packed_shape_ok(const seqa_params &p, uint32_t M, uint32_t N)
+{
+    if (M == 0 || N == 0 || M > PK_MAX_LEN || N > PK_MAX_LEN) return false;
+    const int64_t g = -p.gap, m = p.match;
+    const int64_t lo = (int64_t)(M + N + 2 * PK_R + 2) * g + 300, hi = (int64_t)std::min(M, N) * m + 300;
+    return lo < 30000 && hi < 30000;
+}
+
+size_t free_budget()
+{
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (size_t)1 << 30;
+    return (size_t)((double)fr * 0.80);
+}
+
+int build_plan(seqa_ctx *c)
+{
+    const uint64_t n = c->n;
+    const seqa_params &prm = c->prm;
+    c->perm.clear();
+    c->jobs.clear();
+    c->pk_chunks.clear();
+    c->gidx.clear();
+    c->gdir_off.clear();
+    c->g_chunks.clear();
+    c->lidx.clear();
+    c->pk_max_nw = 0;
+    c->g_max_n = 0;
+    c->cells = 0;
+    for (uint64_t p = 0; p < n; p++) c->cells += (uint64_t)c->hlen1[p] * c->hlen2[p];
+
+    // per-pair op slots: len1+len2 bytes each (an alignment never has more columns)
+    {
+        std::vector<uint64_t> so(n + 1);
+        uint64_t run = 0;
+        for (uint64_t p = 0; p < n; p++) {
+            so[p] = run;
+            run += (uint64_t)c->hlen1[p] + c->hlen2[p];
+        }
+        c->slots_total = run;
+        CKS(c->slot_off.ensure(n));
+        CKS(c->slots.ensure(run));
+        CK(cudaMemcpyAsync(c->slot_off.p, so.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    CKS(c->score.ensure(n));
+    CKS(c->start_i.ensure(n));
+    CKS(c->start_j.ensure(n));
+    CKS(c->end_i.ensure(n));
+    CKS(c->end_j.ensure(n));
+    CKS(c->ops_len.ensure(n));
+    CKS(c->slot_start.ensure(n));
+    CKS(c->ops_off.ensure(n));
+    CKS(c->dense.ensure(c->slots_total));
+    CKS(c->tile_sum.ensure((n + SEQA_SCAN_TILE - 1) / SEQA_SCAN_TILE + 1));
+    CKS(c->total.ensure(1));
+    CKS(c->flags.ensure(4));
+
+    if (prm.algo == SEQA_HIRSCHBERG || prm.algo == SEQA_MYERS_MILLER) {
+        c->lidx.resize(n);
+        std::iota(c->lidx.begin(), c->lidx.end(), 0u);
+        return ls_plan(c->ls, c->hlen1, c->hlen2, c->lidx, prm.algo == SEQA_MYERS_MILLER, c->sms);
+    }
+    if (prm.algo == SEQA_LOCAL_GOTOH) {
+        for (uint64_t p = 0; p < n; p++) {
+            const uint32_t M = c->hlen1[p], N = c->hlen2[p];
+            if ((M == 314 && N == 288) || (M == 60 && N == 57) || (M == 61 && N == 58))
+                return fail(SEQA_ERR_UNSUPPORTED,
+                            "LocalGotoh shape (%u,%u) is undefined behaviour in the reference (SALocalGotoh.h:484-488)", M, N);
+        }
+    }
+
+    const bool pk = packed_scoring_ok(prm) && !c->generic_rerun;
+    std::vector<uint32_t> pkl;
+    bool uniform = true;
+    for (uint64_t p = 0; p < n; p++) {
+        const uint32_t M = c->hlen1[p], N = c->hlen2[p];
+        if (pk && packed_shape_ok(prm, M, N)) {
+            if (!pkl.empty() && (M != c->hlen1[pkl[0]] || N != c->hlen2[pkl[0]])) uniform = false;
+            pkl.push_back((uint32_t)p);
+        } else {
+            c->gidx.push_back((uint32_t)p);
+        }
+    }
+    const size_t budget = free_budget();
+
+    // ---- packed jobs: 64 pairs per warp, similar shapes together ----
+    if (!pkl.empty()) {
+        if (!uniform) {
+            const std::vector<uint32_t> &l1 = c->hlen1, &l2 = c->hlen2;
+            std::sort(pkl.begin(), pkl.end(), [&](uint32_t a, uint32_t b) {
+                const uint32_t ka = (l1[a] + PK_R - 1) / PK_R, kb = (l1[b] + PK_R - 1) / PK_R;
+                if (ka != kb) return ka < kb;
+                if (l2[a] != l2[b]) return l2[a] < l2[b];
+                return a < b;
+            });
+        }
+        const size_t njobs = (pkl.size() + 63) / 64;
+        c->perm.assign(njobs * 64, PK_NULL);
+        std::copy(pkl.begin(), pkl.end(), c->perm.begin());
+        c->jobs.resize(njobs);
+        Chunk ch{0, 0, 0};
+        uint64_t tr = 0, pf = 0, rs = 0; // running offsets inside the chunk
+        auto chunk_bytes = [&](uint64_t t, uint64_t q, uint64_t r) { return t + q * 8 + r * 4 + 4096; };
+        for (size_t w = 0; w < njobs; w++) {
+            uint32_t Mw = 0, Nw = 0;
+            for (int k = 0; k < 64; k++) {
+                const uint32_t p = c->perm[w * 64 + k];
+                if (p == PK_NULL) continue;
+                Mw = std::max(Mw, c->hlen1[p]);
+                Nw = std::max(Nw, c->hlen2[p]);
+            }
+            PkWarpJob &J = c->jobs[w];
+            J.first = (uint32_t)(w * 64);
+            J.Mw = Mw;
+            J.Nw = Nw;
+            J.nstrips = (Mw + PK_R - 1) / PK_R;
+            const uint64_t tbytes = (uint64_t)J.nstrips * Nw * (PK_R / 8) * 512;
+            const uint64_t pelems = (uint64_t)Nw * 32, relems = (uint64_t)J.nstrips * PK_R * 32;
+            if (ch.hi > ch.lo && chunk_bytes(tr + tbytes, pf + pelems, rs + relems) > budget) {
+                ch.scratch_bytes = chunk_bytes(tr, pf, rs);
+                c->pk_chunks.push_back(ch);
+                ch.lo = ch.hi;
+                tr = pf = rs = 0;
+            }
+            J.trace_off = tr;
+            J.prof_off = pf;
+            J.rowsel_off = rs;
+            tr += tbytes;
+            pf += pelems;
+            rs += relems;
+            ch.hi = (uint32_t)(w + 1);
+            c->pk_max_nw = std::max(c->pk_max_nw, Nw);
+        }
+        ch.scratch_bytes = chunk_bytes(tr, pf, rs);
+        c->pk_chunks.push_back(ch);
+        // chunk-relative layout: [trace | prof (8 B) | rowsel (4 B)], offsets resolved at launch
+        CKS(c->d_perm.ensure(c->perm.size()));
+        CKS(c->d_jobs.ensure(c->jobs.size()));
+        CK(cudaMemcpyAsync(c->d_perm.p, c->perm.data(), c->perm.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_jobs.p, c->jobs.data(), c->jobs.size() * sizeof(PkWarpJob), cudaMemcpyHostToDevice, c->stream));
+    }
+
+    // ---- generic jobs: one warp per pair ----
+    if (!c->gidx.empty()) {
+        const bool affine = prm.algo == SEQA_GLOBAL_GOTOH || prm.algo == SEQA_LOCAL_GOTOH;
+        c->gdir_off.resize(c->gidx.size());
+        Chunk ch{0, 0, 0};
+        uint64_t words = 0;
+        for (size_t k = 0; k < c->gidx.size(); k++) {
+            const uint32_t p = c->gidx[k];
+            const uint64_t wds = dir_words((int)c->hlen1[p], (int)c->hlen2[p], GEN_R, affine);
+            if (wds * 4 > budget)
+                return fail(SEQA_ERR_NOMEM, "pair %u (%u x %u) needs a %llu-byte direction matrix: use Hirschberg/MyersMiller",
+                            p, c->hlen1[p], c->hlen2[p], (unsigned long long)(wds * 4));
+            if (ch.hi > ch.lo && (words + wds) * 4 > budget) {
+                ch.scratch_bytes = words * 4;
+                c->g_chunks.push_back(ch);
+                ch.lo = ch.hi;
+                words = 0;
+            }
+            c->gdir_off[k] = words;
+            words += wds;
+            ch.hi = (uint32_t)(k + 1);
+            c->g_max_n = std::max(c->g_max_n, c->hlen2[p]);
+        }
+        ch.scratch_bytes = words * 4;
+        c->g_chunks.push_back(ch);
+        CKS(c->d_gidx.ensure(c->gidx.size()));
+        CKS(c->d_gdir_off.ensure(c->gidx.size()));
+        CK(cudaMemcpyAsync(c->d_gidx.p, c->gidx.data(), c->gidx.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_gdir_off.p, c->gdir_off.data(), c->gidx.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    uint64_t need = 16;
+    for (auto &ch : c->pk_chunks) need = std::max(need, ch.scratch_bytes);
+    for (auto &ch : c->g_chunks) need = std::max(need, ch.scratch_bytes);
+    CKS(c->scratch.ensure(need));
+    CK(cudaStreamSynchronize(c->stream));
+    return SEQA_OK;
+}
+
+cudaEvent_t next_event(seqa_ctx *c)
+{
+    if (c->ev_used == c->ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->ev.push_back(e);
+    }
+    return c->ev[c->ev_used++];
+}
+
+template <bool AFFINE, bool LOCAL> void launch_generic(seqa_ctx *c, const Chunk &ch, int nwarps, int stride, bool want_walk)
+{
+    FillArgs F{};
+    F.bases = c->bases.p;
+    F.off1 = c->off1.p;
+    F.off2 = c->off2.p;
+    F.len1 = c->len1.p;
+    F.len2 = c->len2.p;
+    F.idx = c->d_gidx.p + ch.lo;
+    F.count = ch.hi - ch.lo;
+    F.dir_off = c->d_gdir_off.p + ch.lo;
+    F.dir = reinterpret_cast<uint32_t *>(c->scratch.p);
+    F.bound = c->bound.p;
+    F.bound_stride = stride;
+    F.score = c->score.p;
+    F.end_i = c->end_i.p;
+    F.end_j = c->end_j.p;
+    F.sc = c->sc;
+    F.bd = c->bd;
+    const int blocks = (nwarps + 3) / 4;
+    cudaEventRecord(next_event(c), c->stream);
+    LAUNCH(c, (fill_i32_kernel<AFFINE, LOCAL, GEN_R>), blocks, 128, 0, F);
+    cudaEventRecord(next_event(c), c->stream);
+    if (!want_walk) return;
+    WalkArgs W{};
+    W.len1 = c->len1.p;
+    W.len2 = c->len2.p;
+    W.idx = F.idx;
+    W.count = F.count;
+    W.dir_off = F.dir_off;
+    W.dir = F.dir;
+    W.R = GEN_R;
+    W.end_i = c->end_i.p;
+    W.end_j = c->end_j.p;
+    W.start_i = c->start_i.p;
+    W.start_j = c->start_j.p;
+    W.slots = c->slots.p;
+    W.slot_off = c->slot_off.p;
+    W.slot_start = c->slot_start.p;
+    W.ops_len = c->ops_len.p;
+    LAUNCH(c, (walk_kernel<AFFINE, LOCAL>), (unsigned)((F.count + 127) / 128), 128, 0, W);
+}
+
+int run_generic(seqa_ctx *c, bool want_walk)
+{
+    if (c->gidx.empty()) return SEQA_OK;
+    const int stride = (int)((c->g_max_n + 1 + 63) / 32 * 32);
+    for (const Chunk &ch : c->g_chunks) {
+        const uint64_t cnt = ch.hi - ch.lo;
+        int nwarps = (int)std::min<uint64_t>(cnt, (uint64_t)c->sms * 32);
+        // keep the boundary scratch bounded for very long pairs
+        while (nwarps > 4 && (uint64_t)nwarps * 2 * stride * 4 > ((uint64_t)1 << 30)) nwarps /= 2;
+        nwarps = (nwarps + 3) / 4 * 4;
+        CKS(c->bound.ensure((size_t)nwarps * 2 * stride));
+        switch (c->prm.algo) {
+        case SEQA_NW: launch_generic<false, false>(c, ch, nwarps, stride, want_walk); break;
+        case SEQA_SW: launch_generic<false, true>(c, ch, nwarps, stride, want_walk); break;
+        case SEQA_GLOBAL_GOTOH: launch_generic<true, false>(c, ch, nwarps, stride, want_walk); break;
+        default: launch_generic<true, true>(c, ch, nwarps, stride, want_walk); break;
+        }
+        CK(cudaGetLastError());
+    }
+    if (c->last_kernel[0] == 'n') c->last_kernel = (c->prm.algo >= SEQA_GLOBAL_GOTOH) ? "fill_i32_affine" : "fill_i32_linear";
+    return SEQA_OK;
+}
+
+int run_packed(seqa_ctx *c, bool want_walk)
+{
+    if (c->jobs.empty()) return SEQA_OK;
+    const bool local = c->prm.algo == SEQA_SW;
+    const size_t smem = (size_t)c->pk_max_nw * PK_BLOCK * 4;
+    if (smem > c->smem_optin) return fail(SEQA_ERR_UNSUPPORTED, "internal: packed kernel shared memory %zu", smem);
+    if (local)
+        CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int bps = (int)std::max<size_t>(1, std::min<size_t>(3, (c->smem_optin + 1024) / std::max<size_t>(smem + 1024, 1)));
+    CK(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 4, c->stream));
+    for (const Chunk &ch : c->pk_chunks) {
+        const uint32_t nj = ch.hi - ch.lo;
+        // chunk layout: trace | prof | rowsel
+        uint64_t tr = 0, pf = 0;
+        {
+            const PkWarpJob &L = c->jobs[ch.hi - 1];
+            tr = L.trace_off + (uint64_t)L.nstrips * L.Nw * (PK_R / 8) * 512;
+            pf = L.prof_off + (uint64_t)L.Nw * 32;
+        }
+        PkArgs A{};
+        A.bases = c->bases.p;
+        A.off1 = c->off1.p;
+        A.off2 = c->off2.p;
+        A.len1 = c->len1.p;
+        A.len2 = c->len2.p;
+        A.perm = c->d_perm.p;
+        A.jobs = c->d_jobs.p + ch.lo;
+        A.njobs = nj;
+        A.trace = c->scratch.p;
+        A.prof = reinterpret_cast<uint2 *>(c->scratch.p + ((tr + 255) / 256) * 256);
+        A.rowsel = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(A.prof) + pf * 8);
+        A.score = c->score.p;
+        A.end_i = c->end_i.p;
+        A.end_j = c->end_j.p;
+        A.start_i = c->start_i.p;
+        A.start_j = c->start_j.p;
+        A.slots = c->slots.p;
+        A.slot_off = c->slot_off.p;
+        A.slot_start = c->slot_start.p;
+        A.ops_len = c->ops_len.p;
+        A.bad = c->flags.p;
+        A.gap = c->prm.gap;
+        A.match = c->prm.match;
+        A.mismatch = c->prm.mismatch;
+        A.allow = c->prm.allow_mismatch ? 1 : 0;
+        A.smem_cols = c->pk_max_nw;
+        A.npos = (uint64_t)nj * 64;
+        const unsigned wpb = PK_BLOCK / 32;
+        const unsigned full = (nj + wpb - 1) / wpb;
+        const unsigned grid = std::min<unsigned>(full, (unsigned)(c->sms * bps));
+        LAUNCH(c, (pk_prep_kernel), std::min<unsigned>(full, (unsigned)c->sms * 16), PK_BLOCK, 0, A, PK_R);
+        cudaEventRecord(next_event(c), c->stream);
+        if (local)
+            LAUNCH(c, (pk_fill_kernel<true, PK_R>), grid, PK_BLOCK, smem, A);
+        else
+            LAUNCH(c, (pk_fill_kernel<false, PK_R>), grid, PK_BLOCK, smem, A);
+        cudaEventRecord(next_event(c), c->stream);
+        if (want_walk) {
+            // walk positions are chunk-relative: perm/jobs pointers advanced to the chunk
+            PkArgs Wk = A;
+            Wk.perm = c->d_perm.p + (uint64_t)ch.lo * 64;
+            // jobs' `first` fields are absolute; the walk indexes perm by position, so rebase via pointer only
+            const unsigned wgrid = (unsigned)((Wk.npos + 255) / 256);
+            if (local)
+                LAUNCH(c, (pk_walk_kernel<true>), wgrid, 256, 0, Wk, PK_R);
+            else
+                LAUNCH(c, (pk_walk_kernel<false>), wgrid, 256, 0, Wk, PK_R);
+        }
+        CK(cudaGetLastError());
+    }
+    c->last_kernel = local ? "pk_fill_sw_s16x2" : "pk_fill_nw_s16x2";
+    return SEQA_OK;
+}
+
+int finish_ops(seqa_ctx *c)
+{
+    const uint64_t n = c->n;
+    if (n == 0) return SEQA_OK;
+    const unsigned tiles = (unsigned)((n + SEQA_SCAN_TILE - 1) / SEQA_SCAN_TILE);
+    LAUNCH(c, (scan_tile_sums_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p);
+    LAUNCH(c, (scan_spine_kernel), 1, 1024, 0, c->tile_sum.p, (uint64_t)tiles, c->total.p);
+    LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, c->ops_off.p);
+    GatherArgs G{};
+    G.n_pairs = n;
+    G.slots = c->slots.p;
+    G.slot_off = c->slot_off.p;
+    G.slot_start = c->slot_start.p;
+    G.ops_len = c->ops_len.p;
+    G.ops_off = c->ops_off.p;
+    G.dense = c->dense.p;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n * 8 + 255) / 256, (uint64_t)c->sms * 32);
+    LAUNCH(c, (gather_ops_kernel), blocks, 256, 0, G);
+    CK(cudaGetLastError());
+    return SEQA_OK;
+}
+
+int ctx_set_inputs_common(seqa_ctx *c, const seqa_params *params, uint64_t n)
+{
+    CKS(validate_params(params));
+    c->prm = *params;
+    c->n = n;
+    c->ran = false;
+    c->generic_rerun = false;
+    set_scoring(c);
+    CKS(c->off1.ensure(n));
+    CKS(c->off2.ensure(n));
+    CKS(c->len1.ensure(n));
+    CKS(c->len2.ensure(n));
+    return SEQA_OK;
+}
+
+// upload pairs [pb, pe) of `in`; device offsets are rebased to the byte range the shard touches
+int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in *in, uint64_t pb, uint64_t pe)
+{
+    if (!in) return fail(SEQA_ERR_INVALID, "batch is NULL");
+    const uint64_t n = pe - pb;
+    if (n && (!in->bases || !in->off1 || !in->off2 || !in->len1 || !in->len2))
+        return fail(SEQA_ERR_INVALID, "batch has NULL arrays");
+    if (n > 0xfffffff0ull) return fail(SEQA_ERR_UNSUPPORTED, "more than 2^32-16 pairs per device shard");
+    CK(cudaSetDevice(c->device));
+    CKS(ctx_set_inputs_common(c, params, n));
+    c->hlen1.assign(in->len1 + pb, in->len1 + pe);
+    c->hlen2.assign(in->len2 + pb, in->len2 + pe);
+    uint64_t lo = UINT64_MAX, hi = 0;
+    for (uint64_t p = pb; p < pe; p++) {
+        const uint64_t a0 = in->off1[p], a1 = a0 + in->len1[p], b0 = in->off2[p], b1 = b0 + in->len2[p];
+        if (a1 > in->bases_len || b1 > in->bases_len)
+            return fail(SEQA_ERR_INVALID, "pair %llu reaches past bases_len", (unsigned long long)p);
+        lo = std::min(lo, std::min(a0, b0));
+        hi = std::max(hi, std::max(a1, b1));
+    }
+    if (n == 0 || hi < lo) lo = hi = 0;
+    std::vector<uint64_t> o1(n), o2(n);
+    for (uint64_t p = 0; p < n; p++) {
+        o1[p] = in->off1[pb + p] - lo;
+        o2[p] = in->off2[pb + p] - lo;
+    }
+    c->bases_len = hi - lo;
+    CKS(c->bases.ensure(c->bases_len + 16));
+    if (hi > lo) CK(cudaMemcpyAsync(c->bases.p, in->bases + lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
+    if (n) {
+        CK(cudaMemcpyAsync(c->off1.p, o1.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->off2.p, o2.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->len1.p, c->hlen1.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->len2.p, c->hlen2.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream)); // o1/o2 are stack-owned
+    return build_plan(c);
+}
+
+int ctx_run(seqa_ctx *c)
+{
+    CK(cudaSetDevice(c->device));
+    c->ev_used = 0;
+    c->last_kernel = "none";
+    if (c->n == 0) { c->ran = true; return SEQA_OK; }
+    const bool want_walk = !(c->prm.flags & SEQA_FLAG_SCORE_ONLY);
+    if (!want_walk) CK(cudaMemsetAsync(c->ops_len.p, 0, c->n * 4, c->stream));
+    if (!c->lidx.empty()) {
+        CKS(ls_run(c, want_walk));
+    } else {
+        CKS(run_packed(c, want_walk));
+        CKS(run_generic(c, want_walk));
+    }
+    CKS(finish_ops(c));
+    c->ran = true;
+    return SEQA_OK;
+}
+
+// If the packed path met a base outside ACGT its results are void: re-plan everything onto the generic
+// (8-bit compare) kernels and run again.  Called at the first synchronisation point after a run.
+int ctx_resolve(seqa_ctx *c)
+{
+    CK(cudaStreamSynchronize(c->stream));
+    if (!c->ran || c->jobs.empty() || c->generic_rerun) return SEQA_OK;
+    int bad = 0;
+    CK(cudaMemcpy(&bad, c->flags.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (!bad) return SEQA_OK;
+    c->generic_rerun = true;
+    CKS(build_plan(c));
+    CKS(ctx_run(c));
+    CK(cudaStreamSynchronize(c->stream));
+    return SEQA_OK;
+}
+
+int ctx_download_into(seqa_ctx *c, seqa_batch_out *out, uint64_t pb, uint64_t ops_base, uint64_t *ops_used)
+{
+    CK(cudaSetDevice(c->device));
+    if (!c->ran) return fail(SEQA_ERR_INVALID, "download before run");
+    CKS(ctx_resolve(c));
+    const uint64_t n = c->n;
+    *ops_used = 0;
+    if (n == 0) return SEQA_OK;
+    if (!out || !out->score) return fail(SEQA_ERR_INVALID, "out->score is NULL");
+    CK(cudaMemcpyAsync(out->score + pb, c->score.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out->end_i) CK(cudaMemcpyAsync(out->end_i + pb, c->end_i.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out->end_j) CK(cudaMemcpyAsync(out->end_j + pb, c->end_j.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (c->prm.flags & SEQA_FLAG_SCORE_ONLY) {
+        CK(cudaStreamSynchronize(c->stream));
+        return SEQA_OK;
+    }
+    if (!out->start_i || !out->start_j || !out->end_i || !out->end_j || !out->ops || !out->ops_off || !out->ops_len)
+        return fail(SEQA_ERR_INVALID, "output arrays are NULL (only allowed with SEQA_FLAG_SCORE_ONLY)");
+    uint64_t total = 0;
+    CK(cudaMemcpyAsync(&total, c->total.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out->start_i + pb, c->start_i.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out->start_j + pb, c->start_j.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out->ops_len + pb, c->ops_len.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out->ops_off + pb, c->ops_off.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (ops_base + total > out->ops_capacity)
+        return fail(SEQA_ERR_CAPACITY, "ops_capacity %llu < %llu needed", (unsigned long long)out->ops_capacity,
+                    (unsigned long long)(ops_base + total));
+    if (total) CK(cudaMemcpyAsync(out->ops + ops_base, c->dense.p, total, cudaMemcpyDeviceToHost, c->stream));
+    if (ops_base)
+        for (uint64_t p = 0; p < n; p++) out->ops_off[pb + p] += ops_base;
+    CK(cudaStreamSynchronize(c->stream));
+    *ops_used = total;
+    return SEQA_OK;
+}
+
+} // namespace
+
+#include "seqa_linspace_host.inl"
+
+extern "C" {
+
+const char *seqa_cuda_last_error(void) { return g_err.c_str(); }
+int seqa_cuda_abi_version(void) { return SEQA_ABI_VERSION; }
+
+int seqa_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int seqa_ctx_create(seqa_ctx **out, int device, void *stream)
+{
+    if (!out) return fail(SEQA_ERR_INVALID, "ctx out pointer is NULL");
+    *out = nullptr;
+    const int nd = seqa_cuda_device_count();
+    if (nd <= 0) return fail(SEQA_ERR_NO_DEVICE, "no CUDA device is visible (there is no CPU fallback)");
+    if (device < 0 || device >= nd) return fail(SEQA_ERR_INVALID, "device %d out of range (0..%d)", device, nd - 1);
+    CK(cudaSetDevice(device));
+    seqa_ctx *c = new seqa_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete c;
+        return fail(SEQA_ERR_CUDA, "cudaGetDeviceProperties failed");
+    }
+#ifndef SEQA_EMU
+    if (prop.major != 10) {
+        delete c;
+        return fail(SEQA_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    }
+#endif
+    c->sms = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            return fail(SEQA_ERR_CUDA, "cudaStreamCreate failed");
+        }
+        c->own_stream = true;
+    }
+    *out = c;
+    return SEQA_OK;
+}
+
+void seqa_ctx_destroy(seqa_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->bases.release(); c->off1.release(); c->off2.release(); c->len1.release(); c->len2.release();
+    c->score.release(); c->start_i.release(); c->start_j.release(); c->end_i.release(); c->end_j.release();
+    c->ops_len.release(); c->slot_start.release(); c->slot_off.release(); c->ops_off.release();
+    c->slots.release(); c->dense.release(); c->tile_sum.release(); c->total.release(); c->flags.release();
+    c->d_perm.release(); c->d_jobs.release(); c->d_gidx.release(); c->d_gdir_off.release(); c->bound.release();
+    c->scratch.release();
+    ls_release(c->ls);
+    for (auto e : c->ev) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int seqa_ctx_upload(seqa_ctx *c, const seqa_params *params, const seqa_batch_in *in)
+{
+    if (!c || !in) return fail(SEQA_ERR_INVALID, "NULL argument");
+    return ctx_upload_range(c, params, in, 0, in->n_pairs);
+}
+
+int seqa_ctx_generate(seqa_ctx *c, const seqa_params *params, uint64_t seed, uint64_t first_pair, uint64_t n_pairs,
+                      int32_t len_mode, uint32_t len1, uint32_t len2)
+{
+    if (!c) return fail(SEQA_ERR_INVALID, "NULL ctx");
+    if (n_pairs > 0xfffffff0ull) return fail(SEQA_ERR_UNSUPPORTED, "more than 2^32-16 pairs per device shard");
+    CK(cudaSetDevice(c->device));
+    CKS(ctx_set_inputs_common(c, params, n_pairs));
+    c->hlen1.resize(n_pairs);
+    c->hlen2.resize(n_pairs);
+    std::vector<uint64_t> o1(n_pairs), o2(n_pairs);
+    uint64_t run = 0;
+    for (uint64_t p = 0; p < n_pairs; p++) {
+        const uint32_t a = len_mode ? synth_len(seed, first_pair + p, 0) : len1;
+        const uint32_t b = len_mode ? synth_len(seed, first_pair + p, 1) : len2;
+        c->hlen1[p] = a;
+        c->hlen2[p] = b;
+        o1[p] = run;
+        o2[p] = run + a;
+        run += (uint64_t)a + b;
+    }
+    c->bases_len = run;
+    CKS(c->bases.ensure(run + 16));
+    if (n_pairs) {
+        CK(cudaMemcpyAsync(c->off1.p, o1.data(), n_pairs * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->off2.p, o2.data(), n_pairs * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->len1.p, c->hlen1.data(), n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->len2.p, c->hlen2.data(), n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+        GenArgs G{seed, first_pair, n_pairs, c->off1.p, c->off2.p, c->len1.p, c->len2.p, c->bases.p};
+        const unsigned blocks = (unsigned)std::min<uint64_t>((n_pairs * 32 + 255) / 256, (uint64_t)c->sms * 32);
+        LAUNCH(c, (generate_kernel), blocks, 256, 0, G);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return build_plan(c);
+}
+
+int seqa_ctx_run(seqa_ctx *c)
+{
+    if (!c) return fail(SEQA_ERR_INVALID, "NULL ctx");
+    return ctx_run(c);
+}
+
+int seqa_ctx_sync(seqa_ctx *c)
+{
+    if (!c) return fail(SEQA_ERR_INVALID, "NULL ctx");
+    CK(cudaSetDevice(c->device));
+    return ctx_resolve(c);
+}
+
+int seqa_ctx_download(seqa_ctx *c, seqa_batch_out *out)
+{
+    if (!c || !out) return fail(SEQA_ERR_INVALID, "NULL argument");
+    uint64_t used = 0;
+    CKS(ctx_download_into(c, out, 0, 0, &used));
+    out->ops_used = used;
+    return SEQA_OK;
+}
+
+uint64_t seqa_ctx_launch_count(const seqa_ctx *c) { return c ? c->launches : 0; }
+uint64_t seqa_ctx_cells(const seqa_ctx *c) { return c ? c->cells : 0; }
+const char *seqa_ctx_last_kernel(const seqa_ctx *c) { return c ? c->last_kernel : "none"; }
+
+int seqa_ctx_last_fill_ms(seqa_ctx *c, float *ms, int32_t *n_launches)
+{
+    if (!c || !ms) return fail(SEQA_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    float tot = 0.f;
+    for (size_t k = 0; k + 1 < c->ev_used; k += 2) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, c->ev[k], c->ev[k + 1]));
+        tot += t;
+    }
+    *ms = tot;
+    if (n_launches) *n_launches = (int32_t)(c->ev_used / 2);
+    return SEQA_OK;
+}
+
+int seqa_ctx_download_inputs(seqa_ctx *c, char *bases, uint64_t bases_len, uint64_t *off1, uint64_t *off2,
+                             uint32_t *len1, uint32_t *len2)
+{
+    if (!c) return fail(SEQA_ERR_INVALID, "NULL ctx");
+    CK(cudaSetDevice(c->device));
+    if (bases_len < c->bases_len) return fail(SEQA_ERR_CAPACITY, "bases buffer too small");
+    if (c->bases_len && bases) CK(cudaMemcpyAsync(bases, c->bases.p, c->bases_len, cudaMemcpyDeviceToHost, c->stream));
+    if (c->n) {
+        if (off1) CK(cudaMemcpyAsync(off1, c->off1.p, c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (off2) CK(cudaMemcpyAsync(off2, c->off2.p, c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (len1) CK(cudaMemcpyAsync(len1, c->len1.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (len2) CK(cudaMemcpyAsync(len2, c->len2.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return SEQA_OK;
+}
+
+int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, seqa_batch_out *out)
+{
+    CKS(validate_params(params));
+    if (!in || !out) return fail(SEQA_ERR_INVALID, "NULL argument");
+    const int nd_all = seqa_cuda_device_count();
+    if (nd_all <= 0) return fail(SEQA_ERR_NO_DEVICE, "no CUDA device is visible (there is no CPU fallback)");
+    const int first = params->device_first;
+    int nd = params->device_count > 0 ? params->device_count : nd_all - first;
+    if (first < 0 || first >= nd_all || nd <= 0 || first + nd > nd_all)
+        return fail(SEQA_ERR_INVALID, "device range [%d,%d) outside the %d visible devices", first, first + nd, nd_all);
+    const uint64_t n = in->n_pairs;
+    out->ops_used = 0;
+    if (n == 0) return SEQA_OK;
+    if (!in->len1 || !in->len2) return fail(SEQA_ERR_INVALID, "batch has NULL arrays");
+    if ((uint64_t)nd > n) nd = (int)n;
+    // static split, contiguous, balanced by sum len1*len2
+    std::vector<uint64_t> cut(nd + 1, n);
+    cut[0] = 0;
+    if (nd > 1) {
+        long double tot = 0;
+        for (uint64_t p = 0; p < n; p++) tot += (long double)in->len1[p] * in->len2[p] + 1;
+        long double run = 0;
+        int d = 1;
+        for (uint64_t p = 0; p < n && d < nd; p++) {
+            run += (long double)in->len1[p] * in->len2[p] + 1;
+            if (run >= tot * d / nd) cut[d++] = p + 1;
+        }
+    }
+    std::vector<seqa_ctx *> ctxs(nd, nullptr);
+    std::vector<int> status(nd, SEQA_OK);
+    std::vector<std::string> errs(nd);
+    auto work = [&](int d) {
+        int s = seqa_ctx_create(&ctxs[d], first + d, nullptr);
+        if (s == SEQA_OK) s = ctx_upload_range(ctxs[d], params, in, cut[d], cut[d + 1]);
+        if (s == SEQA_OK) s = ctx_run(ctxs[d]);
+        if (s == SEQA_OK) s = ctx_resolve(ctxs[d]);
+        status[d] = s;
+        if (s != SEQA_OK) errs[d] = g_err;
+    };
+    if (nd == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < nd; d++) th.emplace_back(work, d);
+        for (auto &t : th) t.join();
+    }
+    int rc = SEQA_OK;
+    uint64_t base = 0;
+    for (int d = 0; d < nd; d++) {
+        if (rc == SEQA_OK && status[d] != SEQA_OK) {
+            rc = status[d];
+            g_err = errs[d];
+        }
+        if (rc == SEQA_OK) {
+            uint64_t used = 0;
+            rc = ctx_download_into(ctxs[d], out, cut[d], base, &used);
+            base += used;
+        }
+    }
+    for (auto c : ctxs) seqa_ctx_destroy(c);
+    out->ops_used = base;
+    return rc;
+}
+
+int seqa_cuda_int_peak(int device, int which, double *lane_ops_per_clk_per_sm, double *sm_clock_mhz)
+{
+#ifdef SEQA_EMU
+    (void)device; (void)which; (void)lane_ops_per_clk_per_sm; (void)sm_clock_mhz;
+    return fail(SEQA_ERR_NO_DEVICE, "micro-benchmark needs a GPU");
+#else
+    if (which < 0 || which > 9 || !lane_ops_per_clk_per_sm) return fail(SEQA_ERR_INVALID, "bad argument");
+    if (seqa_cuda_device_count() <= device) return fail(SEQA_ERR_NO_DEVICE, "no such device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    unsigned *out = nullptr;
+    long long *cyc = nullptr;
+    CK(cudaMalloc((void **)&out, (size_t)blocks * 256 * 4));
+    CK(cudaMalloc((void **)&cyc, (size_t)blocks * 8));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(e0, 0));
+        switch (which) {
+        case 0: int_peak_kernel<0><<<blocks, 256>>>(out, iters, 12345u, cyc); break;
+        case 1: int_peak_kernel<1><<<blocks, 256>>>(out, iters, 12345u, cyc); break;
+        case 2: int_peak_kernel<2><<<blocks, 256>>>(out, iters, 12345u, cyc); break;
+        case 3: int_peak_kernel<3><<<blocks, 256>>>(out, iters, 12345u, cyc); break;
+        case 4: int_peak_kernel<4><<<blocks, 256>>>(out, iters, 12345u, cyc); break;
+        case 5: int_peak_kernel<5><<<blocks, 256>>>(out, iters, 12345u, cyc); break;
+        case 6: int_peak_kernel<6><<<blocks, 256>>>(out, iters, 12345u, cyc); break;
+        case 7: int_peak_kernel<7><<<blocks, 256>>>(out, iters, 12345u, cyc); break;
+        case 8: int_peak_kernel<8><<<blocks, 256>>>(out, iters, 12345u, cyc); break;
+        default: int_peak_kernel<9><<<blocks, 256>>>(out, iters, 12345u, cyc); break;
+        }
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    std::vector<long long> h(blocks);
+    CK(cudaMemcpy(h.data(), cyc, (size_t)blocks * 8, cudaMemcpyDeviceToHost));
+    long long cmax = 0;
+    for (auto v : h) cmax = std::max(cmax, v);
+    const double per_thread = (double)iters * 4 * 8 * (which == 9 ? 5 : 1);
+    const double lane_ops = per_thread * 256.0 * blocks;
+    // cycles: every SM runs 8 blocks concurrently (2048 threads); elapsed SM cycles ~ longest block
+    *lane_ops_per_clk_per_sm = lane_ops / prop.multiProcessorCount / (double)cmax;
+    if (sm_clock_mhz) *sm_clock_mhz = (double)cmax / (best * 1e3);
+    cudaFree(out);
+    cudaFree(cyc);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return SEQA_OK;
+#endif
+}
+
+} // extern "C"

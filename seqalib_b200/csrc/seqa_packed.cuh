@@ -1,0 +1,294 @@
+// Inter-sequence fast path for short linear-gap pairs (NeedlemanWunschSA / SmithWatermanSA, reference
+// include/SANeedlemanWunsch.h:40-231, include/SASmithWaterman.h:47-339): one THREAD owns TWO pairs, packed
+// as the two signed 16-bit halves of every register, and the whole recurrence runs on the sm_100a packed
+// integer instructions:
+//
+//     sim  = PRMT(T0_j, T1_j, sel_i)                 one byte-permute = both pairs' match/mismatch score
+//     lg   = VIADD.16x2(Hleft, gap)
+//     t    = VIADDMNMX.S16x2[.RELU](Hdiag, sim, lg)   max(Hdiag+sim, Hleft+gap [,0])
+//     H    = VIADDMNMX.S16x2(Hup, gap, t)             max(Hup+gap, t)          <- the only serial op per row
+//
+// T0_j/T1_j are the "column profile" of the two pairs (4 int8 scores, one per possible row base) and sel_i is
+// a per-row PRMT selector (row base of pair 0 in nibble 0, of pair 1 in nibble 2, sign-extension nibbles 1/3),
+// both precomputed once per batch by pk_prep_kernel, so no per-cell base comparison exists at all.
+//
+// A thread sweeps its matrix in strips of R rows held in registers; the strip's bottom row crosses to the
+// next strip through a private column of shared memory.  Instead of 2-bit direction codes (which would cost
+// several compare/select slots per cell) the kernel stores the LOW BYTE of every H value: one PRMT packs
+// 2 rows x 2 pairs, one 128-bit store per 8 rows, laid out so a warp writes 512 contiguous bytes.  Adjacent
+// cells differ by far less than 128 (checked on the host against the scoring parameters), so the walk kernel
+// recovers exact neighbour values from the low bytes and applies the reference's own equality tests and
+// priority (diag > up > left) -- bit-exact by construction, no direction derivation on the hot loop.
+#pragma once
+#include "seqa_common.cuh"
+
+#define PK_NULL 0xffffffffu
+#define PK_BLOCK 128
+
+struct PkWarpJob {
+    uint32_t first;   // position of this warp's 64 pairs in perm[]
+    uint32_t Mw, Nw;  // max len1 / len2 over the 64 pairs
+    uint32_t nstrips; // ceil(Mw / R)
+    uint64_t trace_off;  // byte offset of the warp's trace region
+    uint64_t prof_off;   // uint2 index of the column profile  [Nw][32]
+    uint64_t rowsel_off; // uint32 index of the row selectors  [nstrips*R][32]
+};
+
+struct PkArgs {
+    const uint8_t *bases;
+    const uint64_t *off1, *off2;
+    const uint32_t *len1, *len2;
+    const uint32_t *perm; // pair ids, PK_NULL = padding
+    const PkWarpJob *jobs;
+    uint32_t njobs;
+    uint2 *prof;
+    uint32_t *rowsel;
+    uint8_t *trace;
+    int32_t *score;
+    uint32_t *end_i, *end_j, *start_i, *start_j;
+    uint8_t *slots;
+    const uint64_t *slot_off;
+    uint32_t *slot_start, *ops_len;
+    int *bad; // set when a base outside ACGT is met
+    int gap, match, mismatch, allow;
+    uint32_t smem_cols; // columns of shared boundary storage per thread
+    uint64_t npos;      // njobs * 64
+};
+
+// 2-bit code of an upper-case DNA letter: A0 C1 T2 G3 ((c>>1)&3); valid only for the four letters.
+__device__ __forceinline__ unsigned pk_code(unsigned c) { return (c >> 1) & 3u; }
+__device__ __forceinline__ bool pk_is_acgt(unsigned c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+// ---- prep: column profiles + row selectors ----------------------------------------------------------------
+__global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    const unsigned mm = A.allow ? ((unsigned)A.mismatch & 0xffu) : 0x80u; // -128 marks "never" (see header)
+    const unsigned mt = (unsigned)A.match & 0xffu;
+    for (uint32_t w = gw; w < A.njobs; w += nw) {
+        const PkWarpJob J = A.jobs[w];
+        const uint32_t p0 = A.perm[J.first + 2 * lane], p1 = A.perm[J.first + 2 * lane + 1];
+        const uint32_t M0 = p0 == PK_NULL ? 0u : A.len1[p0], N0 = p0 == PK_NULL ? 0u : A.len2[p0];
+        const uint32_t M1 = p1 == PK_NULL ? 0u : A.len1[p1], N1 = p1 == PK_NULL ? 0u : A.len2[p1];
+        const uint8_t *a0 = p0 == PK_NULL ? A.bases : A.bases + A.off1[p0];
+        const uint8_t *b0 = p0 == PK_NULL ? A.bases : A.bases + A.off2[p0];
+        const uint8_t *a1 = p1 == PK_NULL ? A.bases : A.bases + A.off1[p1];
+        const uint8_t *b1 = p1 == PK_NULL ? A.bases : A.bases + A.off2[p1];
+        bool bad = false;
+        for (uint32_t j = 0; j < J.Nw; j++) {
+            unsigned t0 = 0x80808080u, t1 = 0x80808080u; // padded column: every score -128
+            if (j < N0) {
+                const unsigned c = b0[j];
+                bad |= !pk_is_acgt(c);
+                t0 = mm * 0x01010101u;
+                t0 = (t0 & ~(0xffu << (8 * pk_code(c)))) | (mt << (8 * pk_code(c)));
+            }
+            if (j < N1) {
+                const unsigned c = b1[j];
+                bad |= !pk_is_acgt(c);
+                t1 = mm * 0x01010101u;
+                t1 = (t1 & ~(0xffu << (8 * pk_code(c)))) | (mt << (8 * pk_code(c)));
+            }
+            A.prof[J.prof_off + (uint64_t)j * 32 + lane] = make_uint2(t0, t1);
+        }
+        const uint32_t rows = J.nstrips * (uint32_t)R;
+        for (uint32_t i = 0; i < rows; i++) {
+            unsigned c0 = 0, c1 = 0;
+            if (i < M0) {
+                const unsigned c = a0[i];
+                bad |= !pk_is_acgt(c);
+                c0 = pk_code(c);
+            }
+            if (i < M1) {
+                const unsigned c = a1[i];
+                bad |= !pk_is_acgt(c);
+                c1 = pk_code(c);
+            }
+            // nibble0: byte c0 of T0; nibble1: its sign; nibble2: byte 4+c1 (= T1); nibble3: its sign
+            const unsigned sel = c0 | ((8u | c0) << 4) | ((4u | c1) << 8) | ((12u | c1) << 12);
+            A.rowsel[J.rowsel_off + (uint64_t)i * 32 + lane] = sel;
+        }
+        if (bad) *A.bad = 1;
+    }
+}
+
+__device__ __forceinline__ unsigned pk_dup(int v) { return ((unsigned)v & 0xffffu) * 0x00010001u; }
+__device__ __forceinline__ int pk_half(unsigned v, int k) { return (int)(int16_t)(k ? (v >> 16) : (v & 0xffffu)); }
+
+// ---- fill -------------------------------------------------------------------------------------------------
+// trace layout of a warp job: byte(pair-half k, row i, column j), i-1 = s*R + r, jj = j-1:
+//   trace_off + (((s*Nw + jj)*(R/8) + r/8)*32 + lane)*16 + ((r%8)/2)*4 + (r%2)*2 + k
+template <bool LOCAL, int R>
+__global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
+{
+    static_assert(R % 8 == 0, "R must be a multiple of 8");
+    SEQA_DYN_SMEM(unsigned, top);
+    constexpr int G = R / 8;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    const unsigned gap2 = pk_dup(A.gap);
+    for (uint32_t w = gw; w < A.njobs; w += nw) {
+        const PkWarpJob J = A.jobs[w];
+        const uint32_t p0 = A.perm[J.first + 2 * lane], p1 = A.perm[J.first + 2 * lane + 1];
+        const int M0 = p0 == PK_NULL ? 0 : (int)A.len1[p0], N0 = p0 == PK_NULL ? 0 : (int)A.len2[p0];
+        const int M1 = p1 == PK_NULL ? 0 : (int)A.len1[p1], N1 = p1 == PK_NULL ? 0 : (int)A.len2[p1];
+        const int Nw = (int)J.Nw;
+        const uint2 *__restrict__ prof = A.prof + J.prof_off + lane;
+        const uint32_t *__restrict__ rowsel = A.rowsel + J.rowsel_off + lane;
+        uint4 *__restrict__ trace = reinterpret_cast<uint4 *>(A.trace + J.trace_off) + lane;
+        int best0 = 0, best1 = 0, bi0 = 0, bi1 = 0; // SW: running (max, last row holding it)
+        int corner0 = 0, corner1 = 0;               // NW: H(M,N)
+        // row 0 of the matrix = first strip's upper boundary (SW 0, NW j*gap: include/SANeedlemanWunsch.h:61-62)
+        for (int jj = 0; jj < Nw; jj++) top[jj * PK_BLOCK + tid] = LOCAL ? 0u : pk_dup((jj + 1) * A.gap);
+        for (int s = 0; s < (int)J.nstrips; s++) {
+            const int i0 = s * R;
+            unsigned H[R], sel[R], rmax[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                sel[r] = rowsel[(uint64_t)(i0 + r) * 32];
+                H[r] = LOCAL ? 0u : pk_dup((i0 + r + 1) * A.gap); // column 0 (include/SANeedlemanWunsch.h:59-60)
+                rmax[r] = 0u;
+            }
+            unsigned diag = LOCAL ? 0u : pk_dup(i0 * A.gap);
+            uint4 *__restrict__ tr = trace + (uint64_t)s * Nw * G * 32;
+            for (int jj = 0; jj < Nw; jj++) {
+                const uint2 T = prof[(uint64_t)jj * 32];
+                const unsigned up = top[jj * PK_BLOCK + tid];
+                unsigned hd = diag, hu = up;
+                diag = up;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const unsigned sim = __byte_perm(T.x, T.y, sel[r]);
+                    const unsigned hold = H[r];
+                    const unsigned lg = __vadd2(hold, gap2);
+                    const unsigned t = LOCAL ? __viaddmax_s16x2_relu(hd, sim, lg) : __viaddmax_s16x2(hd, sim, lg);
+                    const unsigned hn = __viaddmax_s16x2(hu, gap2, t);
+                    H[r] = hn;
+                    hu = hn;
+                    hd = hold;
+                    if (LOCAL) rmax[r] = __vmaxs2(rmax[r], hn);
+                }
+                top[jj * PK_BLOCK + tid] = hu;
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    uint4 v;
+                    v.x = __byte_perm(H[8 * g + 0], H[8 * g + 1], 0x6420);
+                    v.y = __byte_perm(H[8 * g + 2], H[8 * g + 3], 0x6420);
+                    v.z = __byte_perm(H[8 * g + 4], H[8 * g + 5], 0x6420);
+                    v.w = __byte_perm(H[8 * g + 6], H[8 * g + 7], 0x6420);
+                    tr[((uint64_t)jj * G + g) * 32] = v;
+                }
+                if (!LOCAL) {
+                    if (jj + 1 == N0 || jj + 1 == N1) {
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            if (jj + 1 == N0 && i0 + r + 1 == M0) corner0 = pk_half(H[r], 0);
+                            if (jj + 1 == N1 && i0 + r + 1 == M1) corner1 = pk_half(H[r], 1);
+                        }
+                    }
+                }
+            }
+            if (LOCAL) {
+                // last maximum in row-major order (include/SASmithWaterman.h:177): rows ascending, ">="
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int i = i0 + r + 1;
+                    const int v0 = pk_half(rmax[r], 0), v1 = pk_half(rmax[r], 1);
+                    if (i <= M0 && v0 >= best0) { best0 = v0; bi0 = i; }
+                    if (i <= M1 && v1 >= best1) { best1 = v1; bi1 = i; }
+                }
+            }
+        }
+        if (p0 != PK_NULL) {
+            A.score[p0] = LOCAL ? best0 : corner0;
+            A.end_i[p0] = LOCAL ? (uint32_t)bi0 : (uint32_t)M0;
+            if (!LOCAL) A.end_j[p0] = (uint32_t)N0;
+        }
+        if (p1 != PK_NULL) {
+            A.score[p1] = LOCAL ? best1 : corner1;
+            A.end_i[p1] = LOCAL ? (uint32_t)bi1 : (uint32_t)M1;
+            if (!LOCAL) A.end_j[p1] = (uint32_t)N1;
+        }
+    }
+}
+
+// ---- walk -------------------------------------------------------------------------------------------------
+// One thread per pair.  Exact neighbour values are rebuilt from the stored low bytes:
+// H(n) = H(c) + sext8(low(n) - low(H(c))) for any cell n adjacent to the current cell c.
+template <bool LOCAL>
+__global__ void __launch_bounds__(256) pk_walk_kernel(PkArgs A, int R)
+{
+    const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= A.npos) return;
+    const uint32_t p = A.perm[pos];
+    if (p == PK_NULL) return;
+    const PkWarpJob J = A.jobs[pos >> 6];
+    const int lane = (int)((pos & 63) >> 1), half = (int)(pos & 1);
+    const int M = (int)A.len1[p], N = (int)A.len2[p];
+    const int G = R / 8;
+    const uint64_t Nw = J.Nw;
+    const uint8_t *tr = A.trace + J.trace_off + (uint64_t)lane * 16 + half;
+    const uint8_t *a = A.bases + A.off1[p], *b = A.bases + A.off2[p];
+    const int gap = A.gap;
+    auto low = [&](int i, int j) -> int { // i >= 1, j >= 1
+        const int ii = i - 1, s = ii / R, r = ii - s * R;
+        return tr[((((uint64_t)s * Nw + (uint64_t)(j - 1)) * G + (r >> 3)) * 32) * 16 + ((r & 7) >> 1) * 4 + (r & 1) * 2];
+    };
+    auto border = [&](int i, int j) -> int { return LOCAL ? 0 : (i == 0 ? j * gap : i * gap); };
+    auto near = [&](int hc, int i, int j) -> int { // exact H(i,j) given the exact value hc of an adjacent cell
+        if (i == 0 || j == 0) return border(i, j);
+        return hc + (int)(int8_t)(uint8_t)(low(i, j) - (hc & 0xff));
+    };
+    uint8_t *slot = A.slots + A.slot_off[p];
+    int k = M + N;
+    int i, j, h;
+    if (LOCAL) {
+        // MaxCol: the last column of row MaxRow holding MaxScore (include/SASmithWaterman.h:177-182)
+        const int best = A.score[p];
+        i = (int)A.end_i[p];
+        int e = 0, bj = N;
+        for (int jj = 1; jj <= N; jj++) {
+            e += (int)(int8_t)(uint8_t)(low(i, jj) - (e & 0xff));
+            if (e == best) bj = jj;
+        }
+        j = bj;
+        h = best;
+        A.end_j[p] = (uint32_t)j;
+    } else {
+        i = M;
+        j = N;
+        h = A.score[p];
+    }
+    while (i > 0 && j > 0) {
+        if (LOCAL && h == 0) break; // include/SASmithWaterman.h:281-284
+        const bool eq = a[i - 1] == b[j - 1];
+        const int hdg = near(h, i - 1, j - 1);
+        if ((eq || A.allow) && h == hdg + (eq ? A.match : A.mismatch)) { // include/SANeedlemanWunsch.h:190
+            slot[--k] = 0;
+            i--; j--;
+            h = hdg;
+            continue;
+        }
+        const int hup = near(h, i - 1, j);
+        if (h == hup + gap) { // include/SANeedlemanWunsch.h:216
+            slot[--k] = 1;
+            i--;
+            h = hup;
+        } else { // :223
+            h = near(h, i, j - 1);
+            slot[--k] = 2;
+            j--;
+        }
+    }
+    if (!LOCAL) { // borders: column 0 -> up, row 0 -> left
+        while (i > 0) { slot[--k] = 1; i--; }
+        while (j > 0) { slot[--k] = 2; j--; }
+    }
+    A.start_i[p] = (uint32_t)i;
+    A.start_j[p] = (uint32_t)j;
+    A.slot_start[p] = (uint32_t)k;
+    A.ops_len[p] = (uint32_t)(M + N - k);
+}

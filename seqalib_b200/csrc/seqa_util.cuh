@@ -1,0 +1,193 @@
+// Small device utilities of libseqa_cuda.so: exclusive scan, op-slot gather, synthetic-input generator,
+// integer-pipe micro-benchmark.
+#pragma once
+#include "seqa_common.cuh"
+
+// ---- exclusive scan of uint32 -> uint64 (three launches; n up to 2^32) --------------------------------
+#define SEQA_SCAN_TPB 256
+#define SEQA_SCAN_IPT 8
+#define SEQA_SCAN_TILE (SEQA_SCAN_TPB * SEQA_SCAN_IPT)
+
+__global__ void __launch_bounds__(SEQA_SCAN_TPB) scan_tile_sums_kernel(const uint32_t *__restrict__ in, uint64_t n,
+                                                                      uint64_t *__restrict__ tile_sum)
+{
+    __shared__ uint64_t wsum[SEQA_SCAN_TPB / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * SEQA_SCAN_TILE;
+    uint64_t s = 0;
+    for (int k = 0; k < SEQA_SCAN_IPT; k++) {
+        const uint64_t idx = base + (uint64_t)k * SEQA_SCAN_TPB + threadIdx.x;
+        if (idx < n) s += in[idx];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(SEQA_FULL, s, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t t = 0;
+        for (int w = 0; w < SEQA_SCAN_TPB / 32; w++) t += wsum[w];
+        tile_sum[blockIdx.x] = t;
+    }
+}
+
+// single block: in-place exclusive scan of the tile sums; total -> *total
+__global__ void __launch_bounds__(1024) scan_spine_kernel(uint64_t *__restrict__ tile_sum, uint64_t ntiles,
+                                                           uint64_t *__restrict__ total)
+{
+    __shared__ uint64_t part[1024];
+    const uint64_t per = (ntiles + blockDim.x - 1) / blockDim.x;
+    const uint64_t lo = min(ntiles, per * threadIdx.x), hi = min(ntiles, lo + per);
+    uint64_t s = 0;
+    for (uint64_t k = lo; k < hi; k++) s += tile_sum[k];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        for (unsigned k = 0; k < blockDim.x; k++) {
+            const uint64_t v = part[k];
+            part[k] = run;
+            run += v;
+        }
+        *total = run;
+    }
+    __syncthreads();
+    uint64_t run = part[threadIdx.x];
+    for (uint64_t k = lo; k < hi; k++) {
+        const uint64_t v = tile_sum[k];
+        tile_sum[k] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(SEQA_SCAN_TPB) scan_apply_kernel(const uint32_t *__restrict__ in, uint64_t n,
+                                                                  const uint64_t *__restrict__ tile_off,
+                                                                  uint64_t *__restrict__ out)
+{
+    // thread t owns the IPT consecutive items [base + t*IPT, +IPT)
+    __shared__ uint64_t wsum[SEQA_SCAN_TPB / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * SEQA_SCAN_TILE + (uint64_t)threadIdx.x * SEQA_SCAN_IPT;
+    uint32_t v[SEQA_SCAN_IPT];
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SEQA_SCAN_IPT; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        s += v[k];
+    }
+    // inclusive warp scan of s
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(SEQA_FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint64_t woff = 0;
+    for (int w = 0; w < warp; w++) woff += wsum[w];
+    uint64_t run = tile_off[blockIdx.x] + woff + inc - s;
+#pragma unroll
+    for (int k = 0; k < SEQA_SCAN_IPT; k++) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+
+// ---- gather the per-pair op slots (written back-to-front by the walk kernels) into the dense buffer ----
+struct GatherArgs {
+    uint64_t n_pairs;
+    const uint8_t *slots;
+    const uint64_t *slot_off;
+    const uint32_t *slot_start;
+    const uint32_t *ops_len;
+    const uint64_t *ops_off; // exclusive scan of ops_len
+    uint8_t *dense;
+};
+
+__global__ void __launch_bounds__(256) gather_ops_kernel(GatherArgs A)
+{
+    // 8 lanes per pair: local alignments of short reads are a few dozen ops
+    const int sub = threadIdx.x & 7;
+    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const uint64_t ng = ((uint64_t)gridDim.x * blockDim.x) >> 3;
+    for (uint64_t p = g; p < A.n_pairs; p += ng) {
+        const uint8_t *src = A.slots + A.slot_off[p] + A.slot_start[p];
+        uint8_t *dst = A.dense + A.ops_off[p];
+        const uint32_t len = A.ops_len[p];
+        for (uint32_t k = sub; k < len; k += 8) dst[k] = src[k];
+    }
+}
+
+// ---- synthetic inputs: i.i.d. uniform DNA from a counter-based generator ----------------
+// base(pos) of sequence w of pair p = "ACGT"[(splitmix64(key(p,w) + pos/32) >> (2*(pos%32))) & 3]
+struct GenArgs {
+    uint64_t seed, first_pair, n_pairs;
+    const uint64_t *off1, *off2;
+    const uint32_t *len1, *len2;
+    uint8_t *bases;
+};
+
+__global__ void __launch_bounds__(256) generate_kernel(GenArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t p = gw; p < A.n_pairs; p += nw) {
+        for (int w = 0; w < 2; w++) {
+            const uint32_t len = w ? A.len2[p] : A.len1[p];
+            uint8_t *dst = A.bases + (w ? A.off2[p] : A.off1[p]);
+            const uint64_t key = synth_key(A.seed, A.first_pair + p, w);
+            for (uint32_t pos = lane; pos < len; pos += 32) {
+                const uint64_t word = splitmix64(key + (uint64_t)(pos >> 5));
+                dst[pos] = (uint8_t)("ACGT"[(word >> (2 * (pos & 31))) & 3]);
+            }
+        }
+    }
+}
+
+// ---- integer-pipe micro-benchmark (SURVEY.md 8d "Peak") -------------------------------------------------
+// ILP independent dependency chains of one instruction class per thread; reports via clock64.
+#ifndef SEQA_EMU
+template <int WHICH>
+__global__ void __launch_bounds__(256) int_peak_kernel(unsigned *out, int iters, unsigned seed, long long *cycles)
+{
+    constexpr int ILP = 8;
+    unsigned x[ILP], y[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; k++) {
+        x[k] = seed * (k + 1) + threadIdx.x;
+        y[k] = seed ^ (0x9E3779B9u * (k + 3));
+    }
+    const unsigned c = seed | 0x00010001u;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int k = 0; k < ILP; k++) {
+                if (WHICH == 0) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(c));
+                else if (WHICH == 1) asm volatile("max.s32 %0, %0, %1;" : "+r"(x[k]) : "r"(y[k]));
+                else if (WHICH == 2) x[k] = (unsigned)__viaddmax_s32((int)x[k], (int)c, (int)y[k]);
+                else if (WHICH == 3) x[k] = __vimax3_s16x2(x[k], y[k], c);
+                else if (WHICH == 4) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(c), "r"(y[k]));
+                else if (WHICH == 5) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k]) : "r"(c), "r"(y[k]));
+                else if (WHICH == 6) x[k] = __byte_perm(x[k], y[k], 0x6240);
+                else if (WHICH == 7) x[k] = __vadd2(x[k], c);
+                else if (WHICH == 8) x[k] = __viaddmax_s16x2_relu(x[k], c, y[k]);
+                else { // 9: the packed SW cell mix: PRMT + VIADD.16x2 + VIADDMNMX.RELU + VIADDMNMX + VIMNMX
+                    const unsigned sim = __byte_perm(y[k], c, x[k] & 0x7777u);
+                    const unsigned lg = __vadd2(x[k], c);
+                    const unsigned t = __viaddmax_s16x2_relu(y[k], sim, lg);
+                    x[k] = __viaddmax_s16x2(x[k], c, t);
+                    y[k] = __vmaxs2(y[k], x[k]);
+                }
+            }
+        }
+    }
+    const long long t1 = clock64();
+    unsigned acc = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; k++) acc ^= x[k] ^ y[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+#endif

@@ -1,0 +1,61 @@
+"""Shared helpers for the test-suite (test infrastructure; may import oracle/)."""
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import pyoracle as orc  # noqa: E402
+from seqalib_b200 import capi  # noqa: E402
+
+EMU_SO = os.path.join(ROOT, "tests", "emu", "libseqa_emu.so")
+
+
+def scoring_to_params(algo, sc, **kw):
+    """oracle Scoring -> C-ABI seqa_params (allow=False reproduces the 2-argument ScoringSystem)."""
+    return capi.make_params(algo, gap=sc.gap, gap_open=sc.gap_open, gap_extend=sc.gap_extend, match=sc.match,
+                            mismatch=sc.mismatch if sc.allow else 0, allow=sc.allow, **kw)
+
+
+def random_pairs(rng, n, lo, hi, alphabet="ACGT", related=0.0):
+    out = []
+    for _ in range(n):
+        l1, l2 = int(rng.integers(lo, hi + 1)), int(rng.integers(lo, hi + 1))
+        a = "".join(alphabet[k] for k in rng.integers(0, len(alphabet), l1))
+        if related > 0 and l1 > 0:
+            b = []
+            for ch in a:
+                r = rng.random()
+                if r < related * 0.6:
+                    b.append(alphabet[int(rng.integers(0, len(alphabet)))])
+                elif r < related * 0.8:
+                    continue
+                elif r < related:
+                    b.append(ch)
+                    b.append(alphabet[int(rng.integers(0, len(alphabet)))])
+                else:
+                    b.append(ch)
+            b = "".join(b)[:max(hi, 1)]
+        else:
+            b = "".join(alphabet[k] for k in rng.integers(0, len(alphabet), l2))
+        out.append((a, b))
+    return out
+
+
+def check_batch_against_oracle(lib, algo, sc, pairs, flags=0, device_count=1, label=""):
+    """Run `pairs` through seqa_cuda_align_batch and compare every field with the C oracle. Returns #pairs."""
+    bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+    prm = scoring_to_params(algo, sc, flags=flags, device_count=device_count)
+    res = lib.align_batch(prm, bases, off1, off2, len1, len2)
+    for p, (a, b) in enumerate(pairs):
+        o = orc.oracle_align(algo, sc, a, b)
+        got = dict(score=int(res.score[p]), start_i=int(res.start_i[p]), start_j=int(res.start_j[p]),
+                   end_i=int(res.end_i[p]), end_j=int(res.end_j[p]))
+        exp = {k: o[k] for k in got}
+        ops = res.pair_ops(p)
+        if got != exp or not np.array_equal(ops, o["ops"]):
+            raise AssertionError("%s %s %r pair %d (%s | %s): got %r ops %s, expected %r ops %s" % (
+                label, algo, sc, p, a, b, got, ops.tolist(), exp, o["ops"].tolist()))
+    return len(pairs)
