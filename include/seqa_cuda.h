@@ -129,6 +129,10 @@ typedef struct seqa_batch_out {
  * inter-device communication.  Re-entrant for disjoint device sets. */
 int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, seqa_batch_out *out);
 
+/* Frees the per-device contexts (device buffers) that seqa_cuda_align_batch creates lazily and keeps between
+ * calls -- the only hidden state of the library. */
+void seqa_cuda_trim(void);
+
 const char *seqa_cuda_last_error(void);
 int seqa_cuda_device_count(void); /* number of visible CUDA devices, 0 if none / no driver */
 int seqa_cuda_abi_version(void);
@@ -136,7 +140,7 @@ int seqa_cuda_abi_version(void);
 /* ---- resident (device-side) interface ------------------------------------------------------------
  * The same path split into its stages so that a caller (bench.py, a GPU-resident producer/consumer)
  * can keep inputs and results in HBM: create -> upload | generate -> run (repeatable) -> download.
- * `stream` is a cudaStream_t the caller owns (e.g. a torch stream), or NULL for a private stream. */
+ * `stream` is a cudaStream_t the caller owns (the caller's own stream), or NULL for a private stream. */
 typedef struct seqa_ctx seqa_ctx;
 
 int seqa_ctx_create(seqa_ctx **ctx, int device, void *stream);

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -860,6 +861,56 @@ int seqa_ctx_download_inputs(seqa_ctx *c, char *bases, uint64_t bases_len, uint6
     return SEQA_OK;
 }
 
+// Lazily created per-device contexts reused by seqa_cuda_align_batch (device buffers survive between calls;
+// seqa_cuda_trim() frees them).  A device whose cached context is busy gets a temporary one.
+static std::mutex g_cache_mu;
+static seqa_ctx *g_cache[64];
+static bool g_cache_busy[64];
+
+static int cache_acquire(int device, seqa_ctx **out, int *cached)
+{
+    *cached = 0;
+    if (device >= 0 && device < 64) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (g_cache[device] && !g_cache_busy[device]) {
+            g_cache_busy[device] = true;
+            *out = g_cache[device];
+            *cached = 1;
+            return SEQA_OK;
+        }
+        if (!g_cache[device]) {
+            int s = seqa_ctx_create(out, device, nullptr);
+            if (s != SEQA_OK) return s;
+            g_cache[device] = *out;
+            g_cache_busy[device] = true;
+            *cached = 1;
+            return SEQA_OK;
+        }
+    }
+    return seqa_ctx_create(out, device, nullptr);
+}
+
+static void cache_release(seqa_ctx *c, int cached)
+{
+    if (!c) return;
+    if (!cached) {
+        seqa_ctx_destroy(c);
+        return;
+    }
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache_busy[c->device] = false;
+}
+
+void seqa_cuda_trim(void)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (int d = 0; d < 64; d++)
+        if (g_cache[d] && !g_cache_busy[d]) {
+            seqa_ctx_destroy(g_cache[d]);
+            g_cache[d] = nullptr;
+        }
+}
+
 int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, seqa_batch_out *out)
 {
     CKS(validate_params(params));
@@ -889,10 +940,11 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
         }
     }
     std::vector<seqa_ctx *> ctxs(nd, nullptr);
+    std::vector<int> cached(nd, 0);
     std::vector<int> status(nd, SEQA_OK);
     std::vector<std::string> errs(nd);
     auto work = [&](int d) {
-        int s = seqa_ctx_create(&ctxs[d], first + d, nullptr);
+        int s = cache_acquire(first + d, &ctxs[d], &cached[d]);
         if (s == SEQA_OK) s = ctx_upload_range(ctxs[d], params, in, cut[d], cut[d + 1]);
         if (s == SEQA_OK) s = ctx_run(ctxs[d]);
         if (s == SEQA_OK) s = ctx_resolve(ctxs[d]);
@@ -919,7 +971,7 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
             base += used;
         }
     }
-    for (auto c : ctxs) seqa_ctx_destroy(c);
+    for (int d = 0; d < nd; d++) cache_release(ctxs[d], cached[d]);
     out->ops_used = base;
     return rc;
 }

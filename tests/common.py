@@ -38,6 +38,8 @@ def random_pairs(rng, n, lo, hi, alphabet="ACGT", related=0.0):
                 else:
                     b.append(ch)
             b = "".join(b)[:max(hi, 1)]
+            if lo >= 1 and not b:
+                b = alphabet[0]
         else:
             b = "".join(alphabet[k] for k in rng.integers(0, len(alphabet), l2))
         out.append((a, b))

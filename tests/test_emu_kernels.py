@@ -1,0 +1,92 @@
+"""Kernel LOGIC on the CPU: the unmodified kernel sources, compiled for the SIMT emulator under tests/emu, run
+through the same C ABI and are compared with the oracle.  (The real parity tests are the `-m gpu` ones; this keeps
+index arithmetic, tie-breaks and the packed-integer tricks checked where no GPU exists.)"""
+import numpy as np
+import pytest
+
+from common import capi, check_batch_against_oracle, orc, random_pairs, scoring_to_params
+from test_oracle_golden import sc_from
+
+S = orc.Scoring
+EDGE = [("AAAGAATGCAT", "AAACTCAT"), ("AATCG", "AACG"), ("", "ACGT"), ("ACGT", ""), ("", ""), ("A", "A"), ("A", "C"),
+        ("AAAAAAAAAAAAAAAAAAAA", "AAAAA"), ("ACGTNACGT", "ACGTACGT"), ("acgt", "ACGT")]
+
+
+@pytest.mark.parametrize("algo,sc", [
+    ("nw", S.linear(-1, 2)), ("nw", S.linear(-1, 2, -1)), ("nw", S.linear(-3, 4, -2)),
+    ("sw", S.linear(-1, 1, -1)), ("sw", S.linear(-2, 1, -1, False)), ("sw", S.linear(-1, 2)),
+    ("ggotoh", S.affine(-3, -1, 1, -1)), ("ggotoh", S.affine(-3, -1, 1, -1, False)), ("ggotoh", S.affine(0, -2, 3, -1)),
+    ("lgotoh", S.affine(-3, -1, 1, -1)), ("lgotoh", S.affine(-1, -1, 2, -2, False)),
+])
+def test_matrix_algorithms(emu_lib, algo, sc):
+    rng = np.random.default_rng(11)
+    pairs = list(EDGE) + random_pairs(rng, 30, 1, 70) + random_pairs(rng, 8, 1, 50, "AC") + \
+        random_pairs(rng, 6, 120, 180) + random_pairs(rng, 8, 1, 90, related=0.3)
+    for flags in (0, capi.FLAG_FORCE_GENERIC):
+        check_batch_against_oracle(emu_lib, algo, sc, pairs, flags=flags)
+
+
+def test_packed_path_is_taken(emu_lib):
+    rng = np.random.default_rng(3)
+    pairs = random_pairs(rng, 70, 20, 40)
+    bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+    ctx = capi.Ctx(emu_lib)
+    ctx.upload(scoring_to_params("sw", S.linear(-1, 1, -1)), bases, off1, off2, len1, len2)
+    ctx.run()
+    ctx.sync()
+    assert ctx.last_kernel() == "pk_fill_sw_s16x2"
+    assert ctx.cells() == int((len1.astype(np.int64) * len2).sum())
+    # a non-ACGT base voids the packed result: the batch is re-planned onto the 8-bit generic kernels
+    pairs[5] = (pairs[5][0][:10] + "N" + pairs[5][0][10:], pairs[5][1])
+    check_batch_against_oracle(emu_lib, "sw", S.linear(-1, 1, -1), pairs)
+
+
+def test_golden_through_emulated_kernels(emu_lib, golden):
+    groups = {}
+    for v in golden:
+        if v["algo"] in ("hirschberg", "myersmiller") and False:
+            continue
+        groups.setdefault((v["algo"], tuple(v["scoring"])), []).append(v)
+    n = 0
+    for (algo, sct), vs in groups.items():
+        sc = sc_from(sct)
+        pairs = [(v["seq1"], v["seq2"]) for v in vs]
+        bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+        res = emu_lib.align_batch(scoring_to_params(algo, sc), bases, off1, off2, len1, len2)
+        for p, v in enumerate(vs):
+            got = orc.expand(algo, v["seq1"], v["seq2"], int(res.start_i[p]), int(res.start_j[p]), int(res.end_i[p]),
+                             int(res.end_j[p]), res.pair_ops(p))
+            assert got == (v["row1"], v["row2"], v["flags"]), v
+            if v["score"] is not None:
+                assert int(res.score[p]) == v["score"], v
+            n += 1
+    assert n == len(golden)
+
+
+def test_two_device_shards(emu_lib):
+    # the emulator exposes two fake devices: exercises the static split + gather of seqa_cuda_align_batch
+    rng = np.random.default_rng(5)
+    pairs = random_pairs(rng, 41, 1, 60)
+    check_batch_against_oracle(emu_lib, "nw", S.linear(-1, 2, -1), pairs, device_count=2)
+    check_batch_against_oracle(emu_lib, "lgotoh", S.affine(-3, -1, 1, -1), pairs, device_count=2)
+
+
+def test_synthetic_generator_matches_spec(emu_lib):
+    # SURVEY.md 8d generator: regenerate on the CPU, compare with what the device wrote
+    def splitmix64(z):
+        z = (z + 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+        return z ^ (z >> 31)
+    seed, first, n = 20240607, 1000, 9
+    ctx = capi.Ctx(emu_lib)
+    ctx.generate(scoring_to_params("sw", S.linear(-1, 1, -1)), seed, first, n, 1)
+    l1 = [50 + splitmix64(splitmix64(seed ^ (2 * (first + p))) ^ 0xC0FFEE) % 951 for p in range(n)]
+    l2 = [50 + splitmix64(splitmix64(seed ^ (2 * (first + p) + 1)) ^ 0xC0FFEE) % 951 for p in range(n)]
+    bases, off1, off2, len1, len2 = ctx.download_inputs(sum(l1) + sum(l2))
+    assert len1.tolist() == l1 and len2.tolist() == l2
+    for p in range(n):
+        for w, (off, ln) in enumerate(((off1[p], l1[p]), (off2[p], l2[p]))):
+            key = splitmix64(seed ^ (2 * (first + p) + w))
+            exp = "".join("ACGT"[(splitmix64((key + pos // 32) & (2 ** 64 - 1)) >> (2 * (pos % 32))) & 3] for pos in range(ln))
+            assert bytes(bases[int(off):int(off) + ln]).decode() == exp

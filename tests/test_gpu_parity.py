@@ -1,0 +1,187 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (seqa_cuda_align_batch / seqa_ctx_*), against the
+oracle on the same inputs -- bit-exact scores, end points and op strings -- plus the committed golden vectors of
+the unmodified reference and size-independent properties at the BASELINE batch size."""
+import numpy as np
+import pytest
+
+from common import capi, check_batch_against_oracle, orc, random_pairs, scoring_to_params
+from seqalib_b200 import synth
+from test_oracle_golden import sc_from
+
+pytestmark = pytest.mark.gpu
+S = orc.Scoring
+EDGE = [("AAAGAATGCAT", "AAACTCAT"), ("AATCG", "AACG"), ("", "ACGT"), ("ACGT", ""), ("", ""), ("A", "A"), ("A", "C"),
+        ("AAAAAAAAAAAAAAAAAAAA", "AAAAA"), ("ACGTNACGT", "ACGTACGT"), ("acgt", "ACGT"), ("T" * 300, "T" * 299),
+        ("AC" * 200, "CA" * 180)]
+
+MATRIX_CASES = [
+    ("nw", S.linear(-1, 2)), ("nw", S.linear(-1, 2, -1)), ("nw", S.linear(-3, 4, -2)), ("nw", S.linear(-2, 1, -1, False)),
+    ("sw", S.linear(-1, 1, -1)), ("sw", S.linear(-2, 1, -1, False)), ("sw", S.linear(-1, 2)), ("sw", S.linear(-1, 2, -1)),
+    ("ggotoh", S.affine(-3, -1, 1, -1)), ("ggotoh", S.affine(-3, -1, 1, -1, False)), ("ggotoh", S.affine(0, -2, 3, -1)),
+    ("lgotoh", S.affine(-3, -1, 1, -1)), ("lgotoh", S.affine(-1, -1, 2, -2, False)), ("lgotoh", S.affine(-3, -1, 2, -1)),
+]
+LINSPACE_CASES = [
+    ("hirschberg", S.linear(-1, 2, -1)), ("hirschberg", S.linear(-1, 2)), ("hirschberg", S.linear(-2, 3, -2, False)),
+    ("myersmiller", S.affine(-3, -1, 1, -1)), ("myersmiller", S.affine(-3, -1, 1, -1, False)), ("myersmiller", S.affine(0, -1, 2, -1)),
+]
+
+
+def test_golden_vectors(gpu_lib, golden):
+    groups = {}
+    for v in golden:
+        groups.setdefault((v["algo"], tuple(v["scoring"])), []).append(v)
+    n = 0
+    for (algo, sct), vs in groups.items():
+        sc = sc_from(sct)
+        pairs = [(v["seq1"], v["seq2"]) for v in vs]
+        bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+        res = gpu_lib.align_batch(scoring_to_params(algo, sc), bases, off1, off2, len1, len2)
+        for p, v in enumerate(vs):
+            got = orc.expand(algo, v["seq1"], v["seq2"], int(res.start_i[p]), int(res.start_j[p]), int(res.end_i[p]),
+                             int(res.end_j[p]), res.pair_ops(p))
+            assert got == (v["row1"], v["row2"], v["flags"]), v
+            if v["score"] is not None:
+                assert int(res.score[p]) == v["score"], v
+            n += 1
+    assert n == len(golden)
+
+
+@pytest.mark.parametrize("algo,sc", MATRIX_CASES)
+def test_matrix_algorithms_random(gpu_lib, algo, sc):
+    rng = np.random.default_rng(17)
+    lg = algo == "lgotoh"
+    pairs = [e for e in EDGE if not (lg and (not e[0] or not e[1]))]
+    pairs += random_pairs(rng, 600, 1, 200) + random_pairs(rng, 150, 1, 120, "AC") + random_pairs(rng, 150, 1, 250, related=0.3)
+    pairs += random_pairs(rng, 30, 300, 700) + random_pairs(rng, 6, 900, 1300, related=0.2)
+    if lg:
+        pairs = [p for p in pairs if (len(p[0]), len(p[1])) not in ((314, 288), (60, 57), (61, 58))]
+    check_batch_against_oracle(gpu_lib, algo, sc, pairs)
+    check_batch_against_oracle(gpu_lib, algo, sc, pairs[:400], flags=capi.FLAG_FORCE_GENERIC)
+
+
+@pytest.mark.parametrize("algo,sc", LINSPACE_CASES)
+def test_linear_space_algorithms_random(gpu_lib, algo, sc):
+    rng = np.random.default_rng(23)
+    pairs = list(EDGE) + random_pairs(rng, 400, 1, 200) + random_pairs(rng, 100, 1, 120, "AC") + \
+        random_pairs(rng, 100, 1, 250, related=0.3) + random_pairs(rng, 12, 1000, 3000) + \
+        random_pairs(rng, 6, 2000, 5000, related=0.25) + [("A" * 700, "ACGT" * 150), ("ACGT" * 200, "T" * 40)]
+    check_batch_against_oracle(gpu_lib, algo, sc, pairs)
+
+
+@pytest.mark.parametrize("algo", ["sw", "nw"])
+def test_config2_shape_150bp(gpu_lib, algo):
+    """20,000 pairs of the BASELINE 150 bp workload (same generator and seed as bench.py) vs the oracle."""
+    n = 20000
+    sc = S.linear(-1, 1, -1) if algo == "sw" else S.linear(-1, 2, -1)
+    ctx = capi.Ctx(gpu_lib)
+    ctx.generate(scoring_to_params(algo, sc), synth.SEED, 0, n, 0, 150, 150)
+    ctx.run()
+    res = ctx.download(ops_capacity=n * 300)
+    assert ctx.last_kernel().startswith("pk_fill")
+    bases, off1, off2, l1, l2 = ctx.download_inputs(n * 300)
+    hb, _, _, _, _ = synth.batch(synth.SEED, 0, 64, 0, 150, 150)
+    assert np.array_equal(hb, bases[:64 * 300])  # device generator == numpy generator
+    for p in range(n):
+        a = bytes(bases[int(off1[p]):int(off1[p]) + 150]).decode()
+        b = bytes(bases[int(off2[p]):int(off2[p]) + 150]).decode()
+        o = orc.oracle_align(algo, sc, a, b)
+        assert int(res.score[p]) == o["score"], p
+        assert (int(res.start_i[p]), int(res.start_j[p]), int(res.end_i[p]), int(res.end_j[p])) == \
+            (o["start_i"], o["start_j"], o["end_i"], o["end_j"]), p
+        assert np.array_equal(res.pair_ops(p), o["ops"]), p
+
+
+def _rescore_all(bases, off1, off2, res, n, gap, match, mismatch):
+    """Vectorised re-scoring of every alignment of a batch from its ops (linear gaps)."""
+    ops_len = res.ops_len[:n].astype(np.int64)
+    ops_off = res.ops_off[:n].astype(np.int64)
+    tot = int(ops_len.sum())
+    assert np.array_equal(ops_off, np.concatenate(([0], np.cumsum(ops_len)[:-1])))  # dense, in pair order
+    ops = res.ops[:tot]
+    pair = np.repeat(np.arange(n), ops_len)
+    di = (ops != 2).astype(np.int64)
+    dj = (ops != 1).astype(np.int64)
+    ci = np.cumsum(di) - di
+    cj = np.cumsum(dj) - dj
+    first = ops_off[pair]
+    i = ci - ci[np.minimum(first, tot - 1)] * (ops_len[pair] > 0) + res.start_i[:n].astype(np.int64)[pair]
+    j = cj - cj[np.minimum(first, tot - 1)] * (ops_len[pair] > 0) + res.start_j[:n].astype(np.int64)[pair]
+    a = bases[(off1[:n].astype(np.int64)[pair] + i)]
+    b = bases[(off2[:n].astype(np.int64)[pair] + j)]
+    s = np.where(ops == 0, np.where(a == b, match, mismatch), gap).astype(np.int64)
+    score = np.zeros(n, dtype=np.int64)
+    np.add.at(score, pair, s)
+    ni = np.zeros(n, dtype=np.int64)
+    nj = np.zeros(n, dtype=np.int64)
+    np.add.at(ni, pair, di)
+    np.add.at(nj, pair, dj)
+    return score, ni, nj
+
+
+def test_config2_full_size_properties(gpu_lib):
+    """BASELINE configs[1] at full size (1,000,000 x 150 bp SW): size-independent properties of every result +
+    an oracle comparison of a 3,000-pair random sample."""
+    n = 1_000_000
+    sc = S.linear(-1, 1, -1)
+    ctx = capi.Ctx(gpu_lib)
+    ctx.generate(scoring_to_params("sw", sc), synth.SEED, 0, n, 0, 150, 150)
+    ctx.run()
+    res = ctx.download(ops_capacity=n * 300)
+    bases, off1, off2, l1, l2 = ctx.download_inputs(n * 300)
+    score, ni, nj = _rescore_all(bases, off1, off2, res, n, -1, 1, -1)
+    assert np.array_equal(score, res.score[:n].astype(np.int64))       # the ops re-score to the reported score
+    assert np.array_equal(ni, res.end_i[:n].astype(np.int64) - res.start_i[:n])  # ops span [start,end)
+    assert np.array_equal(nj, res.end_j[:n].astype(np.int64) - res.start_j[:n])
+    assert (res.score[:n] > 0).all() and (res.end_i[:n] <= 150).all() and (res.end_j[:n] <= 150).all()
+    # a local alignment starts and ends with a diagonal (match) step
+    has = res.ops_len[:n] > 0
+    assert (res.ops[res.ops_off[:n][has].astype(np.int64)] == 0).all()
+    # idempotence: a second run over the resident batch gives identical results
+    ctx.run()
+    res2 = ctx.download(ops_capacity=n * 300)
+    assert np.array_equal(res.score[:n], res2.score[:n]) and res.c.ops_used == res2.c.ops_used
+    assert np.array_equal(res.ops[:res.c.ops_used], res2.ops[:res2.c.ops_used])
+    rng = np.random.default_rng(99)
+    for p in rng.integers(0, n, 3000):
+        p = int(p)
+        a = bytes(bases[int(off1[p]):int(off1[p]) + 150]).decode()
+        b = bytes(bases[int(off2[p]):int(off2[p]) + 150]).decode()
+        o = orc.oracle_align("sw", sc, a, b)
+        assert int(res.score[p]) == o["score"] and np.array_equal(res.pair_ops(p), o["ops"]), p
+        assert (int(res.start_i[p]), int(res.start_j[p]), int(res.end_i[p]), int(res.end_j[p])) == \
+            (o["start_i"], o["start_j"], o["end_i"], o["end_j"]), p
+
+
+def test_mixed_length_batch(gpu_lib):
+    """BASELINE configs[4] shape (independent U[50,1000] lengths, NW + SW over the same pairs), 3,000 pairs."""
+    n = 3000
+    for algo, sc in (("nw", S.linear(-1, 2, -1)), ("sw", S.linear(-1, 1, -1))):
+        ctx = capi.Ctx(gpu_lib)
+        ctx.generate(scoring_to_params(algo, sc), synth.SEED, 5_000_000, n, 1)
+        ctx.run()
+        l1, l2 = synth.lengths(synth.SEED, 5_000_000, n)
+        tot = int(l1.sum() + l2.sum())
+        res = ctx.download(ops_capacity=tot)
+        bases, off1, off2, d1, d2 = ctx.download_inputs(tot)
+        assert np.array_equal(d1, l1) and np.array_equal(d2, l2)
+        for p in range(n):
+            a = bytes(bases[int(off1[p]):int(off1[p]) + int(l1[p])]).decode()
+            b = bytes(bases[int(off2[p]):int(off2[p]) + int(l2[p])]).decode()
+            o = orc.oracle_align(algo, sc, a, b)
+            assert int(res.score[p]) == o["score"] and np.array_equal(res.pair_ops(p), o["ops"]), (algo, p)
+
+
+def test_multi_device_split(gpu_lib):
+    if gpu_lib.device_count() < 2:
+        pytest.skip("one device visible")
+    rng = np.random.default_rng(5)
+    pairs = random_pairs(rng, 500, 1, 200)
+    check_batch_against_oracle(gpu_lib, "sw", S.linear(-1, 1, -1), pairs, device_count=2)
+    check_batch_against_oracle(gpu_lib, "ggotoh", S.affine(-3, -1, 1, -1), pairs, device_count=gpu_lib.device_count())
+
+
+def test_int_peak_microbenchmark(gpu_lib):
+    import ctypes as C
+    v, mhz = C.c_double(), C.c_double()
+    gpu_lib.check(gpu_lib.L.seqa_cuda_int_peak(0, 0, C.byref(v), C.byref(mhz)))
+    assert 16 <= v.value <= 140 and 500 <= mhz.value <= 2500
