@@ -181,7 +181,8 @@ def run_ours(args):
     n = args.pairs
     prm = capi.make_params("sw", gap=SCORING["gap"], match=SCORING["match"], mismatch=SCORING["mismatch"], allow=True,
                            device_first=local, device_count=1)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # the library launches on this stream; the timing events are recorded on it
+    torch.cuda.set_stream(stream)
     ctx = capi.Ctx(lib, local, stream.cuda_stream)
     ctx.generate(prm, SEED, rank * n, n, 0, LEN, LEN)  # inputs resident in HBM, nothing crosses PCIe
     cells = ctx.cells()

@@ -21,6 +21,20 @@ using std::min;
     type *name = reinterpret_cast<type *>(seqa_dyn_smem_raw_)
 #endif
 
+// PRMT in its native default mode: selector nibble k picks byte (nibble & 7) of {b:a}; nibble bit 3 replicates
+// that byte's sign bit instead.  (The CUDA intrinsic __byte_perm masks the selector with 0x7777 -- an extra LOP3
+// and no sign replication -- so the kernels go to the PTX instruction directly.)
+#ifdef SEQA_EMU
+static inline unsigned seqa_prmt(unsigned a, unsigned b, unsigned s) { return emu_prmt(a, b, s); }
+#else
+__device__ __forceinline__ unsigned seqa_prmt(unsigned a, unsigned b, unsigned s)
+{
+    unsigned r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+    return r;
+}
+#endif
+
 #define SEQA_WARP 32
 #define SEQA_FULL 0xffffffffu
 #define SEQA_GOTOH_NEG (-10000) /* the reference's literal "-infinity", include/SAGlobalGotoh.h:78-79 */

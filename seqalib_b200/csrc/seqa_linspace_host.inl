@@ -1,8 +1,160 @@
+// Host driver of the linear-space aligners (included by seqa_cuda.cu): level-synchronous recursion.
 namespace {
-int ls_plan(LsState &, const std::vector<uint32_t> &, const std::vector<uint32_t> &, const std::vector<uint32_t> &, bool, int)
+
+template <class T> int ls_alloc(T **p, uint64_t n)
 {
-    return fail(SEQA_ERR_UNSUPPORTED, "linear-space algorithms: not built yet");
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    if (cudaMalloc((void **)p, std::max<uint64_t>(n, 1) * sizeof(T)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(SEQA_ERR_NOMEM, "device allocation of %llu bytes failed", (unsigned long long)(n * sizeof(T)));
+    }
+    return SEQA_OK;
 }
-int ls_run(seqa_ctx *, bool) { return fail(SEQA_ERR_UNSUPPORTED, "linear-space algorithms: not built yet"); }
-void ls_release(LsState &) {}
+
+void ls_release(LsState &ls)
+{
+    if (ls.d_nodes[0]) cudaFree(ls.d_nodes[0]);
+    if (ls.d_nodes[1]) cudaFree(ls.d_nodes[1]);
+    if (ls.d_count) cudaFree(ls.d_count);
+    if (ls.d_overflow) cudaFree(ls.d_overflow);
+    if (ls.d_rows) cudaFree(ls.d_rows);
+    if (ls.d_row_off) cudaFree(ls.d_row_off);
+    if (ls.d_row_w) cudaFree(ls.d_row_w);
+    if (ls.d_idx) cudaFree(ls.d_idx);
+    ls = LsState();
+}
+
+int ls_plan(LsState &ls, const std::vector<uint32_t> &len1, const std::vector<uint32_t> &len2,
+            const std::vector<uint32_t> &idx, bool myers_miller, int sms)
+{
+    (void)sms;
+    const uint64_t n = idx.size();
+    ls.mm = myers_miller;
+    ls.roots.resize(n);
+    ls.row_off.assign(len1.size(), 0);
+    ls.row_w.assign(len1.size(), 0);
+    const uint64_t narr = myers_miller ? 6 : 3;
+    uint64_t run = 0, sum_m = 0;
+    for (uint64_t k = 0; k < n; k++) {
+        const uint32_t p = idx[k];
+        const uint64_t M = len1[p], N = len2[p];
+        if (M + N > 0x3fffffffull) return fail(SEQA_ERR_UNSUPPORTED, "pair %u is too long for 32-bit cell indices", p);
+        // an internal node at depth d sits at column offset j0 + q, q < 2^d <= M: one array needs N + M + 2 ints
+        const uint64_t w = N + M + 2;
+        ls.row_off[p] = run;
+        ls.row_w[p] = (uint32_t)w;
+        run += narr * w;
+        sum_m += M;
+        LsNode r;
+        r.pair = (int)p;
+        r.i0 = 0; r.m = (int)M; r.j0 = 0; r.n = (int)N; r.q = 0;
+        r.tb = r.te = 0; // Myers-Miller entry tb = te = GapOpen is filled in at run time (include/SAMyersMiller.h:417)
+        ls.roots[k] = r;
+    }
+    ls.rows_total = run;
+    ls.node_cap = sum_m + n + 64;
+    if (ls.node_cap > ls.cap_nodes) {
+        CKS(ls_alloc(&ls.d_nodes[0], ls.node_cap));
+        CKS(ls_alloc(&ls.d_nodes[1], ls.node_cap));
+        ls.cap_nodes = ls.node_cap;
+    }
+    if (ls.rows_total > ls.cap_rows) {
+        CKS(ls_alloc(&ls.d_rows, ls.rows_total));
+        ls.cap_rows = ls.rows_total;
+    }
+    if (len1.size() > ls.cap_pairs) {
+        CKS(ls_alloc(&ls.d_row_off, len1.size()));
+        CKS(ls_alloc(&ls.d_row_w, len1.size()));
+        CKS(ls_alloc(&ls.d_idx, len1.size()));
+        ls.cap_pairs = len1.size();
+    }
+    if (!ls.d_count) CKS(ls_alloc(&ls.d_count, 1));
+    if (!ls.d_overflow) CKS(ls_alloc(&ls.d_overflow, 1));
+    if (n) {
+        CK(cudaMemcpy(ls.d_row_off, ls.row_off.data(), len1.size() * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ls.d_row_w, ls.row_w.data(), len1.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ls.d_idx, idx.data(), n * 4, cudaMemcpyHostToDevice));
+    }
+    return SEQA_OK;
+}
+
+int ls_run(seqa_ctx *c, bool want_ops)
+{
+    (void)want_ops;
+    LsState &ls = c->ls;
+    const uint64_t n = c->lidx.size();
+    if (n == 0) return SEQA_OK;
+    for (auto &r : ls.roots) r.tb = r.te = c->prm.gap_open;
+    CK(cudaMemsetAsync(c->slots.p, LS_HOLE, c->slots_total, c->stream));
+    CK(cudaMemsetAsync(ls.d_overflow, 0, sizeof(int), c->stream));
+    CK(cudaMemcpyAsync(ls.d_nodes[0], ls.roots.data(), n * sizeof(LsNode), cudaMemcpyHostToDevice, c->stream));
+    LsArgs A{};
+    A.bases = c->bases.p;
+    A.off1 = c->off1.p;
+    A.off2 = c->off2.p;
+    A.len1 = c->len1.p;
+    A.len2 = c->len2.p;
+    A.n_out = ls.d_count;
+    A.out_cap = (uint32_t)std::min<uint64_t>(ls.node_cap, 0xffffffffull);
+    A.overflow = ls.d_overflow;
+    A.rows = ls.d_rows;
+    A.row_off = ls.d_row_off;
+    A.row_w = ls.d_row_w;
+    A.slots = c->slots.p;
+    A.slot_off = c->slot_off.p;
+    A.sc = c->sc;
+    uint32_t count = (uint32_t)n;
+    int cur = 0;
+    ls.levels_run = 0;
+    cudaEventRecord(next_event(c), c->stream);
+    while (count > 0) {
+        A.in = ls.d_nodes[cur];
+        A.n_in = count;
+        A.out = ls.d_nodes[cur ^ 1];
+        CK(cudaMemsetAsync(ls.d_count, 0, sizeof(uint32_t), c->stream));
+        // few nodes: one warp per block so the nodes spread over the SMs
+        const unsigned block = count < (uint32_t)c->sms * 8 ? 32u : 128u;
+        const unsigned wpb = block / 32;
+        const unsigned grid = std::min<unsigned>((count + wpb - 1) / wpb, (unsigned)c->sms * 16);
+        if (ls.mm)
+            LAUNCH(c, (mm_level_kernel), grid, block, 0, A);
+        else
+            LAUNCH(c, (hb_level_kernel), grid, block, 0, A);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&count, ls.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        cur ^= 1;
+        if (++ls.levels_run > 200) return fail(SEQA_ERR_CUDA, "internal: recursion does not terminate");
+    }
+    cudaEventRecord(next_event(c), c->stream);
+    int ovf = 0;
+    CK(cudaMemcpy(&ovf, ls.d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    if (ovf) return fail(SEQA_ERR_CUDA, "internal: node list overflow");
+    LsFinishArgs F{};
+    F.bases = c->bases.p;
+    F.off1 = c->off1.p;
+    F.off2 = c->off2.p;
+    F.len1 = c->len1.p;
+    F.len2 = c->len2.p;
+    F.idx = ls.d_idx;
+    F.count = n;
+    F.slots = c->slots.p;
+    F.slot_off = c->slot_off.p;
+    F.slot_start = c->slot_start.p;
+    F.ops_len = c->ops_len.p;
+    F.start_i = c->start_i.p;
+    F.start_j = c->start_j.p;
+    F.end_i = c->end_i.p;
+    F.end_j = c->end_j.p;
+    F.score = c->score.p;
+    F.sc = c->sc;
+    F.affine = ls.mm ? 1 : 0;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n + 3) / 4, (uint64_t)c->sms * 16);
+    LAUNCH(c, (ls_finish_kernel), blocks, 128, 0, F);
+    CK(cudaGetLastError());
+    c->last_kernel = ls.mm ? "mm_level_i32" : "hb_level_i32";
+    return SEQA_OK;
+}
+
 } // namespace

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                 diag = up;
 #pragma unroll
                 for (int r = 0; r < R; r++) {
-                    const unsigned sim = __byte_perm(T.x, T.y, sel[r]);
+                    const unsigned sim = seqa_prmt(T.x, T.y, sel[r]);
                     const unsigned hold = H[r];
                     const unsigned lg = __vadd2(hold, gap2);
                     const unsigned t = LOCAL ? __viaddmax_s16x2_relu(hd, sim, lg) : __viaddmax_s16x2(hd, sim, lg);
@@ -175,10 +175,10 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     uint4 v;
-                    v.x = __byte_perm(H[8 * g + 0], H[8 * g + 1], 0x6420);
-                    v.y = __byte_perm(H[8 * g + 2], H[8 * g + 3], 0x6420);
-                    v.z = __byte_perm(H[8 * g + 4], H[8 * g + 5], 0x6420);
-                    v.w = __byte_perm(H[8 * g + 6], H[8 * g + 7], 0x6420);
+                    v.x = seqa_prmt(H[8 * g + 0], H[8 * g + 1], 0x6420);
+                    v.y = seqa_prmt(H[8 * g + 2], H[8 * g + 3], 0x6420);
+                    v.z = seqa_prmt(H[8 * g + 4], H[8 * g + 5], 0x6420);
+                    v.w = seqa_prmt(H[8 * g + 6], H[8 * g + 7], 0x6420);
                     tr[((uint64_t)jj * G + g) * 32] = v;
                 }
                 if (!LOCAL) {

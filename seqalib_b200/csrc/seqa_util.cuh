@@ -170,11 +170,11 @@ __global__ void __launch_bounds__(256) int_peak_kernel(unsigned *out, int iters,
                 else if (WHICH == 3) x[k] = __vimax3_s16x2(x[k], y[k], c);
                 else if (WHICH == 4) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(c), "r"(y[k]));
                 else if (WHICH == 5) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k]) : "r"(c), "r"(y[k]));
-                else if (WHICH == 6) x[k] = __byte_perm(x[k], y[k], 0x6240);
+                else if (WHICH == 6) x[k] = seqa_prmt(x[k], y[k], 0x6240);
                 else if (WHICH == 7) x[k] = __vadd2(x[k], c);
                 else if (WHICH == 8) x[k] = __viaddmax_s16x2_relu(x[k], c, y[k]);
                 else { // 9: the packed SW cell mix: PRMT + VIADD.16x2 + VIADDMNMX.RELU + VIADDMNMX + VIMNMX
-                    const unsigned sim = __byte_perm(y[k], c, x[k] & 0x7777u);
+                    const unsigned sim = seqa_prmt(y[k], c, x[k]);
                     const unsigned lg = __vadd2(x[k], c);
                     const unsigned t = __viaddmax_s16x2_relu(y[k], sim, lg);
                     x[k] = __viaddmax_s16x2(x[k], c, t);

@@ -192,7 +192,7 @@ static inline int __viaddmax_s32_relu(int a, int b, int c)
 static inline int __vimax3_s32(int a, int b, int c) { return std::max(std::max(a, b), c); }
 static inline int __vimax3_s32_relu(int a, int b, int c) { return std::max(std::max(std::max(a, b), c), 0); }
 // PRMT, default mode: selector nibble k picks byte (nibble & 7) of {b:a}; bit 3 replicates its sign bit.
-static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s)
+static inline unsigned emu_prmt(unsigned a, unsigned b, unsigned s)
 {
     const uint64_t src = ((uint64_t)b << 32) | a;
     unsigned r = 0;
@@ -204,6 +204,9 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s)
     }
     return r;
 }
+
+// the CUDA intrinsic masks the selector (verified in the PTX nvcc 12.9 emits: and.b32 s, 0x7777)
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) { return emu_prmt(a, b, s & 0x7777u); }
 
 // ---- runtime API subset ----------------------------------------------------------------------------------
 typedef int cudaError_t;

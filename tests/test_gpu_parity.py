@@ -50,7 +50,9 @@ def test_golden_vectors(gpu_lib, golden):
 def test_matrix_algorithms_random(gpu_lib, algo, sc):
     rng = np.random.default_rng(17)
     lg = algo == "lgotoh"
-    pairs = [e for e in EDGE if not (lg and (not e[0] or not e[1]))]
+    dirty = [e for e in EDGE if not (lg and (not e[0] or not e[1]))]
+    check_batch_against_oracle(gpu_lib, algo, sc, dirty + random_pairs(rng, 100, 1, 200))  # non-ACGT symbols -> 8-bit kernels
+    pairs = [e for e in dirty if set(e[0] + e[1]) <= set("ACGT")]
     pairs += random_pairs(rng, 600, 1, 200) + random_pairs(rng, 150, 1, 120, "AC") + random_pairs(rng, 150, 1, 250, related=0.3)
     pairs += random_pairs(rng, 30, 300, 700) + random_pairs(rng, 6, 900, 1300, related=0.2)
     if lg:
