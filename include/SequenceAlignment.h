@@ -1,0 +1,371 @@
+// SequenceAlignment.h -- host-side mirror of SeqALib's header-only C++ API for its DP hot path, backed by the
+// B200 library libseqa_cuda.so through the C ABI in seqa_cuda.h.
+//
+// Same class templates, constructors and call shapes as the reference (przemektmalon/SeqALib):
+//   AlignedSequence<Ty,Blank>, ScoringSystem          reference include/SequenceAlignment.h:13-131
+//   SequenceAligner<ContainerType,Ty,Blank,MatchFnTy>  reference include/SequenceAlignment.h:133-189
+//   NeedlemanWunschSA / SmithWatermanSA / GlobalGotohSA / LocalGotohSA / HirschbergSA / MyersMillerSA
+//                                                      reference include/SA*.h (one class per file there)
+//   ArrayView<ContainerType>, StaticFuncs::useNW / bridgeNW
+//                                                      reference include/ArrayView.h:4-54, include/StaticFuncs.h:6-40
+// plus the batched entry point the reference lacks:
+//   std::vector<AlignedSequence<Ty,Blank>> getAlignments(std::vector<std::pair<ContainerType,ContainerType>>&)
+//   seqa::PackedAlignments getAlignmentsPacked(...)   (scores + op strings, no std::list materialisation)
+//
+// What runs where: the DP fill, the traceback and the Hirschberg / Myers-Miller recursion run on the GPU; this
+// header only packs the inputs, calls seqa_cuda_align_batch and expands the returned op strings (0 diagonal,
+// 1 up, 2 left) into AlignedSequence entries, adding the reference's forceGlobal framing for the two local
+// algorithms.  There is no CPU implementation of the algorithms here.  The GPU path takes 8-bit symbols compared
+// with ==; a user matching functor is accepted when it IS equality on the whole 8-bit domain (checked
+// exhaustively once per aligner: 65,536 calls) -- that is what the reference's own demos pass
+// (test/Test.cpp:44) and what SmithWatermanSA needs in the reference to be defined behaviour.  Any other functor,
+// or a wider symbol type, is outside this path (std::invalid_argument): use the reference implementation there.
+// Errors of the device path surface as std::runtime_error carrying seqa_cuda_last_error().
+#ifndef SEQA_SEQUENCE_ALIGNMENT_H
+#define SEQA_SEQUENCE_ALIGNMENT_H
+
+#include <cstdint>
+#include <functional>
+#include <limits>
+#include <list>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "seqa_cuda.h"
+
+#define ScoreSystemType int
+
+template <typename Ty, Ty Blank = Ty(0)> class AlignedSequence {
+  public:
+    class Entry {
+        Ty First, Second;
+        bool Matching;
+
+      public:
+        Entry() : First(Blank), Second(Blank), Matching(false) {}
+        Entry(Ty V1, Ty V2) : First(V1), Second(V2), Matching(V1 != Blank && V2 != Blank) {}
+        Entry(Ty V1, Ty V2, bool IsMatch) : First(V1), Second(V2), Matching(IsMatch) {}
+        Ty get(size_t Index) const { return Index == 0 ? First : Second; }
+        bool empty() const { return First == Blank && Second == Blank; }
+        bool hasBlank() const { return First == Blank || Second == Blank; }
+        bool match() const { return Matching; }
+        bool mismatch() const { return !Matching; }
+        Ty getNonBlank() const { return First != Blank ? First : Second; }
+    };
+
+    std::list<Entry> Data;
+
+    AlignedSequence() = default;
+    AlignedSequence(const AlignedSequence &) = default;
+    AlignedSequence(AlignedSequence &&) = default;
+    AlignedSequence &operator=(const AlignedSequence &) = default;
+    AlignedSequence &operator=(AlignedSequence &&) = default;
+
+    void append(const AlignedSequence &Other) { Data.insert(Data.end(), Other.Data.begin(), Other.Data.end()); }
+    void splice(AlignedSequence &Other) { Data.splice(Data.end(), Other.Data); }
+    typename std::list<Entry>::iterator begin() { return Data.begin(); }
+    typename std::list<Entry>::iterator end() { return Data.end(); }
+    size_t size() const { return Data.size(); }
+};
+
+// Same three constructors as the reference.  Unlike the reference, members the chosen constructor does not
+// set are zero instead of indeterminate.
+class ScoringSystem {
+    ScoreSystemType Gap = 0, Match = 0, Mismatch = 0, GapOpen = 0, GapExtend = 0;
+    bool AllowMismatch = false;
+
+  public:
+    ScoringSystem(ScoreSystemType Gap, ScoreSystemType Match)
+        : Gap(Gap), Match(Match), Mismatch(std::numeric_limits<ScoreSystemType>::min()), AllowMismatch(false) {}
+    ScoringSystem(ScoreSystemType Gap, ScoreSystemType Match, ScoreSystemType Mismatch, bool AllowMismatch = true)
+        : Gap(Gap), Match(Match), Mismatch(Mismatch), AllowMismatch(AllowMismatch) {}
+    ScoringSystem(ScoreSystemType GapOpen, ScoreSystemType GapExtend, ScoreSystemType Match, ScoreSystemType Mismatch,
+                  bool AllowMismatch = true)
+        : Match(Match), Mismatch(Mismatch), GapOpen(GapOpen), GapExtend(GapExtend), AllowMismatch(AllowMismatch) {}
+
+    bool getAllowMismatch() const { return AllowMismatch; }
+    ScoreSystemType getMismatchPenalty() const { return Mismatch; }
+    ScoreSystemType getGapPenalty() const { return Gap; }
+    ScoreSystemType getMatchProfit() const { return Match; }
+    ScoreSystemType getGapOpenPenalty() const { return GapOpen; }
+    ScoreSystemType getGapExtendPenalty() const { return GapExtend; }
+};
+
+// Non-owning window over a contiguous container (reference include/ArrayView.h:4-54).
+template <typename ContainerType> class ArrayView {
+  public:
+    using value_type = typename ContainerType::value_type;
+    using iterator = const value_type *;
+
+  private:
+    const value_type *Base = nullptr;
+    size_t Lo = 0, Hi = 0;
+
+  public:
+    ArrayView() = default;
+    ArrayView(const ContainerType &C) : Base(C.size() ? &*C.begin() : nullptr), Lo(0), Hi(C.size()) {}
+    // window [Start, End) RELATIVE to the current window
+    void sliceWindow(size_t Start, size_t End)
+    {
+        Hi = Lo + End;
+        Lo = Lo + Start;
+    }
+    size_t size() const { return Hi - Lo; }
+    const value_type &operator[](size_t I) const { return Base[Lo + I]; }
+    iterator begin() const { return Base + Lo; }
+    iterator end() const { return Base + Hi; }
+    const value_type *data() const { return Base + Lo; }
+};
+
+namespace seqa {
+
+// Raw results of a batch: what the C ABI returns, owned by vectors.
+struct PackedAlignments {
+    std::vector<int32_t> Score;
+    std::vector<uint32_t> StartI, StartJ, EndI, EndJ, OpsLen;
+    std::vector<uint64_t> OpsOff;
+    std::vector<uint8_t> Ops; // 0 diagonal, 1 up (Seq1 symbol vs Blank), 2 left (Blank vs Seq2 symbol)
+    size_t size() const { return Score.size(); }
+};
+
+namespace detail {
+
+template <typename C> inline const char *bytes_of(const C &S)
+{
+    static_assert(sizeof(typename C::value_type) == 1, "the GPU path aligns 8-bit symbols");
+    return S.size() ? reinterpret_cast<const char *>(&*S.begin()) : "";
+}
+
+template <typename Ty, typename Fn> inline bool is_equality_on_bytes(Fn &F)
+{
+    for (int A = 0; A < 256; A++)
+        for (int B = 0; B < 256; B++)
+            if (F(static_cast<Ty>(static_cast<unsigned char>(A)), static_cast<Ty>(static_cast<unsigned char>(B))) != (A == B)) return false;
+    return true;
+}
+
+template <typename Fn> inline bool is_null_functor(const Fn &) { return false; }
+template <typename R, typename... A> inline bool is_null_functor(const std::function<R(A...)> &F) { return !F; }
+template <typename R, typename... A> inline bool is_null_functor(R (*F)(A...)) { return F == nullptr; }
+inline bool is_null_functor(std::nullptr_t) { return true; }
+
+} // namespace detail
+} // namespace seqa
+
+template <typename ContainerType, typename Ty = typename ContainerType::value_type, Ty Blank = Ty(0),
+          typename MatchFnTy = std::function<bool(Ty, Ty)>>
+class SequenceAligner {
+    ScoringSystem Scoring;
+    MatchFnTy Match;
+    int EqualityChecked = -1; // -1 unknown, 0 not equality, 1 equality / nullptr
+
+  public:
+    using EntryType = typename AlignedSequence<Ty, Blank>::Entry;
+    using PairType = std::pair<ContainerType, ContainerType>;
+
+    SequenceAligner(ScoringSystem Scoring, MatchFnTy Match = nullptr) : Scoring(Scoring), Match(Match) {}
+    virtual ~SequenceAligner() = default;
+
+    ScoringSystem &getScoring() { return Scoring; }
+    bool match(Ty V1, Ty V2) { return seqa::detail::is_null_functor(Match) ? V1 == V2 : Match(V1, V2); }
+    MatchFnTy getMatchOperation() { return Match; }
+    Ty getBlank() { return Blank; }
+
+    // Scores of the most recent getAlignment / getAlignments call (the reference exposes none).
+    std::vector<int> LastScores;
+
+    virtual AlignedSequence<Ty, Blank> getAlignment(ContainerType &Seq0, ContainerType &Seq1) = 0;
+
+    // Pads a local alignment out to a global one (reference include/SequenceAlignment.h:156-189):
+    // Seq1[0,Idx1) then Seq2[0,Idx2) as gap columns, the local part, Seq1[EndIdx1,..) then Seq2[EndIdx2,..).
+    void forceGlobal(ContainerType &Seq1, ContainerType &Seq2, AlignedSequence<Ty, Blank> &Result, int Idx1, int Idx2,
+                     int EndIdx1, int EndIdx2)
+    {
+        std::list<EntryType> Out;
+        for (int I = 0; I < Idx1; I++) Out.emplace_back(Seq1[I], Blank, false);
+        for (int J = 0; J < Idx2; J++) Out.emplace_back(Blank, Seq2[J], false);
+        Out.splice(Out.end(), Result.Data);
+        for (size_t I = (size_t)EndIdx1; I < Seq1.size(); I++) Out.emplace_back(Seq1[I], Blank, false);
+        for (size_t J = (size_t)EndIdx2; J < Seq2.size(); J++) Out.emplace_back(Blank, Seq2[J], false);
+        Result.Data.swap(Out);
+    }
+
+  protected:
+    // ---- the boundary: everything below funnels into seqa_cuda_align_batch ----
+    void requireGpuEligible()
+    {
+        if (EqualityChecked < 0)
+            EqualityChecked = (seqa::detail::is_null_functor(Match) || seqa::detail::is_equality_on_bytes<Ty>(Match)) ? 1 : 0;
+        if (!EqualityChecked)
+            throw std::invalid_argument("seqalib_b200: the GPU path compares symbols with ==; custom matching functors are "
+                                        "reference-only (see include/SequenceAlignment.h)");
+    }
+
+    seqa::PackedAlignments runBatch(int Algo, const std::vector<const ContainerType *> &S1,
+                                    const std::vector<const ContainerType *> &S2)
+    {
+        static_assert(sizeof(Ty) == 1, "seqalib_b200: the GPU path aligns 8-bit symbols (char); wider types are reference-only");
+        requireGpuEligible();
+        const size_t N = S1.size();
+        std::vector<uint64_t> Off1(N), Off2(N);
+        std::vector<uint32_t> Len1(N), Len2(N);
+        uint64_t Total = 0;
+        for (size_t P = 0; P < N; P++) {
+            Len1[P] = (uint32_t)S1[P]->size();
+            Len2[P] = (uint32_t)S2[P]->size();
+            Off1[P] = Total;
+            Off2[P] = Total + Len1[P];
+            Total += (uint64_t)Len1[P] + Len2[P];
+        }
+        std::string Bases;
+        Bases.resize(Total);
+        for (size_t P = 0; P < N; P++) {
+            Bases.replace(Off1[P], Len1[P], seqa::detail::bytes_of(*S1[P]), Len1[P]);
+            Bases.replace(Off2[P], Len2[P], seqa::detail::bytes_of(*S2[P]), Len2[P]);
+        }
+        seqa_params Prm{};
+        Prm.algo = Algo;
+        Prm.gap = Scoring.getGapPenalty();
+        Prm.gap_open = Scoring.getGapOpenPenalty();
+        Prm.gap_extend = Scoring.getGapExtendPenalty();
+        Prm.match = Scoring.getMatchProfit();
+        Prm.allow_mismatch = Scoring.getAllowMismatch() ? 1 : 0;
+        Prm.mismatch = Scoring.getAllowMismatch() ? Scoring.getMismatchPenalty() : 0;
+        Prm.device_first = 0;
+        Prm.device_count = 0; // every visible device
+        seqa_batch_in In{Bases.data(), Off1.data(), Off2.data(), Len1.data(), Len2.data(), (uint64_t)N, Total};
+        seqa::PackedAlignments R;
+        R.Score.resize(N);
+        R.StartI.resize(N);
+        R.StartJ.resize(N);
+        R.EndI.resize(N);
+        R.EndJ.resize(N);
+        R.OpsLen.resize(N);
+        R.OpsOff.resize(N);
+        R.Ops.resize(Total ? Total : 1);
+        seqa_batch_out Out{R.Score.data(), R.StartI.data(), R.StartJ.data(), R.EndI.data(), R.EndJ.data(), R.Ops.data(),
+                           R.OpsOff.data(), R.OpsLen.data(), (uint64_t)R.Ops.size(), 0};
+        if (seqa_cuda_align_batch(&Prm, &In, &Out) != SEQA_OK)
+            throw std::runtime_error(std::string("seqa_cuda_align_batch: ") + seqa_cuda_last_error());
+        R.Ops.resize(Out.ops_used);
+        LastScores.assign(R.Score.begin(), R.Score.end());
+        return R;
+    }
+
+    // op string -> AlignedSequence; Local adds the forceGlobal framing
+    AlignedSequence<Ty, Blank> expand(const seqa::PackedAlignments &R, size_t P, ContainerType &Seq1, ContainerType &Seq2, bool Local)
+    {
+        AlignedSequence<Ty, Blank> Res;
+        size_t I = R.StartI[P], J = R.StartJ[P];
+        const uint8_t *Ops = R.Ops.data() + R.OpsOff[P];
+        for (uint32_t K = 0; K < R.OpsLen[P]; K++) {
+            if (Ops[K] == SEQA_OP_DIAG) {
+                Res.Data.emplace_back(Seq1[I], Seq2[J], Seq1[I] == Seq2[J]);
+                I++, J++;
+            } else if (Ops[K] == SEQA_OP_UP) {
+                Res.Data.emplace_back(Seq1[I], Blank, false);
+                I++;
+            } else {
+                Res.Data.emplace_back(Blank, Seq2[J], false);
+                J++;
+            }
+        }
+        if (Local) forceGlobal(Seq1, Seq2, Res, (int)R.StartI[P], (int)R.StartJ[P], (int)R.EndI[P], (int)R.EndJ[P]);
+        return Res;
+    }
+
+    AlignedSequence<Ty, Blank> alignOne(int Algo, bool Local, ContainerType &Seq1, ContainerType &Seq2)
+    {
+        std::vector<const ContainerType *> A{&Seq1}, B{&Seq2};
+        seqa::PackedAlignments R = runBatch(Algo, A, B);
+        return expand(R, 0, Seq1, Seq2, Local);
+    }
+
+    std::vector<AlignedSequence<Ty, Blank>> alignMany(int Algo, bool Local, std::vector<PairType> &Pairs)
+    {
+        std::vector<const ContainerType *> A(Pairs.size()), B(Pairs.size());
+        for (size_t P = 0; P < Pairs.size(); P++) {
+            A[P] = &Pairs[P].first;
+            B[P] = &Pairs[P].second;
+        }
+        seqa::PackedAlignments R = runBatch(Algo, A, B);
+        std::vector<AlignedSequence<Ty, Blank>> Out;
+        Out.reserve(Pairs.size());
+        for (size_t P = 0; P < Pairs.size(); P++) Out.push_back(expand(R, P, Pairs[P].first, Pairs[P].second, Local));
+        return Out;
+    }
+
+    seqa::PackedAlignments packMany(int Algo, std::vector<PairType> &Pairs)
+    {
+        std::vector<const ContainerType *> A(Pairs.size()), B(Pairs.size());
+        for (size_t P = 0; P < Pairs.size(); P++) {
+            A[P] = &Pairs[P].first;
+            B[P] = &Pairs[P].second;
+        }
+        return runBatch(Algo, A, B);
+    }
+};
+
+// One concrete aligner per reference class: same name, same constructors, same getDefaultScoring().
+#define SEQA_DEFINE_ALIGNER(NAME, ALGO, LOCAL, DEFAULT_SCORING)                                                              \
+    template <typename ContainerType, typename Ty = typename ContainerType::value_type, Ty Blank = Ty(0),                     \
+              typename MatchFnTy = std::function<bool(Ty, Ty)>>                                                               \
+    class NAME : public SequenceAligner<ContainerType, Ty, Blank, MatchFnTy> {                                                \
+        using BaseType = SequenceAligner<ContainerType, Ty, Blank, MatchFnTy>;                                                \
+                                                                                                                              \
+      public:                                                                                                                 \
+        static ScoringSystem getDefaultScoring() { return DEFAULT_SCORING; }                                                  \
+        NAME() : BaseType(getDefaultScoring(), nullptr) {}                                                                    \
+        NAME(ScoringSystem Scoring, MatchFnTy Match = nullptr) : BaseType(Scoring, Match) {}                                  \
+        AlignedSequence<Ty, Blank> getAlignment(ContainerType &Seq1, ContainerType &Seq2) override                           \
+        {                                                                                                                     \
+            return this->alignOne(ALGO, LOCAL, Seq1, Seq2);                                                                   \
+        }                                                                                                                     \
+        /* batched entry point: all pairs in one device batch, split statically over the visible GPUs */                      \
+        std::vector<AlignedSequence<Ty, Blank>> getAlignments(std::vector<std::pair<ContainerType, ContainerType>> &Pairs)    \
+        {                                                                                                                     \
+            return this->alignMany(ALGO, LOCAL, Pairs);                                                                       \
+        }                                                                                                                     \
+        seqa::PackedAlignments getAlignmentsPacked(std::vector<std::pair<ContainerType, ContainerType>> &Pairs)              \
+        {                                                                                                                     \
+            return this->packMany(ALGO, Pairs);                                                                               \
+        }                                                                                                                     \
+    };
+
+// default scorings: reference include/SANeedlemanWunsch.h:244-247, include/SASmithWaterman.h:352,
+// include/SAGlobalGotoh.h:441, include/SALocalGotoh.h:509, include/SAHirschberg.h:165-168, include/SAMyersMiller.h:406
+SEQA_DEFINE_ALIGNER(NeedlemanWunschSA, SEQA_NW, false, ScoringSystem(-1, 2, -1))
+SEQA_DEFINE_ALIGNER(SmithWatermanSA, SEQA_SW, true, ScoringSystem(-1, 1, -1))
+SEQA_DEFINE_ALIGNER(GlobalGotohSA, SEQA_GLOBAL_GOTOH, false, ScoringSystem(-1, 2, -1))
+SEQA_DEFINE_ALIGNER(LocalGotohSA, SEQA_LOCAL_GOTOH, true, ScoringSystem(-1, 2, -1))
+SEQA_DEFINE_ALIGNER(HirschbergSA, SEQA_HIRSCHBERG, false, ScoringSystem(-1, 2, -1))
+SEQA_DEFINE_ALIGNER(MyersMillerSA, SEQA_MYERS_MILLER, false, ScoringSystem(-1, 2, -1))
+#undef SEQA_DEFINE_ALIGNER
+
+// Hooks by which the reference's heuristic aligners (BLAT, MUMmer, LocalGotoh) reach the NW hot path
+// (reference include/StaticFuncs.h:12-39): NeedlemanWunsch on whole sequences / on a window, appended to Result.
+template <typename ContainerType, typename Ty = typename ContainerType::value_type, Ty Blank = Ty(0),
+          typename MatchFnTy = std::function<bool(Ty, Ty)>>
+class StaticFuncs {
+  public:
+    static void useNW(ContainerType &Seq1, ContainerType &Seq2, AlignedSequence<Ty, Blank> &Result, ScoringSystem Scoring, MatchFnTy Match)
+    {
+        Result.Data.clear();
+        bridgeNW(Seq1, Seq2, Result, Scoring, 0, 0, (int)Seq1.size(), (int)Seq2.size(), Match);
+    }
+    static void bridgeNW(ContainerType &Seq1, ContainerType &Seq2, AlignedSequence<Ty, Blank> &Result, ScoringSystem Scoring, int Idx1,
+                         int Idx2, int EndIdx1, int EndIdx2, MatchFnTy Match)
+    {
+        NeedlemanWunschSA<ArrayView<ContainerType>, Ty, Blank, MatchFnTy> NW(Scoring, Match);
+        ArrayView<ContainerType> V1(Seq1), V2(Seq2);
+        V1.sliceWindow((size_t)Idx1, (size_t)EndIdx1);
+        V2.sliceWindow((size_t)Idx2, (size_t)EndIdx2);
+        AlignedSequence<Ty, Blank> Part = NW.getAlignment(V1, V2);
+        Result.splice(Part);
+    }
+};
+
+#endif // SEQA_SEQUENCE_ALIGNMENT_H

@@ -325,8 +325,8 @@ int build_plan(seqa_ctx *c)
             J.Mw = Mw;
             J.Nw = Nw;
             J.nstrips = (Mw + PK_R - 1) / PK_R;
-            const uint64_t tbytes = (uint64_t)J.nstrips * Nw * (PK_R / 8) * 512;
-            const uint64_t pelems = (uint64_t)Nw * 32, relems = (uint64_t)J.nstrips * PK_R * 32;
+            const uint64_t tbytes = pk_trace_bytes(J.nstrips, Nw, PK_R);
+            const uint64_t pelems = (uint64_t)((Nw + 3) / 4) * 128, relems = (uint64_t)J.nstrips * PK_R * 32;
             if (ch.hi > ch.lo && chunk_bytes(tr + tbytes, pf + pelems, rs + relems) > budget) {
                 ch.scratch_bytes = chunk_bytes(tr, pf, rs);
                 c->pk_chunks.push_back(ch);
@@ -469,7 +469,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
 {
     if (c->jobs.empty()) return SEQA_OK;
     const bool local = c->prm.algo == SEQA_SW;
-    const size_t smem = (size_t)c->pk_max_nw * PK_BLOCK * 4;
+    const size_t smem = (size_t)((c->pk_max_nw + 3) / 4 * 4) * PK_BLOCK * 4;
     if (smem > c->smem_optin) return fail(SEQA_ERR_UNSUPPORTED, "internal: packed kernel shared memory %zu", smem);
     if (local)
         CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -483,8 +483,8 @@ int run_packed(seqa_ctx *c, bool want_walk)
         uint64_t tr = 0, pf = 0;
         {
             const PkWarpJob &L = c->jobs[ch.hi - 1];
-            tr = L.trace_off + (uint64_t)L.nstrips * L.Nw * (PK_R / 8) * 512;
-            pf = L.prof_off + (uint64_t)L.Nw * 32;
+            tr = L.trace_off + pk_trace_bytes(L.nstrips, L.Nw, PK_R);
+            pf = L.prof_off + (uint64_t)((L.Nw + 3) / 4) * 128;
         }
         PkArgs A{};
         A.bases = c->bases.p;

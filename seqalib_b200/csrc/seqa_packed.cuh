@@ -30,7 +30,7 @@ struct PkWarpJob {
     uint32_t Mw, Nw;  // max len1 / len2 over the 64 pairs
     uint32_t nstrips; // ceil(Mw / R)
     uint64_t trace_off;  // byte offset of the warp's trace region
-    uint64_t prof_off;   // uint2 index of the column profile  [Nw][32]
+    uint64_t prof_off;   // uint2 index of the column profile  [ceil(Nw/4)][32][4]
     uint64_t rowsel_off; // uint32 index of the row selectors  [nstrips*R][32]
 };
 
@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
         const uint8_t *a1 = p1 == PK_NULL ? A.bases : A.bases + A.off1[p1];
         const uint8_t *b1 = p1 == PK_NULL ? A.bases : A.bases + A.off2[p1];
         bool bad = false;
-        for (uint32_t j = 0; j < J.Nw; j++) {
+        const uint32_t Nw4 = (J.Nw + 3) & ~3u;
+        for (uint32_t j = 0; j < Nw4; j++) {
             unsigned t0 = 0x80808080u, t1 = 0x80808080u; // padded column: every score -128
             if (j < N0) {
                 const unsigned c = b0[j];
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
                 t1 = mm * 0x01010101u;
                 t1 = (t1 & ~(0xffu << (8 * pk_code(c)))) | (mt << (8 * pk_code(c)));
             }
-            A.prof[J.prof_off + (uint64_t)j * 32 + lane] = make_uint2(t0, t1);
+            A.prof[J.prof_off + ((uint64_t)(j >> 2) * 32 + lane) * 4 + (j & 3)] = make_uint2(t0, t1);
         }
         const uint32_t rows = J.nstrips * (uint32_t)R;
         for (uint32_t i = 0; i < rows; i++) {
@@ -118,14 +119,29 @@ __device__ __forceinline__ unsigned pk_dup(int v) { return ((unsigned)v & 0xffff
 __device__ __forceinline__ int pk_half(unsigned v, int k) { return (int)(int16_t)(k ? (v >> 16) : (v & 0xffffu)); }
 
 // ---- fill -------------------------------------------------------------------------------------------------
-// trace layout of a warp job: byte(pair-half k, row i, column j), i-1 = s*R + r, jj = j-1:
-//   trace_off + (((s*Nw + jj)*(R/8) + r/8)*32 + lane)*16 + ((r%8)/2)*4 + (r%2)*2 + k
+// Trace layout of a warp job (Ng = ceil(Nw/4) column groups): the low byte of H(i,j) of pair-half k, with
+// i-1 = s*R + r, j-1 = 4*cg + c, sits at
+//   trace_off + ((((s*Ng + cg)*(R/2) + r/2)*32 + lane)*16 + c*4 + (r%2)*2 + k
+// i.e. one 16-byte store per thread holds 4 columns x 2 rows x 2 pairs and a warp store covers 512 contiguous
+// bytes.  The stores are streaming (st.global.cs) so the 24 KB/pair trace does not evict the column profiles
+// from L2; the profiles of the next column group are prefetched into registers one group ahead.
+__host__ __device__ inline uint64_t pk_trace_bytes(uint32_t nstrips, uint32_t Nw, int R)
+{
+    return (uint64_t)nstrips * ((Nw + 3) / 4) * (uint64_t)(R / 2) * 512ull;
+}
+
+#ifdef SEQA_EMU
+static inline void pk_store_stream(uint4 *p, uint4 v) { *p = v; }
+#else
+__device__ __forceinline__ void pk_store_stream(uint4 *p, uint4 v) { __stcs(p, v); }
+#endif
+
 template <bool LOCAL, int R>
 __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
 {
-    static_assert(R % 8 == 0, "R must be a multiple of 8");
+    static_assert(R % 2 == 0, "R must be even");
     SEQA_DYN_SMEM(unsigned, top);
-    constexpr int G = R / 8;
+    constexpr int RP = R / 2;
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
@@ -135,14 +151,14 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
         const uint32_t p0 = A.perm[J.first + 2 * lane], p1 = A.perm[J.first + 2 * lane + 1];
         const int M0 = p0 == PK_NULL ? 0 : (int)A.len1[p0], N0 = p0 == PK_NULL ? 0 : (int)A.len2[p0];
         const int M1 = p1 == PK_NULL ? 0 : (int)A.len1[p1], N1 = p1 == PK_NULL ? 0 : (int)A.len2[p1];
-        const int Nw = (int)J.Nw;
-        const uint2 *__restrict__ prof = A.prof + J.prof_off + lane;
+        const int Ng = ((int)J.Nw + 3) >> 2;
+        const uint4 *__restrict__ prof = reinterpret_cast<const uint4 *>(A.prof + J.prof_off) + lane * 2;
         const uint32_t *__restrict__ rowsel = A.rowsel + J.rowsel_off + lane;
         uint4 *__restrict__ trace = reinterpret_cast<uint4 *>(A.trace + J.trace_off) + lane;
         int best0 = 0, best1 = 0, bi0 = 0, bi1 = 0; // SW: running (max, last row holding it)
         int corner0 = 0, corner1 = 0;               // NW: H(M,N)
         // row 0 of the matrix = first strip's upper boundary (SW 0, NW j*gap: include/SANeedlemanWunsch.h:61-62)
-        for (int jj = 0; jj < Nw; jj++) top[jj * PK_BLOCK + tid] = LOCAL ? 0u : pk_dup((jj + 1) * A.gap);
+        for (int jj = 0; jj < Ng * 4; jj++) top[jj * PK_BLOCK + tid] = LOCAL ? 0u : pk_dup((jj + 1) * A.gap);
         for (int s = 0; s < (int)J.nstrips; s++) {
             const int i0 = s * R;
             unsigned H[R], sel[R], rmax[R];
@@ -153,43 +169,52 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                 rmax[r] = 0u;
             }
             unsigned diag = LOCAL ? 0u : pk_dup(i0 * A.gap);
-            uint4 *__restrict__ tr = trace + (uint64_t)s * Nw * G * 32;
-            for (int jj = 0; jj < Nw; jj++) {
-                const uint2 T = prof[(uint64_t)jj * 32];
-                const unsigned up = top[jj * PK_BLOCK + tid];
-                unsigned hd = diag, hu = up;
-                diag = up;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const unsigned sim = seqa_prmt(T.x, T.y, sel[r]);
-                    const unsigned hold = H[r];
-                    const unsigned lg = __vadd2(hold, gap2);
-                    const unsigned t = LOCAL ? __viaddmax_s16x2_relu(hd, sim, lg) : __viaddmax_s16x2(hd, sim, lg);
-                    const unsigned hn = __viaddmax_s16x2(hu, gap2, t);
-                    H[r] = hn;
-                    hu = hn;
-                    hd = hold;
-                    if (LOCAL) rmax[r] = __vmaxs2(rmax[r], hn);
+            uint4 *__restrict__ tr = trace + (uint64_t)s * Ng * RP * 32;
+            uint4 na = prof[0], nb = prof[1]; // profile of the next group: {T0,T1} x 4 columns
+            for (int cg = 0; cg < Ng; cg++) {
+                const uint4 ca = na, cb = nb;
+                if (cg + 1 < Ng) {
+                    na = prof[(uint64_t)(cg + 1) * 64];
+                    nb = prof[(uint64_t)(cg + 1) * 64 + 1];
                 }
-                top[jj * PK_BLOCK + tid] = hu;
+                unsigned up[4];
 #pragma unroll
-                for (int g = 0; g < G; g++) {
-                    uint4 v;
-                    v.x = seqa_prmt(H[8 * g + 0], H[8 * g + 1], 0x6420);
-                    v.y = seqa_prmt(H[8 * g + 2], H[8 * g + 3], 0x6420);
-                    v.z = seqa_prmt(H[8 * g + 4], H[8 * g + 5], 0x6420);
-                    v.w = seqa_prmt(H[8 * g + 6], H[8 * g + 7], 0x6420);
-                    tr[((uint64_t)jj * G + g) * 32] = v;
-                }
-                if (!LOCAL) {
-                    if (jj + 1 == N0 || jj + 1 == N1) {
+                for (int c = 0; c < 4; c++) up[c] = top[(cg * 4 + c) * PK_BLOCK + tid];
+                unsigned W[RP][4];
 #pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            if (jj + 1 == N0 && i0 + r + 1 == M0) corner0 = pk_half(H[r], 0);
-                            if (jj + 1 == N1 && i0 + r + 1 == M1) corner1 = pk_half(H[r], 1);
+                for (int c = 0; c < 4; c++) {
+                    const unsigned T0 = c == 0 ? ca.x : c == 1 ? ca.z : c == 2 ? cb.x : cb.z;
+                    const unsigned T1 = c == 0 ? ca.y : c == 1 ? ca.w : c == 2 ? cb.y : cb.w;
+                    unsigned hd = diag, hu = up[c];
+                    diag = up[c];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const unsigned sim = seqa_prmt(T0, T1, sel[r]);
+                        const unsigned hold = H[r];
+                        const unsigned lg = __vadd2(hold, gap2);
+                        const unsigned t = LOCAL ? __viaddmax_s16x2_relu(hd, sim, lg) : __viaddmax_s16x2(hd, sim, lg);
+                        const unsigned hn = __viaddmax_s16x2(hu, gap2, t);
+                        if (r & 1) W[r >> 1][c] = seqa_prmt(H[r - 1], hn, 0x6420);
+                        H[r] = hn;
+                        hu = hn;
+                        hd = hold;
+                        if (LOCAL && (c & 1)) rmax[r] = __vimax3_s16x2(rmax[r], hold, hn);
+                    }
+                    top[(cg * 4 + c) * PK_BLOCK + tid] = hu;
+                    if (!LOCAL) {
+                        const int j = cg * 4 + c + 1;
+                        if (j == N0 || j == N1) {
+#pragma unroll
+                            for (int r = 0; r < R; r++) {
+                                if (j == N0 && i0 + r + 1 == M0) corner0 = pk_half(H[r], 0);
+                                if (j == N1 && i0 + r + 1 == M1) corner1 = pk_half(H[r], 1);
+                            }
                         }
                     }
                 }
+#pragma unroll
+                for (int rp = 0; rp < RP; rp++)
+                    pk_store_stream(&tr[((uint64_t)cg * RP + rp) * 32], make_uint4(W[rp][0], W[rp][1], W[rp][2], W[rp][3]));
             }
             if (LOCAL) {
                 // last maximum in row-major order (include/SASmithWaterman.h:177): rows ascending, ">="
@@ -228,14 +253,14 @@ __global__ void __launch_bounds__(256) pk_walk_kernel(PkArgs A, int R)
     const PkWarpJob J = A.jobs[pos >> 6];
     const int lane = (int)((pos & 63) >> 1), half = (int)(pos & 1);
     const int M = (int)A.len1[p], N = (int)A.len2[p];
-    const int G = R / 8;
-    const uint64_t Nw = J.Nw;
+    const int RP = R / 2;
+    const uint64_t Ng = (J.Nw + 3) >> 2;
     const uint8_t *tr = A.trace + J.trace_off + (uint64_t)lane * 16 + half;
     const uint8_t *a = A.bases + A.off1[p], *b = A.bases + A.off2[p];
     const int gap = A.gap;
     auto low = [&](int i, int j) -> int { // i >= 1, j >= 1
-        const int ii = i - 1, s = ii / R, r = ii - s * R;
-        return tr[((((uint64_t)s * Nw + (uint64_t)(j - 1)) * G + (r >> 3)) * 32) * 16 + ((r & 7) >> 1) * 4 + (r & 1) * 2];
+        const int ii = i - 1, s = ii / R, r = ii - s * R, jj = j - 1;
+        return tr[(((uint64_t)s * Ng + (uint64_t)(jj >> 2)) * RP + (r >> 1)) * 512 + (jj & 3) * 4 + (r & 1) * 2];
     };
     auto border = [&](int i, int j) -> int { return LOCAL ? 0 : (i == 0 ? j * gap : i * gap); };
     auto near = [&](int hc, int i, int j) -> int { // exact H(i,j) given the exact value hc of an adjacent cell
@@ -246,13 +271,28 @@ __global__ void __launch_bounds__(256) pk_walk_kernel(PkArgs A, int R)
     int k = M + N;
     int i, j, h;
     if (LOCAL) {
-        // MaxCol: the last column of row MaxRow holding MaxScore (include/SASmithWaterman.h:177-182)
+        // MaxCol: the last column of row MaxRow holding MaxScore (include/SASmithWaterman.h:177-182).  One 16-byte
+        // load brings 4 columns of the row; exact values are chained from H(i,0) = 0.
         const int best = A.score[p];
         i = (int)A.end_i[p];
         int e = 0, bj = N;
-        for (int jj = 1; jj <= N; jj++) {
-            e += (int)(int8_t)(uint8_t)(low(i, jj) - (e & 0xff));
-            if (e == best) bj = jj;
+        if (i >= 1) {
+            const int ii = i - 1, s = ii / R, r = ii - s * R;
+            const uint8_t *row = A.trace + J.trace_off + (uint64_t)lane * 16 + ((uint64_t)s * Ng * RP + (r >> 1)) * 512;
+            const int sh = ((r & 1) * 2 + half) * 8;
+            const int ng = (N + 3) >> 2;
+            for (int cg = 0; cg < ng; cg++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(row + (uint64_t)cg * RP * 512);
+                const unsigned wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int jj = cg * 4 + c + 1;
+                    if (jj <= N) {
+                        e += (int)(int8_t)(uint8_t)(((wv[c] >> sh) & 0xffu) - (unsigned)(e & 0xff));
+                        if (e == best) bj = jj;
+                    }
+                }
+            }
         }
         j = bj;
         h = best;

@@ -29,7 +29,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
 #define __restrict__ __restrict
-#define __shared__ static
+#define __shared__ static thread_local
 #define __constant__ static
 
 struct uint3 { unsigned x, y, z; };

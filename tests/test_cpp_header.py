@@ -1,0 +1,27 @@
+"""include/SequenceAlignment.h (the C++ host mirror of the reference API) compiled and run: against the emulator
+build on CPU boxes, against libseqa_cuda.so on the GPU box."""
+import os
+import subprocess
+
+import pytest
+
+from common import ROOT
+
+
+def _build_and_run(libdir, libname, tmp_path):
+    exe = str(tmp_path / "test_header")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_header.cpp"), "-o", exe,
+                           "-L", libdir, "-l" + libname, "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout
+    assert "AAA-GAATGCAT\n|||    | |||\nAAAC---T-CAT" in out.stdout  # reference README.md:34-37
+
+
+def test_header_against_emulated_kernels(emu_lib, tmp_path):
+    _build_and_run(os.path.join(ROOT, "tests", "emu"), "seqa_emu", tmp_path)
+
+
+@pytest.mark.gpu
+def test_header_on_gpu(gpu_lib, tmp_path):
+    _build_and_run(os.path.join(ROOT, "seqalib_b200"), "seqa_cuda", tmp_path)
