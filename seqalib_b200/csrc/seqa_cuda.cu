@@ -469,7 +469,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
 {
     if (c->jobs.empty()) return SEQA_OK;
     const bool local = c->prm.algo == SEQA_SW;
-    const size_t smem = (size_t)((c->pk_max_nw + 3) / 4 * 4) * PK_BLOCK * 4;
+    const size_t smem = (size_t)c->pk_max_nw * PK_BLOCK * 4;
     if (smem > c->smem_optin) return fail(SEQA_ERR_UNSUPPORTED, "internal: packed kernel shared memory %zu", smem);
     if (local)
         CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -77,22 +77,31 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
         const uint8_t *a1 = p1 == PK_NULL ? A.bases : A.bases + A.off1[p1];
         const uint8_t *b1 = p1 == PK_NULL ? A.bases : A.bases + A.off2[p1];
         bool bad = false;
-        const uint32_t Nw4 = (J.Nw + 3) & ~3u;
-        for (uint32_t j = 0; j < Nw4; j++) {
-            unsigned t0 = 0x80808080u, t1 = 0x80808080u; // padded column: every score -128
-            if (j < N0) {
-                const unsigned c = b0[j];
-                bad |= !pk_is_acgt(c);
-                t0 = mm * 0x01010101u;
-                t0 = (t0 & ~(0xffu << (8 * pk_code(c)))) | (mt << (8 * pk_code(c)));
+        const uint32_t Ng = (J.Nw + 3) >> 2;
+        uint4 *pout = reinterpret_cast<uint4 *>(A.prof + J.prof_off) + lane * 2;
+        for (uint32_t cg = 0; cg < Ng; cg++) {
+            unsigned t[8];
+#pragma unroll
+            for (uint32_t c = 0; c < 4; c++) {
+                const uint32_t j = cg * 4 + c;
+                unsigned t0 = 0x80808080u, t1 = 0x80808080u; // padded column: every score -128
+                if (j < N0) {
+                    const unsigned ch = b0[j];
+                    bad |= !pk_is_acgt(ch);
+                    t0 = mm * 0x01010101u;
+                    t0 = (t0 & ~(0xffu << (8 * pk_code(ch)))) | (mt << (8 * pk_code(ch)));
+                }
+                if (j < N1) {
+                    const unsigned ch = b1[j];
+                    bad |= !pk_is_acgt(ch);
+                    t1 = mm * 0x01010101u;
+                    t1 = (t1 & ~(0xffu << (8 * pk_code(ch)))) | (mt << (8 * pk_code(ch)));
+                }
+                t[2 * c] = t0;
+                t[2 * c + 1] = t1;
             }
-            if (j < N1) {
-                const unsigned c = b1[j];
-                bad |= !pk_is_acgt(c);
-                t1 = mm * 0x01010101u;
-                t1 = (t1 & ~(0xffu << (8 * pk_code(c)))) | (mt << (8 * pk_code(c)));
-            }
-            A.prof[J.prof_off + ((uint64_t)(j >> 2) * 32 + lane) * 4 + (j & 3)] = make_uint2(t0, t1);
+            pout[(uint64_t)cg * 64] = make_uint4(t[0], t[1], t[2], t[3]);
+            pout[(uint64_t)cg * 64 + 1] = make_uint4(t[4], t[5], t[6], t[7]);
         }
         const uint32_t rows = J.nstrips * (uint32_t)R;
         for (uint32_t i = 0; i < rows; i++) {
@@ -132,8 +141,15 @@ __host__ __device__ inline uint64_t pk_trace_bytes(uint32_t nstrips, uint32_t Nw
 
 #ifdef SEQA_EMU
 static inline void pk_store_stream(uint4 *p, uint4 v) { *p = v; }
+static inline void pk_prefetch_l2(const void *, unsigned) {}
 #else
 __device__ __forceinline__ void pk_store_stream(uint4 *p, uint4 v) { __stcs(p, v); }
+// one lane asks the L2 to pull a contiguous region (16-byte multiple) in: cp.async.bulk.prefetch, no registers,
+// no shared memory, no completion to wait for
+__device__ __forceinline__ void pk_prefetch_l2(const void *p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 #endif
 
 template <bool LOCAL, int R>
@@ -151,14 +167,14 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
         const uint32_t p0 = A.perm[J.first + 2 * lane], p1 = A.perm[J.first + 2 * lane + 1];
         const int M0 = p0 == PK_NULL ? 0 : (int)A.len1[p0], N0 = p0 == PK_NULL ? 0 : (int)A.len2[p0];
         const int M1 = p1 == PK_NULL ? 0 : (int)A.len1[p1], N1 = p1 == PK_NULL ? 0 : (int)A.len2[p1];
-        const int Ng = ((int)J.Nw + 3) >> 2;
+        const int Ng = ((int)J.Nw + 3) >> 2, Nw = (int)J.Nw;
         const uint4 *__restrict__ prof = reinterpret_cast<const uint4 *>(A.prof + J.prof_off) + lane * 2;
         const uint32_t *__restrict__ rowsel = A.rowsel + J.rowsel_off + lane;
         uint4 *__restrict__ trace = reinterpret_cast<uint4 *>(A.trace + J.trace_off) + lane;
         int best0 = 0, best1 = 0, bi0 = 0, bi1 = 0; // SW: running (max, last row holding it)
         int corner0 = 0, corner1 = 0;               // NW: H(M,N)
         // row 0 of the matrix = first strip's upper boundary (SW 0, NW j*gap: include/SANeedlemanWunsch.h:61-62)
-        for (int jj = 0; jj < Ng * 4; jj++) top[jj * PK_BLOCK + tid] = LOCAL ? 0u : pk_dup((jj + 1) * A.gap);
+        for (int jj = 0; jj < Nw; jj++) top[jj * PK_BLOCK + tid] = LOCAL ? 0u : pk_dup((jj + 1) * A.gap);
         for (int s = 0; s < (int)J.nstrips; s++) {
             const int i0 = s * R;
             unsigned H[R], sel[R], rmax[R];
@@ -170,6 +186,8 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
             }
             unsigned diag = LOCAL ? 0u : pk_dup(i0 * A.gap);
             uint4 *__restrict__ tr = trace + (uint64_t)s * Ng * RP * 32;
+            // every strip re-reads the job's column profile (Ng KB): have the L2 fetch it while the strip starts
+            if (lane == 0) pk_prefetch_l2(A.prof + J.prof_off, (unsigned)Ng * 1024u);
             uint4 na = prof[0], nb = prof[1]; // profile of the next group: {T0,T1} x 4 columns
             for (int cg = 0; cg < Ng; cg++) {
                 const uint4 ca = na, cb = nb;
@@ -179,7 +197,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                 }
                 unsigned up[4];
 #pragma unroll
-                for (int c = 0; c < 4; c++) up[c] = top[(cg * 4 + c) * PK_BLOCK + tid];
+                for (int c = 0; c < 4; c++) up[c] = (cg * 4 + c < Nw) ? top[(cg * 4 + c) * PK_BLOCK + tid] : 0u; // padded columns: no boundary
                 unsigned W[RP][4];
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
@@ -200,7 +218,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                         hd = hold;
                         if (LOCAL && (c & 1)) rmax[r] = __vimax3_s16x2(rmax[r], hold, hn);
                     }
-                    top[(cg * 4 + c) * PK_BLOCK + tid] = hu;
+                    if (cg * 4 + c < Nw) top[(cg * 4 + c) * PK_BLOCK + tid] = hu;
                     if (!LOCAL) {
                         const int j = cg * 4 + c + 1;
                         if (j == N0 || j == N1) {
@@ -255,12 +273,26 @@ __global__ void __launch_bounds__(256) pk_walk_kernel(PkArgs A, int R)
     const int M = (int)A.len1[p], N = (int)A.len2[p];
     const int RP = R / 2;
     const uint64_t Ng = (J.Nw + 3) >> 2;
-    const uint8_t *tr = A.trace + J.trace_off + (uint64_t)lane * 16 + half;
     const uint8_t *a = A.bases + A.off1[p], *b = A.bases + A.off2[p];
     const int gap = A.gap;
+    // The walk touches a 2x2 neighbourhood per step; a 16-byte chunk holds 2 rows x 4 columns.  Two chunks are kept
+    // in registers (one per row-pair parity), so a step costs about one 16-byte load instead of three byte loads.
+    uint4 cv[2];
+    uint64_t ck[2] = {~0ull, ~0ull};
+    const uint4 *trv = reinterpret_cast<const uint4 *>(A.trace + J.trace_off) + lane;
     auto low = [&](int i, int j) -> int { // i >= 1, j >= 1
         const int ii = i - 1, s = ii / R, r = ii - s * R, jj = j - 1;
-        return tr[(((uint64_t)s * Ng + (uint64_t)(jj >> 2)) * RP + (r >> 1)) * 512 + (jj & 3) * 4 + (r & 1) * 2];
+        const uint64_t key = (((uint64_t)s * Ng + (uint64_t)(jj >> 2)) * RP + (r >> 1));
+        const int e = (r >> 1) & 1;
+        if (e == 0) {
+            if (ck[0] != key) { cv[0] = trv[key * 32]; ck[0] = key; }
+        } else {
+            if (ck[1] != key) { cv[1] = trv[key * 32]; ck[1] = key; }
+        }
+        const uint4 v = e == 0 ? cv[0] : cv[1];
+        const int c = jj & 3;
+        const unsigned wv = c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
+        return (int)((wv >> (((r & 1) * 2 + half) * 8)) & 0xffu);
     };
     auto border = [&](int i, int j) -> int { return LOCAL ? 0 : (i == 0 ? j * gap : i * gap); };
     auto near = [&](int hc, int i, int j) -> int { // exact H(i,j) given the exact value hc of an adjacent cell
