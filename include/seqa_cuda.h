@@ -62,6 +62,7 @@ enum {
 /* seqa_params.flags */
 #define SEQA_FLAG_SCORE_ONLY 0x1u  /* skip traceback/ops (scores and end positions only) */
 #define SEQA_FLAG_FORCE_GENERIC 0x2u /* use the generic int32 kernels even where a packed fast path applies */
+#define SEQA_FLAG_TRACE8 0x4u /* packed path: keep 8 trace bits per cell even where 4 suffice (testing) */
 
 /*
  * Mirror of the reference ScoringSystem (include/SequenceAlignment.h:82-131) plus the algorithm and

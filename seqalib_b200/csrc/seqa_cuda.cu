@@ -208,6 +208,12 @@ bool packed_scoring_ok(const seqa_params &p)
     if (m + x + 2 * g > 120) return false; // neighbouring cells must differ by < 128
     return true;
 }
+// 4 trace bits per cell suffice when neighbouring cells differ by less than 8 (seqa_packed.cuh)
+int packed_trace_bits(const seqa_params &p)
+{
+    const int g = -p.gap, m = p.match, x = p.allow_mismatch ? -p.mismatch : 0;
+    return (m + x + 2 * g <= 7 && !(p.flags & SEQA_FLAG_TRACE8)) ? 4 : 8;
+}
 bool packed_shape_ok(const seqa_params &p, uint32_t M, uint32_t N)
 {
     if (M == 0 || N == 0 || M > PK_MAX_LEN || N > PK_MAX_LEN) return false;
@@ -325,7 +331,7 @@ int build_plan(seqa_ctx *c)
             J.Mw = Mw;
             J.Nw = Nw;
             J.nstrips = (Mw + PK_R - 1) / PK_R;
-            const uint64_t tbytes = pk_trace_bytes(J.nstrips, Nw, PK_R);
+            const uint64_t tbytes = pk_trace_bytes(J.nstrips, Nw, PK_R, packed_trace_bits(prm));
             const uint64_t pelems = (uint64_t)((Nw + 3) / 4) * 128, relems = (uint64_t)J.nstrips * PK_R * 32;
             if (ch.hi > ch.lo && chunk_bytes(tr + tbytes, pf + pelems, rs + relems) > budget) {
                 ch.scratch_bytes = chunk_bytes(tr, pf, rs);
@@ -469,12 +475,13 @@ int run_packed(seqa_ctx *c, bool want_walk)
 {
     if (c->jobs.empty()) return SEQA_OK;
     const bool local = c->prm.algo == SEQA_SW;
+    const int tb = packed_trace_bits(c->prm);
     const size_t smem = (size_t)c->pk_max_nw * PK_BLOCK * 4;
     if (smem > c->smem_optin) return fail(SEQA_ERR_UNSUPPORTED, "internal: packed kernel shared memory %zu", smem);
-    if (local)
-        CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-        CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int bps = (int)std::max<size_t>(1, std::min<size_t>(3, (c->smem_optin + 1024) / std::max<size_t>(smem + 1024, 1)));
     CK(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 4, c->stream));
     for (const Chunk &ch : c->pk_chunks) {
@@ -483,7 +490,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
         uint64_t tr = 0, pf = 0;
         {
             const PkWarpJob &L = c->jobs[ch.hi - 1];
-            tr = L.trace_off + pk_trace_bytes(L.nstrips, L.Nw, PK_R);
+            tr = L.trace_off + pk_trace_bytes(L.nstrips, L.Nw, PK_R, tb);
             pf = L.prof_off + (uint64_t)((L.Nw + 3) / 4) * 128;
         }
         PkArgs A{};
@@ -519,10 +526,14 @@ int run_packed(seqa_ctx *c, bool want_walk)
         const unsigned grid = std::min<unsigned>(full, (unsigned)(c->sms * bps));
         LAUNCH(c, (pk_prep_kernel), std::min<unsigned>(full, (unsigned)c->sms * 16), PK_BLOCK, 0, A, PK_R);
         cudaEventRecord(next_event(c), c->stream);
-        if (local)
-            LAUNCH(c, (pk_fill_kernel<true, PK_R>), grid, PK_BLOCK, smem, A);
+        if (local && tb == 4)
+            LAUNCH(c, (pk_fill_kernel<true, PK_R, 4>), grid, PK_BLOCK, smem, A);
+        else if (local)
+            LAUNCH(c, (pk_fill_kernel<true, PK_R, 8>), grid, PK_BLOCK, smem, A);
+        else if (tb == 4)
+            LAUNCH(c, (pk_fill_kernel<false, PK_R, 4>), grid, PK_BLOCK, smem, A);
         else
-            LAUNCH(c, (pk_fill_kernel<false, PK_R>), grid, PK_BLOCK, smem, A);
+            LAUNCH(c, (pk_fill_kernel<false, PK_R, 8>), grid, PK_BLOCK, smem, A);
         cudaEventRecord(next_event(c), c->stream);
         if (want_walk) {
             // walk positions are chunk-relative: perm/jobs pointers advanced to the chunk
@@ -530,14 +541,18 @@ int run_packed(seqa_ctx *c, bool want_walk)
             Wk.perm = c->d_perm.p + (uint64_t)ch.lo * 64;
             // jobs' `first` fields are absolute; the walk indexes perm by position, so rebase via pointer only
             const unsigned wgrid = (unsigned)((Wk.npos + 255) / 256);
-            if (local)
-                LAUNCH(c, (pk_walk_kernel<true>), wgrid, 256, 0, Wk, PK_R);
+            if (local && tb == 4)
+                LAUNCH(c, (pk_walk_kernel<true, 4>), wgrid, 256, 0, Wk, PK_R);
+            else if (local)
+                LAUNCH(c, (pk_walk_kernel<true, 8>), wgrid, 256, 0, Wk, PK_R);
+            else if (tb == 4)
+                LAUNCH(c, (pk_walk_kernel<false, 4>), wgrid, 256, 0, Wk, PK_R);
             else
-                LAUNCH(c, (pk_walk_kernel<false>), wgrid, 256, 0, Wk, PK_R);
+                LAUNCH(c, (pk_walk_kernel<false, 8>), wgrid, 256, 0, Wk, PK_R);
         }
         CK(cudaGetLastError());
     }
-    c->last_kernel = local ? "pk_fill_sw_s16x2" : "pk_fill_nw_s16x2";
+    c->last_kernel = local ? (tb == 4 ? "pk_fill_sw_s16x2_t4" : "pk_fill_sw_s16x2_t8") : (tb == 4 ? "pk_fill_nw_s16x2_t4" : "pk_fill_nw_s16x2_t8");
     return SEQA_OK;
 }
 

@@ -128,34 +128,27 @@ __device__ __forceinline__ unsigned pk_dup(int v) { return ((unsigned)v & 0xffff
 __device__ __forceinline__ int pk_half(unsigned v, int k) { return (int)(int16_t)(k ? (v >> 16) : (v & 0xffffu)); }
 
 // ---- fill -------------------------------------------------------------------------------------------------
-// Trace layout of a warp job (Ng = ceil(Nw/4) column groups): the low byte of H(i,j) of pair-half k, with
-// i-1 = s*R + r, j-1 = 4*cg + c, sits at
-//   trace_off + ((((s*Ng + cg)*(R/2) + r/2)*32 + lane)*16 + c*4 + (r%2)*2 + k
-// i.e. one 16-byte store per thread holds 4 columns x 2 rows x 2 pairs and a warp store covers 512 contiguous
-// bytes.  The stores are streaming (st.global.cs) so the 24 KB/pair trace does not evict the column profiles
-// from L2; the profiles of the next column group are prefetched into registers one group ahead.
-__host__ __device__ inline uint64_t pk_trace_bytes(uint32_t nstrips, uint32_t Nw, int R)
+// Trace: the low TB bits (TB = 8, or 4 when Match + |Mismatch| + 2|Gap| <= 7) of every H value.  Layout of a warp
+// job: one 128-byte line per (strip s, column line cl, lane) holding the thread's 16 rows x (32/TB... see below)
+// columns for both of its pairs, so the walk kernel -- one thread per pair, following a diagonal-ish path --
+// stays inside one line for many steps:
+//   line(s, cl, lane)  at  trace_off + ((s*NL + cl)*32 + lane) * (R/2)*16
+//   16-byte piece rp = (row pair r/2) inside the line; inside a piece
+//     TB == 8: 4 columns,  byte  c*4 + (r%2)*2 + k                     (cl = jj/4, c = jj%4)
+//     TB == 4: 8 columns,  byte (c/2)*4 + (r%2)*2 + k, nibble c%2      (cl = jj/8, c = jj%8)
+// (k = pair half).  The fill writes a piece with one 16-byte (TB 8) or two 8-byte (TB 4) stores per 4 columns.
+// The column profiles of the next 4-column group are prefetched into registers one group ahead.
+__host__ __device__ inline uint32_t pk_lines(uint32_t Nw, int TB) { return TB == 4 ? (Nw + 7) / 8 : (Nw + 3) / 4; }
+__host__ __device__ inline uint64_t pk_trace_bytes(uint32_t nstrips, uint32_t Nw, int R, int TB)
 {
-    return (uint64_t)nstrips * ((Nw + 3) / 4) * (uint64_t)(R / 2) * 512ull;
+    return (uint64_t)nstrips * pk_lines(Nw, TB) * 32ull * (uint64_t)(R / 2) * 16ull;
 }
 
-#ifdef SEQA_EMU
-static inline void pk_store_stream(uint4 *p, uint4 v) { *p = v; }
-static inline void pk_prefetch_l2(const void *, unsigned) {}
-#else
-__device__ __forceinline__ void pk_store_stream(uint4 *p, uint4 v) { __stcs(p, v); }
-// one lane asks the L2 to pull a contiguous region (16-byte multiple) in: cp.async.bulk.prefetch, no registers,
-// no shared memory, no completion to wait for
-__device__ __forceinline__ void pk_prefetch_l2(const void *p, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-#endif
-
-template <bool LOCAL, int R>
+template <bool LOCAL, int R, int TB>
 __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
 {
     static_assert(R % 2 == 0, "R must be even");
+    static_assert(TB == 4 || TB == 8, "trace bits");
     SEQA_DYN_SMEM(unsigned, top);
     constexpr int RP = R / 2;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -168,9 +161,10 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
         const int M0 = p0 == PK_NULL ? 0 : (int)A.len1[p0], N0 = p0 == PK_NULL ? 0 : (int)A.len2[p0];
         const int M1 = p1 == PK_NULL ? 0 : (int)A.len1[p1], N1 = p1 == PK_NULL ? 0 : (int)A.len2[p1];
         const int Ng = ((int)J.Nw + 3) >> 2, Nw = (int)J.Nw;
+        const int NL = (int)pk_lines(J.Nw, TB);
         const uint4 *__restrict__ prof = reinterpret_cast<const uint4 *>(A.prof + J.prof_off) + lane * 2;
         const uint32_t *__restrict__ rowsel = A.rowsel + J.rowsel_off + lane;
-        uint4 *__restrict__ trace = reinterpret_cast<uint4 *>(A.trace + J.trace_off) + lane;
+        uint8_t *__restrict__ trace = A.trace + J.trace_off + (uint64_t)lane * (RP * 16);
         int best0 = 0, best1 = 0, bi0 = 0, bi1 = 0; // SW: running (max, last row holding it)
         int corner0 = 0, corner1 = 0;               // NW: H(M,N)
         // row 0 of the matrix = first strip's upper boundary (SW 0, NW j*gap: include/SANeedlemanWunsch.h:61-62)
@@ -185,9 +179,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                 rmax[r] = 0u;
             }
             unsigned diag = LOCAL ? 0u : pk_dup(i0 * A.gap);
-            uint4 *__restrict__ tr = trace + (uint64_t)s * Ng * RP * 32;
-            // every strip re-reads the job's column profile (Ng KB): have the L2 fetch it while the strip starts
-            if (lane == 0) pk_prefetch_l2(A.prof + J.prof_off, (unsigned)Ng * 1024u);
+            uint8_t *__restrict__ tr = trace + (uint64_t)s * NL * (32 * RP * 16);
             uint4 na = prof[0], nb = prof[1]; // profile of the next group: {T0,T1} x 4 columns
             for (int cg = 0; cg < Ng; cg++) {
                 const uint4 ca = na, cb = nb;
@@ -198,7 +190,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                 unsigned up[4];
 #pragma unroll
                 for (int c = 0; c < 4; c++) up[c] = (cg * 4 + c < Nw) ? top[(cg * 4 + c) * PK_BLOCK + tid] : 0u; // padded columns: no boundary
-                unsigned W[RP][4];
+                unsigned W[RP][TB == 8 ? 4 : 2];
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const unsigned T0 = c == 0 ? ca.x : c == 1 ? ca.z : c == 2 ? cb.x : cb.z;
@@ -212,7 +204,15 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                         const unsigned lg = __vadd2(hold, gap2);
                         const unsigned t = LOCAL ? __viaddmax_s16x2_relu(hd, sim, lg) : __viaddmax_s16x2(hd, sim, lg);
                         const unsigned hn = __viaddmax_s16x2(hu, gap2, t);
-                        if (r & 1) W[r >> 1][c] = seqa_prmt(H[r - 1], hn, 0x6420);
+                        if (r & 1) {
+                            const unsigned w8 = seqa_prmt(H[r - 1], hn, 0x6420); // low bytes: [p0 r-1, p1 r-1, p0 r, p1 r]
+                            if (TB == 8)
+                                W[r >> 1][c] = w8;
+                            else if ((c & 1) == 0)
+                                W[r >> 1][c >> 1] = w8;
+                            else // low nibbles of column c-1, high nibbles from column c
+                                W[r >> 1][c >> 1] = (W[r >> 1][c >> 1] & 0x0f0f0f0fu) | ((w8 << 4) & 0xf0f0f0f0u);
+                        }
                         H[r] = hn;
                         hu = hn;
                         hd = hold;
@@ -230,9 +230,15 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                         }
                     }
                 }
+                if (TB == 8) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(tr + (uint64_t)cg * (32 * RP * 16));
 #pragma unroll
-                for (int rp = 0; rp < RP; rp++)
-                    pk_store_stream(&tr[((uint64_t)cg * RP + rp) * 32], make_uint4(W[rp][0], W[rp][1], W[rp][2], W[rp][3]));
+                    for (int rp = 0; rp < RP; rp++) dst[rp] = make_uint4(W[rp][0], W[rp][1], W[rp][2], W[rp][3]);
+                } else {
+                    uint2 *dst = reinterpret_cast<uint2 *>(tr + (uint64_t)(cg >> 1) * (32 * RP * 16) + (cg & 1) * 8);
+#pragma unroll
+                    for (int rp = 0; rp < RP; rp++) dst[rp * 2] = make_uint2(W[rp][0], W[rp][1]);
+                }
             }
             if (LOCAL) {
                 // last maximum in row-major order (include/SASmithWaterman.h:177): rows ascending, ">="
@@ -259,9 +265,9 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
 }
 
 // ---- walk -------------------------------------------------------------------------------------------------
-// One thread per pair.  Exact neighbour values are rebuilt from the stored low bytes:
-// H(n) = H(c) + sext8(low(n) - low(H(c))) for any cell n adjacent to the current cell c.
-template <bool LOCAL>
+// One thread per pair.  Exact neighbour values are rebuilt from the stored low bits:
+// H(n) = H(c) + sext_TB(low(n) - low(H(c))) for any cell n adjacent to the current cell c.
+template <bool LOCAL, int TB>
 __global__ void __launch_bounds__(256) pk_walk_kernel(PkArgs A, int R)
 {
     const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -272,55 +278,61 @@ __global__ void __launch_bounds__(256) pk_walk_kernel(PkArgs A, int R)
     const int lane = (int)((pos & 63) >> 1), half = (int)(pos & 1);
     const int M = (int)A.len1[p], N = (int)A.len2[p];
     const int RP = R / 2;
-    const uint64_t Ng = (J.Nw + 3) >> 2;
+    const uint32_t NL = pk_lines(J.Nw, TB);
+    constexpr int CSH = TB == 8 ? 2 : 3; // log2(columns per line)
+    constexpr unsigned MASK = TB == 8 ? 0xffu : 0xfu;
     const uint8_t *a = A.bases + A.off1[p], *b = A.bases + A.off2[p];
     const int gap = A.gap;
-    // The walk touches a 2x2 neighbourhood per step; a 16-byte chunk holds 2 rows x 4 columns.  Two chunks are kept
-    // in registers (one per row-pair parity), so a step costs about one 16-byte load instead of three byte loads.
+    // pieces (16 B = 2 rows x 4|8 columns x 2 pairs) of this thread-pair: piece index = ((s*NL + cl)*32 + lane)*RP + rp
+    const uint4 *pieces = reinterpret_cast<const uint4 *>(A.trace + J.trace_off);
     uint4 cv[2];
-    uint64_t ck[2] = {~0ull, ~0ull};
-    const uint4 *trv = reinterpret_cast<const uint4 *>(A.trace + J.trace_off) + lane;
-    auto low = [&](int i, int j) -> int { // i >= 1, j >= 1
+    uint32_t ck[2] = {0xffffffffu, 0xffffffffu};
+    auto low = [&](int i, int j) -> unsigned { // i >= 1, j >= 1
         const int ii = i - 1, s = ii / R, r = ii - s * R, jj = j - 1;
-        const uint64_t key = (((uint64_t)s * Ng + (uint64_t)(jj >> 2)) * RP + (r >> 1));
+        const uint32_t key = (((uint32_t)s * NL + (uint32_t)(jj >> CSH)) * 32u + (uint32_t)lane) * (uint32_t)RP + (uint32_t)(r >> 1);
         const int e = (r >> 1) & 1;
         if (e == 0) {
-            if (ck[0] != key) { cv[0] = trv[key * 32]; ck[0] = key; }
+            if (ck[0] != key) { cv[0] = pieces[key]; ck[0] = key; }
         } else {
-            if (ck[1] != key) { cv[1] = trv[key * 32]; ck[1] = key; }
+            if (ck[1] != key) { cv[1] = pieces[key]; ck[1] = key; }
         }
         const uint4 v = e == 0 ? cv[0] : cv[1];
-        const int c = jj & 3;
-        const unsigned wv = c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
-        return (int)((wv >> (((r & 1) * 2 + half) * 8)) & 0xffu);
+        const int c = jj & ((1 << CSH) - 1);
+        const int wsel = TB == 8 ? c : (c >> 1);
+        const unsigned wv = wsel == 0 ? v.x : wsel == 1 ? v.y : wsel == 2 ? v.z : v.w;
+        const int sh = ((r & 1) * 2 + half) * 8 + (TB == 4 ? (c & 1) * 4 : 0);
+        return (wv >> sh) & MASK;
+    };
+    auto sext = [&](unsigned d) -> int { // signed difference from its low TB bits
+        return TB == 8 ? (int)(int8_t)(uint8_t)d : ((int)((d & 0xfu) ^ 8u) - 8);
     };
     auto border = [&](int i, int j) -> int { return LOCAL ? 0 : (i == 0 ? j * gap : i * gap); };
     auto near = [&](int hc, int i, int j) -> int { // exact H(i,j) given the exact value hc of an adjacent cell
         if (i == 0 || j == 0) return border(i, j);
-        return hc + (int)(int8_t)(uint8_t)(low(i, j) - (hc & 0xff));
+        return hc + sext(low(i, j) - ((unsigned)hc & MASK));
     };
     uint8_t *slot = A.slots + A.slot_off[p];
     int k = M + N;
     int i, j, h;
     if (LOCAL) {
         // MaxCol: the last column of row MaxRow holding MaxScore (include/SASmithWaterman.h:177-182).  One 16-byte
-        // load brings 4 columns of the row; exact values are chained from H(i,0) = 0.
+        // load brings 4 (8) columns of the row; exact values are chained from H(i,0) = 0.
         const int best = A.score[p];
         i = (int)A.end_i[p];
         int e = 0, bj = N;
         if (i >= 1) {
             const int ii = i - 1, s = ii / R, r = ii - s * R;
-            const uint8_t *row = A.trace + J.trace_off + (uint64_t)lane * 16 + ((uint64_t)s * Ng * RP + (r >> 1)) * 512;
-            const int sh = ((r & 1) * 2 + half) * 8;
-            const int ng = (N + 3) >> 2;
-            for (int cg = 0; cg < ng; cg++) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(row + (uint64_t)cg * RP * 512);
+            const int rsh = ((r & 1) * 2 + half) * 8;
+            const int nl = (N + (1 << CSH) - 1) >> CSH;
+            for (int cl = 0; cl < nl; cl++) {
+                const uint4 v = pieces[(((uint32_t)s * NL + (uint32_t)cl) * 32u + (uint32_t)lane) * (uint32_t)RP + (uint32_t)(r >> 1)];
                 const unsigned wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int jj = cg * 4 + c + 1;
+                for (int c = 0; c < (1 << CSH); c++) {
+                    const int jj = (cl << CSH) + c + 1;
                     if (jj <= N) {
-                        e += (int)(int8_t)(uint8_t)(((wv[c] >> sh) & 0xffu) - (unsigned)(e & 0xff));
+                        const unsigned lo = TB == 8 ? ((wv[c] >> rsh) & 0xffu) : ((wv[c >> 1] >> (rsh + (c & 1) * 4)) & 0xfu);
+                        e += sext(lo - ((unsigned)e & MASK));
                         if (e == best) bj = jj;
                     }
                 }

@@ -22,7 +22,9 @@ def test_matrix_algorithms(emu_lib, algo, sc):
     rng = np.random.default_rng(11)
     pairs = list(EDGE) + random_pairs(rng, 30, 1, 70) + random_pairs(rng, 8, 1, 50, "AC") + \
         random_pairs(rng, 6, 120, 180) + random_pairs(rng, 8, 1, 90, related=0.3)
-    for flags in (0, capi.FLAG_FORCE_GENERIC):
+    for flags in (0, capi.FLAG_TRACE8, capi.FLAG_FORCE_GENERIC):
+        if flags == capi.FLAG_TRACE8 and algo not in ('nw', 'sw'):
+            continue
         check_batch_against_oracle(emu_lib, algo, sc, pairs, flags=flags)
 
 
@@ -34,7 +36,7 @@ def test_packed_path_is_taken(emu_lib):
     ctx.upload(scoring_to_params("sw", S.linear(-1, 1, -1)), bases, off1, off2, len1, len2)
     ctx.run()
     ctx.sync()
-    assert ctx.last_kernel() == "pk_fill_sw_s16x2"
+    assert ctx.last_kernel() == "pk_fill_sw_s16x2_t4"
     assert ctx.cells() == int((len1.astype(np.int64) * len2).sum())
     # a non-ACGT base voids the packed result: the batch is re-planned onto the 8-bit generic kernels
     pairs[5] = (pairs[5][0][:10] + "N" + pairs[5][0][10:], pairs[5][1])
