@@ -129,20 +129,25 @@ __device__ __forceinline__ int pk_half(unsigned v, int k) { return (int)(int16_t
 
 // ---- fill -------------------------------------------------------------------------------------------------
 // Trace: the low TB bits (TB = 8, or 4 when Match + |Mismatch| + 2|Gap| <= 7) of every H value.  Layout of a warp
-// job: one 128-byte line per (strip s, column line cl, lane) holding the thread's 16 rows x (32/TB... see below)
-// columns for both of its pairs, so the walk kernel -- one thread per pair, following a diagonal-ish path --
-// stays inside one line for many steps:
-//   line(s, cl, lane)  at  trace_off + ((s*NL + cl)*32 + lane) * (R/2)*16
-//   16-byte piece rp = (row pair r/2) inside the line; inside a piece
-//     TB == 8: 4 columns,  byte  c*4 + (r%2)*2 + k                     (cl = jj/4, c = jj%4)
-//     TB == 4: 8 columns,  byte (c/2)*4 + (r%2)*2 + k, nibble c%2      (cl = jj/8, c = jj%8)
-// (k = pair half).  The fill writes a piece with one 16-byte (TB 8) or two 8-byte (TB 4) stores per 4 columns.
+// job (Ng = ceil(Nw/4) column groups, RP = R/2 row pairs): one piece of PB = 2*TB bytes per (strip s, column
+// group cg, row pair rp, lane) holding 2 rows x 4 columns x 2 pairs,
+//   piece(s, cg, rp, lane)  at  trace_off + (((s*Ng + cg)*RP + rp)*32 + lane) * PB
+//     TB == 8: byte  c*4 + (r%2)*2 + k            TB == 4: byte (c/2)*4 + (r%2)*2 + k, nibble c%2
+// (c = column inside the group, k = pair half), so that every warp store is one contiguous 512 / 256-byte run
+// (thread-major 128-byte lines were measured 2x slower: 32 lines per store instruction saturate the LSU).
 // The column profiles of the next 4-column group are prefetched into registers one group ahead.
-__host__ __device__ inline uint32_t pk_lines(uint32_t Nw, int TB) { return TB == 4 ? (Nw + 7) / 8 : (Nw + 3) / 4; }
 __host__ __device__ inline uint64_t pk_trace_bytes(uint32_t nstrips, uint32_t Nw, int R, int TB)
 {
-    return (uint64_t)nstrips * pk_lines(Nw, TB) * 32ull * (uint64_t)(R / 2) * 16ull;
+    return (uint64_t)nstrips * ((Nw + 3) / 4) * (uint64_t)(R / 2) * 32ull * (uint64_t)(2 * TB);
 }
+
+#ifdef SEQA_EMU
+static inline void pk_store_stream(uint4 *p, uint4 v) { *p = v; }
+static inline void pk_store_stream(uint2 *p, uint2 v) { *p = v; }
+#else
+__device__ __forceinline__ void pk_store_stream(uint4 *p, uint4 v) { __stcs(p, v); }
+__device__ __forceinline__ void pk_store_stream(uint2 *p, uint2 v) { __stcs(p, v); }
+#endif
 
 template <bool LOCAL, int R, int TB>
 __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
@@ -161,10 +166,9 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
         const int M0 = p0 == PK_NULL ? 0 : (int)A.len1[p0], N0 = p0 == PK_NULL ? 0 : (int)A.len2[p0];
         const int M1 = p1 == PK_NULL ? 0 : (int)A.len1[p1], N1 = p1 == PK_NULL ? 0 : (int)A.len2[p1];
         const int Ng = ((int)J.Nw + 3) >> 2, Nw = (int)J.Nw;
-        const int NL = (int)pk_lines(J.Nw, TB);
         const uint4 *__restrict__ prof = reinterpret_cast<const uint4 *>(A.prof + J.prof_off) + lane * 2;
         const uint32_t *__restrict__ rowsel = A.rowsel + J.rowsel_off + lane;
-        uint8_t *__restrict__ trace = A.trace + J.trace_off + (uint64_t)lane * (RP * 16);
+        uint8_t *__restrict__ trace = A.trace + J.trace_off + (uint64_t)lane * (2 * TB);
         int best0 = 0, best1 = 0, bi0 = 0, bi1 = 0; // SW: running (max, last row holding it)
         int corner0 = 0, corner1 = 0;               // NW: H(M,N)
         // row 0 of the matrix = first strip's upper boundary (SW 0, NW j*gap: include/SANeedlemanWunsch.h:61-62)
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                 rmax[r] = 0u;
             }
             unsigned diag = LOCAL ? 0u : pk_dup(i0 * A.gap);
-            uint8_t *__restrict__ tr = trace + (uint64_t)s * NL * (32 * RP * 16);
+            uint8_t *__restrict__ tr = trace + (uint64_t)s * Ng * (RP * 32 * 2 * TB);
             uint4 na = prof[0], nb = prof[1]; // profile of the next group: {T0,T1} x 4 columns
             for (int cg = 0; cg < Ng; cg++) {
                 const uint4 ca = na, cb = nb;
@@ -231,13 +235,13 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                     }
                 }
                 if (TB == 8) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(tr + (uint64_t)cg * (32 * RP * 16));
+                    uint4 *dst = reinterpret_cast<uint4 *>(tr + (uint64_t)cg * (RP * 32 * 16));
 #pragma unroll
-                    for (int rp = 0; rp < RP; rp++) dst[rp] = make_uint4(W[rp][0], W[rp][1], W[rp][2], W[rp][3]);
+                    for (int rp = 0; rp < RP; rp++) pk_store_stream(&dst[rp * 32], make_uint4(W[rp][0], W[rp][1], W[rp][2], W[rp][3]));
                 } else {
-                    uint2 *dst = reinterpret_cast<uint2 *>(tr + (uint64_t)(cg >> 1) * (32 * RP * 16) + (cg & 1) * 8);
+                    uint2 *dst = reinterpret_cast<uint2 *>(tr + (uint64_t)cg * (RP * 32 * 8));
 #pragma unroll
-                    for (int rp = 0; rp < RP; rp++) dst[rp * 2] = make_uint2(W[rp][0], W[rp][1]);
+                    for (int rp = 0; rp < RP; rp++) pk_store_stream(&dst[rp * 32], make_uint2(W[rp][0], W[rp][1]));
                 }
             }
             if (LOCAL) {
@@ -278,30 +282,35 @@ __global__ void __launch_bounds__(256) pk_walk_kernel(PkArgs A, int R)
     const int lane = (int)((pos & 63) >> 1), half = (int)(pos & 1);
     const int M = (int)A.len1[p], N = (int)A.len2[p];
     const int RP = R / 2;
-    const uint32_t NL = pk_lines(J.Nw, TB);
-    constexpr int CSH = TB == 8 ? 2 : 3; // log2(columns per line)
+    const uint32_t Ng = (J.Nw + 3) >> 2;
     constexpr unsigned MASK = TB == 8 ? 0xffu : 0xfu;
     const uint8_t *a = A.bases + A.off1[p], *b = A.bases + A.off2[p];
     const int gap = A.gap;
-    // pieces (16 B = 2 rows x 4|8 columns x 2 pairs) of this thread-pair: piece index = ((s*NL + cl)*32 + lane)*RP + rp
-    const uint4 *pieces = reinterpret_cast<const uint4 *>(A.trace + J.trace_off);
+    // pieces (2 rows x 4 columns x 2 pairs, 2*TB bytes): index ((s*Ng + cg)*RP + rp)*32 + lane; two of them are
+    // kept in registers (one per row-pair parity), so a step costs about one load instead of three
+    const uint8_t *pieces = A.trace + J.trace_off;
     uint4 cv[2];
     uint32_t ck[2] = {0xffffffffu, 0xffffffffu};
-    auto low = [&](int i, int j) -> unsigned { // i >= 1, j >= 1
-        const int ii = i - 1, s = ii / R, r = ii - s * R, jj = j - 1;
-        const uint32_t key = (((uint32_t)s * NL + (uint32_t)(jj >> CSH)) * 32u + (uint32_t)lane) * (uint32_t)RP + (uint32_t)(r >> 1);
-        const int e = (r >> 1) & 1;
-        if (e == 0) {
-            if (ck[0] != key) { cv[0] = pieces[key]; ck[0] = key; }
-        } else {
-            if (ck[1] != key) { cv[1] = pieces[key]; ck[1] = key; }
-        }
-        const uint4 v = e == 0 ? cv[0] : cv[1];
-        const int c = jj & ((1 << CSH) - 1);
+    auto fetch = [&](uint32_t key) -> uint4 {
+        if (TB == 8) return reinterpret_cast<const uint4 *>(pieces)[key];
+        const uint2 t = reinterpret_cast<const uint2 *>(pieces)[key];
+        return make_uint4(t.x, t.y, 0u, 0u);
+    };
+    auto pick = [&](const uint4 &v, int r, int c) -> unsigned { // low bits of (row parity r&1, column c of the group)
         const int wsel = TB == 8 ? c : (c >> 1);
         const unsigned wv = wsel == 0 ? v.x : wsel == 1 ? v.y : wsel == 2 ? v.z : v.w;
-        const int sh = ((r & 1) * 2 + half) * 8 + (TB == 4 ? (c & 1) * 4 : 0);
-        return (wv >> sh) & MASK;
+        return (wv >> (((r & 1) * 2 + half) * 8 + (TB == 4 ? (c & 1) * 4 : 0))) & MASK;
+    };
+    auto low = [&](int i, int j) -> unsigned { // i >= 1, j >= 1
+        const int ii = i - 1, s = ii / R, r = ii - s * R, jj = j - 1;
+        const uint32_t key = (((uint32_t)s * Ng + (uint32_t)(jj >> 2)) * (uint32_t)RP + (uint32_t)(r >> 1)) * 32u + (uint32_t)lane;
+        const int e = (r >> 1) & 1;
+        if (e == 0) {
+            if (ck[0] != key) { cv[0] = fetch(key); ck[0] = key; }
+        } else {
+            if (ck[1] != key) { cv[1] = fetch(key); ck[1] = key; }
+        }
+        return pick(e == 0 ? cv[0] : cv[1], r, jj & 3);
     };
     auto sext = [&](unsigned d) -> int { // signed difference from its low TB bits
         return TB == 8 ? (int)(int8_t)(uint8_t)d : ((int)((d & 0xfu) ^ 8u) - 8);
@@ -322,17 +331,14 @@ __global__ void __launch_bounds__(256) pk_walk_kernel(PkArgs A, int R)
         int e = 0, bj = N;
         if (i >= 1) {
             const int ii = i - 1, s = ii / R, r = ii - s * R;
-            const int rsh = ((r & 1) * 2 + half) * 8;
-            const int nl = (N + (1 << CSH) - 1) >> CSH;
-            for (int cl = 0; cl < nl; cl++) {
-                const uint4 v = pieces[(((uint32_t)s * NL + (uint32_t)cl) * 32u + (uint32_t)lane) * (uint32_t)RP + (uint32_t)(r >> 1)];
-                const unsigned wv[4] = {v.x, v.y, v.z, v.w};
+            const int ng = (N + 3) >> 2;
+            for (int cg = 0; cg < ng; cg++) {
+                const uint4 v = fetch((((uint32_t)s * Ng + (uint32_t)cg) * (uint32_t)RP + (uint32_t)(r >> 1)) * 32u + (uint32_t)lane);
 #pragma unroll
-                for (int c = 0; c < (1 << CSH); c++) {
-                    const int jj = (cl << CSH) + c + 1;
+                for (int c = 0; c < 4; c++) {
+                    const int jj = cg * 4 + c + 1;
                     if (jj <= N) {
-                        const unsigned lo = TB == 8 ? ((wv[c] >> rsh) & 0xffu) : ((wv[c >> 1] >> (rsh + (c & 1) * 4)) & 0xfu);
-                        e += sext(lo - ((unsigned)e & MASK));
+                        e += sext(pick(v, r, c) - ((unsigned)e & MASK));
                         if (e == best) bj = jj;
                     }
                 }
