@@ -271,8 +271,14 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
 // ---- walk -------------------------------------------------------------------------------------------------
 // One thread per pair.  Exact neighbour values are rebuilt from the stored low bits:
 // H(n) = H(c) + sext_TB(low(n) - low(H(c))) for any cell n adjacent to the current cell c.
+#ifdef SEQA_EMU
+static inline void pk_prefetch_l2_line(const void *) {}
+#else
+__device__ __forceinline__ void pk_prefetch_l2_line(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
 template <bool LOCAL, int TB>
-__global__ void __launch_bounds__(256) pk_walk_kernel(PkArgs A, int R)
+__global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A, int R)
 {
     const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= A.npos) return;
@@ -305,10 +311,19 @@ __global__ void __launch_bounds__(256) pk_walk_kernel(PkArgs A, int R)
         const int ii = i - 1, s = ii / R, r = ii - s * R, jj = j - 1;
         const uint32_t key = (((uint32_t)s * Ng + (uint32_t)(jj >> 2)) * (uint32_t)RP + (uint32_t)(r >> 1)) * 32u + (uint32_t)lane;
         const int e = (r >> 1) & 1;
-        if (e == 0) {
-            if (ck[0] != key) { cv[0] = fetch(key); ck[0] = key; }
-        } else {
-            if (ck[1] != key) { cv[1] = fetch(key); ck[1] = key; }
+        const bool miss = e == 0 ? (ck[0] != key) : (ck[1] != key);
+        if (miss) {
+            if (e == 0) { cv[0] = fetch(key); ck[0] = key; }
+            else { cv[1] = fetch(key); ck[1] = key; }
+            // the path mostly climbs diagonally: ask the L2 for the piece one row pair up (same and previous
+            // column group) while this one is being used
+            int s2 = s, rp2 = (r >> 1) - 1;
+            if (rp2 < 0) { s2 = s - 1; rp2 = RP - 1; }
+            if (s2 >= 0) {
+                const uint32_t k2 = (((uint32_t)s2 * Ng + (uint32_t)(jj >> 2)) * (uint32_t)RP + (uint32_t)rp2) * 32u + (uint32_t)lane;
+                pk_prefetch_l2_line(pieces + (uint64_t)k2 * (2 * TB));
+                if (jj >= 4) pk_prefetch_l2_line(pieces + (uint64_t)(k2 - (uint32_t)RP * 32u) * (2 * TB));
+            }
         }
         return pick(e == 0 ? cv[0] : cv[1], r, jj & 3);
     };
