@@ -245,19 +245,23 @@ int build_plan(seqa_ctx *c)
     c->cells = 0;
     for (uint64_t p = 0; p < n; p++) c->cells += (uint64_t)c->hlen1[p] * c->hlen2[p];
 
-    // per-pair op slots: len1+len2 bytes each (an alignment never has more columns)
+    // per-pair op slots: len1+len2 bytes each (an alignment never has more columns); offsets by a device scan
     {
-        std::vector<uint64_t> so(n + 1);
         uint64_t run = 0;
-        for (uint64_t p = 0; p < n; p++) {
-            so[p] = run;
-            run += (uint64_t)c->hlen1[p] + c->hlen2[p];
-        }
+        for (uint64_t p = 0; p < n; p++) run += (uint64_t)c->hlen1[p] + c->hlen2[p];
         c->slots_total = run;
         CKS(c->slot_off.ensure(n));
         CKS(c->slots.ensure(run));
-        CK(cudaMemcpyAsync(c->slot_off.p, so.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        CKS(c->ops_len.ensure(n));
+        CKS(c->tile_sum.ensure((n + SEQA_SCAN_TILE - 1) / SEQA_SCAN_TILE + 1));
+        CKS(c->total.ensure(1));
+        if (n) {
+            const unsigned tiles = (unsigned)((n + SEQA_SCAN_TILE - 1) / SEQA_SCAN_TILE);
+            LAUNCH(c, (lensum_kernel), (unsigned)((n + 255) / 256), 256, 0, c->len1.p, c->len2.p, c->ops_len.p, n);
+            LAUNCH(c, (scan_tile_sums_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p);
+            LAUNCH(c, (scan_spine_kernel), 1, 1024, 0, c->tile_sum.p, (uint64_t)tiles, c->total.p);
+            LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, c->slot_off.p);
+        }
     }
     CKS(c->score.ensure(n));
     CKS(c->start_i.ensure(n));
@@ -391,8 +395,7 @@ int build_plan(seqa_ctx *c)
     for (auto &ch : c->pk_chunks) need = std::max(need, ch.scratch_bytes);
     for (auto &ch : c->g_chunks) need = std::max(need, ch.scratch_bytes);
     CKS(c->scratch.ensure(need));
-    CK(cudaStreamSynchronize(c->stream));
-    return SEQA_OK;
+    return SEQA_OK; // everything above is stream-ordered; the host vectors it copies from are ctx members
 }
 
 cudaEvent_t next_event(seqa_ctx *c)
@@ -614,21 +617,16 @@ int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in
         hi = std::max(hi, std::max(a1, b1));
     }
     if (n == 0 || hi < lo) lo = hi = 0;
-    std::vector<uint64_t> o1(n), o2(n);
-    for (uint64_t p = 0; p < n; p++) {
-        o1[p] = in->off1[pb + p] - lo;
-        o2[p] = in->off2[pb + p] - lo;
-    }
     c->bases_len = hi - lo;
     CKS(c->bases.ensure(c->bases_len + 16));
     if (hi > lo) CK(cudaMemcpyAsync(c->bases.p, in->bases + lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
     if (n) {
-        CK(cudaMemcpyAsync(c->off1.p, o1.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->off2.p, o2.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->len1.p, c->hlen1.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->len2.p, c->hlen2.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->off1.p, in->off1 + pb, n * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->off2.p, in->off2 + pb, n * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->len1.p, in->len1 + pb, n * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->len2.p, in->len2 + pb, n * 4, cudaMemcpyHostToDevice, c->stream));
+        if (lo) LAUNCH(c, (rebase_kernel), (unsigned)((n + 255) / 256), 256, 0, c->off1.p, c->off2.p, n, lo);
     }
-    CK(cudaStreamSynchronize(c->stream)); // o1/o2 are stack-owned
     return build_plan(c);
 }
 
@@ -877,30 +875,34 @@ int seqa_ctx_download_inputs(seqa_ctx *c, char *bases, uint64_t bases_len, uint6
 }
 
 // Lazily created per-device contexts reused by seqa_cuda_align_batch (device buffers survive between calls;
-// seqa_cuda_trim() frees them).  A device whose cached context is busy gets a temporary one.
+// seqa_cuda_trim() frees them).  Up to SEQA_CACHE_SLOTS contexts per device so that the waves of one call can be
+// in flight together; a device whose cached contexts are all busy gets a temporary one.
+#define SEQA_CACHE_SLOTS 3
 static std::mutex g_cache_mu;
-static seqa_ctx *g_cache[64];
-static bool g_cache_busy[64];
+static seqa_ctx *g_cache[64][SEQA_CACHE_SLOTS];
+static bool g_cache_busy[64][SEQA_CACHE_SLOTS];
 
 static int cache_acquire(int device, seqa_ctx **out, int *cached)
 {
-    *cached = 0;
+    *cached = -1;
     if (device >= 0 && device < 64) {
         std::lock_guard<std::mutex> lk(g_cache_mu);
-        if (g_cache[device] && !g_cache_busy[device]) {
-            g_cache_busy[device] = true;
-            *out = g_cache[device];
-            *cached = 1;
-            return SEQA_OK;
-        }
-        if (!g_cache[device]) {
-            int s = seqa_ctx_create(out, device, nullptr);
-            if (s != SEQA_OK) return s;
-            g_cache[device] = *out;
-            g_cache_busy[device] = true;
-            *cached = 1;
-            return SEQA_OK;
-        }
+        for (int k = 0; k < SEQA_CACHE_SLOTS; k++)
+            if (g_cache[device][k] && !g_cache_busy[device][k]) {
+                g_cache_busy[device][k] = true;
+                *out = g_cache[device][k];
+                *cached = k;
+                return SEQA_OK;
+            }
+        for (int k = 0; k < SEQA_CACHE_SLOTS; k++)
+            if (!g_cache[device][k]) {
+                int s = seqa_ctx_create(out, device, nullptr);
+                if (s != SEQA_OK) return s;
+                g_cache[device][k] = *out;
+                g_cache_busy[device][k] = true;
+                *cached = k;
+                return SEQA_OK;
+            }
     }
     return seqa_ctx_create(out, device, nullptr);
 }
@@ -908,24 +910,31 @@ static int cache_acquire(int device, seqa_ctx **out, int *cached)
 static void cache_release(seqa_ctx *c, int cached)
 {
     if (!c) return;
-    if (!cached) {
+    if (cached < 0) {
         seqa_ctx_destroy(c);
         return;
     }
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    g_cache_busy[c->device] = false;
+    g_cache_busy[c->device][cached] = false;
 }
 
 void seqa_cuda_trim(void)
 {
     std::lock_guard<std::mutex> lk(g_cache_mu);
     for (int d = 0; d < 64; d++)
-        if (g_cache[d] && !g_cache_busy[d]) {
-            seqa_ctx_destroy(g_cache[d]);
-            g_cache[d] = nullptr;
-        }
+        for (int k = 0; k < SEQA_CACHE_SLOTS; k++)
+            if (g_cache[d][k] && !g_cache_busy[d][k]) {
+                seqa_ctx_destroy(g_cache[d][k]);
+                g_cache[d][k] = nullptr;
+            }
 }
 
+// One-shot entry.  The batch is cut into contiguous per-device shards (balanced by sum len1*len2) and every
+// shard into WAVES of ~3e9 cells; up to three worker threads per device, each with its own context and stream,
+// take the waves round-robin, so the host->device copy of one wave, the kernels of another and the device->host
+// copy of a third overlap.  A wave's ops land in the caller's buffer at the prefix sum of (len1+len2) of the
+// pairs before it (the ABI lets ops_off point anywhere), which needs no ordering between waves; when
+// ops_capacity is smaller than sum(len1+len2) the waves are packed densely in order instead.
 int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, seqa_batch_out *out)
 {
     CKS(validate_params(params));
@@ -941,53 +950,110 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
     if (n == 0) return SEQA_OK;
     if (!in->len1 || !in->len2) return fail(SEQA_ERR_INVALID, "batch has NULL arrays");
     if ((uint64_t)nd > n) nd = (int)n;
-    // static split, contiguous, balanced by sum len1*len2
-    std::vector<uint64_t> cut(nd + 1, n);
-    cut[0] = 0;
+
+    // waves: contiguous, ~3e9 cells or 256k pairs each; linear-space pairs (huge sweeps) go one wave per 4e10 cells
+    const bool linspace = params->algo == SEQA_HIRSCHBERG || params->algo == SEQA_MYERS_MILLER;
+    const long double wave_cells = linspace ? 4e10L : 3e9L;
+    std::vector<uint64_t> wave_lo, wave_slots; // first pair, prefix sum of (len1+len2) before the wave
+    long double tot = 0;
+    {
+        long double acc = 0;
+        uint64_t slots = 0, cnt = 0;
+        wave_lo.push_back(0);
+        wave_slots.push_back(0);
+        for (uint64_t p = 0; p < n; p++) {
+            if (cnt > 0 && (acc >= wave_cells || cnt >= 262144)) {
+                wave_lo.push_back(p);
+                wave_slots.push_back(slots);
+                acc = 0;
+                cnt = 0;
+            }
+            const long double cells = (long double)in->len1[p] * in->len2[p] + 1;
+            acc += cells;
+            tot += cells;
+            slots += (uint64_t)in->len1[p] + in->len2[p];
+            cnt++;
+        }
+        wave_lo.push_back(n);
+        wave_slots.push_back(slots);
+    }
+    const size_t nwaves = wave_lo.size() - 1;
+    const uint64_t slots_total = wave_slots.back();
+    const bool sparse = out->ops_capacity >= slots_total || (params->flags & SEQA_FLAG_SCORE_ONLY);
+    // waves -> devices: contiguous runs of waves with ~equal cells (SURVEY.md 8e static split)
+    std::vector<size_t> dev_lo(nd + 1, nwaves);
+    dev_lo[0] = 0;
     if (nd > 1) {
-        long double tot = 0;
-        for (uint64_t p = 0; p < n; p++) tot += (long double)in->len1[p] * in->len2[p] + 1;
+        std::vector<long double> wc(nwaves, 0);
+        for (size_t w = 0; w < nwaves; w++)
+            for (uint64_t p = wave_lo[w]; p < wave_lo[w + 1]; p++) wc[w] += (long double)in->len1[p] * in->len2[p] + 1;
         long double run = 0;
         int d = 1;
-        for (uint64_t p = 0; p < n && d < nd; p++) {
-            run += (long double)in->len1[p] * in->len2[p] + 1;
-            if (run >= tot * d / nd) cut[d++] = p + 1;
+        for (size_t w = 0; w < nwaves && d < nd; w++) {
+            run += wc[w];
+            if (run >= tot * d / nd) dev_lo[d++] = w + 1;
         }
     }
-    std::vector<seqa_ctx *> ctxs(nd, nullptr);
-    std::vector<int> cached(nd, 0);
-    std::vector<int> status(nd, SEQA_OK);
-    std::vector<std::string> errs(nd);
-    auto work = [&](int d) {
-        int s = cache_acquire(first + d, &ctxs[d], &cached[d]);
-        if (s == SEQA_OK) s = ctx_upload_range(ctxs[d], params, in, cut[d], cut[d + 1]);
-        if (s == SEQA_OK) s = ctx_run(ctxs[d]);
-        if (s == SEQA_OK) s = ctx_resolve(ctxs[d]);
-        status[d] = s;
-        if (s != SEQA_OK) errs[d] = g_err;
+    std::vector<int> wstatus(nwaves, SEQA_OK);
+    std::vector<std::string> werr(nwaves);
+    std::vector<uint64_t> wused(nwaves, 0);
+    auto worker = [&](int d, int t, int nthreads) {
+        seqa_ctx *c = nullptr;
+        int cached = -1;
+        for (size_t w = dev_lo[d] + t; w < dev_lo[d + 1]; w += nthreads) {
+            int s = SEQA_OK;
+            if (!c) s = cache_acquire(first + d, &c, &cached);
+            if (s == SEQA_OK) s = ctx_upload_range(c, params, in, wave_lo[w], wave_lo[w + 1]);
+            if (s == SEQA_OK) s = ctx_run(c);
+            if (s == SEQA_OK) s = ctx_resolve(c);
+            if (s == SEQA_OK) s = ctx_download_into(c, out, wave_lo[w], wave_slots[w], &wused[w]);
+            wstatus[w] = s;
+            if (s != SEQA_OK) {
+                werr[w] = g_err;
+                break;
+            }
+        }
+        if (c) cache_release(c, cached);
     };
-    if (nd == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (int d = 0; d < nd; d++) th.emplace_back(work, d);
-        for (auto &t : th) t.join();
-    }
     int rc = SEQA_OK;
-    uint64_t base = 0;
-    for (int d = 0; d < nd; d++) {
-        if (rc == SEQA_OK && status[d] != SEQA_OK) {
-            rc = status[d];
-            g_err = errs[d];
+    uint64_t used = 0;
+    if (sparse) {
+        std::vector<std::thread> th;
+        for (int d = 0; d < nd; d++) {
+            const size_t nw = dev_lo[d + 1] - dev_lo[d];
+            const int nthreads = (int)std::min<size_t>(SEQA_CACHE_SLOTS, nw);
+            for (int t = 0; t < nthreads; t++) {
+                if (nd == 1 && nthreads == 1)
+                    worker(d, t, nthreads);
+                else
+                    th.emplace_back(worker, d, t, nthreads);
+            }
         }
-        if (rc == SEQA_OK) {
-            uint64_t used = 0;
-            rc = ctx_download_into(ctxs[d], out, cut[d], base, &used);
-            base += used;
+        for (auto &t : th) t.join();
+        for (size_t w = 0; w < nwaves; w++) {
+            if (rc == SEQA_OK && wstatus[w] != SEQA_OK) {
+                rc = wstatus[w];
+                g_err = werr[w];
+            }
+            used += wused[w];
+        }
+    } else {
+        // small caller buffer: waves one after another, ops packed densely in pair order
+        for (int d = 0; d < nd && rc == SEQA_OK; d++) {
+            seqa_ctx *c = nullptr;
+            int cached = -1;
+            rc = cache_acquire(first + d, &c, &cached);
+            for (size_t w = dev_lo[d]; w < dev_lo[d + 1] && rc == SEQA_OK; w++) {
+                uint64_t u = 0;
+                rc = ctx_upload_range(c, params, in, wave_lo[w], wave_lo[w + 1]);
+                if (rc == SEQA_OK) rc = ctx_run(c);
+                if (rc == SEQA_OK) rc = ctx_download_into(c, out, wave_lo[w], used, &u);
+                used += u;
+            }
+            if (c) cache_release(c, cached);
         }
     }
-    for (int d = 0; d < nd; d++) cache_release(ctxs[d], cached[d]);
-    out->ops_used = base;
+    out->ops_used = used;
     return rc;
 }
 

@@ -92,6 +92,23 @@ __global__ void __launch_bounds__(SEQA_SCAN_TPB) scan_apply_kernel(const uint32_
     }
 }
 
+__global__ void __launch_bounds__(256) lensum_kernel(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+                                                     uint32_t *__restrict__ out, uint64_t n)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = a[k] + b[k];
+}
+
+// device offsets are relative to the first byte the shard touches
+__global__ void __launch_bounds__(256) rebase_kernel(uint64_t *__restrict__ off1, uint64_t *__restrict__ off2, uint64_t n, uint64_t lo)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        off1[k] -= lo;
+        off2[k] -= lo;
+    }
+}
+
 // ---- gather the per-pair op slots (written back-to-front by the walk kernels) into the dense buffer ----
 struct GatherArgs {
     uint64_t n_pairs;
