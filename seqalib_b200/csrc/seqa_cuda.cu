@@ -4,7 +4,9 @@
 // seqa_linspace.cuh (Hirschberg / Myers-Miller recursion on the GPU).  No CPU fallback exists here: with no
 // CUDA device every compute entry point fails with SEQA_ERR_NO_DEVICE.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -997,16 +999,26 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
     std::vector<int> wstatus(nwaves, SEQA_OK);
     std::vector<std::string> werr(nwaves);
     std::vector<uint64_t> wused(nwaves, 0);
+    const bool dbg = getenv("SEQA_DEBUG_TIMING") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     auto worker = [&](int d, int t, int nthreads) {
         seqa_ctx *c = nullptr;
         int cached = -1;
         for (size_t w = dev_lo[d] + t; w < dev_lo[d + 1]; w += nthreads) {
             int s = SEQA_OK;
+            const double t0 = since();
             if (!c) s = cache_acquire(first + d, &c, &cached);
             if (s == SEQA_OK) s = ctx_upload_range(c, params, in, wave_lo[w], wave_lo[w + 1]);
+            const double t1 = since();
             if (s == SEQA_OK) s = ctx_run(c);
+            const double t2 = since();
             if (s == SEQA_OK) s = ctx_resolve(c);
+            const double t3 = since();
             if (s == SEQA_OK) s = ctx_download_into(c, out, wave_lo[w], wave_slots[w], &wused[w]);
+            if (dbg)
+                fprintf(stderr, "[seqa] dev %d thr %d wave %zu: start %.2f upload+plan %.2f launch %.2f wait %.2f download %.2f ms\n", d, t, w,
+                        t0, t1 - t0, t2 - t1, t3 - t2, since() - t3);
             wstatus[w] = s;
             if (s != SEQA_OK) {
                 werr[w] = g_err;

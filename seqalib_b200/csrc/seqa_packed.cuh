@@ -129,16 +129,17 @@ __device__ __forceinline__ int pk_half(unsigned v, int k) { return (int)(int16_t
 
 // ---- fill -------------------------------------------------------------------------------------------------
 // Trace: the low TB bits (TB = 8, or 4 when Match + |Mismatch| + 2|Gap| <= 7) of every H value.  Layout of a warp
-// job (Ng = ceil(Nw/4) column groups, RP = R/2 row pairs): one piece of PB = 2*TB bytes per (strip s, column
-// group cg, row pair rp, lane) holding 2 rows x 4 columns x 2 pairs,
-//   piece(s, cg, rp, lane)  at  trace_off + (((s*Ng + cg)*RP + rp)*32 + lane) * PB
-//     TB == 8: byte  c*4 + (r%2)*2 + k            TB == 4: byte (c/2)*4 + (r%2)*2 + k, nibble c%2
-// (c = column inside the group, k = pair half), so that every warp store is one contiguous 512 / 256-byte run
-// (thread-major 128-byte lines were measured 2x slower: 32 lines per store instruction saturate the LSU).
+// job (Ng = ceil(Nw/4) column groups): 16-byte pieces of PR = 16/TB rows x 4 columns x 2 pairs,
+//   piece(s, cg, rg, lane)  at  trace_off + (((s*Ng + cg)*(R/PR) + rg)*32 + lane) * 16       (rg = r / PR)
+//     TB == 8 (2 rows): byte c*4 + (r%2)*2 + k
+//     TB == 4 (4 rows): byte ((r%4)/2)*8 + (c/2)*4 + (r%2)*2 + k, nibble c%2
+// (c = column inside the group, k = pair half), so that every warp store is one contiguous 512-byte run and a
+// walk step usually stays inside the piece it already holds (thread-major 128-byte lines were measured 2x slower
+// in the fill: 32 lines per store instruction saturate the LSU).
 // The column profiles of the next 4-column group are prefetched into registers one group ahead.
 __host__ __device__ inline uint64_t pk_trace_bytes(uint32_t nstrips, uint32_t Nw, int R, int TB)
 {
-    return (uint64_t)nstrips * ((Nw + 3) / 4) * (uint64_t)(R / 2) * 32ull * (uint64_t)(2 * TB);
+    return (uint64_t)nstrips * ((Nw + 3) / 4) * (uint64_t)(R * TB / 16) * 32ull * 16ull;
 }
 
 #ifdef SEQA_EMU
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
         const int Ng = ((int)J.Nw + 3) >> 2, Nw = (int)J.Nw;
         const uint4 *__restrict__ prof = reinterpret_cast<const uint4 *>(A.prof + J.prof_off) + lane * 2;
         const uint32_t *__restrict__ rowsel = A.rowsel + J.rowsel_off + lane;
-        uint8_t *__restrict__ trace = A.trace + J.trace_off + (uint64_t)lane * (2 * TB);
+        uint8_t *__restrict__ trace = A.trace + J.trace_off + (uint64_t)lane * 16;
         int best0 = 0, best1 = 0, bi0 = 0, bi1 = 0; // SW: running (max, last row holding it)
         int corner0 = 0, corner1 = 0;               // NW: H(M,N)
         // row 0 of the matrix = first strip's upper boundary (SW 0, NW j*gap: include/SANeedlemanWunsch.h:61-62)
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                 rmax[r] = 0u;
             }
             unsigned diag = LOCAL ? 0u : pk_dup(i0 * A.gap);
-            uint8_t *__restrict__ tr = trace + (uint64_t)s * Ng * (RP * 32 * 2 * TB);
+            uint8_t *__restrict__ tr = trace + (uint64_t)s * Ng * (R * TB / 16 * 512);
             uint4 na = prof[0], nb = prof[1]; // profile of the next group: {T0,T1} x 4 columns
             for (int cg = 0; cg < Ng; cg++) {
                 const uint4 ca = na, cb = nb;
@@ -239,9 +240,11 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
 #pragma unroll
                     for (int rp = 0; rp < RP; rp++) pk_store_stream(&dst[rp * 32], make_uint4(W[rp][0], W[rp][1], W[rp][2], W[rp][3]));
                 } else {
-                    uint2 *dst = reinterpret_cast<uint2 *>(tr + (uint64_t)cg * (RP * 32 * 8));
+                    static_assert(TB == 8 || R % 4 == 0, "4-bit trace pieces hold 4 rows");
+                    uint4 *dst = reinterpret_cast<uint4 *>(tr + (uint64_t)cg * (R / 4 * 32 * 16));
 #pragma unroll
-                    for (int rp = 0; rp < RP; rp++) pk_store_stream(&dst[rp * 32], make_uint2(W[rp][0], W[rp][1]));
+                    for (int rq = 0; rq < R / 4; rq++)
+                        pk_store_stream(&dst[rq * 32], make_uint4(W[2 * rq][0], W[2 * rq][1], W[2 * rq + 1][0], W[2 * rq + 1][1]));
                 }
             }
             if (LOCAL) {
@@ -287,43 +290,30 @@ __global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A, int R)
     const PkWarpJob J = A.jobs[pos >> 6];
     const int lane = (int)((pos & 63) >> 1), half = (int)(pos & 1);
     const int M = (int)A.len1[p], N = (int)A.len2[p];
-    const int RP = R / 2;
     const uint32_t Ng = (J.Nw + 3) >> 2;
     constexpr unsigned MASK = TB == 8 ? 0xffu : 0xfu;
     const uint8_t *a = A.bases + A.off1[p], *b = A.bases + A.off2[p];
     const int gap = A.gap;
-    // pieces (2 rows x 4 columns x 2 pairs, 2*TB bytes): index ((s*Ng + cg)*RP + rp)*32 + lane; two of them are
-    // kept in registers (one per row-pair parity), so a step costs about one load instead of three
-    const uint8_t *pieces = A.trace + J.trace_off;
+    // 16-byte pieces (PR rows x 4 columns x 2 pairs): index ((s*Ng + cg)*RG + rg)*32 + lane; two of them are kept
+    // in registers (one per row-group parity), so a step usually costs no load at all
+    constexpr int PR = 16 / TB, PRSH = TB == 8 ? 1 : 2;
+    const uint32_t RG = (uint32_t)(R / PR);
+    const uint4 *pieces = reinterpret_cast<const uint4 *>(A.trace + J.trace_off);
     uint4 cv[2];
     uint32_t ck[2] = {0xffffffffu, 0xffffffffu};
-    auto fetch = [&](uint32_t key) -> uint4 {
-        if (TB == 8) return reinterpret_cast<const uint4 *>(pieces)[key];
-        const uint2 t = reinterpret_cast<const uint2 *>(pieces)[key];
-        return make_uint4(t.x, t.y, 0u, 0u);
-    };
-    auto pick = [&](const uint4 &v, int r, int c) -> unsigned { // low bits of (row parity r&1, column c of the group)
-        const int wsel = TB == 8 ? c : (c >> 1);
+    auto pick = [&](const uint4 &v, int r, int c) -> unsigned { // low bits of (row r of the strip, column c of the group)
+        const int wsel = TB == 8 ? c : (((r & 3) >> 1) * 2 + (c >> 1));
         const unsigned wv = wsel == 0 ? v.x : wsel == 1 ? v.y : wsel == 2 ? v.z : v.w;
         return (wv >> (((r & 1) * 2 + half) * 8 + (TB == 4 ? (c & 1) * 4 : 0))) & MASK;
     };
     auto low = [&](int i, int j) -> unsigned { // i >= 1, j >= 1
         const int ii = i - 1, s = ii / R, r = ii - s * R, jj = j - 1;
-        const uint32_t key = (((uint32_t)s * Ng + (uint32_t)(jj >> 2)) * (uint32_t)RP + (uint32_t)(r >> 1)) * 32u + (uint32_t)lane;
-        const int e = (r >> 1) & 1;
+        const uint32_t key = (((uint32_t)s * Ng + (uint32_t)(jj >> 2)) * RG + (uint32_t)(r >> PRSH)) * 32u + (uint32_t)lane;
+        const int e = (r >> PRSH) & 1;
         const bool miss = e == 0 ? (ck[0] != key) : (ck[1] != key);
         if (miss) {
-            if (e == 0) { cv[0] = fetch(key); ck[0] = key; }
-            else { cv[1] = fetch(key); ck[1] = key; }
-            // the path mostly climbs diagonally: ask the L2 for the piece one row pair up (same and previous
-            // column group) while this one is being used
-            int s2 = s, rp2 = (r >> 1) - 1;
-            if (rp2 < 0) { s2 = s - 1; rp2 = RP - 1; }
-            if (s2 >= 0) {
-                const uint32_t k2 = (((uint32_t)s2 * Ng + (uint32_t)(jj >> 2)) * (uint32_t)RP + (uint32_t)rp2) * 32u + (uint32_t)lane;
-                pk_prefetch_l2_line(pieces + (uint64_t)k2 * (2 * TB));
-                if (jj >= 4) pk_prefetch_l2_line(pieces + (uint64_t)(k2 - (uint32_t)RP * 32u) * (2 * TB));
-            }
+            if (e == 0) { cv[0] = pieces[key]; ck[0] = key; }
+            else { cv[1] = pieces[key]; ck[1] = key; }
         }
         return pick(e == 0 ? cv[0] : cv[1], r, jj & 3);
     };
@@ -348,7 +338,7 @@ __global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A, int R)
             const int ii = i - 1, s = ii / R, r = ii - s * R;
             const int ng = (N + 3) >> 2;
             for (int cg = 0; cg < ng; cg++) {
-                const uint4 v = fetch((((uint32_t)s * Ng + (uint32_t)cg) * (uint32_t)RP + (uint32_t)(r >> 1)) * 32u + (uint32_t)lane);
+                const uint4 v = pieces[(((uint32_t)s * Ng + (uint32_t)cg) * RG + (uint32_t)(r >> PRSH)) * 32u + (uint32_t)lane];
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const int jj = cg * 4 + c + 1;
