@@ -72,6 +72,33 @@ template <class T> struct DBuf {
     }
 };
 
+// grow-only pinned host staging buffer: plan arrays are built here so that their upload is a true async DMA
+// (a pageable source makes cudaMemcpyAsync wait behind every bulk copy queued on the copy engine)
+template <class T> struct HBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap) return SEQA_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = std::max<size_t>(n + n / 4, 1024);
+        if (cudaMallocHost((void **)&p, want * sizeof(T)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(SEQA_ERR_NOMEM, "pinned host allocation of %zu bytes failed", want * sizeof(T));
+        }
+        cap = want;
+        return SEQA_OK;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 constexpr int GEN_R = 4;          // rows per lane of the generic wavefront
 constexpr int PK_R = 16;          // rows per register strip of the packed kernel
 constexpr uint32_t PK_MAX_LEN = 320; // longest side the thread-per-pair kernel takes (shared-memory column)
@@ -117,8 +144,11 @@ struct seqa_ctx {
     DBuf<int> flags; // [0] packed path met a non-ACGT base
 
     // packed plan
-    std::vector<uint32_t> perm;
-    std::vector<PkWarpJob> jobs;
+    HBuf<uint32_t> perm;
+    size_t perm_n = 0;
+    std::vector<PkWarpJob> jobs; // small: uploaded through jobs_pin
+    HBuf<PkWarpJob> jobs_pin;
+    size_t budget = 0;
     std::vector<Chunk> pk_chunks;
     uint32_t pk_max_nw = 0;
     DBuf<uint32_t> d_perm;
@@ -126,6 +156,8 @@ struct seqa_ctx {
     // generic plan
     std::vector<uint32_t> gidx;
     std::vector<uint64_t> gdir_off;
+    HBuf<uint32_t> gidx_pin;
+    HBuf<uint64_t> gdir_pin;
     std::vector<Chunk> g_chunks;
     uint32_t g_max_n = 0;
     DBuf<uint32_t> d_gidx;
@@ -224,18 +256,20 @@ bool packed_shape_ok(const seqa_params &p, uint32_t M, uint32_t N)
     return lo < 30000 && hi < 30000;
 }
 
+// scratch budget of one context (trace / direction matrices of one chunk): a quarter of the device, so that the
+// three contexts of a pipelined call and a resident context fit together; queried once per context
 size_t free_budget()
 {
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (size_t)1 << 30;
-    return (size_t)((double)fr * 0.80);
+    return (size_t)std::min((double)fr * 0.8, (double)tot * 0.25);
 }
 
 int build_plan(seqa_ctx *c)
 {
     const uint64_t n = c->n;
     const seqa_params &prm = c->prm;
-    c->perm.clear();
+    c->perm_n = 0;
     c->jobs.clear();
     c->pk_chunks.clear();
     c->gidx.clear();
@@ -304,7 +338,8 @@ int build_plan(seqa_ctx *c)
             c->gidx.push_back((uint32_t)p);
         }
     }
-    const size_t budget = free_budget();
+    if (!c->budget) c->budget = free_budget();
+    const size_t budget = c->budget;
 
     // ---- packed jobs: 64 pairs per warp, similar shapes together ----
     if (!pkl.empty()) {
@@ -318,8 +353,10 @@ int build_plan(seqa_ctx *c)
             });
         }
         const size_t njobs = (pkl.size() + 63) / 64;
-        c->perm.assign(njobs * 64, PK_NULL);
-        std::copy(pkl.begin(), pkl.end(), c->perm.begin());
+        CKS(c->perm.ensure(njobs * 64));
+        c->perm_n = njobs * 64;
+        std::copy(pkl.begin(), pkl.end(), c->perm.p);
+        std::fill(c->perm.p + pkl.size(), c->perm.p + njobs * 64, PK_NULL);
         c->jobs.resize(njobs);
         Chunk ch{0, 0, 0};
         uint64_t tr = 0, pf = 0, rs = 0; // running offsets inside the chunk
@@ -327,7 +364,7 @@ int build_plan(seqa_ctx *c)
         for (size_t w = 0; w < njobs; w++) {
             uint32_t Mw = 0, Nw = 0;
             for (int k = 0; k < 64; k++) {
-                const uint32_t p = c->perm[w * 64 + k];
+                const uint32_t p = c->perm.p[w * 64 + k];
                 if (p == PK_NULL) continue;
                 Mw = std::max(Mw, c->hlen1[p]);
                 Nw = std::max(Nw, c->hlen2[p]);
@@ -357,10 +394,12 @@ int build_plan(seqa_ctx *c)
         ch.scratch_bytes = chunk_bytes(tr, pf, rs);
         c->pk_chunks.push_back(ch);
         // chunk-relative layout: [trace | prof (8 B) | rowsel (4 B)], offsets resolved at launch
-        CKS(c->d_perm.ensure(c->perm.size()));
+        CKS(c->d_perm.ensure(c->perm_n));
         CKS(c->d_jobs.ensure(c->jobs.size()));
-        CK(cudaMemcpyAsync(c->d_perm.p, c->perm.data(), c->perm.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->d_jobs.p, c->jobs.data(), c->jobs.size() * sizeof(PkWarpJob), cudaMemcpyHostToDevice, c->stream));
+        CKS(c->jobs_pin.ensure(c->jobs.size()));
+        std::copy(c->jobs.begin(), c->jobs.end(), c->jobs_pin.p);
+        CK(cudaMemcpyAsync(c->d_perm.p, c->perm.p, c->perm_n * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_jobs.p, c->jobs_pin.p, c->jobs.size() * sizeof(PkWarpJob), cudaMemcpyHostToDevice, c->stream));
     }
 
     // ---- generic jobs: one warp per pair ----
@@ -390,8 +429,12 @@ int build_plan(seqa_ctx *c)
         c->g_chunks.push_back(ch);
         CKS(c->d_gidx.ensure(c->gidx.size()));
         CKS(c->d_gdir_off.ensure(c->gidx.size()));
-        CK(cudaMemcpyAsync(c->d_gidx.p, c->gidx.data(), c->gidx.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->d_gdir_off.p, c->gdir_off.data(), c->gidx.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CKS(c->gidx_pin.ensure(c->gidx.size()));
+        CKS(c->gdir_pin.ensure(c->gidx.size()));
+        std::copy(c->gidx.begin(), c->gidx.end(), c->gidx_pin.p);
+        std::copy(c->gdir_off.begin(), c->gdir_off.end(), c->gdir_pin.p);
+        CK(cudaMemcpyAsync(c->d_gidx.p, c->gidx_pin.p, c->gidx.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_gdir_off.p, c->gdir_pin.p, c->gidx.size() * 8, cudaMemcpyHostToDevice, c->stream));
     }
     uint64_t need = 16;
     for (auto &ch : c->pk_chunks) need = std::max(need, ch.scratch_bytes);
@@ -767,6 +810,7 @@ void seqa_ctx_destroy(seqa_ctx *c)
     c->score.release(); c->start_i.release(); c->start_j.release(); c->end_i.release(); c->end_j.release();
     c->ops_len.release(); c->slot_start.release(); c->slot_off.release(); c->ops_off.release();
     c->slots.release(); c->dense.release(); c->tile_sum.release(); c->total.release(); c->flags.release();
+    c->perm.release(); c->jobs_pin.release(); c->gidx_pin.release(); c->gdir_pin.release();
     c->d_perm.release(); c->d_jobs.release(); c->d_gidx.release(); c->d_gdir_off.release(); c->bound.release();
     c->scratch.release();
     ls_release(c->ls);
