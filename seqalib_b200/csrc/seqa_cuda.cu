@@ -923,7 +923,8 @@ int seqa_ctx_download_inputs(seqa_ctx *c, char *bases, uint64_t bases_len, uint6
 // Lazily created per-device contexts reused by seqa_cuda_align_batch (device buffers survive between calls;
 // seqa_cuda_trim() frees them).  Up to SEQA_CACHE_SLOTS contexts per device so that the waves of one call can be
 // in flight together; a device whose cached contexts are all busy gets a temporary one.
-#define SEQA_CACHE_SLOTS 3
+#define SEQA_CACHE_SLOTS 4
+#define SEQA_WORKERS 2 /* host threads per device; each double-buffers two contexts */
 static std::mutex g_cache_mu;
 static seqa_ctx *g_cache[64][SEQA_CACHE_SLOTS];
 static bool g_cache_busy[64][SEQA_CACHE_SLOTS];
@@ -999,29 +1000,33 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
 
     // waves: contiguous, ~3e9 cells or 256k pairs each; linear-space pairs (huge sweeps) go one wave per 4e10 cells
     const bool linspace = params->algo == SEQA_HIRSCHBERG || params->algo == SEQA_MYERS_MILLER;
-    const long double wave_cells = linspace ? 4e10L : 3e9L;
-    std::vector<uint64_t> wave_lo, wave_slots; // first pair, prefix sum of (len1+len2) before the wave
-    long double tot = 0;
+    const uint64_t wave_cells = linspace ? 40000000000ull : 3000000000ull;
+    std::vector<uint64_t> wave_lo, wave_slots, wave_cellsum; // first pair; (len1+len2) before the wave; cells of the wave
+    uint64_t tot = 0;
     {
-        long double acc = 0;
-        uint64_t slots = 0, cnt = 0;
+        uint64_t acc = 0, slots = 0, cnt = 0;
+        // several devices: at least two waves per device even for small batches
+        const uint64_t maxcnt = nd > 1 ? std::min<uint64_t>(262144, std::max<uint64_t>(1, (n + 2 * nd - 1) / (2 * nd))) : 262144;
         wave_lo.push_back(0);
         wave_slots.push_back(0);
+        const uint32_t *l1 = in->len1, *l2 = in->len2;
         for (uint64_t p = 0; p < n; p++) {
-            if (cnt > 0 && (acc >= wave_cells || cnt >= 262144)) {
+            if (cnt > 0 && (acc >= wave_cells || cnt >= maxcnt)) {
                 wave_lo.push_back(p);
                 wave_slots.push_back(slots);
+                wave_cellsum.push_back(acc);
                 acc = 0;
                 cnt = 0;
             }
-            const long double cells = (long double)in->len1[p] * in->len2[p] + 1;
+            const uint64_t cells = (uint64_t)l1[p] * l2[p] + 1;
             acc += cells;
             tot += cells;
-            slots += (uint64_t)in->len1[p] + in->len2[p];
+            slots += (uint64_t)l1[p] + l2[p];
             cnt++;
         }
         wave_lo.push_back(n);
         wave_slots.push_back(slots);
+        wave_cellsum.push_back(acc);
     }
     const size_t nwaves = wave_lo.size() - 1;
     const uint64_t slots_total = wave_slots.back();
@@ -1030,14 +1035,11 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
     std::vector<size_t> dev_lo(nd + 1, nwaves);
     dev_lo[0] = 0;
     if (nd > 1) {
-        std::vector<long double> wc(nwaves, 0);
-        for (size_t w = 0; w < nwaves; w++)
-            for (uint64_t p = wave_lo[w]; p < wave_lo[w + 1]; p++) wc[w] += (long double)in->len1[p] * in->len2[p] + 1;
-        long double run = 0;
+        uint64_t run = 0;
         int d = 1;
         for (size_t w = 0; w < nwaves && d < nd; w++) {
-            run += wc[w];
-            if (run >= tot * d / nd) dev_lo[d++] = w + 1;
+            run += wave_cellsum[w];
+            if ((long double)run >= (long double)tot * d / nd) dev_lo[d++] = w + 1;
         }
     }
     std::vector<int> wstatus(nwaves, SEQA_OK);
@@ -1046,30 +1048,52 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
     const bool dbg = getenv("SEQA_DEBUG_TIMING") != nullptr;
     const auto t_start = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+    // A worker owns two contexts and software-pipelines its waves: wave k+1 is uploaded and launched before the
+    // worker blocks on wave k, so the device queue never drains while the host packs or downloads.
     auto worker = [&](int d, int t, int nthreads) {
-        seqa_ctx *c = nullptr;
-        int cached = -1;
-        for (size_t w = dev_lo[d] + t; w < dev_lo[d + 1]; w += nthreads) {
+        seqa_ctx *c[2] = {nullptr, nullptr};
+        int cached[2] = {-1, -1};
+        int k = 0;
+        long pend = -1;
+        int pk = 0;
+        auto finish = [&](long w, int slot) {
+            const double t2 = since();
+            int s = ctx_resolve(c[slot]);
+            const double t3 = since();
+            if (s == SEQA_OK) s = ctx_download_into(c[slot], out, wave_lo[w], wave_slots[w], &wused[w]);
+            if (dbg) fprintf(stderr, "[seqa] dev %d thr %d wave %ld: wait %.2f..%.2f download ..%.2f ms\n", d, t, w, t2, t3, since());
+            if (s != SEQA_OK) {
+                wstatus[w] = s;
+                werr[w] = g_err;
+            }
+            return s;
+        };
+        bool ok = true;
+        for (size_t w = dev_lo[d] + t; ok && w < dev_lo[d + 1]; w += nthreads) {
             int s = SEQA_OK;
             const double t0 = since();
-            if (!c) s = cache_acquire(first + d, &c, &cached);
-            if (s == SEQA_OK) s = ctx_upload_range(c, params, in, wave_lo[w], wave_lo[w + 1]);
+            if (!c[k]) s = cache_acquire(first + d, &c[k], &cached[k]);
+            if (s == SEQA_OK) s = ctx_upload_range(c[k], params, in, wave_lo[w], wave_lo[w + 1]);
             const double t1 = since();
-            if (s == SEQA_OK) s = ctx_run(c);
-            const double t2 = since();
-            if (s == SEQA_OK) s = ctx_resolve(c);
-            const double t3 = since();
-            if (s == SEQA_OK) s = ctx_download_into(c, out, wave_lo[w], wave_slots[w], &wused[w]);
-            if (dbg)
-                fprintf(stderr, "[seqa] dev %d thr %d wave %zu: start %.2f upload+plan %.2f launch %.2f wait %.2f download %.2f ms\n", d, t, w,
-                        t0, t1 - t0, t2 - t1, t3 - t2, since() - t3);
-            wstatus[w] = s;
+            if (s == SEQA_OK) s = ctx_run(c[k]);
+            if (dbg) fprintf(stderr, "[seqa] dev %d thr %d wave %zu: upload+plan %.2f..%.2f launched ..%.2f ms\n", d, t, w, t0, t1, since());
             if (s != SEQA_OK) {
+                wstatus[w] = s;
                 werr[w] = g_err;
-                break;
+                ok = false;
             }
+            if (pend >= 0 && finish(pend, pk) != SEQA_OK) ok = false;
+            pend = ok ? (long)w : -1;
+            pk = k;
+            k ^= 1;
         }
-        if (c) cache_release(c, cached);
+        if (pend >= 0) finish(pend, pk);
+        for (int q = 0; q < 2; q++)
+            if (c[q]) {
+                cudaSetDevice(c[q]->device);
+                cudaStreamSynchronize(c[q]->stream);
+                cache_release(c[q], cached[q]);
+            }
     };
     int rc = SEQA_OK;
     uint64_t used = 0;
@@ -1077,7 +1101,7 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
         std::vector<std::thread> th;
         for (int d = 0; d < nd; d++) {
             const size_t nw = dev_lo[d + 1] - dev_lo[d];
-            const int nthreads = (int)std::min<size_t>(SEQA_CACHE_SLOTS, nw);
+            const int nthreads = (int)std::min<size_t>(SEQA_WORKERS, nw);
             for (int t = 0; t < nthreads; t++) {
                 if (nd == 1 && nthreads == 1)
                     worker(d, t, nthreads);
