@@ -63,6 +63,7 @@ enum {
 #define SEQA_FLAG_SCORE_ONLY 0x1u  /* skip traceback/ops (scores and end positions only) */
 #define SEQA_FLAG_FORCE_GENERIC 0x2u /* use the generic int32 kernels even where a packed fast path applies */
 #define SEQA_FLAG_TRACE8 0x4u /* packed path: keep 8 trace bits per cell even where 4 suffice (testing) */
+#define SEQA_FLAG_LS_R1 0x8u /* linear-space path: 32-row blocks everywhere (testing: deep row-block pipelines on short pairs) */
 
 /*
  * Mirror of the reference ScoringSystem (include/SequenceAlignment.h:82-131) plus the algorithm and

@@ -15,6 +15,7 @@ ALGOS = {"nw": 0, "sw": 1, "ggotoh": 2, "lgotoh": 3, "hirschberg": 4, "myersmill
 FLAG_SCORE_ONLY = 1
 FLAG_FORCE_GENERIC = 2
 FLAG_TRACE8 = 4
+FLAG_LS_R1 = 8
 OK = 0
 ERR_NAMES = {0: "SEQA_OK", -1: "SEQA_ERR_INVALID", -2: "SEQA_ERR_UNSUPPORTED", -3: "SEQA_ERR_NO_DEVICE",
              -4: "SEQA_ERR_CUDA", -5: "SEQA_ERR_CAPACITY", -6: "SEQA_ERR_NOMEM"}

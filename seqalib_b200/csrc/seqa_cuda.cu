@@ -113,7 +113,7 @@ struct Chunk {
 struct seqa_ctx;
 namespace {
 // linear-space algorithms (seqa_linspace_host.inl)
-int ls_plan(LsState &ls, const std::vector<uint32_t> &len1, const std::vector<uint32_t> &len2,
+int ls_plan(LsState &ls, const seqa_params &prm, const std::vector<uint32_t> &len1, const std::vector<uint32_t> &len2,
             const std::vector<uint32_t> &idx, bool myers_miller, int sms);
 int ls_run(seqa_ctx *c, bool want_ops);
 void ls_release(LsState &ls);
@@ -315,7 +315,7 @@ int build_plan(seqa_ctx *c)
     if (prm.algo == SEQA_HIRSCHBERG || prm.algo == SEQA_MYERS_MILLER) {
         c->lidx.resize(n);
         std::iota(c->lidx.begin(), c->lidx.end(), 0u);
-        return ls_plan(c->ls, c->hlen1, c->hlen2, c->lidx, prm.algo == SEQA_MYERS_MILLER, c->sms);
+        return ls_plan(c->ls, prm, c->hlen1, c->hlen2, c->lidx, prm.algo == SEQA_MYERS_MILLER, c->sms);
     }
     if (prm.algo == SEQA_LOCAL_GOTOH) {
         for (uint64_t p = 0; p < n; p++) {

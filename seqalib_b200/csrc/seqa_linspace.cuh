@@ -1,14 +1,26 @@
 // Linear-space global aligners on the GPU: HirschbergSA (reference include/SAHirschberg.h:11-184) and
 // MyersMillerSA (reference include/SAMyersMiller.h:43-420).
 //
-// The reference recursion is run level by level: one launch per recursion depth processes every live
-// sub-problem ("node") of every pair of the batch, one warp per node.  An internal node runs the forward and
-// the reverse score-only sweep with the int32 warp-wavefront engine (seqa_wavefront.cuh, boundary values by
-// __shfl_up_sync), finds the reference's split column with a warp reduction that reproduces its tie rule, and
-// appends its two children to the next level's node list.  A leaf writes its ops straight into the pair's
-// op slot at position i0 + j0 (at most i0 + j0 ops precede a node that starts at cell (i0, j0) and a node
-// covering m rows and n columns emits at most m + n ops, so leaves never collide); a final pass squeezes out
-// the unused slot bytes and scores the alignment.
+// The reference recursion is run level by level.  Per recursion depth three kernels run over every live
+// sub-problem ("node") of every pair of the batch:
+//
+//   ls_expand_kernel  one warp per node: leaves write their ops; an internal node becomes two score-only SWEEPS
+//                     (forward over its top rows, reverse over its bottom rows), each cut into ROW BLOCKS of 32*R
+//                     rows; every (sweep, row block) is one TASK appended to the level's task list.
+//   ls_sweep_kernel   persistent: warps draw tasks from an atomic ticket counter.  A task runs the anti-diagonal
+//                     warp wavefront (boundary H / gap-state values by __shfl_up_sync) over ALL columns of its
+//                     row block; its bottom row streams to the task of the next row block through a global
+//                     (L2-resident) boundary row guarded by a progress counter, so the row blocks of one sweep
+//                     form a software pipeline across warps and SMs: a 100 kbp x 50 kbp sweep is ~200 warps
+//                     deep.  Tickets are handed out in an order in which a task's producer always holds an
+//                     earlier ticket, so the producer is running or done whenever its consumer waits: no deadlock
+//                     without any residency assumption.  The last row block writes the sweep's final row(s).
+//   ls_split_kernel   one warp per internal node: the reference's split rule (with its tie rule) over the final
+//                     rows of the two sweeps; pushes the two children onto the next level's node list.
+//
+// A leaf writes its ops straight into the pair's op slot at position i0 + j0 (at most i0 + j0 ops precede a
+// node that starts at cell (i0, j0) and a node covering m rows and n columns emits at most m + n ops, so leaves
+// never collide); a final pass squeezes out the unused slot bytes and scores the alignment.
 //
 // Bit-exactness notes: the recursion is followed all the way down to the
 // reference's own leaves -- never short-circuited into a full-matrix aligner, because HirschbergSA's split
@@ -19,8 +31,21 @@
 #include "seqa_common.cuh"
 #include "seqa_wavefront.cuh"
 
-#define LS_R 8
 #define LS_HOLE 0xffu
+#define LS_MAXR 8                 /* rows per lane of a full row block */
+#define LS_NEG (-(1 << 30))       /* "never" diagonal candidate (AllowMismatch == false); |H| < 2^29 is checked on the host */
+#define LS_BLOCK 128              /* threads per CTA of the sweep kernel */
+
+// One score-only sweep of an internal node.
+struct LsSweep {
+    int node;       // index into the level's node list
+    int rows;       // rows of the sweep; bit 31 set = reverse sweep (bottom rows, both sequences reversed)
+    int nblk;       // row blocks; bits 28-30 = log2(R)
+    uint32_t task0; // progress counters of its row blocks live at prog[task0 + rb]
+};
+struct LsTask {
+    uint32_t sweep, rb;
+};
 
 struct LsArgs {
     const uint8_t *bases;
@@ -29,29 +54,37 @@ struct LsArgs {
     const LsNode *in;
     uint32_t n_in;
     LsNode *out;
-    uint32_t *n_out;
     uint32_t out_cap;
+    uint32_t *cnt;           // [0] nodes pushed to `out`, [1] sweeps, [2] tasks, [3] ticket
     int *overflow;
+    LsSweep *sweeps;
+    LsTask *tasks;
+    uint32_t task_cap;
+    int *prog;               // per task: columns of its bottom row published so far
     int *rows;               // scratch rows
-    const uint64_t *row_off; // per pair: int offset of its 6 arrays
+    const uint64_t *row_off; // per pair: int offset of its arrays
     const uint32_t *row_w;   // per pair: stride of one array
     uint8_t *slots;
     const uint64_t *slot_off;
     DevScoring sc;
+    int force_r;             // > 0: use this many rows per lane everywhere (testing: many row blocks on short pairs)
 };
+
+#ifdef SEQA_EMU
+static inline int ls_ld_volatile(const int *p) { return *(const volatile int *)p; }
+static inline void ls_st_volatile(int *p, int v) { *(volatile int *)p = v; }
+static inline int ls_ldcg(const int *p) { return *p; }
+static inline void ls_pause() { emu_yield(); }
+#else
+__device__ __forceinline__ int ls_ld_volatile(const int *p) { return *(const volatile int *)p; }
+__device__ __forceinline__ void ls_st_volatile(int *p, int v) { *(volatile int *)p = v; }
+__device__ __forceinline__ int ls_ldcg(const int *p) { return __ldcg(p); } // L2 only: written by another SM
+__device__ __forceinline__ void ls_pause() { __nanosleep(64); }
+#endif
 
 __device__ __forceinline__ void ls_emit_run(uint8_t *slot, int from, int count, uint8_t op, int lane)
 {
     for (int k = lane; k < count; k += 32) slot[from + k] = op;
-}
-
-__device__ __forceinline__ void ls_push(const LsArgs &A, const LsNode &nd)
-{
-    const uint32_t k = atomicAdd(A.n_out, 1u);
-    if (k < A.out_cap)
-        A.out[k] = nd;
-    else
-        *A.overflow = 1;
 }
 
 // ---- Hirschberg ---------------------------------------------------------------------------------------------
@@ -119,14 +152,274 @@ __device__ void hb_leaf_thin(const DevScoring &sc, const uint8_t *a, int m, cons
     }
 }
 
-__global__ void __launch_bounds__(128) hb_level_kernel(LsArgs A)
+
+// ---- one row block of a score-only sweep -----------------------------------------------------------------------
+// Rows [rb*32R, rb*32R + 32R) of an m x n sweep, all n columns, on one warp.  Lane l owns R consecutive rows; at
+// step t it computes column t - l + 1.  Lane 0 takes the row above the block from `inH/inX` (published by the task
+// of row block rb-1; staged 32 columns at a time through shared memory, one chunk ahead) or from the sweep's
+// border; lane 31's bottom row goes out through shared memory in coalesced 32-column pieces, followed by the
+// progress counter.  PARTIAL: rows >= m pass the value above them through unchanged, so the sweep's last row
+// arrives at lane 31 like any other bottom row.
+template <bool AFFINE, int R, bool PARTIAL>
+__device__ __forceinline__ void ls_block(const DevScoring &sc, const Borders &bd, const uint8_t *__restrict__ a, int m,
+                                         const uint8_t *__restrict__ b, int n, bool rev, int rb,
+                                         const int *inH, const int *inX, const int *in_prog,
+                                         int *outH, int *outX, int *out_prog, int *sm)
+{
+    const int lane = threadIdx.x & 31;
+    const int row0 = rb * (32 * R) + lane * R; // rows above my strip
+    const int nact = PARTIAL ? min(max(m - row0, 0), R) : R;
+    const int gogo = sc.go + sc.ge;
+    const int simx = sc.allow ? sc.mismatch : LS_NEG;
+    int ab[R], h[R], f[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int i = row0 + r + 1;
+        ab[r] = (r < nact) ? (int)(rev ? a[m - i] : a[i - 1]) : 0;
+        h[r] = bd.hcolA + i * bd.hcolB;
+        f[r] = AFFINE ? bd.iyA + i * bd.iyB : 0;
+    }
+    int diag_top = border_hcol(bd, row0);
+    int send_h = 0, send_x = 0;
+    int *smInH = sm, *smInX = sm + 32, *smOutH = sm + 64, *smOutX = sm + 96;
+    const int nsteps = n + 31;
+    int nextH = 0, nextX = 0, known = 0;
+    auto wait_for = [&](int need) { // until the producer has published `need` columns
+        if (known < need) {
+            if (lane == 0) {
+                int v;
+                while ((v = ls_ld_volatile(in_prog)) < need) ls_pause();
+                known = v;
+                __threadfence();
+            }
+            known = __shfl_sync(SEQA_FULL, known, 0);
+        }
+    };
+    if (rb > 0) {
+        wait_for(min(32, n));
+        const int jj = 1 + lane;
+        if (jj <= n) {
+            nextH = ls_ldcg(inH + jj);
+            if (AFFINE) nextX = ls_ldcg(inX + jj);
+        }
+    }
+    for (int t0 = 0; t0 < nsteps; t0 += 32) {
+        if (rb > 0) {
+            __syncwarp();
+            smInH[lane] = nextH;
+            if (AFFINE) smInX[lane] = nextX;
+            const int base = t0 + 32;
+            if (base < n) { // boundary of the next chunk, one chunk ahead of its use
+                wait_for(min(base + 32, n));
+                const int jj = base + 1 + lane;
+                if (jj <= n) {
+                    nextH = ls_ldcg(inH + jj);
+                    if (AFFINE) nextX = ls_ldcg(inX + jj);
+                }
+            }
+            __syncwarp();
+        }
+        const int send = min(32, nsteps - t0);
+        for (int s = 0; s < send; s++) {
+            const int t = t0 + s;
+            int up_h = __shfl_up_sync(SEQA_FULL, send_h, 1);
+            int up_x = AFFINE ? __shfl_up_sync(SEQA_FULL, send_x, 1) : 0;
+            const int j = t - lane + 1;
+            if (lane == 0) {
+                if (rb > 0) {
+                    up_h = smInH[s];
+                    if (AFFINE) up_x = smInX[s];
+                } else {
+                    up_h = border_hrow(bd, j);
+                    if (AFFINE) up_x = bd.ixA + j * bd.ixB;
+                }
+            }
+            if (j >= 1 && j <= n) {
+                const int bj = (int)(rev ? b[n - j] : b[j - 1]);
+                int dg = diag_top, uh = up_h, ux = up_x;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int left = h[r];
+                    const int sim = (ab[r] == bj) ? sc.match : simx;
+                    int hv, ix = ux;
+                    if (!AFFINE) {
+                        const int tl = __viaddmax_s32(dg, sim, left + sc.gap); // max(D, L)
+                        hv = __viaddmax_s32(uh, sc.gap, tl);                  // max(U, .)
+                    } else {
+                        ix = __viaddmax_s32(uh, gogo, ux + sc.ge);
+                        const int iy = __viaddmax_s32(left, gogo, f[r] + sc.ge);
+                        hv = __viaddmax_s32(dg, sim, max(ix, iy));
+                        if (!PARTIAL || r < nact) f[r] = iy;
+                    }
+                    if (PARTIAL && r >= nact) { // below the sweep: hand the last row down
+                        hv = uh;
+                        ix = ux;
+                    }
+                    dg = left;
+                    uh = hv;
+                    ux = ix;
+                    h[r] = hv;
+                }
+                diag_top = up_h;
+                send_h = uh;
+                send_x = ux;
+            }
+            const int j31 = t - 30; // the column lane 31 has just finished
+            if (j31 >= 1 && j31 <= n) {
+                if (lane == 31) {
+                    smOutH[(j31 - 1) & 31] = send_h;
+                    if (AFFINE) smOutX[(j31 - 1) & 31] = send_x;
+                }
+                if (((j31 - 1) & 31) == 31 || j31 == n) {
+                    __syncwarp();
+                    const int base = (j31 - 1) & ~31;
+                    if (lane < j31 - base) {
+                        outH[base + 1 + lane] = smOutH[lane];
+                        if (AFFINE) outX[base + 1 + lane] = smOutX[lane];
+                    }
+                    if (out_prog) {
+                        __threadfence();
+                        __syncwarp();
+                        if (lane == 0) ls_st_volatile(out_prog, j31);
+                    } else {
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// scratch arrays of one node (stride w ints): Hirschberg  F, Rv, fwd boundary x2, rev boundary x2           (6)
+//                                             MyersMiller CC, DD, RR, SS, fwd (H x2, X x2), rev (H x2, X x2) (12)
+template <bool MM> struct LsArr {
+    static constexpr int COUNT = MM ? 12 : 6;
+    static constexpr int LAST_H_F = 0, LAST_X_F = 1, LAST_H_R = MM ? 2 : 1, LAST_X_R = 3;
+    static constexpr int BND_F = MM ? 4 : 2, BND_R = MM ? 8 : 4; // H ping, H pong [, X ping, X pong]
+};
+
+template <bool MM, int R>
+__device__ __forceinline__ void ls_run_task(const LsArgs &A, const LsSweep &S, const LsNode &nd, int rb, int *sm)
+{
+    const uint32_t p = (uint32_t)nd.pair;
+    const bool rev = S.rows < 0;
+    const int rows = S.rows & 0x7fffffff, nblk = S.nblk & 0x0fffffff;
+    const int mid = nd.m / 2; // include/SAHirschberg.h:129, include/SAMyersMiller.h:164
+    const uint8_t *a = A.bases + A.off1[p] + nd.i0 + (rev ? mid : 0);
+    const uint8_t *b = A.bases + A.off2[p] + nd.j0;
+    const int n = nd.n;
+    const uint64_t w = A.row_w[p];
+    int *base = A.rows + A.row_off[p] + nd.j0 + nd.q;
+    Borders bd;
+    if (!MM) { // NWScore borders, include/SAHirschberg.h:25-29,37
+        bd.hcolA = 0; bd.hcolB = A.sc.gap; bd.hrowA = 0; bd.hrowB = A.sc.gap;
+        bd.ixA = bd.ixB = bd.iyA = bd.iyB = 0;
+    } else { // include/SAMyersMiller.h:172-198 (forward, tb) / :247-270 (reverse, te):
+             // H(i,0)=t+i*h, H(0,j)=g+j*h, DD(0,j)=H(0,j)+g, e(i,0)=H(i,0)+g
+        const int g = A.sc.go, h = A.sc.ge, t = rev ? nd.te : nd.tb;
+        bd.hcolA = t; bd.hcolB = h; bd.hrowA = g; bd.hrowB = h;
+        bd.ixA = 2 * g; bd.ixB = h; bd.iyA = t + g; bd.iyB = h;
+    }
+    const int bnd = rev ? LsArr<MM>::BND_R : LsArr<MM>::BND_F;
+    const bool last = rb == nblk - 1;
+    const int *inH = base + (uint64_t)(bnd + ((rb - 1) & 1)) * w;
+    const int *inX = base + (uint64_t)(bnd + 2 + ((rb - 1) & 1)) * w;
+    int *outH = last ? base + (uint64_t)(rev ? LsArr<MM>::LAST_H_R : LsArr<MM>::LAST_H_F) * w
+                     : base + (uint64_t)(bnd + (rb & 1)) * w;
+    int *outX = last ? base + (uint64_t)(rev ? LsArr<MM>::LAST_X_R : LsArr<MM>::LAST_X_F) * w
+                     : base + (uint64_t)(bnd + 2 + (rb & 1)) * w;
+    const int *in_prog = A.prog + S.task0 + (rb > 0 ? rb - 1 : 0);
+    int *out_prog = last ? nullptr : A.prog + S.task0 + rb;
+    const bool full = (rb + 1) * 32 * R <= rows;
+    if (full)
+        ls_block<MM, R, false>(A.sc, bd, a, rows, b, n, rev, rb, inH, inX, in_prog, outH, outX, out_prog, sm);
+    else
+        ls_block<MM, R, true>(A.sc, bd, a, rows, b, n, rev, rb, inH, inX, in_prog, outH, outX, out_prog, sm);
+}
+
+template <bool MM>
+__global__ void __launch_bounds__(LS_BLOCK) ls_sweep_kernel(LsArgs A)
+{
+    __shared__ int smem[LS_BLOCK / 32][128];
+    const int lane = threadIdx.x & 31;
+    int *sm = smem[threadIdx.x >> 5];
+    const uint32_t ntasks = A.cnt[2];
+    if (*A.overflow) return;
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(&A.cnt[3], 1u);
+        g = __shfl_sync(SEQA_FULL, g, 0);
+        if (g >= ntasks) break;
+        const LsTask T = A.tasks[g];
+        const LsSweep S = A.sweeps[T.sweep];
+        const LsNode nd = A.in[S.node];
+        switch ((S.nblk >> 28) & 7) {
+        case 0: ls_run_task<MM, 1>(A, S, nd, (int)T.rb, sm); break;
+        case 1: ls_run_task<MM, 2>(A, S, nd, (int)T.rb, sm); break;
+        case 2: ls_run_task<MM, 4>(A, S, nd, (int)T.rb, sm); break;
+        default: ls_run_task<MM, 8>(A, S, nd, (int)T.rb, sm); break;
+        }
+    }
+}
+
+// ---- expand: leaves emit their ops, internal nodes become sweeps + tasks ------------------------------------------
+__device__ __forceinline__ void ls_push(const LsArgs &A, const LsNode &nd)
+{
+    const uint32_t k = atomicAdd(&A.cnt[0], 1u);
+    if (k < A.out_cap)
+        A.out[k] = nd;
+    else
+        *A.overflow = 1;
+}
+
+// rows per lane for a sweep of `rows` rows: the smallest of 1/2/4/8 whose single block covers it, else 8
+__device__ __forceinline__ int ls_pick_rsel(const LsArgs &A, int rows)
+{
+    if (A.force_r > 0) return A.force_r == 1 ? 0 : A.force_r == 2 ? 1 : A.force_r == 4 ? 2 : 3;
+    return rows <= 32 ? 0 : rows <= 64 ? 1 : rows <= 128 ? 2 : 3;
+}
+
+__device__ __forceinline__ void ls_make_sweeps(const LsArgs &A, uint32_t node, int rows_f, int rows_r, int lane)
+{
+    const int rf = ls_pick_rsel(A, rows_f), rr = ls_pick_rsel(A, rows_r);
+    const int nf = (rows_f + (32 << rf) - 1) / (32 << rf), nr = (rows_r + (32 << rr) - 1) / (32 << rr);
+    uint32_t s0 = 0, t0 = 0;
+    if (lane == 0) {
+        s0 = atomicAdd(&A.cnt[1], 2u);
+        t0 = atomicAdd(&A.cnt[2], (uint32_t)(nf + nr));
+        if (t0 + (uint32_t)(nf + nr) > A.task_cap) {
+            *A.overflow = 1; // the sweep / split kernels do nothing once this is set; the host fails the call
+            t0 = 0xffffffffu;
+        }
+    }
+    s0 = __shfl_sync(SEQA_FULL, s0, 0);
+    t0 = __shfl_sync(SEQA_FULL, t0, 0);
+    if (t0 == 0xffffffffu) return;
+    if (lane == 0) {
+        LsSweep F, Rv;
+        F.node = (int)node; F.rows = rows_f; F.nblk = nf | (rf << 28); F.task0 = t0;
+        Rv.node = (int)node; Rv.rows = (int)((unsigned)rows_r | 0x80000000u); Rv.nblk = nr | (rr << 28); Rv.task0 = t0 + (uint32_t)nf;
+        A.sweeps[s0] = F;
+        A.sweeps[s0 + 1] = Rv;
+    }
+    // task order: forward and reverse row blocks alternate, each chain in ascending row-block order
+    for (int rb = lane; rb < nf; rb += 32) {
+        LsTask T; T.sweep = s0; T.rb = (uint32_t)rb;
+        A.tasks[t0 + (uint32_t)(rb + min(rb, nr))] = T;
+    }
+    for (int rb = lane; rb < nr; rb += 32) {
+        LsTask T; T.sweep = s0 + 1; T.rb = (uint32_t)rb;
+        A.tasks[t0 + (uint32_t)(rb + min(rb + 1, nf))] = T;
+    }
+}
+
+template <bool MM>
+__global__ void __launch_bounds__(128) ls_expand_kernel(LsArgs A)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-    Borders bd;
-    bd.hcolA = 0; bd.hcolB = A.sc.gap; bd.hrowA = 0; bd.hrowB = A.sc.gap;
-    bd.ixA = bd.ixB = bd.iyA = bd.iyB = 0;
     for (uint32_t k = gw; k < A.n_in; k += nw) {
         const LsNode nd = A.in[k];
         const uint32_t p = (uint32_t)nd.pair;
@@ -134,29 +427,73 @@ __global__ void __launch_bounds__(128) hb_level_kernel(LsArgs A)
         const uint8_t *b = A.bases + A.off2[p] + nd.j0;
         uint8_t *slot = A.slots + A.slot_off[p] + nd.i0 + nd.j0;
         const int m = nd.m, n = nd.n;
-        if (m == 0) { // include/SAHirschberg.h:105
-            ls_emit_run(slot, 0, n, 2, lane);
-        } else if (n == 0) { // :112
-            ls_emit_run(slot, 0, m, 1, lane);
-        } else if (m == 1 || n == 1) { // :119
-            hb_leaf_thin(A.sc, a, m, b, n, slot, lane);
-        } else {
-            const uint64_t w = A.row_w[p];
-            int *base = A.rows + A.row_off[p] + nd.j0 + nd.q;
-            int *F = base, *Rv = base + w, *BH = base + 2 * w;
-            const int mid = m / 2; // :129
-            wavefront<false, false, false, LS_R>(A.sc, bd, a, mid, b, n, false, nullptr, BH, nullptr, F, nullptr);
-            __syncwarp();
-            wavefront<false, false, false, LS_R>(A.sc, bd, a + mid, m - mid, b, n, true, nullptr, BH, nullptr, Rv, nullptr);
-            if (lane == 0) {
-                F[0] = mid * A.sc.gap;
-                Rv[0] = (m - mid) * A.sc.gap;
+        if (!MM) {
+            if (m == 0) { // include/SAHirschberg.h:105
+                ls_emit_run(slot, 0, n, 2, lane);
+            } else if (n == 0) { // :112
+                ls_emit_run(slot, 0, m, 1, lane);
+            } else if (m == 1 || n == 1) { // :119
+                hb_leaf_thin(A.sc, a, m, b, n, slot, lane);
+            } else {
+                ls_make_sweeps(A, k, m / 2, m - m / 2, lane); // :129-139
             }
-            __syncwarp();
-            // Seq2Mid = argmax over i in [0, n-1] of F[i] + Rv[n-i], ties -> largest i (:141-149)
+        } else {
+            const int g = A.sc.go, h = A.sc.ge, tb = nd.tb, te = nd.te;
+            if (n == 0) { // include/SAMyersMiller.h:57
+                ls_emit_run(slot, 0, m, 1, lane);
+            } else if (m == 0) { // :67
+                ls_emit_run(slot, 0, n, 2, lane);
+            } else if (m == 1) { // :75-160
+                const int mx = max(tb, te) + h + (g + h * n);
+                int best = INT_MIN, bj = 0;
+                for (int j = 1 + lane; j <= n; j += 32) {
+                    const bool eq = a[0] == b[j - 1];
+                    int v = mx;
+                    if (A.sc.allow || eq) v = max(g + h * (j - 1) + (eq ? A.sc.match : A.sc.mismatch) + g + h * (n - j), mx); // :104-113
+                    if (v > best) { best = v; bj = j; } // first strictly greatest (:121); lanes ascend in j
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const int ov = __shfl_xor_sync(SEQA_FULL, best, o);
+                    const int oj = __shfl_xor_sync(SEQA_FULL, bj, o);
+                    if (oj != 0 && (bj == 0 || ov > best || (ov == best && oj < bj))) { best = ov; bj = oj; }
+                }
+                const bool split = !A.sc.allow && a[0] != b[bj - 1]; // :142-147: (a,-) then (-,b)
+                ls_emit_run(slot, 0, bj - 1, 2, lane);
+                if (lane == 0) {
+                    if (split) { slot[bj - 1] = 1; slot[bj] = 2; }
+                    else slot[bj - 1] = 0;
+                }
+                ls_emit_run(slot, bj + (split ? 1 : 0), n - bj, 2, lane);
+            } else {
+                ls_make_sweeps(A, k, m / 2, m - m / 2, lane); // :164, :190, :272
+            }
+        }
+    }
+}
+
+// ---- split: the reference's midpoint rule over the final rows of the two sweeps ------------------------------------
+template <bool MM>
+__global__ void __launch_bounds__(128) ls_split_kernel(LsArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nint = *A.overflow ? 0u : A.cnt[1] / 2; // internal nodes of this level
+    for (uint32_t k = gw; k < nint; k += nw) {
+        const LsNode nd = A.in[A.sweeps[2 * k].node];
+        const uint32_t p = (uint32_t)nd.pair;
+        const int m = nd.m, n = nd.n, mid = m / 2;
+        const uint64_t w = A.row_w[p];
+        const int *base = A.rows + A.row_off[p] + nd.j0 + nd.q;
+        if (!MM) {
+            const int *F = base, *Rv = base + w;
+            // Seq2Mid = argmax over i in [0, n-1] of F[i] + Rv[n-i], ties -> largest i (include/SAHirschberg.h:141-149);
+            // column 0 of both rows is the border value
             int best = INT_MIN, bi = 0;
             for (int i = lane; i < n; i += 32) {
-                const int v = F[i] + Rv[n - i];
+                const int f = i == 0 ? mid * A.sc.gap : F[i];
+                const int v = f + Rv[n - i];
                 if (v >= best) { best = v; bi = i; }
             }
 #pragma unroll
@@ -165,7 +502,6 @@ __global__ void __launch_bounds__(128) hb_level_kernel(LsArgs A)
                 const int oi = __shfl_xor_sync(SEQA_FULL, bi, o);
                 if (ov > best || (ov == best && oi > bi)) { best = ov; bi = oi; }
             }
-            __syncwarp();
             if (lane == 0) {
                 LsNode l = nd, r = nd;
                 l.m = mid; l.n = bi; l.q = 2 * nd.q;
@@ -173,75 +509,17 @@ __global__ void __launch_bounds__(128) hb_level_kernel(LsArgs A)
                 ls_push(A, l); // :151-155
                 ls_push(A, r); // :157-161
             }
-        }
-    }
-}
-
-// ---- Myers-Miller ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) mm_level_kernel(LsArgs A)
-{
-    const int lane = threadIdx.x & 31;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-    const int g = A.sc.go, h = A.sc.ge;
-    for (uint32_t k = gw; k < A.n_in; k += nw) {
-        const LsNode nd = A.in[k];
-        const uint32_t p = (uint32_t)nd.pair;
-        const uint8_t *a = A.bases + A.off1[p] + nd.i0;
-        const uint8_t *b = A.bases + A.off2[p] + nd.j0;
-        uint8_t *slot = A.slots + A.slot_off[p] + nd.i0 + nd.j0;
-        const int M = nd.m, N = nd.n, tb = nd.tb, te = nd.te;
-        if (N == 0) { // include/SAMyersMiller.h:57
-            ls_emit_run(slot, 0, M, 1, lane);
-        } else if (M == 0) { // :67
-            ls_emit_run(slot, 0, N, 2, lane);
-        } else if (M == 1) { // :75-160
-            const int mx = max(tb, te) + h + (g + h * N);
-            int best = INT_MIN, bj = 0;
-            for (int j = 1 + lane; j <= N; j += 32) {
-                const bool eq = a[0] == b[j - 1];
-                int v = mx;
-                if (A.sc.allow || eq) v = max(g + h * (j - 1) + (eq ? A.sc.match : A.sc.mismatch) + g + h * (N - j), mx); // :104-113
-                if (v > best) { best = v; bj = j; } // first strictly greatest (:121); lanes ascend in j
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const int ov = __shfl_xor_sync(SEQA_FULL, best, o);
-                const int oj = __shfl_xor_sync(SEQA_FULL, bj, o);
-                if (oj != 0 && (bj == 0 || ov > best || (ov == best && oj < bj))) { best = ov; bj = oj; }
-            }
-            const bool split = !A.sc.allow && a[0] != b[bj - 1]; // :142-147: (a,-) then (-,b)
-            ls_emit_run(slot, 0, bj - 1, 2, lane);
-            if (lane == 0) {
-                if (split) { slot[bj - 1] = 1; slot[bj] = 2; }
-                else slot[bj - 1] = 0;
-            }
-            ls_emit_run(slot, bj + (split ? 1 : 0), N - bj, 2, lane);
         } else {
-            const uint64_t w = A.row_w[p];
-            int *base = A.rows + A.row_off[p] + nd.j0 + nd.q;
-            int *CC = base, *DD = base + w, *RR = base + 2 * w, *SS = base + 3 * w, *BH = base + 4 * w, *BX = base + 5 * w;
-            const int mid = M / 2;
-            Borders bf; // forward sweep borders (:172-198): H(i,0)=tb+i*h, H(0,j)=g+j*h, DD(0,j)=H(0,j)+g, e(i,0)=H(i,0)+g
-            bf.hcolA = tb; bf.hcolB = h; bf.hrowA = g; bf.hrowB = h;
-            bf.ixA = 2 * g; bf.ixB = h; bf.iyA = tb + g; bf.iyB = h;
-            wavefront<true, false, false, LS_R>(A.sc, bf, a, mid, b, N, false, nullptr, BH, BX, CC, DD);
-            __syncwarp();
-            Borders br = bf; // reverse sweep (:247-313): same with te
-            br.hcolA = te; br.iyA = te + g;
-            wavefront<true, false, false, LS_R>(A.sc, br, a + mid, M - mid, b, N, true, nullptr, BH, BX, RR, SS);
-            if (lane == 0) {
-                CC[0] = tb + mid * h;
-                DD[0] = CC[0]; // :238
-                RR[0] = te + (M - mid) * h;
-                SS[0] = RR[0]; // :313
-            }
-            __syncwarp();
+            const int g = A.sc.go, h = A.sc.ge;
+            const int *CC = base, *DD = base + w, *RR = base + 2 * w, *SS = base + 3 * w;
+            const int c0 = nd.tb + mid * h, r0 = nd.te + (m - mid) * h; // CC[0] = DD[0] (:238), RR[0] = SS[0] (:313)
             // midpoint (:315-340): first strictly greatest of max(CC+RR, DD+SS-g) over j = 0..N; RR/SS are stored
             // by reversed column index
             int best = INT_MIN, bj = -1, bt = 0;
-            for (int j = lane; j <= N; j += 32) {
-                const int v1 = CC[j] + RR[N - j], v2 = DD[j] + SS[N - j] - g;
+            for (int j = lane; j <= n; j += 32) {
+                const int cc = j == 0 ? c0 : CC[j], dd = j == 0 ? c0 : DD[j];
+                const int rr = j == n ? r0 : RR[n - j], ss = j == n ? r0 : SS[n - j];
+                const int v1 = cc + rr, v2 = dd + ss - g;
                 const int v = max(v1, v2);
                 if (v > best) { best = v; bj = j; bt = !(v1 > v2); }
             }
@@ -252,20 +530,20 @@ __global__ void __launch_bounds__(128) mm_level_kernel(LsArgs A)
                 const int ot = __shfl_xor_sync(SEQA_FULL, bt, o);
                 if (oj >= 0 && (bj < 0 || ov > best || (ov == best && oj < bj))) { best = ov; bj = oj; bt = ot; }
             }
-            __syncwarp();
             if (lane == 0) {
+                uint8_t *slot = A.slots + A.slot_off[p] + nd.i0 + nd.j0;
                 LsNode l = nd, r = nd;
                 l.q = 2 * nd.q;
                 r.q = 2 * nd.q + 1;
                 l.n = bj;
                 r.j0 = nd.j0 + bj;
-                r.n = N - bj;
+                r.n = n - bj;
                 if (!bt) { // type 1 (:358-374)
                     l.m = mid; l.te = g;
-                    r.i0 = nd.i0 + mid; r.m = M - mid; r.tb = g;
+                    r.i0 = nd.i0 + mid; r.m = m - mid; r.tb = g;
                 } else { // type 2 (:375-395): rows mid-1 and mid are deleted
                     l.m = mid - 1; l.te = 0;
-                    r.i0 = nd.i0 + mid + 1; r.m = M - mid - 1; r.tb = 0;
+                    r.i0 = nd.i0 + mid + 1; r.m = m - mid - 1; r.tb = 0;
                     slot[(mid - 1) + bj] = 1;
                     slot[(mid - 1) + bj + 1] = 1;
                 }
@@ -361,8 +639,13 @@ struct LsState {
     bool mm = false;
     // device
     LsNode *d_nodes[2] = {nullptr, nullptr};
-    uint32_t *d_count = nullptr;
+    uint32_t *d_count = nullptr; // cnt[4]
     int *d_overflow = nullptr;
+    LsSweep *d_sweeps = nullptr;
+    LsTask *d_tasks = nullptr;
+    int *d_prog = nullptr;
+    uint64_t task_cap = 0, sum_blocks = 0, cap_tasks = 0;
+    int sweep_blocks = 0;
     int *d_rows = nullptr;
     uint64_t *d_row_off = nullptr;
     uint32_t *d_row_w = nullptr;

@@ -61,6 +61,13 @@ def main():
     lib = capi.Lib()
     S = orc.Scoring
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+    only = sys.argv[2] if len(sys.argv) > 2 else ""   # substring filter on the config name
+    global run
+    run_all = run
+
+    def run(lib, name, *a, **k):
+        if only in name:
+            run_all(lib, name, *a, **k)
     run(lib, "config2 NW 150bp", "nw", S.linear(-1, 2, -1), int(1_000_000 * scale), 0, 150, 150, 20000)
     run(lib, "config3 GlobalGotoh 250bp", "ggotoh", S.affine(-3, -1, 1, -1), int(200_000 * scale), 0, 250, 250, 8000)
     run(lib, "config3 LocalGotoh 250bp", "lgotoh", S.affine(-3, -1, 1, -1), int(200_000 * scale), 0, 250, 250, 8000)
@@ -69,6 +76,8 @@ def main():
     run(lib, "config4 Hirschberg 20kbp x16", "hirschberg", S.linear(-1, 2, -1), 16, 0, 20000, 20000, 0, reps=1)
     run(lib, "config4 MyersMiller 20kbp x16", "myersmiller", S.affine(-3, -1, 1, -1), 16, 0, 20000, 20000, 0, reps=1)
     run(lib, "config4 Hirschberg 100kbp x8", "hirschberg", S.linear(-1, 2, -1), 8, 0, 100000, 100000, 0, reps=1)
+    run(lib, "config4 Hirschberg 100kbp x64", "hirschberg", S.linear(-1, 2, -1), 64, 0, 100000, 100000, 0, reps=1)
+    run(lib, "config4 MyersMiller 100kbp x64", "myersmiller", S.affine(-3, -1, 1, -1), 64, 0, 100000, 100000, 0, reps=1)
 
 
 if __name__ == "__main__":

@@ -28,6 +28,20 @@ def test_matrix_algorithms(emu_lib, algo, sc):
         check_batch_against_oracle(emu_lib, algo, sc, pairs, flags=flags)
 
 
+@pytest.mark.parametrize("algo,sc", [
+    ("hirschberg", S.linear(-1, 2, -1)), ("hirschberg", S.linear(-2, 3, -2, False)),
+    ("myersmiller", S.affine(-3, -1, 1, -1)), ("myersmiller", S.affine(-3, -1, 1, -1, False)),
+])
+def test_linear_space_algorithms(emu_lib, algo, sc):
+    """expand / sweep / split kernels incl. the row-block pipeline between warps (FLAG_LS_R1 = 32-row blocks, so a
+    150-row sweep is 5 tasks deep; the emulator's fibers yield inside the progress-counter spin)."""
+    rng = np.random.default_rng(12)
+    pairs = list(EDGE) + random_pairs(rng, 10, 1, 70) + random_pairs(rng, 4, 1, 50, "AC") + \
+        random_pairs(rng, 2, 150, 300) + random_pairs(rng, 3, 1, 200, related=0.3)
+    check_batch_against_oracle(emu_lib, algo, sc, pairs)
+    check_batch_against_oracle(emu_lib, algo, sc, pairs[-12:], flags=capi.FLAG_LS_R1)
+
+
 def test_packed_path_is_taken(emu_lib):
     rng = np.random.default_rng(3)
     pairs = random_pairs(rng, 70, 20, 40)

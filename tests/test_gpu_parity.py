@@ -70,6 +70,18 @@ def test_linear_space_algorithms_random(gpu_lib, algo, sc):
         random_pairs(rng, 100, 1, 250, related=0.3) + random_pairs(rng, 12, 1000, 3000) + \
         random_pairs(rng, 6, 2000, 5000, related=0.25) + [("A" * 700, "ACGT" * 150), ("ACGT" * 200, "T" * 40)]
     check_batch_against_oracle(gpu_lib, algo, sc, pairs)
+    # 32-row blocks everywhere: every sweep becomes a deep row-block pipeline across warps (progress-flag protocol)
+    check_batch_against_oracle(gpu_lib, algo, sc, pairs[-24:] + pairs[:100], flags=capi.FLAG_LS_R1)
+
+
+@pytest.mark.parametrize("algo,sc,n,lo,hi", [("hirschberg", S.linear(-1, 2, -1), 6, 9000, 20000),
+                                             ("myersmiller", S.affine(-3, -1, 1, -1), 6, 5000, 9000)])
+def test_linear_space_long_pairs(gpu_lib, algo, sc, n, lo, hi):
+    """Sweeps tens of row blocks deep (the config-4 regime at a size the oracle finishes in seconds): unrelated and
+    related pairs (10 % substitutions + indels), bit-exact including the reference's sub-optimal splits."""
+    rng = np.random.default_rng(31)
+    pairs = random_pairs(rng, n // 2, lo, hi) + random_pairs(rng, n - n // 2, lo, hi, related=0.14)
+    check_batch_against_oracle(gpu_lib, algo, sc, pairs)
 
 
 @pytest.mark.parametrize("algo", ["sw", "nw"])
