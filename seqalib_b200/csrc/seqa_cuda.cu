@@ -19,6 +19,7 @@
 #include "seqa_util.cuh"
 #include "seqa_wavefront.cuh"
 #include "seqa_packed.cuh"
+#include "seqa_packed_affine.cuh"
 #include "seqa_linspace.cuh"
 #include "../../include/seqa_cuda.h"
 
@@ -102,6 +103,7 @@ template <class T> struct HBuf {
 constexpr int GEN_R = 4;          // rows per lane of the generic wavefront
 constexpr int PK_R = 16;          // rows per register strip of the packed kernel
 constexpr uint32_t PK_MAX_LEN = 320; // longest side the thread-per-pair kernel takes (shared-memory column)
+constexpr uint32_t PKG_MAX_LEN = 2048; // affine thread-per-pair kernel: boundary rows live in global memory
 
 struct Chunk {
     uint32_t lo, hi;       // range of jobs / list entries
@@ -153,6 +155,7 @@ struct seqa_ctx {
     uint32_t pk_max_nw = 0;
     DBuf<uint32_t> d_perm;
     DBuf<PkWarpJob> d_jobs;
+    DBuf<uint4> pk_bound; // affine packed kernel: per-warp strip boundary rows
     // generic plan
     std::vector<uint32_t> gidx;
     std::vector<uint64_t> gdir_off;
@@ -233,10 +236,19 @@ void set_scoring(seqa_ctx *c)
 }
 
 // Can the s16x2 thread-per-pair kernel take (M,N) under the current scoring?  See seqa_packed.cuh.
+bool packed_affine(const seqa_params &p) { return p.algo == SEQA_GLOBAL_GOTOH || p.algo == SEQA_LOCAL_GOTOH; }
 bool packed_scoring_ok(const seqa_params &p)
 {
-    if (p.algo != SEQA_NW && p.algo != SEQA_SW) return false;
     if (p.flags & SEQA_FLAG_FORCE_GENERIC) return false;
+    if (packed_affine(p)) {
+        // seqa_packed_affine.cuh: profile scores minus (go+ge) must fit int8, every difference the walk tests on low
+        // bytes must stay far inside (-128, 128), and the -128 "never" marker must lose against a gap open
+        const int g = -(p.gap_open + p.gap_extend), m = p.match, x = p.allow_mismatch ? -p.mismatch : 0;
+        if (m > 100 || g > 50 || x > 100 || m + g > 120) return false;
+        if (m + x + 3 * g - p.gap_open > 120) return false;
+        return true;
+    }
+    if (p.algo != SEQA_NW && p.algo != SEQA_SW) return false;
     const int g = -p.gap, m = p.match, x = p.allow_mismatch ? -p.mismatch : 0;
     if (m > 100 || g > 50 || x > 100) return false;
     if (m + x + 2 * g > 120) return false; // neighbouring cells must differ by < 128
@@ -250,6 +262,12 @@ int packed_trace_bits(const seqa_params &p)
 }
 bool packed_shape_ok(const seqa_params &p, uint32_t M, uint32_t N)
 {
+    if (packed_affine(p)) {
+        // 16-bit values, and nothing real may come near the reference's -10000 "minus infinity"
+        if (M == 0 || N == 0 || M > PKG_MAX_LEN || N > PKG_MAX_LEN) return false;
+        const int64_t unit = -(int64_t)(p.gap_open + p.gap_extend) + p.match + (p.allow_mismatch ? -p.mismatch : 0);
+        return (int64_t)(M + N + 2 * PK_R + 2) * unit < 9000;
+    }
     if (M == 0 || N == 0 || M > PK_MAX_LEN || N > PK_MAX_LEN) return false;
     const int64_t g = -p.gap, m = p.match;
     const int64_t lo = (int64_t)(M + N + 2 * PK_R + 2) * g + 300, hi = (int64_t)std::min(M, N) * m + 300;
@@ -374,7 +392,8 @@ int build_plan(seqa_ctx *c)
             J.Mw = Mw;
             J.Nw = Nw;
             J.nstrips = (Mw + PK_R - 1) / PK_R;
-            const uint64_t tbytes = pk_trace_bytes(J.nstrips, Nw, PK_R, packed_trace_bits(prm));
+            const uint64_t tbytes = packed_affine(prm) ? pkg_trace_bytes(J.nstrips, Nw, PK_R)
+                                                       : pk_trace_bytes(J.nstrips, Nw, PK_R, packed_trace_bits(prm));
             const uint64_t pelems = (uint64_t)((Nw + 3) / 4) * 128, relems = (uint64_t)J.nstrips * PK_R * 32;
             if (ch.hi > ch.lo && chunk_bytes(tr + tbytes, pf + pelems, rs + relems) > budget) {
                 ch.scratch_bytes = chunk_bytes(tr, pf, rs);
@@ -522,15 +541,18 @@ int run_generic(seqa_ctx *c, bool want_walk)
 int run_packed(seqa_ctx *c, bool want_walk)
 {
     if (c->jobs.empty()) return SEQA_OK;
-    const bool local = c->prm.algo == SEQA_SW;
+    const bool affine = packed_affine(c->prm);
+    const bool local = c->prm.algo == SEQA_SW || c->prm.algo == SEQA_LOCAL_GOTOH;
     const int tb = packed_trace_bits(c->prm);
-    const size_t smem = (size_t)c->pk_max_nw * PK_BLOCK * 4;
+    const size_t smem = affine ? 0 : (size_t)c->pk_max_nw * PK_BLOCK * 4;
     if (smem > c->smem_optin) return fail(SEQA_ERR_UNSUPPORTED, "internal: packed kernel shared memory %zu", smem);
     CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int bps = (int)std::max<size_t>(1, std::min<size_t>(3, (c->smem_optin + 1024) / std::max<size_t>(smem + 1024, 1)));
+    const int bps = affine ? 2 : (int)std::max<size_t>(1, std::min<size_t>(3, (c->smem_optin + 1024) / std::max<size_t>(smem + 1024, 1)));
+    const uint64_t bound_stride = (uint64_t)((c->pk_max_nw + 3) / 4) * 64;
+    if (affine) CKS(c->pk_bound.ensure((size_t)c->sms * bps * (PK_BLOCK / 32) * bound_stride));
     CK(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 4, c->stream));
     for (const Chunk &ch : c->pk_chunks) {
         const uint32_t nj = ch.hi - ch.lo;
@@ -538,7 +560,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
         uint64_t tr = 0, pf = 0;
         {
             const PkWarpJob &L = c->jobs[ch.hi - 1];
-            tr = L.trace_off + pk_trace_bytes(L.nstrips, L.Nw, PK_R, tb);
+            tr = L.trace_off + (affine ? pkg_trace_bytes(L.nstrips, L.Nw, PK_R) : pk_trace_bytes(L.nstrips, L.Nw, PK_R, tb));
             pf = L.prof_off + (uint64_t)((L.Nw + 3) / 4) * 128;
         }
         PkArgs A{};
@@ -569,12 +591,21 @@ int run_packed(seqa_ctx *c, bool want_walk)
         A.allow = c->prm.allow_mismatch ? 1 : 0;
         A.smem_cols = c->pk_max_nw;
         A.npos = (uint64_t)nj * 64;
+        A.go = c->prm.gap_open;
+        A.ge = c->prm.gap_extend;
+        A.prof_bias = affine ? c->prm.gap_open + c->prm.gap_extend : 0;
+        A.bound = c->pk_bound.p;
+        A.bound_stride = bound_stride;
         const unsigned wpb = PK_BLOCK / 32;
         const unsigned full = (nj + wpb - 1) / wpb;
         const unsigned grid = std::min<unsigned>(full, (unsigned)(c->sms * bps));
         LAUNCH(c, (pk_prep_kernel), std::min<unsigned>(full, (unsigned)c->sms * 16), PK_BLOCK, 0, A, PK_R);
         cudaEventRecord(next_event(c), c->stream);
-        if (local && tb == 4)
+        if (affine && local)
+            LAUNCH(c, (pkg_fill_kernel<true, PK_R>), grid, PK_BLOCK, 0, A);
+        else if (affine)
+            LAUNCH(c, (pkg_fill_kernel<false, PK_R>), grid, PK_BLOCK, 0, A);
+        else if (local && tb == 4)
             LAUNCH(c, (pk_fill_kernel<true, PK_R, 4>), grid, PK_BLOCK, smem, A);
         else if (local)
             LAUNCH(c, (pk_fill_kernel<true, PK_R, 8>), grid, PK_BLOCK, smem, A);
@@ -589,7 +620,11 @@ int run_packed(seqa_ctx *c, bool want_walk)
             Wk.perm = c->d_perm.p + (uint64_t)ch.lo * 64;
             // jobs' `first` fields are absolute; the walk indexes perm by position, so rebase via pointer only
             const unsigned wgrid = (unsigned)((Wk.npos + 255) / 256);
-            if (local && tb == 4)
+            if (affine && local)
+                LAUNCH(c, (pkg_walk_kernel<true>), wgrid, 256, 0, Wk, PK_R);
+            else if (affine)
+                LAUNCH(c, (pkg_walk_kernel<false>), wgrid, 256, 0, Wk, PK_R);
+            else if (local && tb == 4)
                 LAUNCH(c, (pk_walk_kernel<true, 4>), wgrid, 256, 0, Wk, PK_R);
             else if (local)
                 LAUNCH(c, (pk_walk_kernel<true, 8>), wgrid, 256, 0, Wk, PK_R);
@@ -600,7 +635,10 @@ int run_packed(seqa_ctx *c, bool want_walk)
         }
         CK(cudaGetLastError());
     }
-    c->last_kernel = local ? (tb == 4 ? "pk_fill_sw_s16x2_t4" : "pk_fill_sw_s16x2_t8") : (tb == 4 ? "pk_fill_nw_s16x2_t4" : "pk_fill_nw_s16x2_t8");
+    if (affine)
+        c->last_kernel = local ? "pkg_fill_lgotoh_s16x2" : "pkg_fill_ggotoh_s16x2";
+    else
+        c->last_kernel = local ? (tb == 4 ? "pk_fill_sw_s16x2_t4" : "pk_fill_sw_s16x2_t8") : (tb == 4 ? "pk_fill_nw_s16x2_t4" : "pk_fill_nw_s16x2_t8");
     return SEQA_OK;
 }
 
@@ -811,7 +849,7 @@ void seqa_ctx_destroy(seqa_ctx *c)
     c->ops_len.release(); c->slot_start.release(); c->slot_off.release(); c->ops_off.release();
     c->slots.release(); c->dense.release(); c->tile_sum.release(); c->total.release(); c->flags.release();
     c->perm.release(); c->jobs_pin.release(); c->gidx_pin.release(); c->gdir_pin.release();
-    c->d_perm.release(); c->d_jobs.release(); c->d_gidx.release(); c->d_gdir_off.release(); c->bound.release();
+    c->d_perm.release(); c->d_jobs.release(); c->pk_bound.release(); c->d_gidx.release(); c->d_gdir_off.release(); c->bound.release();
     c->scratch.release();
     ls_release(c->ls);
     for (auto e : c->ev) cudaEventDestroy(e);

@@ -53,6 +53,11 @@ struct PkArgs {
     int gap, match, mismatch, allow;
     uint32_t smem_cols; // columns of shared boundary storage per thread
     uint64_t npos;      // njobs * 64
+    // affine kernels (seqa_packed_affine.cuh)
+    int go, ge;
+    int prof_bias;         // subtracted from every profile score (affine: GapOpen + GapExtend)
+    uint4 *bound;          // per-warp strip boundary rows
+    uint64_t bound_stride; // uint4 per warp
 };
 
 // 2-bit code of an upper-case DNA letter: A0 C1 T2 G3 ((c>>1)&3); valid only for the four letters.
@@ -65,8 +70,8 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
     const int lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-    const unsigned mm = A.allow ? ((unsigned)A.mismatch & 0xffu) : 0x80u; // -128 marks "never" (see header)
-    const unsigned mt = (unsigned)A.match & 0xffu;
+    const unsigned mm = A.allow ? ((unsigned)(A.mismatch - A.prof_bias) & 0xffu) : 0x80u; // -128 marks "never" (see header)
+    const unsigned mt = (unsigned)(A.match - A.prof_bias) & 0xffu;
     for (uint32_t w = gw; w < A.njobs; w += nw) {
         const PkWarpJob J = A.jobs[w];
         const uint32_t p0 = A.perm[J.first + 2 * lane], p1 = A.perm[J.first + 2 * lane + 1];

@@ -1,0 +1,308 @@
+// Inter-sequence fast path for short AFFINE-gap pairs (GlobalGotohSA / LocalGotohSA, reference
+// include/SAGlobalGotoh.h:53-422, include/SALocalGotoh.h:56-490): like seqa_packed.cuh one THREAD owns TWO pairs in
+// the two signed 16-bit halves of every register.  With G = H + (GapOpen+GapExtend) kept instead of H, a cell is
+//
+//     sim' = PRMT(T0_j, T1_j, sel_i)                       match/mismatch score MINUS (GapOpen+GapExtend), both pairs
+//     ix   = VIADDMNMX.S16x2(Ix_up, GapExtend, G_up)        max(Ix(i-1,j)+ge, H(i-1,j)+go+ge)   include/SAGlobalGotoh.h:172-176
+//     iy   = VIADDMNMX.S16x2(Iy_left, GapExtend, G_left)    max(Iy(i,j-1)+ge, H(i,j-1)+go+ge)   :179-183
+//     m    = VIMNMX.S16x2(ix, iy)
+//     H    = VIADDMNMX.S16x2[.RELU](G_diag, sim', m)        max(H(i-1,j-1)+sim, ix, iy [,0])     :192 / SALocalGotoh.h:216
+//     G    = VIADD.16x2(H, go+ge)
+//
+// = 6 ALU-pipe instructions per two cells, no per-cell comparison.  The strip's bottom row (G and Ix) crosses to
+// the next strip through a per-warp boundary row in global memory (L2-resident; read one column group ahead), so
+// the pair length is not limited by shared memory.
+//
+// Traceback: the LOW BYTES of G, Ix and Iy (three planes, 1.5 PRMT per two cells).  The walk keeps the exact
+// value of the matrix it is in and evaluates the reference's own equality tests in its own order (diag > Ix > Iy,
+// extend before open, include/SAGlobalGotoh.h:260-419) on low bytes: every tested difference is far inside
+// (-128, 128) for the scoring ranges the host admits, so equality of low bytes is equality.
+#pragma once
+#include "seqa_packed.cuh"
+
+#define PKG_NEG (-10000) /* the reference's literal "-infinity" */
+
+__host__ __device__ inline uint64_t pkg_trace_bytes(uint32_t nstrips, uint32_t Nw, int R)
+{
+    return (uint64_t)nstrips * Nw * 3ull * (uint64_t)(R / 8) * 512ull;
+}
+
+// Trace piece (16 B = 8 rows x 1 column x 2 pairs of one plane), per warp job:
+//   piece(s, j, plane, hf, lane) at trace_off + ((((s*Nw + j-1)*3 + plane)*(R/8) + hf)*32 + lane) * 16
+//   word (r%8)/2, byte (r%2)*2 + k      (r = row inside the strip, hf = r/8, k = pair half)
+template <bool LOCAL, int R>
+__global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
+{
+    static_assert(R % 8 == 0, "strips are cut into 8-row trace pieces");
+    constexpr int RP = R / 2, RH = R / 8;
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    const int gogo = A.go + A.ge;
+    const unsigned ge2 = pk_dup(A.ge), gogo2 = pk_dup(gogo), neg2 = pk_dup(PKG_NEG);
+    uint4 *__restrict__ bnd = A.bound + (uint64_t)gw * A.bound_stride + lane * 2; // [cg][lane][{G,Ix} x 4 columns]
+    for (uint32_t w = gw; w < A.njobs; w += nw) {
+        const PkWarpJob J = A.jobs[w];
+        const uint32_t p0 = A.perm[J.first + 2 * lane], p1 = A.perm[J.first + 2 * lane + 1];
+        const int M0 = p0 == PK_NULL ? 0 : (int)A.len1[p0], N0 = p0 == PK_NULL ? 0 : (int)A.len2[p0];
+        const int M1 = p1 == PK_NULL ? 0 : (int)A.len1[p1], N1 = p1 == PK_NULL ? 0 : (int)A.len2[p1];
+        const int Ng = ((int)J.Nw + 3) >> 2, Nw = (int)J.Nw;
+        const uint4 *__restrict__ prof = reinterpret_cast<const uint4 *>(A.prof + J.prof_off) + lane * 2;
+        const uint32_t *__restrict__ rowsel = A.rowsel + J.rowsel_off + lane;
+        uint4 *__restrict__ trace = reinterpret_cast<uint4 *>(A.trace + J.trace_off) + lane;
+        int best0 = 0, best1 = 0, bi0 = 0, bi1 = 0; // local: running (max, last row holding it)
+        int corner0 = 0, corner1 = 0;               // global: H(M,N)
+        const int nstrips = (int)J.nstrips;
+        for (int s = 0; s < nstrips; s++) {
+            const int i0 = s * R;
+            const bool first = s == 0, keep = s + 1 < nstrips;
+            unsigned G[R], Y[R], sel[R], rmax[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                sel[r] = rowsel[(uint64_t)(i0 + r) * 32];
+                // column 0: H(i,0) = 0 (local, include/SALocalGotoh.h:77-82) or go + i*ge (global, include/SAGlobalGotoh.h:75-80)
+                G[r] = pk_dup((LOCAL ? 0 : A.go + (i0 + r + 1) * A.ge) + gogo);
+                Y[r] = neg2;
+                rmax[r] = gogo2;
+            }
+            unsigned diag = pk_dup((LOCAL || i0 == 0 ? 0 : A.go + i0 * A.ge) + gogo); // G(i0, 0)
+            uint4 *__restrict__ tr = trace + (uint64_t)s * Nw * (3 * RH * 32);
+            uint4 na = prof[0], nb = prof[1];
+            uint4 nu0 = make_uint4(0, 0, 0, 0), nu1 = nu0;
+            if (!first) {
+                nu0 = bnd[0];
+                nu1 = bnd[1];
+            }
+            for (int cg = 0; cg < Ng; cg++) {
+                const uint4 ca = na, cb = nb, cu0 = nu0, cu1 = nu1;
+                if (cg + 1 < Ng) {
+                    na = prof[(uint64_t)(cg + 1) * 64];
+                    nb = prof[(uint64_t)(cg + 1) * 64 + 1];
+                    if (!first) {
+                        nu0 = bnd[(uint64_t)(cg + 1) * 64];
+                        nu1 = bnd[(uint64_t)(cg + 1) * 64 + 1];
+                    }
+                }
+                unsigned outG[4], outX[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int j = cg * 4 + c + 1;
+                    const unsigned T0 = c == 0 ? ca.x : c == 1 ? ca.z : c == 2 ? cb.x : cb.z;
+                    const unsigned T1 = c == 0 ? ca.y : c == 1 ? ca.w : c == 2 ? cb.y : cb.w;
+                    unsigned gu, xu; // G and Ix of the row above the strip in this column
+                    if (first) {     // matrix row 0: H(0,j) = 0 / go + j*ge, Ix(0,j) = -10000
+                        gu = pk_dup((LOCAL ? 0 : A.go + j * A.ge) + gogo);
+                        xu = neg2;
+                    } else {
+                        gu = c == 0 ? cu0.x : c == 1 ? cu0.z : c == 2 ? cu1.x : cu1.z;
+                        xu = c == 0 ? cu0.y : c == 1 ? cu0.w : c == 2 ? cu1.y : cu1.w;
+                    }
+                    unsigned gd = diag;
+                    diag = gu;
+                    unsigned Wg[RP], Wx[RP], Wy[RP];
+                    unsigned pg = 0, px = 0, py = 0;
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const unsigned sim = seqa_prmt(T0, T1, sel[r]);
+                        const unsigned gl = G[r];
+                        const unsigned ix = __viaddmax_s16x2(xu, ge2, gu);
+                        const unsigned iy = __viaddmax_s16x2(Y[r], ge2, gl);
+                        const unsigned m = __vmaxs2(ix, iy);
+                        const unsigned hn = LOCAL ? __viaddmax_s16x2_relu(gd, sim, m) : __viaddmax_s16x2(gd, sim, m);
+                        const unsigned gn = __vadd2(hn, gogo2);
+                        if (r & 1) {
+                            Wg[r >> 1] = seqa_prmt(pg, gn, 0x6420); // low bytes: [p0 r-1, p1 r-1, p0 r, p1 r]
+                            Wx[r >> 1] = seqa_prmt(px, ix, 0x6420);
+                            Wy[r >> 1] = seqa_prmt(py, iy, 0x6420);
+                        }
+                        pg = gn;
+                        px = ix;
+                        py = iy;
+                        if (LOCAL && (c & 1)) rmax[r] = __vimax3_s16x2(rmax[r], gl, gn);
+                        G[r] = gn;
+                        Y[r] = iy;
+                        gd = gl;
+                        gu = gn;
+                        xu = ix;
+                    }
+                    outG[c] = gu;
+                    outX[c] = xu;
+                    if (j <= Nw) {
+                        uint4 *dst = tr + (uint64_t)(j - 1) * (3 * RH * 32);
+#pragma unroll
+                        for (int hf = 0; hf < RH; hf++) {
+                            pk_store_stream(&dst[(0 * RH + hf) * 32], make_uint4(Wg[hf * 4], Wg[hf * 4 + 1], Wg[hf * 4 + 2], Wg[hf * 4 + 3]));
+                            pk_store_stream(&dst[(1 * RH + hf) * 32], make_uint4(Wx[hf * 4], Wx[hf * 4 + 1], Wx[hf * 4 + 2], Wx[hf * 4 + 3]));
+                            pk_store_stream(&dst[(2 * RH + hf) * 32], make_uint4(Wy[hf * 4], Wy[hf * 4 + 1], Wy[hf * 4 + 2], Wy[hf * 4 + 3]));
+                        }
+                    }
+                    if (!LOCAL) {
+                        if (j == N0 || j == N1) {
+#pragma unroll
+                            for (int r = 0; r < R; r++) {
+                                if (j == N0 && i0 + r + 1 == M0) corner0 = pk_half(G[r], 0) - gogo;
+                                if (j == N1 && i0 + r + 1 == M1) corner1 = pk_half(G[r], 1) - gogo;
+                            }
+                        }
+                    }
+                }
+                if (keep) {
+                    bnd[(uint64_t)cg * 64] = make_uint4(outG[0], outX[0], outG[1], outX[1]);
+                    bnd[(uint64_t)cg * 64 + 1] = make_uint4(outG[2], outX[2], outG[3], outX[3]);
+                }
+            }
+            if (LOCAL) {
+                // last maximum in row-major order (include/SALocalGotoh.h:220-225): rows ascending, ">="
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int i = i0 + r + 1;
+                    const int v0 = pk_half(rmax[r], 0) - gogo, v1 = pk_half(rmax[r], 1) - gogo;
+                    if (i <= M0 && v0 >= best0) { best0 = v0; bi0 = i; }
+                    if (i <= M1 && v1 >= best1) { best1 = v1; bi1 = i; }
+                }
+            }
+        }
+        if (p0 != PK_NULL) {
+            A.score[p0] = LOCAL ? best0 : corner0;
+            A.end_i[p0] = LOCAL ? (uint32_t)bi0 : (uint32_t)M0;
+            if (!LOCAL) A.end_j[p0] = (uint32_t)N0;
+        }
+        if (p1 != PK_NULL) {
+            A.score[p1] = LOCAL ? best1 : corner1;
+            A.end_i[p1] = LOCAL ? (uint32_t)bi1 : (uint32_t)M1;
+            if (!LOCAL) A.end_j[p1] = (uint32_t)N1;
+        }
+    }
+}
+
+// ---- walk -------------------------------------------------------------------------------------------------
+// One thread per pair; state machine = reference buildResult (include/SAGlobalGotoh.h:235-422,
+// include/SALocalGotoh.h:275-473).  h / x / y are the EXACT values of H / Ix / Iy at the current cell.
+template <bool LOCAL>
+__global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A, int R)
+{
+    const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= A.npos) return;
+    const uint32_t p = A.perm[pos];
+    if (p == PK_NULL) return;
+    const PkWarpJob J = A.jobs[pos >> 6];
+    const int lane = (int)((pos & 63) >> 1), half = (int)(pos & 1);
+    const int M = (int)A.len1[p], N = (int)A.len2[p];
+    const uint32_t Nw = J.Nw, RH = (uint32_t)(R / 8);
+    const uint8_t *a = A.bases + A.off1[p], *b = A.bases + A.off2[p];
+    const int go = A.go, ge = A.ge, gogo = go + ge;
+    const uint4 *pieces = reinterpret_cast<const uint4 *>(A.trace + J.trace_off);
+    uint4 cv0 = make_uint4(0, 0, 0, 0), cv1 = cv0, cv2 = cv0;
+    uint32_t ck0 = 0xffffffffu, ck1 = 0xffffffffu, ck2 = 0xffffffffu;
+    auto pick = [&](const uint4 &v, int r) -> unsigned {
+        const int wsel = (r & 7) >> 1;
+        const unsigned wv = wsel == 0 ? v.x : wsel == 1 ? v.y : wsel == 2 ? v.z : v.w;
+        return (wv >> (((r & 1) * 2 + half) * 8)) & 0xffu;
+    };
+    auto key_of = [&](int plane, int i, int j, int &r) -> uint32_t { // i >= 1, j >= 1
+        const int ii = i - 1, s = ii / R;
+        r = ii - s * R;
+        return ((((uint32_t)s * Nw + (uint32_t)(j - 1)) * 3u + (uint32_t)plane) * RH + (uint32_t)(r >> 3)) * 32u + (uint32_t)lane;
+    };
+    auto lowG = [&](int i, int j) -> unsigned {
+        int r;
+        const uint32_t k = key_of(0, i, j, r);
+        if (ck0 != k) { cv0 = pieces[k]; ck0 = k; }
+        return pick(cv0, r);
+    };
+    auto lowX = [&](int i, int j) -> unsigned {
+        int r;
+        const uint32_t k = key_of(1, i, j, r);
+        if (ck1 != k) { cv1 = pieces[k]; ck1 = k; }
+        return pick(cv1, r);
+    };
+    auto lowY = [&](int i, int j) -> unsigned {
+        int r;
+        const uint32_t k = key_of(2, i, j, r);
+        if (ck2 != k) { cv2 = pieces[k]; ck2 = k; }
+        return pick(cv2, r);
+    };
+    auto borderH = [&](int i, int j) -> int { // i == 0 or j == 0
+        if (LOCAL || (i == 0 && j == 0)) return 0;
+        return go + (i == 0 ? j : i) * ge;
+    };
+    uint8_t *slot = A.slots + A.slot_off[p];
+    int k = M + N;
+    int i, j, h, x = 0, y = 0, state = 0;
+    if (LOCAL) {
+        // MaxCol: the last column of row MaxRow holding MaxScore (include/SALocalGotoh.h:220-225); exact values are
+        // chained from H(i,0) = 0 through the low bytes of G = H + go + ge
+        const int best = A.score[p];
+        i = (int)A.end_i[p];
+        int e = 0, bj = N;
+        if (i >= 1) {
+            for (int jj = 1; jj <= N; jj++) {
+                e += (int)(int8_t)(uint8_t)(lowG(i, jj) - (unsigned)(e + gogo));
+                if (e == best) bj = jj;
+            }
+        }
+        j = bj;
+        h = best;
+        A.end_j[p] = (uint32_t)j;
+    } else {
+        i = M;
+        j = N;
+        h = A.score[p];
+    }
+    for (;;) {
+        if (LOCAL) {
+            if (i <= 0 || j <= 0) break; // include/SALocalGotoh.h:289
+        } else {
+            if (i == 0 && j == 0) break;
+            if (j == 0) { slot[--k] = 1; i--; continue; } // include/SAGlobalGotoh.h:312
+            if (i == 0) { slot[--k] = 2; j--; continue; } // :370
+        }
+        if (state == 0) {
+            if (LOCAL && h == 0) break; // H == max(D,0) == 0 (include/SALocalGotoh.h:334)
+            const bool eq = a[i - 1] == b[j - 1];
+            if (eq || A.allow) {
+                const int t = h - (eq ? A.match : A.mismatch); // H(i-1,j-1) if this cell came from the diagonal
+                const bool isd = (i == 1 || j == 1) ? (t == borderH(i - 1, j - 1))
+                                                    : (lowG(i - 1, j - 1) == ((unsigned)(t + gogo) & 0xffu));
+                if (isd) { // include/SAGlobalGotoh.h:286
+                    slot[--k] = 0;
+                    i--; j--;
+                    h = t;
+                    continue;
+                }
+            }
+            if (lowX(i, j) == ((unsigned)h & 0xffu)) { // H == Ix (:355), before H == Iy (:411)
+                state = 1;
+                x = h;
+            } else {
+                state = 2;
+                y = h;
+            }
+        }
+        if (state == 1) {
+            slot[--k] = 1;
+            const bool ext = (i == 1) ? (x == PKG_NEG + ge) : (lowX(i - 1, j) == ((unsigned)(x - ge) & 0xffu)); // :336 before :344
+            if (ext) {
+                x -= ge;
+            } else {
+                h = x - gogo;
+                state = 0;
+            }
+            i--;
+        } else {
+            slot[--k] = 2;
+            const bool ext = (j == 1) ? (y == PKG_NEG + ge) : (lowY(i, j - 1) == ((unsigned)(y - ge) & 0xffu)); // :394 before :402
+            if (ext) {
+                y -= ge;
+            } else {
+                h = y - gogo;
+                state = 0;
+            }
+            j--;
+        }
+    }
+    A.start_i[p] = (uint32_t)i;
+    A.start_j[p] = (uint32_t)j;
+    A.slot_start[p] = (uint32_t)k;
+    A.ops_len[p] = (uint32_t)(M + N - k);
+}

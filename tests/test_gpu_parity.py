@@ -107,6 +107,28 @@ def test_config2_shape_150bp(gpu_lib, algo):
         assert np.array_equal(res.pair_ops(p), o["ops"]), p
 
 
+@pytest.mark.parametrize("algo,sc", [("ggotoh", S.affine(-3, -1, 1, -1)), ("lgotoh", S.affine(-3, -1, 1, -1)),
+                                     ("ggotoh", S.affine(-3, -1, 1, -1, False)), ("lgotoh", S.affine(-3, -1, 1, -1, False))])
+def test_config3_shape_250bp(gpu_lib, algo, sc):
+    """6,000 pairs of the BASELINE config-3 workload (250 bp, Gotoh (-3,-1,1,-1), + the AllowMismatch=false variant)
+    through the packed affine kernels vs the oracle."""
+    n = 6000 if sc.allow else 2000
+    ctx = capi.Ctx(gpu_lib)
+    ctx.generate(scoring_to_params(algo, sc), synth.SEED, 7_000_000, n, 0, 250, 250)
+    ctx.run()
+    res = ctx.download(ops_capacity=n * 500)
+    assert ctx.last_kernel().startswith("pkg_fill")
+    bases, off1, off2, l1, l2 = ctx.download_inputs(n * 500)
+    for p in range(n):
+        a = bytes(bases[int(off1[p]):int(off1[p]) + 250]).decode()
+        b = bytes(bases[int(off2[p]):int(off2[p]) + 250]).decode()
+        o = orc.oracle_align(algo, sc, a, b)
+        assert int(res.score[p]) == o["score"], p
+        assert (int(res.start_i[p]), int(res.start_j[p]), int(res.end_i[p]), int(res.end_j[p])) == \
+            (o["start_i"], o["start_j"], o["end_i"], o["end_j"]), p
+        assert np.array_equal(res.pair_ops(p), o["ops"]), p
+
+
 def _rescore_all(bases, off1, off2, res, n, gap, match, mismatch):
     """Vectorised re-scoring of every alignment of a batch from its ops (linear gaps)."""
     ops_len = res.ops_len[:n].astype(np.int64)
