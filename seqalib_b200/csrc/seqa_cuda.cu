@@ -268,7 +268,7 @@ bool packed_shape_ok(const seqa_params &p, uint32_t M, uint32_t N)
         const int64_t unit = -(int64_t)(p.gap_open + p.gap_extend) + p.match + (p.allow_mismatch ? -p.mismatch : 0);
         return (int64_t)(M + N + 2 * PK_R + 2) * unit < 9000;
     }
-    if (M == 0 || N == 0 || M > PK_MAX_LEN || N > PK_MAX_LEN) return false;
+    if (M == 0 || N == 0 || M > PKG_MAX_LEN || N > PKG_MAX_LEN) return false;
     const int64_t g = -p.gap, m = p.match;
     const int64_t lo = (int64_t)(M + N + 2 * PK_R + 2) * g + 300, hi = (int64_t)std::min(M, N) * m + 300;
     return lo < 30000 && hi < 30000;
@@ -364,9 +364,10 @@ int build_plan(seqa_ctx *c)
         if (!uniform) {
             const std::vector<uint32_t> &l1 = c->hlen1, &l2 = c->hlen2;
             std::sort(pkl.begin(), pkl.end(), [&](uint32_t a, uint32_t b) {
+                // largest first: the fill kernels hand jobs out through a ticket counter
                 const uint32_t ka = (l1[a] + PK_R - 1) / PK_R, kb = (l1[b] + PK_R - 1) / PK_R;
-                if (ka != kb) return ka < kb;
-                if (l2[a] != l2[b]) return l2[a] < l2[b];
+                if (ka != kb) return ka > kb;
+                if (l2[a] != l2[b]) return l2[a] > l2[b];
                 return a < b;
             });
         }
@@ -544,15 +545,18 @@ int run_packed(seqa_ctx *c, bool want_walk)
     const bool affine = packed_affine(c->prm);
     const bool local = c->prm.algo == SEQA_SW || c->prm.algo == SEQA_LOCAL_GOTOH;
     const int tb = packed_trace_bits(c->prm);
-    const size_t smem = affine ? 0 : (size_t)c->pk_max_nw * PK_BLOCK * 4;
+    const bool gb = !affine && c->pk_max_nw > PK_MAX_LEN; // strip boundaries in global memory
+    const size_t smem = (affine || gb) ? 0 : (size_t)c->pk_max_nw * PK_BLOCK * 4;
     if (smem > c->smem_optin) return fail(SEQA_ERR_UNSUPPORTED, "internal: packed kernel shared memory %zu", smem);
-    CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem) {
+        CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const int bps = affine ? 2 : (int)std::max<size_t>(1, std::min<size_t>(3, (c->smem_optin + 1024) / std::max<size_t>(smem + 1024, 1)));
-    const uint64_t bound_stride = (uint64_t)((c->pk_max_nw + 3) / 4) * 64;
-    if (affine) CKS(c->pk_bound.ensure((size_t)c->sms * bps * (PK_BLOCK / 32) * bound_stride));
+    const uint64_t bound_stride = (uint64_t)((c->pk_max_nw + 3) / 4) * (affine ? 64 : 32);
+    if (affine || gb) CKS(c->pk_bound.ensure((size_t)c->sms * bps * (PK_BLOCK / 32) * bound_stride));
     CK(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 4, c->stream));
     for (const Chunk &ch : c->pk_chunks) {
         const uint32_t nj = ch.hi - ch.lo;
@@ -596,6 +600,8 @@ int run_packed(seqa_ctx *c, bool want_walk)
         A.prof_bias = affine ? c->prm.gap_open + c->prm.gap_extend : 0;
         A.bound = c->pk_bound.p;
         A.bound_stride = bound_stride;
+        A.ticket = reinterpret_cast<uint32_t *>(c->flags.p + 1);
+        CK(cudaMemsetAsync(c->flags.p + 1, 0, sizeof(int), c->stream));
         const unsigned wpb = PK_BLOCK / 32;
         const unsigned full = (nj + wpb - 1) / wpb;
         const unsigned grid = std::min<unsigned>(full, (unsigned)(c->sms * bps));
@@ -605,14 +611,22 @@ int run_packed(seqa_ctx *c, bool want_walk)
             LAUNCH(c, (pkg_fill_kernel<true, PK_R>), grid, PK_BLOCK, 0, A);
         else if (affine)
             LAUNCH(c, (pkg_fill_kernel<false, PK_R>), grid, PK_BLOCK, 0, A);
+        else if (gb && local && tb == 4)
+            LAUNCH(c, (pk_fill_kernel<true, PK_R, 4, true>), grid, PK_BLOCK, 0, A);
+        else if (gb && local)
+            LAUNCH(c, (pk_fill_kernel<true, PK_R, 8, true>), grid, PK_BLOCK, 0, A);
+        else if (gb && tb == 4)
+            LAUNCH(c, (pk_fill_kernel<false, PK_R, 4, true>), grid, PK_BLOCK, 0, A);
+        else if (gb)
+            LAUNCH(c, (pk_fill_kernel<false, PK_R, 8, true>), grid, PK_BLOCK, 0, A);
         else if (local && tb == 4)
-            LAUNCH(c, (pk_fill_kernel<true, PK_R, 4>), grid, PK_BLOCK, smem, A);
+            LAUNCH(c, (pk_fill_kernel<true, PK_R, 4, false>), grid, PK_BLOCK, smem, A);
         else if (local)
-            LAUNCH(c, (pk_fill_kernel<true, PK_R, 8>), grid, PK_BLOCK, smem, A);
+            LAUNCH(c, (pk_fill_kernel<true, PK_R, 8, false>), grid, PK_BLOCK, smem, A);
         else if (tb == 4)
-            LAUNCH(c, (pk_fill_kernel<false, PK_R, 4>), grid, PK_BLOCK, smem, A);
+            LAUNCH(c, (pk_fill_kernel<false, PK_R, 4, false>), grid, PK_BLOCK, smem, A);
         else
-            LAUNCH(c, (pk_fill_kernel<false, PK_R, 8>), grid, PK_BLOCK, smem, A);
+            LAUNCH(c, (pk_fill_kernel<false, PK_R, 8, false>), grid, PK_BLOCK, smem, A);
         cudaEventRecord(next_event(c), c->stream);
         if (want_walk) {
             // walk positions are chunk-relative: perm/jobs pointers advanced to the chunk

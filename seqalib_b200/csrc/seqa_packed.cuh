@@ -56,9 +56,18 @@ struct PkArgs {
     // affine kernels (seqa_packed_affine.cuh)
     int go, ge;
     int prof_bias;         // subtracted from every profile score (affine: GapOpen + GapExtend)
-    uint4 *bound;          // per-warp strip boundary rows
+    uint4 *bound;          // per-warp strip boundary rows (kernels that keep them in global memory)
     uint64_t bound_stride; // uint4 per warp
+    uint32_t *ticket;      // job counter: warps draw jobs (largest first) instead of striding over them
 };
+
+// next job of this warp: dynamic (ticket) so that ragged batches, sorted largest-first, balance across warps
+__device__ __forceinline__ uint32_t pk_next_job(const PkArgs &A, int lane)
+{
+    uint32_t w = 0;
+    if (lane == 0) w = atomicAdd(A.ticket, 1u);
+    return __shfl_sync(SEQA_FULL, w, 0);
+}
 
 // 2-bit code of an upper-case DNA letter: A0 C1 T2 G3 ((c>>1)&3); valid only for the four letters.
 __device__ __forceinline__ unsigned pk_code(unsigned c) { return (c >> 1) & 3u; }
@@ -155,7 +164,9 @@ __device__ __forceinline__ void pk_store_stream(uint4 *p, uint4 v) { __stcs(p, v
 __device__ __forceinline__ void pk_store_stream(uint2 *p, uint2 v) { __stcs(p, v); }
 #endif
 
-template <bool LOCAL, int R, int TB>
+// GB = false: the strip boundary row lives in shared memory (pairs up to 320 columns); GB = true: in a per-warp
+// global (L2-resident) row, read one column group ahead -- any length whose scores fit 16 bits.
+template <bool LOCAL, int R, int TB, bool GB>
 __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
 {
     static_assert(R % 2 == 0, "R must be even");
@@ -164,9 +175,11 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
     constexpr int RP = R / 2;
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
     const unsigned gap2 = pk_dup(A.gap);
-    for (uint32_t w = gw; w < A.njobs; w += nw) {
+    uint4 *__restrict__ bnd = A.bound + (uint64_t)gw * A.bound_stride + lane; // GB: [cg][lane] x 4 columns
+    for (;;) {
+        const uint32_t w = pk_next_job(A, lane);
+        if (w >= A.njobs) break;
         const PkWarpJob J = A.jobs[w];
         const uint32_t p0 = A.perm[J.first + 2 * lane], p1 = A.perm[J.first + 2 * lane + 1];
         const int M0 = p0 == PK_NULL ? 0 : (int)A.len1[p0], N0 = p0 == PK_NULL ? 0 : (int)A.len2[p0];
@@ -178,9 +191,11 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
         int best0 = 0, best1 = 0, bi0 = 0, bi1 = 0; // SW: running (max, last row holding it)
         int corner0 = 0, corner1 = 0;               // NW: H(M,N)
         // row 0 of the matrix = first strip's upper boundary (SW 0, NW j*gap: include/SANeedlemanWunsch.h:61-62)
-        for (int jj = 0; jj < Nw; jj++) top[jj * PK_BLOCK + tid] = LOCAL ? 0u : pk_dup((jj + 1) * A.gap);
+        if (!GB)
+            for (int jj = 0; jj < Nw; jj++) top[jj * PK_BLOCK + tid] = LOCAL ? 0u : pk_dup((jj + 1) * A.gap);
         for (int s = 0; s < (int)J.nstrips; s++) {
             const int i0 = s * R;
+            const bool first = s == 0, keep = s + 1 < (int)J.nstrips;
             unsigned H[R], sel[R], rmax[R];
 #pragma unroll
             for (int r = 0; r < R; r++) {
@@ -191,15 +206,28 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
             unsigned diag = LOCAL ? 0u : pk_dup(i0 * A.gap);
             uint8_t *__restrict__ tr = trace + (uint64_t)s * Ng * (R * TB / 16 * 512);
             uint4 na = prof[0], nb = prof[1]; // profile of the next group: {T0,T1} x 4 columns
+            uint4 nu = make_uint4(0, 0, 0, 0);  // GB: boundary of the next group
+            if (GB && !first) nu = bnd[0];
             for (int cg = 0; cg < Ng; cg++) {
-                const uint4 ca = na, cb = nb;
+                const uint4 ca = na, cb = nb, cu = nu;
                 if (cg + 1 < Ng) {
                     na = prof[(uint64_t)(cg + 1) * 64];
                     nb = prof[(uint64_t)(cg + 1) * 64 + 1];
+                    if (GB && !first) nu = bnd[(uint64_t)(cg + 1) * 32];
                 }
                 unsigned up[4];
+                if (GB) {
+                    if (first) { // matrix row 0 (SW 0, NW j*gap: include/SANeedlemanWunsch.h:61-62)
 #pragma unroll
-                for (int c = 0; c < 4; c++) up[c] = (cg * 4 + c < Nw) ? top[(cg * 4 + c) * PK_BLOCK + tid] : 0u; // padded columns: no boundary
+                        for (int c = 0; c < 4; c++) up[c] = LOCAL ? 0u : pk_dup((cg * 4 + c + 1) * A.gap);
+                    } else {
+                        up[0] = cu.x; up[1] = cu.y; up[2] = cu.z; up[3] = cu.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) up[c] = (cg * 4 + c < Nw) ? top[(cg * 4 + c) * PK_BLOCK + tid] : 0u; // padded columns: no boundary
+                }
+                unsigned bot[4];
                 unsigned W[RP][TB == 8 ? 4 : 2];
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
@@ -228,7 +256,10 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                         hd = hold;
                         if (LOCAL && (c & 1)) rmax[r] = __vimax3_s16x2(rmax[r], hold, hn);
                     }
-                    if (cg * 4 + c < Nw) top[(cg * 4 + c) * PK_BLOCK + tid] = hu;
+                    if (GB)
+                        bot[c] = hu;
+                    else if (cg * 4 + c < Nw)
+                        top[(cg * 4 + c) * PK_BLOCK + tid] = hu;
                     if (!LOCAL) {
                         const int j = cg * 4 + c + 1;
                         if (j == N0 || j == N1) {
@@ -240,6 +271,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                         }
                     }
                 }
+                if (GB && keep) bnd[(uint64_t)cg * 32] = make_uint4(bot[0], bot[1], bot[2], bot[3]);
                 if (TB == 8) {
                     uint4 *dst = reinterpret_cast<uint4 *>(tr + (uint64_t)cg * (RP * 32 * 16));
 #pragma unroll

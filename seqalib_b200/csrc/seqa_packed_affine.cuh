@@ -37,11 +37,12 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
     constexpr int RP = R / 2, RH = R / 8;
     const int lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
     const int gogo = A.go + A.ge;
     const unsigned ge2 = pk_dup(A.ge), gogo2 = pk_dup(gogo), neg2 = pk_dup(PKG_NEG);
     uint4 *__restrict__ bnd = A.bound + (uint64_t)gw * A.bound_stride + lane * 2; // [cg][lane][{G,Ix} x 4 columns]
-    for (uint32_t w = gw; w < A.njobs; w += nw) {
+    for (;;) {
+        const uint32_t w = pk_next_job(A, lane);
+        if (w >= A.njobs) break;
         const PkWarpJob J = A.jobs[w];
         const uint32_t p0 = A.perm[J.first + 2 * lane], p1 = A.perm[J.first + 2 * lane + 1];
         const int M0 = p0 == PK_NULL ? 0 : (int)A.len1[p0], N0 = p0 == PK_NULL ? 0 : (int)A.len2[p0];

@@ -71,8 +71,8 @@ def main():
     run(lib, "config2 NW 150bp", "nw", S.linear(-1, 2, -1), int(1_000_000 * scale), 0, 150, 150, 20000)
     run(lib, "config3 GlobalGotoh 250bp", "ggotoh", S.affine(-3, -1, 1, -1), int(200_000 * scale), 0, 250, 250, 8000)
     run(lib, "config3 LocalGotoh 250bp", "lgotoh", S.affine(-3, -1, 1, -1), int(200_000 * scale), 0, 250, 250, 8000)
-    run(lib, "config5 mixed 50-1000bp NW", "nw", S.linear(-1, 2, -1), int(100_000 * scale), 1, 0, 0, 2000)
-    run(lib, "config5 mixed 50-1000bp SW", "sw", S.linear(-1, 1, -1), int(100_000 * scale), 1, 0, 0, 2000)
+    run(lib, "config5 mixed 50-1000bp NW", "nw", S.linear(-1, 2, -1), int(500_000 * scale), 1, 0, 0, 2000)
+    run(lib, "config5 mixed 50-1000bp SW", "sw", S.linear(-1, 1, -1), int(500_000 * scale), 1, 0, 0, 2000)
     run(lib, "config4 Hirschberg 20kbp x16", "hirschberg", S.linear(-1, 2, -1), 16, 0, 20000, 20000, 0, reps=1)
     run(lib, "config4 MyersMiller 20kbp x16", "myersmiller", S.affine(-3, -1, 1, -1), 16, 0, 20000, 20000, 0, reps=1)
     run(lib, "config4 Hirschberg 100kbp x8", "hirschberg", S.linear(-1, 2, -1), 8, 0, 100000, 100000, 0, reps=1)
