@@ -27,6 +27,7 @@
 // search skips column N (include/SAHirschberg.h:141) and MyersMillerSA's M == 1 leaf is not the textbook one
 // (include/SAMyersMiller.h:75-160): both are sub-optimal in a specific way that has to be reproduced.
 #pragma once
+#include <type_traits>
 #include <vector>
 #include "seqa_common.cuh"
 #include "seqa_wavefront.cuh"
@@ -155,11 +156,16 @@ __device__ void hb_leaf_thin(const DevScoring &sc, const uint8_t *a, int m, cons
 
 // ---- one row block of a score-only sweep -----------------------------------------------------------------------
 // Rows [rb*32R, rb*32R + 32R) of an m x n sweep, all n columns, on one warp.  Lane l owns R consecutive rows; at
-// step t it computes column t - l + 1.  Lane 0 takes the row above the block from `inH/inX` (published by the task
-// of row block rb-1; staged 32 columns at a time through shared memory, one chunk ahead) or from the sweep's
-// border; lane 31's bottom row goes out through shared memory in coalesced 32-column pieces, followed by the
-// progress counter.  PARTIAL: rows >= m pass the value above them through unchanged, so the sweep's last row
-// arrives at lane 31 like any other bottom row.
+// step t it computes column t - l + 1.  Columns are taken in chunks of 32 steps.  At the start of a chunk the warp
+// stages, in shared memory, the row above the block for the chunk's 32 columns (from the border for rb == 0, else
+// from `inH/inX`, published by the task of row block rb-1 and fetched one chunk ahead) and the chunk's 32 column
+// symbols (one coalesced load); lane 0 reads its upper neighbour from there, every lane its column symbol.  Lane
+// 31's bottom row leaves through shared memory in coalesced 32-column pieces, followed by the progress counter.
+// Chunks in which every lane is inside the matrix for all 32 steps run a branch-free step.
+// PARTIAL: rows >= m pass the value above them through unchanged, so the sweep's last row arrives at lane 31 like
+// any other bottom row.
+#define LS_SMEM_INTS 192 /* per warp: inH[32] inX[32] outH[32] outX[32] sym[64] */
+
 template <bool AFFINE, int R, bool PARTIAL>
 __device__ __forceinline__ void ls_block(const DevScoring &sc, const Borders &bd, const uint8_t *__restrict__ a, int m,
                                          const uint8_t *__restrict__ b, int n, bool rev, int rb,
@@ -169,19 +175,20 @@ __device__ __forceinline__ void ls_block(const DevScoring &sc, const Borders &bd
     const int lane = threadIdx.x & 31;
     const int row0 = rb * (32 * R) + lane * R; // rows above my strip
     const int nact = PARTIAL ? min(max(m - row0, 0), R) : R;
-    const int gogo = sc.go + sc.ge;
+    const int gap = sc.gap, ge = sc.ge, gogo = sc.go + sc.ge, match = sc.match;
     const int simx = sc.allow ? sc.mismatch : LS_NEG;
     int ab[R], h[R], f[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int i = row0 + r + 1;
-        ab[r] = (r < nact) ? (int)(rev ? a[m - i] : a[i - 1]) : 0;
+        ab[r] = (r < nact) ? (int)(rev ? a[m - i] : a[i - 1]) : 0x100; // 0x100 never equals a symbol
         h[r] = bd.hcolA + i * bd.hcolB;
         f[r] = AFFINE ? bd.iyA + i * bd.iyB : 0;
     }
     int diag_top = border_hcol(bd, row0);
     int send_h = 0, send_x = 0;
-    int *smInH = sm, *smInX = sm + 32, *smOutH = sm + 64, *smOutX = sm + 96;
+    int *smInH = sm, *smInX = sm + 32, *smOutH = sm + 64, *smOutX = sm + 96, *smSym = sm + 128;
+    const int *mySym = smSym + 32 - lane; // mySym[s] = symbol of column t0 + s - lane + 1
     const int nsteps = n + 31;
     int nextH = 0, nextX = 0, known = 0;
     auto wait_for = [&](int need) { // until the producer has published `need` columns
@@ -195,6 +202,80 @@ __device__ __forceinline__ void ls_block(const DevScoring &sc, const Borders &bd
             known = __shfl_sync(SEQA_FULL, known, 0);
         }
     };
+    auto flush = [&](int j31) { // columns ((j31-1) & ~31) + 1 .. j31 of the bottom row leave the warp
+        __syncwarp();
+        const int base = (j31 - 1) & ~31;
+        if (lane < j31 - base) {
+            outH[base + 1 + lane] = smOutH[lane];
+            if (AFFINE) outX[base + 1 + lane] = smOutX[lane];
+        }
+        if (out_prog) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) ls_st_volatile(out_prog, j31);
+        } else {
+            __syncwarp();
+        }
+    };
+    // one anti-diagonal step; CHECK = lanes may be outside the matrix (first / last chunks)
+    auto step = [&](auto chk, int s, int t0) {
+        constexpr bool CHECK = decltype(chk)::value;
+        int up_h = __shfl_up_sync(SEQA_FULL, send_h, 1);
+        int up_x = AFFINE ? __shfl_up_sync(SEQA_FULL, send_x, 1) : 0;
+        const int bh = smInH[s], bx = AFFINE ? smInX[s] : 0;
+        if (lane == 0) {
+            up_h = bh;
+            up_x = bx;
+        }
+        const int j = t0 + s - lane + 1;
+        if (!CHECK || (j >= 1 && j <= n)) {
+            const int bj = mySym[s];
+            int dg = diag_top, uh = up_h, ux = up_x;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int left = h[r];
+                const int sim = (ab[r] == bj) ? match : simx;
+                int hv, ix = ux;
+                if (!AFFINE) {
+                    const int tl = __viaddmax_s32(dg, sim, left + gap); // max(D, L)
+                    hv = __viaddmax_s32(uh, gap, tl);                  // max(U, .)
+                } else {
+                    ix = __viaddmax_s32(uh, gogo, ux + ge);
+                    const int iy = __viaddmax_s32(left, gogo, f[r] + ge);
+                    hv = __viaddmax_s32(dg, sim, max(ix, iy));
+                    f[r] = iy;
+                }
+                if (PARTIAL && r >= nact) { // below the sweep: hand the last row down
+                    hv = uh;
+                    ix = ux;
+                }
+                dg = left;
+                uh = hv;
+                ux = ix;
+                h[r] = hv;
+            }
+            diag_top = up_h;
+            send_h = uh;
+            send_x = ux;
+        }
+        // lane 31 has just finished column j31 = t0 + s - 30; its slot in the outgoing piece is (j31 - 1) & 31
+        if (!CHECK) {
+            if (lane == 31) {
+                smOutH[(s + 1) & 31] = send_h;
+                if (AFFINE) smOutX[(s + 1) & 31] = send_x;
+            }
+            if (s == 30) flush(t0);
+        } else {
+            const int j31 = t0 + s - 30;
+            if (j31 >= 1 && j31 <= n) {
+                if (lane == 31) {
+                    smOutH[(j31 - 1) & 31] = send_h;
+                    if (AFFINE) smOutX[(j31 - 1) & 31] = send_x;
+                }
+                if (((j31 - 1) & 31) == 31 || j31 == n) flush(j31);
+            }
+        }
+    };
     if (rb > 0) {
         wait_for(min(32, n));
         const int jj = 1 + lane;
@@ -203,89 +284,32 @@ __device__ __forceinline__ void ls_block(const DevScoring &sc, const Borders &bd
             if (AFFINE) nextX = ls_ldcg(inX + jj);
         }
     }
+    smSym[32 + lane] = 0x200;
     for (int t0 = 0; t0 < nsteps; t0 += 32) {
-        if (rb > 0) {
-            __syncwarp();
-            smInH[lane] = nextH;
-            if (AFFINE) smInX[lane] = nextX;
+        __syncwarp();
+        {
+            const int jj = t0 + 1 + lane; // stage the row above and the symbols of columns t0+1 .. t0+32
+            smInH[lane] = rb > 0 ? nextH : border_hrow(bd, jj);
+            if (AFFINE) smInX[lane] = rb > 0 ? nextX : bd.ixA + jj * bd.ixB;
+            const int prev = smSym[32 + lane];
+            smSym[lane] = prev;
+            smSym[32 + lane] = (jj <= n) ? (int)(rev ? b[n - jj] : b[jj - 1]) : 0x200;
             const int base = t0 + 32;
-            if (base < n) { // boundary of the next chunk, one chunk ahead of its use
+            if (rb > 0 && base < n) { // boundary of the next chunk, one chunk ahead of its use
                 wait_for(min(base + 32, n));
-                const int jj = base + 1 + lane;
-                if (jj <= n) {
-                    nextH = ls_ldcg(inH + jj);
-                    if (AFFINE) nextX = ls_ldcg(inX + jj);
+                if (jj + 32 <= n) {
+                    nextH = ls_ldcg(inH + jj + 32);
+                    if (AFFINE) nextX = ls_ldcg(inX + jj + 32);
                 }
             }
-            __syncwarp();
         }
-        const int send = min(32, nsteps - t0);
-        for (int s = 0; s < send; s++) {
-            const int t = t0 + s;
-            int up_h = __shfl_up_sync(SEQA_FULL, send_h, 1);
-            int up_x = AFFINE ? __shfl_up_sync(SEQA_FULL, send_x, 1) : 0;
-            const int j = t - lane + 1;
-            if (lane == 0) {
-                if (rb > 0) {
-                    up_h = smInH[s];
-                    if (AFFINE) up_x = smInX[s];
-                } else {
-                    up_h = border_hrow(bd, j);
-                    if (AFFINE) up_x = bd.ixA + j * bd.ixB;
-                }
-            }
-            if (j >= 1 && j <= n) {
-                const int bj = (int)(rev ? b[n - j] : b[j - 1]);
-                int dg = diag_top, uh = up_h, ux = up_x;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    const int left = h[r];
-                    const int sim = (ab[r] == bj) ? sc.match : simx;
-                    int hv, ix = ux;
-                    if (!AFFINE) {
-                        const int tl = __viaddmax_s32(dg, sim, left + sc.gap); // max(D, L)
-                        hv = __viaddmax_s32(uh, sc.gap, tl);                  // max(U, .)
-                    } else {
-                        ix = __viaddmax_s32(uh, gogo, ux + sc.ge);
-                        const int iy = __viaddmax_s32(left, gogo, f[r] + sc.ge);
-                        hv = __viaddmax_s32(dg, sim, max(ix, iy));
-                        if (!PARTIAL || r < nact) f[r] = iy;
-                    }
-                    if (PARTIAL && r >= nact) { // below the sweep: hand the last row down
-                        hv = uh;
-                        ix = ux;
-                    }
-                    dg = left;
-                    uh = hv;
-                    ux = ix;
-                    h[r] = hv;
-                }
-                diag_top = up_h;
-                send_h = uh;
-                send_x = ux;
-            }
-            const int j31 = t - 30; // the column lane 31 has just finished
-            if (j31 >= 1 && j31 <= n) {
-                if (lane == 31) {
-                    smOutH[(j31 - 1) & 31] = send_h;
-                    if (AFFINE) smOutX[(j31 - 1) & 31] = send_x;
-                }
-                if (((j31 - 1) & 31) == 31 || j31 == n) {
-                    __syncwarp();
-                    const int base = (j31 - 1) & ~31;
-                    if (lane < j31 - base) {
-                        outH[base + 1 + lane] = smOutH[lane];
-                        if (AFFINE) outX[base + 1 + lane] = smOutX[lane];
-                    }
-                    if (out_prog) {
-                        __threadfence();
-                        __syncwarp();
-                        if (lane == 0) ls_st_volatile(out_prog, j31);
-                    } else {
-                        __syncwarp();
-                    }
-                }
-            }
+        __syncwarp();
+        if (t0 >= 32 && t0 + 32 <= n) {
+#pragma unroll 4
+            for (int s = 0; s < 32; s++) step(std::false_type(), s, t0);
+        } else {
+            const int send = min(32, nsteps - t0);
+            for (int s = 0; s < send; s++) step(std::true_type(), s, t0);
         }
     }
     __syncwarp();
@@ -341,7 +365,7 @@ __device__ __forceinline__ void ls_run_task(const LsArgs &A, const LsSweep &S, c
 template <bool MM>
 __global__ void __launch_bounds__(LS_BLOCK) ls_sweep_kernel(LsArgs A)
 {
-    __shared__ int smem[LS_BLOCK / 32][128];
+    __shared__ int smem[LS_BLOCK / 32][LS_SMEM_INTS];
     const int lane = threadIdx.x & 31;
     int *sm = smem[threadIdx.x >> 5];
     const uint32_t ntasks = A.cnt[2];
