@@ -32,6 +32,17 @@ ALG_TRACE_BITS = 2    # algorithmic traceback bits per cell (linea
 METRIC = "GCUPS (score+traceback) batched 150bp SW/NW at 1/2/4/8 B200 vs host CPU"
 
 
+def kernel_traffic(kernel, pairs):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu` capture of this same command
+    (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), scaled by the pair count."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return float(t["dram_bytes_per_launch"]) * pairs / float(t["pairs"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -123,7 +134,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = host_threads()
-    n = max(threads * 600, 2000)  # ~0.3 s per core per step at 0.08 GCUPS/core
+    n = max(threads * 6000, 8000)  # ~1 s per step on all host threads at ~0.15 GCUPS/core
     vals, kind = [], "port"
     for k in range(args.warmup + args.steps):
         g, kind, sec = cpu_reference_gcups(n, threads)
@@ -258,19 +269,25 @@ def run_ours(args):
     cells_per_launch = cells / max(fill_launches, 1)
     achieved = cells_per_launch * W_OPS_PER_CELL / fill_s / 1e12
     trace_alg_bytes = cells_per_launch * ALG_TRACE_BITS / 8 + n * 2 * LEN / 4.0 / max(fill_launches, 1)
+    # what the kernel really issues: 5.25 ALU-pipe warp instructions per TWO cells (seqa_packed.cuh), against the
+    # ALU-pipe ceiling measured by tests/int_peak.py on this pool (63.8 lane-ops/clk/SM, profiles/r01_int_peak.json)
+    alu_ops = cells_per_launch / 2 * 5.25 / fill_s / 1e12
+    alu_peak = 148 * 63.8 * f_clk / 1e12
     roofline = {"bound": "int32_issue", "kernel": kernel, "achieved": achieved, "peak": p_int, "unit": "Tlane-op/s",
-                "frac": achieved / p_int, "traffic": None, "ops_per_cell": W_OPS_PER_CELL,
+                "frac": achieved / p_int, "traffic": kernel_traffic(kernel, n), "ops_per_cell": W_OPS_PER_CELL,
+                "alu_pipe": {"achieved": alu_ops, "peak": alu_peak, "unit": "Tlane-op/s", "frac": alu_ops / alu_peak,
+                             "note": "issued packed instructions (5.25 per 2 cells) vs the measured ALU-pipe rate"},
                 "kernel_ms_per_launch": fill_s * 1e3, "kernel_gcups": cells_per_launch / fill_s / 1e9,
                 "peak_def": "148 SMs x 128 lane-ops/clk x SM clock observed under load (SURVEY.md 8d)",
                 "hbm": {"bound": "hbm", "achieved": trace_alg_bytes / fill_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": trace_alg_bytes / fill_s / 1e9 / hbm_peak, "peak_source": how,
-                        "stored_bytes_per_cell": 1.0 * ((LEN + 15) // 16 * 16) / LEN,
-                        "stored_gbs": cells_per_launch * ((LEN + 15) // 16 * 16) / LEN / fill_s / 1e9}}
+                        "stored_bytes_per_cell": 0.5 * ((LEN + 15) // 16 * 16) * ((LEN + 3) // 4 * 4) / (LEN * LEN),
+                        "stored_gbs": cells_per_launch * 0.5 * ((LEN + 15) // 16 * 16) * ((LEN + 3) // 4 * 4) / (LEN * LEN) / fill_s / 1e9}}
 
     cpu = None
     if world == 1 and not args.no_cpu:
         threads = host_threads()
-        sample_pairs = max(threads * 3000, 4000)
+        sample_pairs = min(n, max(threads * 40000, 50000))  # ~5-15 s of CPU work on all host threads
         g, kind, sec = cpu_reference_gcups(sample_pairs, threads)
         cpu = {"value": g, "unit": "GCUPS", "cores": threads, "kind": kind, "seconds": sec,
                "sample": "first %d pairs of the same workload (same generator/seed)" % sample_pairs}
@@ -281,7 +298,7 @@ def run_ours(args):
             "config": {"workload": "SmithWatermanSA linear gap (-1,1,-1), %d random DNA pairs of %d bp per GPU, score+traceback" % (n, LEN),
                        "pairs_per_gpu": n, "len": LEN, "parallelism": "pairs sharded statically over %d GPU(s), no collective" % world,
                        "l2": "no flush needed: every step streams %.1f GB of trace + %.0f MB of inputs through HBM (L2 is 126 MB)"
-                             % (cells / 1e9 * 16 / 15, tot_bases / 1e6),
+                             % (cells / 1e9 * 0.5 * 16 / 15 * 152 / 150, tot_bases / 1e6),
                        "result_checksum": checksum},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

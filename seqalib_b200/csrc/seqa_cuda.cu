@@ -635,17 +635,17 @@ int run_packed(seqa_ctx *c, bool want_walk)
             // jobs' `first` fields are absolute; the walk indexes perm by position, so rebase via pointer only
             const unsigned wgrid = (unsigned)((Wk.npos + 255) / 256);
             if (affine && local)
-                LAUNCH(c, (pkg_walk_kernel<true>), wgrid, 256, 0, Wk, PK_R);
+                LAUNCH(c, (pkg_walk_kernel<true, PK_R>), wgrid, 256, 0, Wk);
             else if (affine)
-                LAUNCH(c, (pkg_walk_kernel<false>), wgrid, 256, 0, Wk, PK_R);
+                LAUNCH(c, (pkg_walk_kernel<false, PK_R>), wgrid, 256, 0, Wk);
             else if (local && tb == 4)
-                LAUNCH(c, (pk_walk_kernel<true, 4>), wgrid, 256, 0, Wk, PK_R);
+                LAUNCH(c, (pk_walk_kernel<true, 4, PK_R>), wgrid, 256, 0, Wk);
             else if (local)
-                LAUNCH(c, (pk_walk_kernel<true, 8>), wgrid, 256, 0, Wk, PK_R);
+                LAUNCH(c, (pk_walk_kernel<true, 8, PK_R>), wgrid, 256, 0, Wk);
             else if (tb == 4)
-                LAUNCH(c, (pk_walk_kernel<false, 4>), wgrid, 256, 0, Wk, PK_R);
+                LAUNCH(c, (pk_walk_kernel<false, 4, PK_R>), wgrid, 256, 0, Wk);
             else
-                LAUNCH(c, (pk_walk_kernel<false, 8>), wgrid, 256, 0, Wk, PK_R);
+                LAUNCH(c, (pk_walk_kernel<false, 8, PK_R>), wgrid, 256, 0, Wk);
         }
         CK(cudaGetLastError());
     }

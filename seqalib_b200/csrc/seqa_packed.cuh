@@ -74,6 +74,29 @@ __device__ __forceinline__ unsigned pk_code(unsigned c) { return (c >> 1) & 3u; 
 __device__ __forceinline__ bool pk_is_acgt(unsigned c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 
 // ---- prep: column profiles + row selectors ----------------------------------------------------------------
+// Sequences are read as ALIGNED 32-bit words (one load per 4 symbols; a funnel shift restores the pair's own
+// alignment): a warp's lanes read 32 different sequences, so the number of load instructions, not bytes, is the
+// cost.  Words may reach 3 bytes before / after a sequence; `bases` is 4-byte aligned with 16 bytes of slack.
+struct PkSeqReader {
+    const uint32_t *w; // aligned word pointer
+    unsigned sh;       // bit shift of the first symbol inside *w
+    uint32_t carry;
+    __device__ __forceinline__ void init(const uint8_t *base, const uint8_t *p)
+    {
+        const uint64_t o = (uint64_t)(p - base);
+        w = reinterpret_cast<const uint32_t *>(base) + (o >> 2);
+        sh = (unsigned)(o & 3u) * 8u;
+        carry = *w++;
+    }
+    __device__ __forceinline__ uint32_t next4() // the next 4 symbols, first in the low byte
+    {
+        const uint32_t hi = *w++;
+        const uint32_t v = sh ? ((carry >> sh) | (hi << (32u - sh))) : carry;
+        carry = hi;
+        return v;
+    }
+};
+
 __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
 {
     const int lane = threadIdx.x & 31;
@@ -81,35 +104,37 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
     const unsigned mm = A.allow ? ((unsigned)(A.mismatch - A.prof_bias) & 0xffu) : 0x80u; // -128 marks "never" (see header)
     const unsigned mt = (unsigned)(A.match - A.prof_bias) & 0xffu;
+    const unsigned mm4 = mm * 0x01010101u, mx = mt ^ mm;
     for (uint32_t w = gw; w < A.njobs; w += nw) {
         const PkWarpJob J = A.jobs[w];
         const uint32_t p0 = A.perm[J.first + 2 * lane], p1 = A.perm[J.first + 2 * lane + 1];
         const uint32_t M0 = p0 == PK_NULL ? 0u : A.len1[p0], N0 = p0 == PK_NULL ? 0u : A.len2[p0];
         const uint32_t M1 = p1 == PK_NULL ? 0u : A.len1[p1], N1 = p1 == PK_NULL ? 0u : A.len2[p1];
-        const uint8_t *a0 = p0 == PK_NULL ? A.bases : A.bases + A.off1[p0];
-        const uint8_t *b0 = p0 == PK_NULL ? A.bases : A.bases + A.off2[p0];
-        const uint8_t *a1 = p1 == PK_NULL ? A.bases : A.bases + A.off1[p1];
-        const uint8_t *b1 = p1 == PK_NULL ? A.bases : A.bases + A.off2[p1];
+        PkSeqReader a0, b0, a1, b1;
+        a0.init(A.bases, p0 == PK_NULL ? A.bases : A.bases + A.off1[p0]);
+        b0.init(A.bases, p0 == PK_NULL ? A.bases : A.bases + A.off2[p0]);
+        a1.init(A.bases, p1 == PK_NULL ? A.bases : A.bases + A.off1[p1]);
+        b1.init(A.bases, p1 == PK_NULL ? A.bases : A.bases + A.off2[p1]);
         bool bad = false;
         const uint32_t Ng = (J.Nw + 3) >> 2;
         uint4 *pout = reinterpret_cast<uint4 *>(A.prof + J.prof_off) + lane * 2;
         for (uint32_t cg = 0; cg < Ng; cg++) {
+            const uint32_t j0 = cg * 4;
+            const uint32_t w0 = j0 < N0 ? b0.next4() : 0u, w1 = j0 < N1 ? b1.next4() : 0u;
             unsigned t[8];
 #pragma unroll
             for (uint32_t c = 0; c < 4; c++) {
-                const uint32_t j = cg * 4 + c;
+                const uint32_t j = j0 + c;
                 unsigned t0 = 0x80808080u, t1 = 0x80808080u; // padded column: every score -128
                 if (j < N0) {
-                    const unsigned ch = b0[j];
+                    const unsigned ch = (w0 >> (8 * c)) & 0xffu;
                     bad |= !pk_is_acgt(ch);
-                    t0 = mm * 0x01010101u;
-                    t0 = (t0 & ~(0xffu << (8 * pk_code(ch)))) | (mt << (8 * pk_code(ch)));
+                    t0 = mm4 ^ (mx << (8 * pk_code(ch)));
                 }
                 if (j < N1) {
-                    const unsigned ch = b1[j];
+                    const unsigned ch = (w1 >> (8 * c)) & 0xffu;
                     bad |= !pk_is_acgt(ch);
-                    t1 = mm * 0x01010101u;
-                    t1 = (t1 & ~(0xffu << (8 * pk_code(ch)))) | (mt << (8 * pk_code(ch)));
+                    t1 = mm4 ^ (mx << (8 * pk_code(ch)));
                 }
                 t[2 * c] = t0;
                 t[2 * c + 1] = t1;
@@ -118,21 +143,26 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
             pout[(uint64_t)cg * 64 + 1] = make_uint4(t[4], t[5], t[6], t[7]);
         }
         const uint32_t rows = J.nstrips * (uint32_t)R;
-        for (uint32_t i = 0; i < rows; i++) {
-            unsigned c0 = 0, c1 = 0;
-            if (i < M0) {
-                const unsigned c = a0[i];
-                bad |= !pk_is_acgt(c);
-                c0 = pk_code(c);
+        for (uint32_t i0 = 0; i0 < rows; i0 += 4) {
+            const uint32_t w0 = i0 < M0 ? a0.next4() : 0u, w1 = i0 < M1 ? a1.next4() : 0u;
+#pragma unroll
+            for (uint32_t c = 0; c < 4; c++) {
+                const uint32_t i = i0 + c;
+                unsigned c0 = 0, c1 = 0;
+                if (i < M0) {
+                    const unsigned ch = (w0 >> (8 * c)) & 0xffu;
+                    bad |= !pk_is_acgt(ch);
+                    c0 = pk_code(ch);
+                }
+                if (i < M1) {
+                    const unsigned ch = (w1 >> (8 * c)) & 0xffu;
+                    bad |= !pk_is_acgt(ch);
+                    c1 = pk_code(ch);
+                }
+                // nibble0: byte c0 of T0; nibble1: its sign; nibble2: byte 4+c1 (= T1); nibble3: its sign
+                const unsigned sel = c0 | ((8u | c0) << 4) | ((4u | c1) << 8) | ((12u | c1) << 12);
+                A.rowsel[J.rowsel_off + (uint64_t)i * 32 + lane] = sel;
             }
-            if (i < M1) {
-                const unsigned c = a1[i];
-                bad |= !pk_is_acgt(c);
-                c1 = pk_code(c);
-            }
-            // nibble0: byte c0 of T0; nibble1: its sign; nibble2: byte 4+c1 (= T1); nibble3: its sign
-            const unsigned sel = c0 | ((8u | c0) << 4) | ((4u | c1) << 8) | ((12u | c1) << 12);
-            A.rowsel[J.rowsel_off + (uint64_t)i * 32 + lane] = sel;
         }
         if (bad) *A.bad = 1;
     }
@@ -146,7 +176,12 @@ __device__ __forceinline__ int pk_half(unsigned v, int k) { return (int)(int16_t
 // job (Ng = ceil(Nw/4) column groups): 16-byte pieces of PR = 16/TB rows x 4 columns x 2 pairs,
 //   piece(s, cg, rg, lane)  at  trace_off + (((s*Ng + cg)*(R/PR) + rg)*32 + lane) * 16       (rg = r / PR)
 //     TB == 8 (2 rows): byte c*4 + (r%2)*2 + k
-//     TB == 4 (4 rows): byte ((r%4)/2)*8 + (c/2)*4 + (r%2)*2 + k, nibble c%2
+//     TB == 4: the two pairs are separated (two more PRMT per 8 words) so that a piece belongs to ONE pair and covers
+//              8 rows x 4 columns: piece(s, cg, hs, k, lane) at trace_off + ((((s*Ng + cg)*(R/8) + hs)*2 + k)*32 + lane)*16,
+//              word ((r%8)/4)*2 + c/2, byte r%4, nibble c%2.
+//              (Measured alternatives, profiles/r01_notes_walk_layout.md: pair-major 128-byte lines cut the walk's HBM
+//              reads 10.4 -> 6.2 GB but cost the fill more than the walk gains -- scattered stores +41 %, staging
+//              through shared memory costs the third resident CTA.)
 // (c = column inside the group, k = pair half), so that every warp store is one contiguous 512-byte run and a
 // walk step usually stays inside the piece it already holds (thread-major 128-byte lines were measured 2x slower
 // in the fill: 32 lines per store instruction saturate the LSU).
@@ -277,11 +312,18 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
 #pragma unroll
                     for (int rp = 0; rp < RP; rp++) pk_store_stream(&dst[rp * 32], make_uint4(W[rp][0], W[rp][1], W[rp][2], W[rp][3]));
                 } else {
-                    static_assert(TB == 8 || R % 4 == 0, "4-bit trace pieces hold 4 rows");
+                    static_assert(TB == 8 || R % 8 == 0, "4-bit trace pieces hold 8 rows");
                     uint4 *dst = reinterpret_cast<uint4 *>(tr + (uint64_t)cg * (R / 4 * 32 * 16));
 #pragma unroll
-                    for (int rq = 0; rq < R / 4; rq++)
-                        pk_store_stream(&dst[rq * 32], make_uint4(W[2 * rq][0], W[2 * rq][1], W[2 * rq + 1][0], W[2 * rq + 1][1]));
+                    for (int hs = 0; hs < R / 8; hs++) {
+                        // W[rp][cc]: rows (2rp, 2rp+1) x pairs x column pair cc  ->  per pair: 4 rows per word
+                        const unsigned a0 = W[4 * hs][0], a1 = W[4 * hs + 1][0], a2 = W[4 * hs + 2][0], a3 = W[4 * hs + 3][0];
+                        const unsigned b0 = W[4 * hs][1], b1 = W[4 * hs + 1][1], b2 = W[4 * hs + 2][1], b3 = W[4 * hs + 3][1];
+                        pk_store_stream(&dst[(hs * 2 + 0) * 32], make_uint4(seqa_prmt(a0, a1, 0x6420), seqa_prmt(b0, b1, 0x6420),
+                                                                            seqa_prmt(a2, a3, 0x6420), seqa_prmt(b2, b3, 0x6420)));
+                        pk_store_stream(&dst[(hs * 2 + 1) * 32], make_uint4(seqa_prmt(a0, a1, 0x7531), seqa_prmt(b0, b1, 0x7531),
+                                                                            seqa_prmt(a2, a3, 0x7531), seqa_prmt(b2, b3, 0x7531)));
+                    }
                 }
             }
             if (LOCAL) {
@@ -317,8 +359,8 @@ static inline void pk_prefetch_l2_line(const void *) {}
 __device__ __forceinline__ void pk_prefetch_l2_line(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
 
-template <bool LOCAL, int TB>
-__global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A, int R)
+template <bool LOCAL, int TB, int R>
+__global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A)
 {
     const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= A.npos) return;
@@ -331,21 +373,25 @@ __global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A, int R)
     constexpr unsigned MASK = TB == 8 ? 0xffu : 0xfu;
     const uint8_t *a = A.bases + A.off1[p], *b = A.bases + A.off2[p];
     const int gap = A.gap;
-    // 16-byte pieces (PR rows x 4 columns x 2 pairs): index ((s*Ng + cg)*RG + rg)*32 + lane; two of them are kept
-    // in registers (one per row-group parity), so a step usually costs no load at all
-    constexpr int PR = 16 / TB, PRSH = TB == 8 ? 1 : 2;
-    const uint32_t RG = (uint32_t)(R / PR);
+    // 16-byte pieces (TB 8: 2 rows x 4 columns x 2 pairs; TB 4: 8 rows x 4 columns of this pair), see pk_fill_kernel;
+    // two of them are kept in registers (one per row-group parity), so a step usually costs no load at all
+    constexpr int PRSH = TB == 8 ? 1 : 3;
+    const uint32_t RG = (uint32_t)(R >> PRSH);
+    auto pkey = [&](int s, int cg, int r) -> uint32_t {
+        const uint32_t g = ((uint32_t)s * Ng + (uint32_t)cg) * RG + (uint32_t)(r >> PRSH);
+        return (TB == 8 ? g : g * 2u + (uint32_t)half) * 32u + (uint32_t)lane;
+    };
     const uint4 *pieces = reinterpret_cast<const uint4 *>(A.trace + J.trace_off);
     uint4 cv[2];
     uint32_t ck[2] = {0xffffffffu, 0xffffffffu};
     auto pick = [&](const uint4 &v, int r, int c) -> unsigned { // low bits of (row r of the strip, column c of the group)
-        const int wsel = TB == 8 ? c : (((r & 3) >> 1) * 2 + (c >> 1));
+        const int wsel = TB == 8 ? c : (((r & 7) >> 2) * 2 + (c >> 1));
         const unsigned wv = wsel == 0 ? v.x : wsel == 1 ? v.y : wsel == 2 ? v.z : v.w;
-        return (wv >> (((r & 1) * 2 + half) * 8 + (TB == 4 ? (c & 1) * 4 : 0))) & MASK;
+        return (wv >> (TB == 8 ? ((r & 1) * 2 + half) * 8 : (r & 3) * 8 + (c & 1) * 4)) & MASK;
     };
     auto low = [&](int i, int j) -> unsigned { // i >= 1, j >= 1
         const int ii = i - 1, s = ii / R, r = ii - s * R, jj = j - 1;
-        const uint32_t key = (((uint32_t)s * Ng + (uint32_t)(jj >> 2)) * RG + (uint32_t)(r >> PRSH)) * 32u + (uint32_t)lane;
+        const uint32_t key = pkey(s, jj >> 2, r);
         const int e = (r >> PRSH) & 1;
         const bool miss = e == 0 ? (ck[0] != key) : (ck[1] != key);
         if (miss) {
@@ -374,14 +420,20 @@ __global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A, int R)
         if (i >= 1) {
             const int ii = i - 1, s = ii / R, r = ii - s * R;
             const int ng = (N + 3) >> 2;
-            for (int cg = 0; cg < ng; cg++) {
-                const uint4 v = pieces[(((uint32_t)s * Ng + (uint32_t)cg) * RG + (uint32_t)(r >> PRSH)) * 32u + (uint32_t)lane];
+            for (int cg0 = 0; cg0 < ng; cg0 += 4) { // four independent piece loads in flight
+                uint4 v4[4];
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int jj = cg * 4 + c + 1;
-                    if (jj <= N) {
-                        e += sext(pick(v, r, c) - ((unsigned)e & MASK));
-                        if (e == best) bj = jj;
+                for (int u = 0; u < 4; u++) v4[u] = pieces[pkey(s, min(cg0 + u, ng - 1), r)];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int cg = cg0 + u;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const int jj = cg * 4 + c + 1;
+                        if (jj <= N) {
+                            e += sext(pick(v4[u], r, c) - ((unsigned)e & MASK));
+                            if (e == best) bj = jj;
+                        }
                     }
                 }
             }

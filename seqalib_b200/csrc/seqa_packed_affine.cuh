@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
 // ---- walk -------------------------------------------------------------------------------------------------
 // One thread per pair; state machine = reference buildResult (include/SAGlobalGotoh.h:235-422,
 // include/SALocalGotoh.h:275-473).  h / x / y are the EXACT values of H / Ix / Iy at the current cell.
-template <bool LOCAL>
-__global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A, int R)
+template <bool LOCAL, int R>
+__global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
 {
     const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= A.npos) return;
