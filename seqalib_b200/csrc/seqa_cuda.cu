@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -123,7 +124,9 @@ void ls_release(LsState &ls);
 
 struct seqa_ctx {
     int device = 0;
-    cudaStream_t stream = 0;
+    cudaStream_t stream = 0;    // kernels
+    cudaStream_t up = 0, down = 0; // host->device / device->host copies; == stream except inside the pipelined one-shot call
+    cudaEvent_t ev_up = nullptr, ev_run = nullptr; // order the three streams: uploads -> kernels -> downloads
     bool own_stream = false;
     int sms = 0;
     size_t smem_optin = 0;
@@ -133,6 +136,9 @@ struct seqa_ctx {
     Borders bd{};
     uint64_t n = 0, cells = 0, slots_total = 0, bases_len = 0;
     std::vector<uint32_t> hlen1, hlen2;
+    // batch statistics gathered by the one pass over the pairs that the upload makes anyway
+    bool have_stats = false, st_uniform = false;
+    uint64_t st_cells = 0, st_slots = 0;
 
     DBuf<uint8_t> bases;
     DBuf<uint64_t> off1, off2;
@@ -143,9 +149,11 @@ struct seqa_ctx {
     DBuf<uint64_t> slot_off, ops_off;
     DBuf<uint8_t> slots, dense;
     DBuf<uint64_t> tile_sum, total;
-    DBuf<int> flags; // [0] packed path met a non-ACGT base
+    DBuf<int> flags; // [0] packed path met a non-ACGT base, [1] job ticket of the packed fill kernels
+    HBuf<uint64_t> h_tail; // pinned: [0] dense ops bytes of the last run, [1] flags[0]; copied at the end of every run
 
     // packed plan
+    std::vector<uint32_t> pkl; // pairs the packed kernels take (kept between calls: no reallocation)
     HBuf<uint32_t> perm;
     size_t perm_n = 0;
     std::vector<PkWarpJob> jobs; // small: uploaded through jobs_pin
@@ -174,6 +182,7 @@ struct seqa_ctx {
     bool generic_rerun = false;
 
     uint64_t launches = 0;
+    cudaEvent_t dbg_ev[4] = {nullptr, nullptr, nullptr, nullptr}; // SEQA_DEBUG_TIMING: upload start / H2D done / kernels done / D2H done
     std::vector<cudaEvent_t> ev; // pairs of events around the DP fill launches of the last run
     size_t ev_used = 0;
     const char *last_kernel = "none";
@@ -283,6 +292,8 @@ size_t free_budget()
     return (size_t)std::min((double)fr * 0.8, (double)tot * 0.25);
 }
 
+int order_after(seqa_ctx *c, cudaStream_t from, cudaStream_t to);
+
 int build_plan(seqa_ctx *c)
 {
     const uint64_t n = c->n;
@@ -296,13 +307,24 @@ int build_plan(seqa_ctx *c)
     c->lidx.clear();
     c->pk_max_nw = 0;
     c->g_max_n = 0;
-    c->cells = 0;
-    for (uint64_t p = 0; p < n; p++) c->cells += (uint64_t)c->hlen1[p] * c->hlen2[p];
+    if (!c->have_stats) {
+        uint64_t cells = 0, run = 0;
+        bool uni = true;
+        for (uint64_t p = 0; p < n; p++) {
+            cells += (uint64_t)c->hlen1[p] * c->hlen2[p];
+            run += (uint64_t)c->hlen1[p] + c->hlen2[p];
+            uni &= c->hlen1[p] == c->hlen1[0] && c->hlen2[p] == c->hlen2[0];
+        }
+        c->st_cells = cells;
+        c->st_slots = run;
+        c->st_uniform = uni;
+        c->have_stats = true;
+    }
+    c->cells = c->st_cells;
 
     // per-pair op slots: len1+len2 bytes each (an alignment never has more columns); offsets by a device scan
     {
-        uint64_t run = 0;
-        for (uint64_t p = 0; p < n; p++) run += (uint64_t)c->hlen1[p] + c->hlen2[p];
+        const uint64_t run = c->st_slots;
         c->slots_total = run;
         CKS(c->slot_off.ensure(n));
         CKS(c->slots.ensure(run));
@@ -336,7 +358,7 @@ int build_plan(seqa_ctx *c)
         return ls_plan(c->ls, prm, c->hlen1, c->hlen2, c->lidx, prm.algo == SEQA_MYERS_MILLER, c->sms);
     }
     if (prm.algo == SEQA_LOCAL_GOTOH) {
-        for (uint64_t p = 0; p < n; p++) {
+        for (uint64_t p = 0; p < (c->st_uniform ? std::min<uint64_t>(n, 1) : n); p++) {
             const uint32_t M = c->hlen1[p], N = c->hlen2[p];
             if ((M == 314 && N == 288) || (M == 60 && N == 57) || (M == 61 && N == 58))
                 return fail(SEQA_ERR_UNSUPPORTED,
@@ -345,15 +367,24 @@ int build_plan(seqa_ctx *c)
     }
 
     const bool pk = packed_scoring_ok(prm) && !c->generic_rerun;
-    std::vector<uint32_t> pkl;
+    std::vector<uint32_t> &pkl = c->pkl;
+    pkl.clear();
     bool uniform = true;
-    for (uint64_t p = 0; p < n; p++) {
-        const uint32_t M = c->hlen1[p], N = c->hlen2[p];
-        if (pk && packed_shape_ok(prm, M, N)) {
-            if (!pkl.empty() && (M != c->hlen1[pkl[0]] || N != c->hlen2[pkl[0]])) uniform = false;
-            pkl.push_back((uint32_t)p);
-        } else {
-            c->gidx.push_back((uint32_t)p);
+    // uniform batch (every pair the same shape): one eligibility test, identity permutation, identical jobs
+    const bool fast = c->st_uniform && n > 0 && pk && packed_shape_ok(prm, c->hlen1[0], c->hlen2[0]);
+    if (fast) {
+        pkl.resize(n);
+        std::iota(pkl.begin(), pkl.end(), 0u);
+    } else {
+        if (pk) pkl.reserve(n);
+        for (uint64_t p = 0; p < n; p++) {
+            const uint32_t M = c->hlen1[p], N = c->hlen2[p];
+            if (pk && packed_shape_ok(prm, M, N)) {
+                if (!pkl.empty() && (M != c->hlen1[pkl[0]] || N != c->hlen2[pkl[0]])) uniform = false;
+                pkl.push_back((uint32_t)p);
+            } else {
+                c->gidx.push_back((uint32_t)p);
+            }
         }
     }
     if (!c->budget) c->budget = free_budget();
@@ -382,11 +413,16 @@ int build_plan(seqa_ctx *c)
         auto chunk_bytes = [&](uint64_t t, uint64_t q, uint64_t r) { return t + q * 8 + r * 4 + 4096; };
         for (size_t w = 0; w < njobs; w++) {
             uint32_t Mw = 0, Nw = 0;
-            for (int k = 0; k < 64; k++) {
-                const uint32_t p = c->perm.p[w * 64 + k];
-                if (p == PK_NULL) continue;
-                Mw = std::max(Mw, c->hlen1[p]);
-                Nw = std::max(Nw, c->hlen2[p]);
+            if (fast) {
+                Mw = c->hlen1[0];
+                Nw = c->hlen2[0];
+            } else {
+                for (int k = 0; k < 64; k++) {
+                    const uint32_t p = c->perm.p[w * 64 + k];
+                    if (p == PK_NULL) continue;
+                    Mw = std::max(Mw, c->hlen1[p]);
+                    Nw = std::max(Nw, c->hlen2[p]);
+                }
             }
             PkWarpJob &J = c->jobs[w];
             J.first = (uint32_t)(w * 64);
@@ -418,8 +454,8 @@ int build_plan(seqa_ctx *c)
         CKS(c->d_jobs.ensure(c->jobs.size()));
         CKS(c->jobs_pin.ensure(c->jobs.size()));
         std::copy(c->jobs.begin(), c->jobs.end(), c->jobs_pin.p);
-        CK(cudaMemcpyAsync(c->d_perm.p, c->perm.p, c->perm_n * 4, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->d_jobs.p, c->jobs_pin.p, c->jobs.size() * sizeof(PkWarpJob), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_perm.p, c->perm.p, c->perm_n * 4, cudaMemcpyHostToDevice, c->up));
+        CK(cudaMemcpyAsync(c->d_jobs.p, c->jobs_pin.p, c->jobs.size() * sizeof(PkWarpJob), cudaMemcpyHostToDevice, c->up));
     }
 
     // ---- generic jobs: one warp per pair ----
@@ -453,14 +489,25 @@ int build_plan(seqa_ctx *c)
         CKS(c->gdir_pin.ensure(c->gidx.size()));
         std::copy(c->gidx.begin(), c->gidx.end(), c->gidx_pin.p);
         std::copy(c->gdir_off.begin(), c->gdir_off.end(), c->gdir_pin.p);
-        CK(cudaMemcpyAsync(c->d_gidx.p, c->gidx_pin.p, c->gidx.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->d_gdir_off.p, c->gdir_pin.p, c->gidx.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_gidx.p, c->gidx_pin.p, c->gidx.size() * 4, cudaMemcpyHostToDevice, c->up));
+        CK(cudaMemcpyAsync(c->d_gdir_off.p, c->gdir_pin.p, c->gidx.size() * 8, cudaMemcpyHostToDevice, c->up));
     }
     uint64_t need = 16;
     for (auto &ch : c->pk_chunks) need = std::max(need, ch.scratch_bytes);
     for (auto &ch : c->g_chunks) need = std::max(need, ch.scratch_bytes);
     CKS(c->scratch.ensure(need));
+    CKS(order_after(c, c->up, c->stream)); // the run reads perm / jobs
     return SEQA_OK; // everything above is stream-ordered; the host vectors it copies from are ctx members
+}
+
+// work queued on `to` from now on starts after everything queued on `from` so far (no-op for one stream)
+int order_after(seqa_ctx *c, cudaStream_t from, cudaStream_t to)
+{
+    if (from == to) return SEQA_OK;
+    cudaEvent_t e = from == c->stream ? c->ev_run : c->ev_up;
+    CK(cudaEventRecord(e, from));
+    CK(cudaStreamWaitEvent(to, e, 0));
+    return SEQA_OK;
 }
 
 cudaEvent_t next_event(seqa_ctx *c)
@@ -685,6 +732,7 @@ int ctx_set_inputs_common(seqa_ctx *c, const seqa_params *params, uint64_t n)
     c->n = n;
     c->ran = false;
     c->generic_rerun = false;
+    c->have_stats = false;
     set_scoring(c);
     CKS(c->off1.ensure(n));
     CKS(c->off2.ensure(n));
@@ -702,29 +750,46 @@ int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in
         return fail(SEQA_ERR_INVALID, "batch has NULL arrays");
     if (n > 0xfffffff0ull) return fail(SEQA_ERR_UNSUPPORTED, "more than 2^32-16 pairs per device shard");
     CK(cudaSetDevice(c->device));
+    const bool dbgt = getenv("SEQA_DEBUG_TIMING") != nullptr;
+    const auto tu0 = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     CKS(ctx_set_inputs_common(c, params, n));
     c->hlen1.assign(in->len1 + pb, in->len1 + pe);
     c->hlen2.assign(in->len2 + pb, in->len2 + pe);
-    uint64_t lo = UINT64_MAX, hi = 0;
+    uint64_t lo = UINT64_MAX, hi = 0, st_cells = 0, st_slots = 0;
+    bool st_uni = true;
+    const uint32_t M0 = n ? in->len1[pb] : 0, N0 = n ? in->len2[pb] : 0;
     for (uint64_t p = pb; p < pe; p++) {
-        const uint64_t a0 = in->off1[p], a1 = a0 + in->len1[p], b0 = in->off2[p], b1 = b0 + in->len2[p];
+        const uint64_t l1 = in->len1[p], l2 = in->len2[p];
+        const uint64_t a0 = in->off1[p], a1 = a0 + l1, b0 = in->off2[p], b1 = b0 + l2;
         if (a1 > in->bases_len || b1 > in->bases_len)
             return fail(SEQA_ERR_INVALID, "pair %llu reaches past bases_len", (unsigned long long)p);
         lo = std::min(lo, std::min(a0, b0));
         hi = std::max(hi, std::max(a1, b1));
+        st_cells += l1 * l2;
+        st_slots += l1 + l2;
+        st_uni &= l1 == M0 && l2 == N0;
     }
+    c->have_stats = true;
+    c->st_cells = st_cells;
+    c->st_slots = st_slots;
+    c->st_uniform = st_uni;
     if (n == 0 || hi < lo) lo = hi = 0;
     c->bases_len = hi - lo;
     CKS(c->bases.ensure(c->bases_len + 16));
-    if (hi > lo) CK(cudaMemcpyAsync(c->bases.p, in->bases + lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
+    if (hi > lo) CK(cudaMemcpyAsync(c->bases.p, in->bases + lo, hi - lo, cudaMemcpyHostToDevice, c->up));
     if (n) {
-        CK(cudaMemcpyAsync(c->off1.p, in->off1 + pb, n * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->off2.p, in->off2 + pb, n * 8, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->len1.p, in->len1 + pb, n * 4, cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(c->len2.p, in->len2 + pb, n * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->off1.p, in->off1 + pb, n * 8, cudaMemcpyHostToDevice, c->up));
+        CK(cudaMemcpyAsync(c->off2.p, in->off2 + pb, n * 8, cudaMemcpyHostToDevice, c->up));
+        CK(cudaMemcpyAsync(c->len1.p, in->len1 + pb, n * 4, cudaMemcpyHostToDevice, c->up));
+        CK(cudaMemcpyAsync(c->len2.p, in->len2 + pb, n * 4, cudaMemcpyHostToDevice, c->up));
+        CKS(order_after(c, c->up, c->stream)); // the planning kernels read len1/len2/off
         if (lo) LAUNCH(c, (rebase_kernel), (unsigned)((n + 255) / 256), 256, 0, c->off1.p, c->off2.p, n, lo);
     }
-    return build_plan(c);
+    const double t_up = ms_since(tu0);
+    const int rc = build_plan(c);
+    if (dbgt) fprintf(stderr, "[seqa]   upload %.3f ms, plan %.3f ms (%llu pairs)\n", t_up, ms_since(tu0) - t_up, (unsigned long long)n);
+    return rc;
 }
 
 int ctx_run(seqa_ctx *c)
@@ -742,23 +807,40 @@ int ctx_run(seqa_ctx *c)
         CKS(run_generic(c, want_walk));
     }
     CKS(finish_ops(c));
+    CK(cudaEventRecord(c->ev_run, c->stream)); // downloads are ordered behind this (ctx_resolve)
     c->ran = true;
     return SEQA_OK;
 }
 
 // If the packed path met a base outside ACGT its results are void: re-plan everything onto the generic
 // (8-bit compare) kernels and run again.  Called at the first synchronisation point after a run.
+int ctx_fetch_tail(seqa_ctx *c)
+{
+    // what the host must know before it can fetch results (dense ops bytes, the packed path's "bad symbol" flag):
+    // two small copies behind the run, one synchronisation.  Queued here, not at the end of ctx_run: on a download
+    // stream shared by a ring of contexts they would sit in front of an earlier wave's result copies.
+    CKS(c->h_tail.ensure(2));
+    CK(cudaStreamWaitEvent(c->down, c->ev_run, 0));
+    CK(cudaMemcpyAsync(&c->h_tail.p[0], c->total.p, 8, cudaMemcpyDeviceToHost, c->down));
+    CK(cudaMemcpyAsync(&c->h_tail.p[1], c->flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->down));
+    CK(cudaStreamSynchronize(c->down));
+    return SEQA_OK;
+}
+
 int ctx_resolve(seqa_ctx *c)
 {
-    CK(cudaStreamSynchronize(c->stream));
-    if (!c->ran || c->jobs.empty() || c->generic_rerun) return SEQA_OK;
-    int bad = 0;
-    CK(cudaMemcpy(&bad, c->flags.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (!c->ran || c->n == 0) {
+        CK(cudaStreamSynchronize(c->stream));
+        return SEQA_OK;
+    }
+    CKS(ctx_fetch_tail(c));
+    if (c->jobs.empty() || c->generic_rerun) return SEQA_OK;
+    const int bad = (int)(c->h_tail.p[1] & 0xffffffffu);
     if (!bad) return SEQA_OK;
     c->generic_rerun = true;
     CKS(build_plan(c));
     CKS(ctx_run(c));
-    CK(cudaStreamSynchronize(c->stream));
+    CKS(ctx_fetch_tail(c));
     return SEQA_OK;
 }
 
@@ -771,29 +853,27 @@ int ctx_download_into(seqa_ctx *c, seqa_batch_out *out, uint64_t pb, uint64_t op
     *ops_used = 0;
     if (n == 0) return SEQA_OK;
     if (!out || !out->score) return fail(SEQA_ERR_INVALID, "out->score is NULL");
-    CK(cudaMemcpyAsync(out->score + pb, c->score.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (out->end_i) CK(cudaMemcpyAsync(out->end_i + pb, c->end_i.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (out->end_j) CK(cudaMemcpyAsync(out->end_j + pb, c->end_j.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out->score + pb, c->score.p, n * 4, cudaMemcpyDeviceToHost, c->down));
+    if (out->end_i) CK(cudaMemcpyAsync(out->end_i + pb, c->end_i.p, n * 4, cudaMemcpyDeviceToHost, c->down));
+    if (out->end_j) CK(cudaMemcpyAsync(out->end_j + pb, c->end_j.p, n * 4, cudaMemcpyDeviceToHost, c->down));
     if (c->prm.flags & SEQA_FLAG_SCORE_ONLY) {
-        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaStreamSynchronize(c->down));
         return SEQA_OK;
     }
     if (!out->start_i || !out->start_j || !out->end_i || !out->end_j || !out->ops || !out->ops_off || !out->ops_len)
         return fail(SEQA_ERR_INVALID, "output arrays are NULL (only allowed with SEQA_FLAG_SCORE_ONLY)");
-    uint64_t total = 0;
-    CK(cudaMemcpyAsync(&total, c->total.p, 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(out->start_i + pb, c->start_i.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(out->start_j + pb, c->start_j.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(out->ops_len + pb, c->ops_len.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(out->ops_off + pb, c->ops_off.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    const uint64_t total = c->h_tail.p[0]; // valid: ctx_resolve synchronised the stream behind the run
     if (ops_base + total > out->ops_capacity)
         return fail(SEQA_ERR_CAPACITY, "ops_capacity %llu < %llu needed", (unsigned long long)out->ops_capacity,
                     (unsigned long long)(ops_base + total));
-    if (total) CK(cudaMemcpyAsync(out->ops + ops_base, c->dense.p, total, cudaMemcpyDeviceToHost, c->stream));
-    if (ops_base)
-        for (uint64_t p = 0; p < n; p++) out->ops_off[pb + p] += ops_base;
-    CK(cudaStreamSynchronize(c->stream));
+    if (ops_base) { c->launches++; SEQA_LAUNCH((add_base_kernel), (unsigned)((n + 255) / 256), 256, 0, c->down, c->ops_off.p, n, ops_base); }
+    CK(cudaMemcpyAsync(out->start_i + pb, c->start_i.p, n * 4, cudaMemcpyDeviceToHost, c->down));
+    CK(cudaMemcpyAsync(out->start_j + pb, c->start_j.p, n * 4, cudaMemcpyDeviceToHost, c->down));
+    CK(cudaMemcpyAsync(out->ops_len + pb, c->ops_len.p, n * 4, cudaMemcpyDeviceToHost, c->down));
+    CK(cudaMemcpyAsync(out->ops_off + pb, c->ops_off.p, n * 8, cudaMemcpyDeviceToHost, c->down));
+    if (total) CK(cudaMemcpyAsync(out->ops + ops_base, c->dense.p, total, cudaMemcpyDeviceToHost, c->down));
+    if (ops_base) { c->launches++; SEQA_LAUNCH((add_base_kernel), (unsigned)((n + 255) / 256), 256, 0, c->down, c->ops_off.p, n, (uint64_t)0 - ops_base); } // restore: a second download stays valid
+    CK(cudaStreamSynchronize(c->down));
     *ops_used = total;
     return SEQA_OK;
 }
@@ -849,6 +929,12 @@ int seqa_ctx_create(seqa_ctx **out, int device, void *stream)
         }
         c->own_stream = true;
     }
+    c->up = c->down = c->stream;
+    if (cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_run, cudaEventDisableTiming) != cudaSuccess) {
+        delete c;
+        return fail(SEQA_ERR_CUDA, "cudaEventCreate failed");
+    }
     *out = c;
     return SEQA_OK;
 }
@@ -862,11 +948,15 @@ void seqa_ctx_destroy(seqa_ctx *c)
     c->score.release(); c->start_i.release(); c->start_j.release(); c->end_i.release(); c->end_j.release();
     c->ops_len.release(); c->slot_start.release(); c->slot_off.release(); c->ops_off.release();
     c->slots.release(); c->dense.release(); c->tile_sum.release(); c->total.release(); c->flags.release();
-    c->perm.release(); c->jobs_pin.release(); c->gidx_pin.release(); c->gdir_pin.release();
+    c->perm.release(); c->jobs_pin.release(); c->h_tail.release(); c->gidx_pin.release(); c->gdir_pin.release();
     c->d_perm.release(); c->d_jobs.release(); c->pk_bound.release(); c->d_gidx.release(); c->d_gdir_off.release(); c->bound.release();
     c->scratch.release();
     ls_release(c->ls);
     for (auto e : c->ev) cudaEventDestroy(e);
+    if (c->ev_up) cudaEventDestroy(c->ev_up);
+    if (c->ev_run) cudaEventDestroy(c->ev_run);
+    for (auto e : c->dbg_ev)
+        if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -975,9 +1065,17 @@ int seqa_ctx_download_inputs(seqa_ctx *c, char *bases, uint64_t bases_len, uint6
 // Lazily created per-device contexts reused by seqa_cuda_align_batch (device buffers survive between calls;
 // seqa_cuda_trim() frees them).  Up to SEQA_CACHE_SLOTS contexts per device so that the waves of one call can be
 // in flight together; a device whose cached contexts are all busy gets a temporary one.
-#define SEQA_CACHE_SLOTS 4
-#define SEQA_WORKERS 2 /* host threads per device; each double-buffers two contexts */
+#define SEQA_CACHE_SLOTS 8
+#define SEQA_WORKERS 2 /* default host threads per device; each double-buffers two contexts */
+static int env_int(const char *name, int dflt, int lo, int hi)
+{
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    const long x = strtol(v, nullptr, 10);
+    return (int)std::min<long>(hi, std::max<long>(lo, x));
+}
 static std::mutex g_cache_mu;
+static cudaStream_t g_pipe_stream[64][4]; // per device: upload / kernel (even waves) / download / kernel (odd waves) streams of the pipelined one-shot call
 static seqa_ctx *g_cache[64][SEQA_CACHE_SLOTS];
 static bool g_cache_busy[64][SEQA_CACHE_SLOTS];
 
@@ -1052,33 +1150,74 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
 
     // waves: contiguous, ~3e9 cells or 256k pairs each; linear-space pairs (huge sweeps) go one wave per 4e10 cells
     const bool linspace = params->algo == SEQA_HIRSCHBERG || params->algo == SEQA_MYERS_MILLER;
-    const uint64_t wave_cells = linspace ? 40000000000ull : 3000000000ull;
+    const uint64_t wave_cells = linspace ? 40000000000ull : (uint64_t)env_int("SEQA_WAVE_MCELLS", 3000, 10, 100000) * 1000000ull;
     std::vector<uint64_t> wave_lo, wave_slots, wave_cellsum; // first pair; (len1+len2) before the wave; cells of the wave
     uint64_t tot = 0;
     {
         uint64_t acc = 0, slots = 0, cnt = 0;
         // several devices: at least two waves per device even for small batches
-        const uint64_t maxcnt = nd > 1 ? std::min<uint64_t>(262144, std::max<uint64_t>(1, (n + 2 * nd - 1) / (2 * nd))) : 262144;
+        uint64_t maxcnt = nd > 1 ? std::min<uint64_t>(262144, std::max<uint64_t>(1, (n + 2 * nd - 1) / (2 * nd))) : 262144;
+        const uint32_t *l1 = in->len1, *l2 = in->len2;
+        bool uni = true; // every pair the same shape: one cheap pass, then the waves are plain arithmetic
+        {
+            const uint32_t M0 = l1[0], N0 = l2[0];
+            unsigned diff = 0;
+            for (uint64_t p = 0; p < n; p++) diff |= (l1[p] ^ M0) | (l2[p] ^ N0);
+            uni = diff == 0;
+        }
+        // Uniform batch on the packed kernels: cut waves at whole "rounds" of the fill kernel (one 64-pair job per
+        // resident warp), otherwise every wave pays a mostly idle last round.
+        if (uni && !linspace && n > 1 && packed_scoring_ok(*params) && packed_shape_ok(*params, l1[0], l2[0])) {
+            static int sms_cache[64];
+            const int dev = first < 64 ? first : 0;
+            if (!sms_cache[dev]) {
+                cudaDeviceProp prop;
+                if (cudaGetDeviceProperties(&prop, first) == cudaSuccess) sms_cache[dev] = prop.multiProcessorCount;
+                (void)cudaGetLastError();
+            }
+            if (sms_cache[dev] > 0) {
+                const uint64_t per_cta = PK_BLOCK / 32 * 64;
+                const uint64_t cta_per_sm = packed_affine(*params) ? 2 : (l2[0] > PK_MAX_LEN ? 3 : std::max<uint64_t>(1, std::min<uint64_t>(3, (227 * 1024) / ((uint64_t)l2[0] * PK_BLOCK * 4 + 1024))));
+                const uint64_t round = (uint64_t)sms_cache[dev] * cta_per_sm * per_cta;
+                const uint64_t round_cells = round * ((uint64_t)l1[0] * l2[0] + 1);
+                const uint64_t rounds = std::max<uint64_t>(1, (wave_cells + round_cells / 2) / round_cells);
+                if (round * rounds * 2 <= n) maxcnt = std::min<uint64_t>(n, round * rounds);
+            }
+        }
         wave_lo.push_back(0);
         wave_slots.push_back(0);
-        const uint32_t *l1 = in->len1, *l2 = in->len2;
-        for (uint64_t p = 0; p < n; p++) {
-            if (cnt > 0 && (acc >= wave_cells || cnt >= maxcnt)) {
-                wave_lo.push_back(p);
-                wave_slots.push_back(slots);
-                wave_cellsum.push_back(acc);
-                acc = 0;
-                cnt = 0;
+        if (uni) {
+            const uint64_t cells1 = (uint64_t)l1[0] * l2[0] + 1, slots1 = (uint64_t)l1[0] + l2[0];
+            uint64_t per = maxcnt < 262144 ? maxcnt : std::min<uint64_t>(maxcnt, std::max<uint64_t>(1, (wave_cells + cells1 - 1) / cells1));
+            for (uint64_t p = 0; p < n; p += per) {
+                const uint64_t q = std::min(n, p + per);
+                if (p) {
+                    wave_lo.push_back(p);
+                    wave_slots.push_back(p * slots1);
+                }
+                wave_cellsum.push_back((q - p) * cells1);
             }
-            const uint64_t cells = (uint64_t)l1[p] * l2[p] + 1;
-            acc += cells;
-            tot += cells;
-            slots += (uint64_t)l1[p] + l2[p];
-            cnt++;
+            tot = n * cells1;
+            slots = n * slots1;
+        } else {
+            for (uint64_t p = 0; p < n; p++) {
+                if (cnt > 0 && (acc >= wave_cells || cnt >= maxcnt)) {
+                    wave_lo.push_back(p);
+                    wave_slots.push_back(slots);
+                    wave_cellsum.push_back(acc);
+                    acc = 0;
+                    cnt = 0;
+                }
+                const uint64_t cells = (uint64_t)l1[p] * l2[p] + 1;
+                acc += cells;
+                tot += cells;
+                slots += (uint64_t)l1[p] + l2[p];
+                cnt++;
+            }
+            wave_cellsum.push_back(acc);
         }
         wave_lo.push_back(n);
         wave_slots.push_back(slots);
-        wave_cellsum.push_back(acc);
     }
     const size_t nwaves = wave_lo.size() - 1;
     const uint64_t slots_total = wave_slots.back();
@@ -1100,68 +1239,147 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
     const bool dbg = getenv("SEQA_DEBUG_TIMING") != nullptr;
     const auto t_start = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
-    // A worker owns two contexts and software-pipelines its waves: wave k+1 is uploaded and launched before the
-    // worker blocks on wave k, so the device queue never drains while the host packs or downloads.
-    auto worker = [&](int d, int t, int nthreads) {
-        seqa_ctx *c[2] = {nullptr, nullptr};
-        int cached[2] = {-1, -1};
-        int k = 0;
-        long pend = -1;
-        int pk = 0;
-        auto finish = [&](long w, int slot) {
-            const double t2 = since();
-            int s = ctx_resolve(c[slot]);
-            const double t3 = since();
-            if (s == SEQA_OK) s = ctx_download_into(c[slot], out, wave_lo[w], wave_slots[w], &wused[w]);
-            if (dbg) fprintf(stderr, "[seqa] dev %d thr %d wave %ld: wait %.2f..%.2f download ..%.2f ms\n", d, t, w, t2, t3, since());
-            if (s != SEQA_OK) {
-                wstatus[w] = s;
-                werr[w] = g_err;
+    // Per device a PRODUCER thread uploads, plans and launches wave after wave into a ring of contexts (each with its
+    // own stream) and a CONSUMER thread, in the same order, waits for a wave and copies its results out: the host
+    // planning of wave k+1, the kernels of wave k and the device->host copy of wave k-1 overlap, and the device
+    // queue is fed in wave order.
+    const int ring = env_int("SEQA_RING", 3, 2, SEQA_CACHE_SLOTS);
+    const bool one_comp = getenv("SEQA_ONE_COMPUTE_STREAM") != nullptr;
+    struct DevPipe {
+        std::mutex mu;
+        std::condition_variable cv;
+        long produced = 0, consumed = 0;
+        bool stop = false;
+        seqa_ctx *c[SEQA_CACHE_SLOTS] = {};
+        int cached[SEQA_CACHE_SLOTS];
+        cudaStream_t saved[SEQA_CACHE_SLOTS] = {};
+        cudaStream_t st[4] = {}; // shared by the ring: uploads and downloads run in wave order; kernels of even and
+                                 // odd waves go to two streams so that one wave's kernels fill the tail of the previous one's
+    };
+    std::vector<DevPipe> pipes(nd);
+    auto producer = [&](int d) {
+        DevPipe &P = pipes[d];
+        const long nw = (long)(dev_lo[d + 1] - dev_lo[d]);
+        for (long k = 0; k < nw; k++) {
+            const size_t w = dev_lo[d] + (size_t)k;
+            const int slot = (int)(k % ring);
+            {
+                std::unique_lock<std::mutex> lk(P.mu);
+                P.cv.wait(lk, [&] { return P.consumed > k - ring || P.stop; });
+                if (P.stop) break;
             }
-            return s;
-        };
-        bool ok = true;
-        for (size_t w = dev_lo[d] + t; ok && w < dev_lo[d + 1]; w += nthreads) {
             int s = SEQA_OK;
             const double t0 = since();
-            if (!c[k]) s = cache_acquire(first + d, &c[k], &cached[k]);
-            if (s == SEQA_OK) s = ctx_upload_range(c[k], params, in, wave_lo[w], wave_lo[w + 1]);
+            if (!P.c[slot]) {
+                s = cache_acquire(first + d, &P.c[slot], &P.cached[slot]);
+                if (s == SEQA_OK && P.st[0]) {
+                    seqa_ctx *cx = P.c[slot];
+                    P.saved[slot] = cx->stream;
+                    cx->up = P.st[0];
+                    cx->down = P.st[2];
+                }
+            }
+            if (s == SEQA_OK && P.st[0]) P.c[slot]->stream = (k & 1) && !one_comp ? P.st[3] : P.st[1];
+            if (dbg && s == SEQA_OK) {
+                for (auto &e : P.c[slot]->dbg_ev)
+                    if (!e) cudaEventCreate(&e);
+                cudaEventRecord(P.c[slot]->dbg_ev[0], P.c[slot]->stream);
+            }
+            if (s == SEQA_OK) s = ctx_upload_range(P.c[slot], params, in, wave_lo[w], wave_lo[w + 1]);
+            if (dbg && s == SEQA_OK) cudaEventRecord(P.c[slot]->dbg_ev[1], P.c[slot]->stream);
             const double t1 = since();
-            if (s == SEQA_OK) s = ctx_run(c[k]);
-            if (dbg) fprintf(stderr, "[seqa] dev %d thr %d wave %zu: upload+plan %.2f..%.2f launched ..%.2f ms\n", d, t, w, t0, t1, since());
+            if (s == SEQA_OK) s = ctx_run(P.c[slot]);
+            if (dbg && s == SEQA_OK) cudaEventRecord(P.c[slot]->dbg_ev[2], P.c[slot]->stream);
+            if (dbg) fprintf(stderr, "[seqa] dev %d wave %zu: upload+plan %.2f..%.2f launched ..%.2f ms\n", d, w, t0, t1, since());
+            std::lock_guard<std::mutex> lk(P.mu);
             if (s != SEQA_OK) {
                 wstatus[w] = s;
                 werr[w] = g_err;
-                ok = false;
+                P.stop = true;
+                P.cv.notify_all();
+                break;
             }
-            if (pend >= 0 && finish(pend, pk) != SEQA_OK) ok = false;
-            pend = ok ? (long)w : -1;
-            pk = k;
-            k ^= 1;
+            P.produced = k + 1;
+            P.cv.notify_all();
         }
-        if (pend >= 0) finish(pend, pk);
-        for (int q = 0; q < 2; q++)
-            if (c[q]) {
-                cudaSetDevice(c[q]->device);
-                cudaStreamSynchronize(c[q]->stream);
-                cache_release(c[q], cached[q]);
+        std::lock_guard<std::mutex> lk(P.mu);
+        P.stop = true;
+        P.cv.notify_all();
+    };
+    auto consumer = [&](int d) {
+        DevPipe &P = pipes[d];
+        for (long k = 0;; k++) {
+            {
+                std::unique_lock<std::mutex> lk(P.mu);
+                P.cv.wait(lk, [&] { return P.produced > k || P.stop; });
+                if (P.produced <= k) break;
             }
+            const size_t w = dev_lo[d] + (size_t)k;
+            const int slot = (int)(k % ring);
+            const double t2 = since();
+            int s = ctx_resolve(P.c[slot]);
+            const double t3 = since();
+            if (s == SEQA_OK) s = ctx_download_into(P.c[slot], out, wave_lo[w], wave_slots[w], &wused[w]);
+            if (dbg) {
+                fprintf(stderr, "[seqa] dev %d wave %zu: wait %.2f..%.2f download ..%.2f ms\n", d, w, t2, t3, since());
+                if (s == SEQA_OK && P.c[0] && P.c[0]->dbg_ev[0]) {
+                    cudaEventRecord(P.c[slot]->dbg_ev[3], P.c[slot]->down);
+                    cudaEventSynchronize(P.c[slot]->dbg_ev[3]);
+                    float a = 0, b = 0, cc = 0, dd = 0;
+                    static thread_local cudaEvent_t base = nullptr;
+                    if (k == 0) base = P.c[0]->dbg_ev[0];
+                    // note: slot 0's first event is re-recorded when the ring wraps; times are then relative to that re-record
+                    cudaEventElapsedTime(&a, base, P.c[slot]->dbg_ev[0]);
+                    cudaEventElapsedTime(&b, base, P.c[slot]->dbg_ev[1]);
+                    cudaEventElapsedTime(&cc, base, P.c[slot]->dbg_ev[2]);
+                    cudaEventElapsedTime(&dd, base, P.c[slot]->dbg_ev[3]);
+                    fprintf(stderr, "[seqa]   device timeline wave %zu: start %.2f  H2D+plan done %.2f  kernels done %.2f  D2H done %.2f ms\n", w, a, b, cc, dd);
+                }
+            }
+            std::lock_guard<std::mutex> lk(P.mu);
+            if (s != SEQA_OK) {
+                wstatus[w] = s;
+                werr[w] = g_err;
+                P.stop = true;
+            }
+            P.consumed = k + 1;
+            P.cv.notify_all();
+            if (s != SEQA_OK) break;
+        }
     };
     int rc = SEQA_OK;
     uint64_t used = 0;
     if (sparse) {
         std::vector<std::thread> th;
         for (int d = 0; d < nd; d++) {
-            const size_t nw = dev_lo[d + 1] - dev_lo[d];
-            const int nthreads = (int)std::min<size_t>(SEQA_WORKERS, nw);
-            for (int t = 0; t < nthreads; t++) {
-                if (nd == 1 && nthreads == 1)
-                    worker(d, t, nthreads);
-                else
-                    th.emplace_back(worker, d, t, nthreads);
+            for (int q = 0; q < SEQA_CACHE_SLOTS; q++) pipes[d].cached[q] = -1;
+            if (dev_lo[d + 1] == dev_lo[d]) continue;
+            if (first + d < 64 && !getenv("SEQA_ONE_STREAM")) {
+                std::lock_guard<std::mutex> lk(g_cache_mu);
+                bool ok = cudaSetDevice(first + d) == cudaSuccess;
+                for (int q = 0; q < 4 && ok; q++)
+                    if (!g_pipe_stream[first + d][q])
+                        ok = cudaStreamCreateWithFlags(&g_pipe_stream[first + d][q], cudaStreamNonBlocking) == cudaSuccess;
+                if (ok)
+                    for (int q = 0; q < 4; q++) pipes[d].st[q] = g_pipe_stream[first + d][q];
+                (void)cudaGetLastError();
             }
+            th.emplace_back(producer, d);
+            th.emplace_back(consumer, d);
         }
         for (auto &t : th) t.join();
+        for (int d = 0; d < nd; d++)
+            for (int q = 0; q < SEQA_CACHE_SLOTS; q++)
+                if (pipes[d].c[q]) {
+                    seqa_ctx *cx = pipes[d].c[q];
+                    cudaSetDevice(cx->device);
+                    cudaStreamSynchronize(cx->up);
+                    cudaStreamSynchronize(cx->stream);
+                    cudaStreamSynchronize(cx->down);
+                    if (pipes[d].st[0]) cx->stream = pipes[d].saved[q]; // back to its own single stream
+                    cx->up = cx->down = cx->stream;
+                    cache_release(cx, pipes[d].cached[q]);
+                }
         for (size_t w = 0; w < nwaves; w++) {
             if (rc == SEQA_OK && wstatus[w] != SEQA_OK) {
                 rc = wstatus[w];

@@ -3,6 +3,12 @@
 #pragma once
 #include "seqa_common.cuh"
 
+__global__ void add_base_kernel(uint64_t *__restrict__ v, uint64_t n, uint64_t base)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) v[k] += base;
+}
+
 // ---- exclusive scan of uint32 -> uint64 (three launches; n up to 2^32) --------------------------------
 #define SEQA_SCAN_TPB 256
 #define SEQA_SCAN_IPT 8
