@@ -269,6 +269,14 @@ int packed_trace_bits(const seqa_params &p)
     const int g = -p.gap, m = p.match, x = p.allow_mismatch ? -p.mismatch : 0;
     return (m + x + 2 * g <= 7 && !(p.flags & SEQA_FLAG_TRACE8)) ? 4 : 8;
 }
+// affine packed path: 4 trace bits per plane suffice when every difference the walk tests on low bits stays below 16
+// (and the row scan of the local aligner inside [-8, 7]); bounds: seqa_packed_affine.cuh / DESIGN.md 4.3
+int packed_affine_trace_bits(const seqa_params &p)
+{
+    const int g = -(p.gap_open + p.gap_extend), m = p.match, x = p.allow_mismatch ? -p.mismatch : 0;
+    if (p.flags & SEQA_FLAG_TRACE8) return 8;
+    return (m + x + 2 * g <= 12 && m + g <= 7) ? 4 : 8;
+}
 bool packed_shape_ok(const seqa_params &p, uint32_t M, uint32_t N)
 {
     if (packed_affine(p)) {
@@ -429,7 +437,7 @@ int build_plan(seqa_ctx *c)
             J.Mw = Mw;
             J.Nw = Nw;
             J.nstrips = (Mw + PK_R - 1) / PK_R;
-            const uint64_t tbytes = packed_affine(prm) ? pkg_trace_bytes(J.nstrips, Nw, PK_R)
+            const uint64_t tbytes = packed_affine(prm) ? pkg_trace_bytes(J.nstrips, Nw, PK_R, packed_affine_trace_bits(prm))
                                                        : pk_trace_bytes(J.nstrips, Nw, PK_R, packed_trace_bits(prm));
             const uint64_t pelems = (uint64_t)((Nw + 3) / 4) * 128, relems = (uint64_t)J.nstrips * PK_R * 32;
             if (ch.hi > ch.lo && chunk_bytes(tr + tbytes, pf + pelems, rs + relems) > budget) {
@@ -591,7 +599,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
     if (c->jobs.empty()) return SEQA_OK;
     const bool affine = packed_affine(c->prm);
     const bool local = c->prm.algo == SEQA_SW || c->prm.algo == SEQA_LOCAL_GOTOH;
-    const int tb = packed_trace_bits(c->prm);
+    const int tb = affine ? packed_affine_trace_bits(c->prm) : packed_trace_bits(c->prm);
     const bool gb = !affine && c->pk_max_nw > PK_MAX_LEN; // strip boundaries in global memory
     const size_t smem = (affine || gb) ? 0 : (size_t)c->pk_max_nw * PK_BLOCK * 4;
     if (smem > c->smem_optin) return fail(SEQA_ERR_UNSUPPORTED, "internal: packed kernel shared memory %zu", smem);
@@ -611,7 +619,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
         uint64_t tr = 0, pf = 0;
         {
             const PkWarpJob &L = c->jobs[ch.hi - 1];
-            tr = L.trace_off + (affine ? pkg_trace_bytes(L.nstrips, L.Nw, PK_R) : pk_trace_bytes(L.nstrips, L.Nw, PK_R, tb));
+            tr = L.trace_off + (affine ? pkg_trace_bytes(L.nstrips, L.Nw, PK_R, tb) : pk_trace_bytes(L.nstrips, L.Nw, PK_R, tb));
             pf = L.prof_off + (uint64_t)((L.Nw + 3) / 4) * 128;
         }
         PkArgs A{};
@@ -654,10 +662,14 @@ int run_packed(seqa_ctx *c, bool want_walk)
         const unsigned grid = std::min<unsigned>(full, (unsigned)(c->sms * bps));
         LAUNCH(c, (pk_prep_kernel), std::min<unsigned>(full, (unsigned)c->sms * 16), PK_BLOCK, 0, A, PK_R);
         cudaEventRecord(next_event(c), c->stream);
-        if (affine && local)
-            LAUNCH(c, (pkg_fill_kernel<true, PK_R>), grid, PK_BLOCK, 0, A);
+        if (affine && local && tb == 4)
+            LAUNCH(c, (pkg_fill_kernel<true, PK_R, 4>), grid, PK_BLOCK, 0, A);
+        else if (affine && local)
+            LAUNCH(c, (pkg_fill_kernel<true, PK_R, 8>), grid, PK_BLOCK, 0, A);
+        else if (affine && tb == 4)
+            LAUNCH(c, (pkg_fill_kernel<false, PK_R, 4>), grid, PK_BLOCK, 0, A);
         else if (affine)
-            LAUNCH(c, (pkg_fill_kernel<false, PK_R>), grid, PK_BLOCK, 0, A);
+            LAUNCH(c, (pkg_fill_kernel<false, PK_R, 8>), grid, PK_BLOCK, 0, A);
         else if (gb && local && tb == 4)
             LAUNCH(c, (pk_fill_kernel<true, PK_R, 4, true>), grid, PK_BLOCK, 0, A);
         else if (gb && local)
@@ -681,10 +693,14 @@ int run_packed(seqa_ctx *c, bool want_walk)
             Wk.perm = c->d_perm.p + (uint64_t)ch.lo * 64;
             // jobs' `first` fields are absolute; the walk indexes perm by position, so rebase via pointer only
             const unsigned wgrid = (unsigned)((Wk.npos + 255) / 256);
-            if (affine && local)
-                LAUNCH(c, (pkg_walk_kernel<true, PK_R>), wgrid, 256, 0, Wk);
+            if (affine && local && tb == 4)
+                LAUNCH(c, (pkg_walk_kernel<true, PK_R, 4>), wgrid, 256, 0, Wk);
+            else if (affine && local)
+                LAUNCH(c, (pkg_walk_kernel<true, PK_R, 8>), wgrid, 256, 0, Wk);
+            else if (affine && tb == 4)
+                LAUNCH(c, (pkg_walk_kernel<false, PK_R, 4>), wgrid, 256, 0, Wk);
             else if (affine)
-                LAUNCH(c, (pkg_walk_kernel<false, PK_R>), wgrid, 256, 0, Wk);
+                LAUNCH(c, (pkg_walk_kernel<false, PK_R, 8>), wgrid, 256, 0, Wk);
             else if (local && tb == 4)
                 LAUNCH(c, (pk_walk_kernel<true, 4, PK_R>), wgrid, 256, 0, Wk);
             else if (local)
@@ -697,7 +713,8 @@ int run_packed(seqa_ctx *c, bool want_walk)
         CK(cudaGetLastError());
     }
     if (affine)
-        c->last_kernel = local ? "pkg_fill_lgotoh_s16x2" : "pkg_fill_ggotoh_s16x2";
+        c->last_kernel = local ? (tb == 4 ? "pkg_fill_lgotoh_s16x2_t4" : "pkg_fill_lgotoh_s16x2_t8")
+                               : (tb == 4 ? "pkg_fill_ggotoh_s16x2_t4" : "pkg_fill_ggotoh_s16x2_t8");
     else
         c->last_kernel = local ? (tb == 4 ? "pk_fill_sw_s16x2_t4" : "pk_fill_sw_s16x2_t8") : (tb == 4 ? "pk_fill_nw_s16x2_t4" : "pk_fill_nw_s16x2_t8");
     return SEQA_OK;

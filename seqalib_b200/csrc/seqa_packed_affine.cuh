@@ -22,17 +22,21 @@
 
 #define PKG_NEG (-10000) /* the reference's literal "-infinity" */
 
-__host__ __device__ inline uint64_t pkg_trace_bytes(uint32_t nstrips, uint32_t Nw, int R)
+__host__ __device__ inline uint64_t pkg_trace_bytes(uint32_t nstrips, uint32_t Nw, int R, int TB)
 {
-    return (uint64_t)nstrips * Nw * 3ull * (uint64_t)(R / 8) * 512ull;
+    return (uint64_t)nstrips * (TB == 8 ? Nw : (Nw + 1) / 2) * 3ull * (uint64_t)(R / 8) * 512ull;
 }
 
-// Trace piece (16 B = 8 rows x 1 column x 2 pairs of one plane), per warp job:
-//   piece(s, j, plane, hf, lane) at trace_off + ((((s*Nw + j-1)*3 + plane)*(R/8) + hf)*32 + lane) * 16
+// Trace piece (16 B = 8 rows x 1 column x 2 pairs of one plane; TB == 4: 8 rows x 2 columns, low nibbles), per warp job:
+//   piece(s, jc, plane, hf, lane) at trace_off + ((((s*NC + jc)*3 + plane)*(R/8) + hf)*32 + lane) * 16
+//   jc = j-1 and NC = Nw (TB 8) or jc = (j-1)/2 and NC = ceil(Nw/2), nibble (j-1)%2 (TB 4)
 //   word (r%8)/2, byte (r%2)*2 + k      (r = row inside the strip, hf = r/8, k = pair half)
-template <bool LOCAL, int R>
+// TB == 4 halves the HBM write stream that bounds the 8-bit variant; the host admits it when every difference the
+// walk tests stays below 16 (packed_affine_trace_bits in seqa_cuda.cu).
+template <bool LOCAL, int R, int TB>
 __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
 {
+    static_assert(TB == 4 || TB == 8, "trace bits");
     static_assert(R % 8 == 0, "strips are cut into 8-row trace pieces");
     constexpr int RP = R / 2, RH = R / 8;
     const int lane = threadIdx.x & 31;
@@ -67,7 +71,8 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
                 rmax[r] = gogo2;
             }
             unsigned diag = pk_dup((LOCAL || i0 == 0 ? 0 : A.go + i0 * A.ge) + gogo); // G(i0, 0)
-            uint4 *__restrict__ tr = trace + (uint64_t)s * Nw * (3 * RH * 32);
+            const int NC = TB == 8 ? Nw : (Nw + 1) >> 1;
+            uint4 *__restrict__ tr = trace + (uint64_t)s * NC * (3 * RH * 32);
             uint4 na = prof[0], nb = prof[1];
             uint4 nu0 = make_uint4(0, 0, 0, 0), nu1 = nu0;
             if (!first) {
@@ -85,6 +90,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
                     }
                 }
                 unsigned outG[4], outX[4];
+                unsigned Wg[RP], Wx[RP], Wy[RP];
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const int j = cg * 4 + c + 1;
@@ -100,7 +106,6 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
                     }
                     unsigned gd = diag;
                     diag = gu;
-                    unsigned Wg[RP], Wx[RP], Wy[RP];
                     unsigned pg = 0, px = 0, py = 0;
 #pragma unroll
                     for (int r = 0; r < R; r++) {
@@ -112,9 +117,18 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
                         const unsigned hn = LOCAL ? __viaddmax_s16x2_relu(gd, sim, m) : __viaddmax_s16x2(gd, sim, m);
                         const unsigned gn = __vadd2(hn, gogo2);
                         if (r & 1) {
-                            Wg[r >> 1] = seqa_prmt(pg, gn, 0x6420); // low bytes: [p0 r-1, p1 r-1, p0 r, p1 r]
-                            Wx[r >> 1] = seqa_prmt(px, ix, 0x6420);
-                            Wy[r >> 1] = seqa_prmt(py, iy, 0x6420);
+                            const unsigned wg = seqa_prmt(pg, gn, 0x6420); // low bytes: [p0 r-1, p1 r-1, p0 r, p1 r]
+                            const unsigned wx = seqa_prmt(px, ix, 0x6420);
+                            const unsigned wy = seqa_prmt(py, iy, 0x6420);
+                            if (TB == 8 || (c & 1) == 0) {
+                                Wg[r >> 1] = wg;
+                                Wx[r >> 1] = wx;
+                                Wy[r >> 1] = wy;
+                            } else { // low nibbles of the even column, high nibbles from the odd one
+                                Wg[r >> 1] = (Wg[r >> 1] & 0x0f0f0f0fu) | ((wg << 4) & 0xf0f0f0f0u);
+                                Wx[r >> 1] = (Wx[r >> 1] & 0x0f0f0f0fu) | ((wx << 4) & 0xf0f0f0f0u);
+                                Wy[r >> 1] = (Wy[r >> 1] & 0x0f0f0f0fu) | ((wy << 4) & 0xf0f0f0f0u);
+                            }
                         }
                         pg = gn;
                         px = ix;
@@ -128,8 +142,8 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
                     }
                     outG[c] = gu;
                     outX[c] = xu;
-                    if (j <= Nw) {
-                        uint4 *dst = tr + (uint64_t)(j - 1) * (3 * RH * 32);
+                    if (TB == 8 ? (j <= Nw) : ((c & 1) && j - 1 <= Nw)) {
+                        uint4 *dst = tr + (uint64_t)(TB == 8 ? j - 1 : (j - 1) >> 1) * (3 * RH * 32);
 #pragma unroll
                         for (int hf = 0; hf < RH; hf++) {
                             pk_store_stream(&dst[(0 * RH + hf) * 32], make_uint4(Wg[hf * 4], Wg[hf * 4 + 1], Wg[hf * 4 + 2], Wg[hf * 4 + 3]));
@@ -179,9 +193,10 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
 // ---- walk -------------------------------------------------------------------------------------------------
 // One thread per pair; state machine = reference buildResult (include/SAGlobalGotoh.h:235-422,
 // include/SALocalGotoh.h:275-473).  h / x / y are the EXACT values of H / Ix / Iy at the current cell.
-template <bool LOCAL, int R>
+template <bool LOCAL, int R, int TB>
 __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
 {
+    constexpr unsigned MASK = TB == 8 ? 0xffu : 0xfu;
     const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= A.npos) return;
     const uint32_t p = A.perm[pos];
@@ -189,39 +204,43 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
     const PkWarpJob J = A.jobs[pos >> 6];
     const int lane = (int)((pos & 63) >> 1), half = (int)(pos & 1);
     const int M = (int)A.len1[p], N = (int)A.len2[p];
-    const uint32_t Nw = J.Nw, RH = (uint32_t)(R / 8);
+    const uint32_t NC = TB == 8 ? J.Nw : (J.Nw + 1) >> 1, RH = (uint32_t)(R / 8);
     const uint8_t *a = A.bases + A.off1[p], *b = A.bases + A.off2[p];
     const int go = A.go, ge = A.ge, gogo = go + ge;
     const uint4 *pieces = reinterpret_cast<const uint4 *>(A.trace + J.trace_off);
     uint4 cv0 = make_uint4(0, 0, 0, 0), cv1 = cv0, cv2 = cv0;
     uint32_t ck0 = 0xffffffffu, ck1 = 0xffffffffu, ck2 = 0xffffffffu;
-    auto pick = [&](const uint4 &v, int r) -> unsigned {
+    auto pick = [&](const uint4 &v, int r, int j) -> unsigned {
         const int wsel = (r & 7) >> 1;
         const unsigned wv = wsel == 0 ? v.x : wsel == 1 ? v.y : wsel == 2 ? v.z : v.w;
-        return (wv >> (((r & 1) * 2 + half) * 8)) & 0xffu;
+        return (wv >> (((r & 1) * 2 + half) * 8 + (TB == 4 ? ((j - 1) & 1) * 4 : 0))) & MASK;
     };
     auto key_of = [&](int plane, int i, int j, int &r) -> uint32_t { // i >= 1, j >= 1
         const int ii = i - 1, s = ii / R;
         r = ii - s * R;
-        return ((((uint32_t)s * Nw + (uint32_t)(j - 1)) * 3u + (uint32_t)plane) * RH + (uint32_t)(r >> 3)) * 32u + (uint32_t)lane;
+        const uint32_t jc = TB == 8 ? (uint32_t)(j - 1) : (uint32_t)(j - 1) >> 1;
+        return ((((uint32_t)s * NC + jc) * 3u + (uint32_t)plane) * RH + (uint32_t)(r >> 3)) * 32u + (uint32_t)lane;
     };
     auto lowG = [&](int i, int j) -> unsigned {
         int r;
         const uint32_t k = key_of(0, i, j, r);
         if (ck0 != k) { cv0 = pieces[k]; ck0 = k; }
-        return pick(cv0, r);
+        return pick(cv0, r, j);
     };
     auto lowX = [&](int i, int j) -> unsigned {
         int r;
         const uint32_t k = key_of(1, i, j, r);
         if (ck1 != k) { cv1 = pieces[k]; ck1 = k; }
-        return pick(cv1, r);
+        return pick(cv1, r, j);
     };
     auto lowY = [&](int i, int j) -> unsigned {
         int r;
         const uint32_t k = key_of(2, i, j, r);
         if (ck2 != k) { cv2 = pieces[k]; ck2 = k; }
-        return pick(cv2, r);
+        return pick(cv2, r, j);
+    };
+    auto sext = [&](unsigned d) -> int { // signed difference from its low TB bits
+        return TB == 8 ? (int)(int8_t)(uint8_t)d : ((int)((d & 0xfu) ^ 8u) - 8);
     };
     auto borderH = [&](int i, int j) -> int { // i == 0 or j == 0
         if (LOCAL || (i == 0 && j == 0)) return 0;
@@ -238,7 +257,7 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
         int e = 0, bj = N;
         if (i >= 1) {
             for (int jj = 1; jj <= N; jj++) {
-                e += (int)(int8_t)(uint8_t)(lowG(i, jj) - (unsigned)(e + gogo));
+                e += sext(lowG(i, jj) - (unsigned)(e + gogo));
                 if (e == best) bj = jj;
             }
         }
@@ -264,7 +283,7 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
             if (eq || A.allow) {
                 const int t = h - (eq ? A.match : A.mismatch); // H(i-1,j-1) if this cell came from the diagonal
                 const bool isd = (i == 1 || j == 1) ? (t == borderH(i - 1, j - 1))
-                                                    : (lowG(i - 1, j - 1) == ((unsigned)(t + gogo) & 0xffu));
+                                                    : (lowG(i - 1, j - 1) == ((unsigned)(t + gogo) & MASK));
                 if (isd) { // include/SAGlobalGotoh.h:286
                     slot[--k] = 0;
                     i--; j--;
@@ -272,7 +291,7 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
                     continue;
                 }
             }
-            if (lowX(i, j) == ((unsigned)h & 0xffu)) { // H == Ix (:355), before H == Iy (:411)
+            if (lowX(i, j) == ((unsigned)h & MASK)) { // H == Ix (:355), before H == Iy (:411)
                 state = 1;
                 x = h;
             } else {
@@ -282,7 +301,7 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
         }
         if (state == 1) {
             slot[--k] = 1;
-            const bool ext = (i == 1) ? (x == PKG_NEG + ge) : (lowX(i - 1, j) == ((unsigned)(x - ge) & 0xffu)); // :336 before :344
+            const bool ext = (i == 1) ? (x == PKG_NEG + ge) : (lowX(i - 1, j) == ((unsigned)(x - ge) & MASK)); // :336 before :344
             if (ext) {
                 x -= ge;
             } else {
@@ -292,7 +311,7 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
             i--;
         } else {
             slot[--k] = 2;
-            const bool ext = (j == 1) ? (y == PKG_NEG + ge) : (lowY(i, j - 1) == ((unsigned)(y - ge) & 0xffu)); // :394 before :402
+            const bool ext = (j == 1) ? (y == PKG_NEG + ge) : (lowY(i, j - 1) == ((unsigned)(y - ge) & MASK)); // :394 before :402
             if (ext) {
                 y -= ge;
             } else {

@@ -23,8 +23,6 @@ def test_matrix_algorithms(emu_lib, algo, sc):
     pairs = list(EDGE) + random_pairs(rng, 30, 1, 70) + random_pairs(rng, 8, 1, 50, "AC") + \
         random_pairs(rng, 6, 120, 180) + random_pairs(rng, 8, 1, 90, related=0.3)
     for flags in (0, capi.FLAG_TRACE8, capi.FLAG_FORCE_GENERIC):
-        if flags == capi.FLAG_TRACE8 and algo not in ('nw', 'sw'):
-            continue
         check_batch_against_oracle(emu_lib, algo, sc, pairs, flags=flags)
 
 

@@ -59,8 +59,7 @@ def test_matrix_algorithms_random(gpu_lib, algo, sc):
         pairs = [p for p in pairs if (len(p[0]), len(p[1])) not in ((314, 288), (60, 57), (61, 58))]
     check_batch_against_oracle(gpu_lib, algo, sc, pairs)
     check_batch_against_oracle(gpu_lib, algo, sc, pairs[:400], flags=capi.FLAG_FORCE_GENERIC)
-    if algo in ('nw', 'sw'):
-        check_batch_against_oracle(gpu_lib, algo, sc, pairs[:400], flags=capi.FLAG_TRACE8)
+    check_batch_against_oracle(gpu_lib, algo, sc, pairs[:400], flags=capi.FLAG_TRACE8)  # 8-bit trace variants
 
 
 @pytest.mark.parametrize("algo,sc", LINSPACE_CASES)
