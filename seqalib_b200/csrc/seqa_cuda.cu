@@ -22,6 +22,7 @@
 #include "seqa_packed.cuh"
 #include "seqa_packed_affine.cuh"
 #include "seqa_linspace.cuh"
+#include "seqa_linspace_packed.cuh"
 #include "../../include/seqa_cuda.h"
 
 namespace {

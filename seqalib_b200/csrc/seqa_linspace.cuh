@@ -69,6 +69,7 @@ struct LsArgs {
     const uint64_t *slot_off;
     DevScoring sc;
     int force_r;             // > 0: use this many rows per lane everywhere (testing: many row blocks on short pairs)
+    int packed;              // forward + reverse sweep of a node as one s16x2 wavefront (seqa_linspace_packed.cuh)
 };
 
 #ifdef SEQA_EMU
@@ -406,6 +407,32 @@ __device__ __forceinline__ int ls_pick_rsel(const LsArgs &A, int rows)
 
 __device__ __forceinline__ void ls_make_sweeps(const LsArgs &A, uint32_t node, int rows_f, int rows_r, int lane)
 {
+    if (A.packed) { // one dual sweep: row block rb of both sweeps is one task (rows_f <= rows_r <= rows_f + 1)
+        const int rs = ls_pick_rsel(A, rows_r);
+        const int nb = (rows_r + (32 << rs) - 1) / (32 << rs);
+        uint32_t s0 = 0, t0 = 0;
+        if (lane == 0) {
+            s0 = atomicAdd(&A.cnt[1], 1u);
+            t0 = atomicAdd(&A.cnt[2], (uint32_t)nb);
+            if (t0 + (uint32_t)nb > A.task_cap) {
+                *A.overflow = 1;
+                t0 = 0xffffffffu;
+            }
+        }
+        s0 = __shfl_sync(SEQA_FULL, s0, 0);
+        t0 = __shfl_sync(SEQA_FULL, t0, 0);
+        if (t0 == 0xffffffffu) return;
+        if (lane == 0) {
+            LsSweep D;
+            D.node = (int)node; D.rows = rows_r; D.nblk = nb | (rs << 28); D.task0 = t0;
+            A.sweeps[s0] = D;
+        }
+        for (int rb = lane; rb < nb; rb += 32) {
+            LsTask T; T.sweep = s0; T.rb = (uint32_t)rb;
+            A.tasks[t0 + (uint32_t)rb] = T;
+        }
+        return;
+    }
     const int rf = ls_pick_rsel(A, rows_f), rr = ls_pick_rsel(A, rows_r);
     const int nf = (rows_f + (32 << rf) - 1) / (32 << rf), nr = (rows_r + (32 << rr) - 1) / (32 << rr);
     uint32_t s0 = 0, t0 = 0;
@@ -503,9 +530,10 @@ __global__ void __launch_bounds__(128) ls_split_kernel(LsArgs A)
     const int lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t nint = *A.overflow ? 0u : A.cnt[1] / 2; // internal nodes of this level
+    const uint32_t per = A.packed ? 1u : 2u; // sweep entries per internal node
+    const uint32_t nint = *A.overflow ? 0u : A.cnt[1] / per; // internal nodes of this level
     for (uint32_t k = gw; k < nint; k += nw) {
-        const LsNode nd = A.in[A.sweeps[2 * k].node];
+        const LsNode nd = A.in[A.sweeps[per * k].node];
         const uint32_t p = (uint32_t)nd.pair;
         const int m = nd.m, n = nd.n, mid = m / 2;
         const uint64_t w = A.row_w[p];
@@ -669,7 +697,7 @@ struct LsState {
     LsTask *d_tasks = nullptr;
     int *d_prog = nullptr;
     uint64_t task_cap = 0, sum_blocks = 0, cap_tasks = 0;
-    int sweep_blocks = 0;
+    int sweep_blocks = 0, sweep2_blocks = 0;
     int *d_rows = nullptr;
     uint64_t *d_row_off = nullptr;
     uint32_t *d_row_w = nullptr;

@@ -95,12 +95,15 @@ int ls_plan(LsState &ls, const seqa_params &prm, const std::vector<uint32_t> &le
     if (!ls.d_overflow) CKS(ls_alloc(&ls.d_overflow, 1));
     if (!ls.sweep_blocks) {
 #ifdef SEQA_EMU
-        ls.sweep_blocks = sms;
+        ls.sweep_blocks = ls.sweep2_blocks = sms;
 #else
         int nb_hb = 0, nb_mm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_hb, ls_sweep_kernel<false>, LS_BLOCK, 0));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_mm, ls_sweep_kernel<true>, LS_BLOCK, 0));
         ls.sweep_blocks = sms * std::max(1, std::min(nb_hb, nb_mm));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_hb, ls_sweep2_kernel<false>, LS_BLOCK, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_mm, ls_sweep2_kernel<true>, LS_BLOCK, 0));
+        ls.sweep2_blocks = sms * std::max(1, std::min(nb_hb, nb_mm));
 #endif
     }
     if (n) {
@@ -141,6 +144,22 @@ int ls_run(seqa_ctx *c, bool want_ops)
     A.slot_off = c->slot_off.p;
     A.sc = c->sc;
     A.force_r = (c->prm.flags & SEQA_FLAG_LS_R1) ? 1 : 0;
+    // packed dual sweeps: small scoring constants (int8 profiles, 16-bit windows) and symbols in {A,C,G,T}
+    {
+        const seqa_params &q = c->prm;
+        const int g = ls.mm ? -(q.gap_open + q.gap_extend) : -q.gap, x = q.allow_mismatch ? -q.mismatch : 0;
+        bool ok = !(q.flags & SEQA_FLAG_FORCE_GENERIC) && q.match <= 100 && x <= 100 && g <= 50 && q.match + g <= 120 && x - g >= -120;
+        if (ok) {
+            CK(cudaMemsetAsync(c->flags.p + 2, 0, sizeof(int), c->stream));
+            const unsigned blocks = (unsigned)std::min<uint64_t>((c->bases_len + 256 * 16 - 1) / (256 * 16) + 1, (uint64_t)c->sms * 8);
+            LAUNCH(c, (ls_check_acgt_kernel), blocks, 256, 0, c->bases.p, c->bases_len, c->flags.p + 2);
+            int bad = 0;
+            CK(cudaMemcpyAsync(&bad, c->flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            ok = !bad;
+        }
+        A.packed = ok ? 1 : 0;
+    }
     uint32_t count = (uint32_t)n;
     int cur = 0;
     ls.levels_run = 0;
@@ -155,11 +174,17 @@ int ls_run(seqa_ctx *c, bool want_ops)
         const unsigned egrid = std::min<unsigned>((count + 3) / 4, (unsigned)c->sms * 16);
         if (ls.mm) {
             LAUNCH(c, (ls_expand_kernel<true>), egrid, 128, 0, A);
-            LAUNCH(c, (ls_sweep_kernel<true>), (unsigned)ls.sweep_blocks, LS_BLOCK, 0, A);
+            if (A.packed)
+                LAUNCH(c, (ls_sweep2_kernel<true>), (unsigned)ls.sweep2_blocks, LS_BLOCK, 0, A);
+            else
+                LAUNCH(c, (ls_sweep_kernel<true>), (unsigned)ls.sweep_blocks, LS_BLOCK, 0, A);
             LAUNCH(c, (ls_split_kernel<true>), egrid, 128, 0, A);
         } else {
             LAUNCH(c, (ls_expand_kernel<false>), egrid, 128, 0, A);
-            LAUNCH(c, (ls_sweep_kernel<false>), (unsigned)ls.sweep_blocks, LS_BLOCK, 0, A);
+            if (A.packed)
+                LAUNCH(c, (ls_sweep2_kernel<false>), (unsigned)ls.sweep2_blocks, LS_BLOCK, 0, A);
+            else
+                LAUNCH(c, (ls_sweep_kernel<false>), (unsigned)ls.sweep_blocks, LS_BLOCK, 0, A);
             LAUNCH(c, (ls_split_kernel<false>), egrid, 128, 0, A);
         }
         CK(cudaGetLastError());
@@ -194,7 +219,7 @@ int ls_run(seqa_ctx *c, bool want_ops)
     const unsigned blocks = (unsigned)std::min<uint64_t>((n + 3) / 4, (uint64_t)c->sms * 16);
     LAUNCH(c, (ls_finish_kernel), blocks, 128, 0, F);
     CK(cudaGetLastError());
-    c->last_kernel = ls.mm ? "ls_sweep_mm_i32" : "ls_sweep_hb_i32";
+    c->last_kernel = A.packed ? (ls.mm ? "ls_sweep2_mm_s16x2" : "ls_sweep2_hb_s16x2") : (ls.mm ? "ls_sweep_mm_i32" : "ls_sweep_hb_i32");
     return SEQA_OK;
 }
 

@@ -36,8 +36,11 @@ def test_linear_space_algorithms(emu_lib, algo, sc):
     rng = np.random.default_rng(12)
     pairs = list(EDGE) + random_pairs(rng, 10, 1, 70) + random_pairs(rng, 4, 1, 50, "AC") + \
         random_pairs(rng, 2, 150, 300) + random_pairs(rng, 3, 1, 200, related=0.3)
-    check_batch_against_oracle(emu_lib, algo, sc, pairs)
+    check_batch_against_oracle(emu_lib, algo, sc, pairs)  # contains non-ACGT symbols: int32 sweeps
     check_batch_against_oracle(emu_lib, algo, sc, pairs[-12:], flags=capi.FLAG_LS_R1)
+    clean = [p for p in pairs if set(p[0] + p[1]) <= set("ACGT")]  # packed forward+reverse s16x2 sweeps
+    check_batch_against_oracle(emu_lib, algo, sc, clean)
+    check_batch_against_oracle(emu_lib, algo, sc, clean[-12:], flags=capi.FLAG_LS_R1)
 
 
 def test_packed_path_is_taken(emu_lib):

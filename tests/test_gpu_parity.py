@@ -62,25 +62,47 @@ def test_matrix_algorithms_random(gpu_lib, algo, sc):
     check_batch_against_oracle(gpu_lib, algo, sc, pairs[:400], flags=capi.FLAG_TRACE8)  # 8-bit trace variants
 
 
+def _kernel_used(lib, algo, sc, pairs, flags=0):
+    bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+    ctx = capi.Ctx(lib)
+    ctx.upload(scoring_to_params(algo, sc, flags=flags), bases, off1, off2, len1, len2)
+    ctx.run()
+    ctx.sync()
+    k = ctx.last_kernel()
+    ctx.close()
+    return k
+
+
 @pytest.mark.parametrize("algo,sc", LINSPACE_CASES)
 def test_linear_space_algorithms_random(gpu_lib, algo, sc):
     rng = np.random.default_rng(23)
     pairs = list(EDGE) + random_pairs(rng, 400, 1, 200) + random_pairs(rng, 100, 1, 120, "AC") + \
         random_pairs(rng, 100, 1, 250, related=0.3) + random_pairs(rng, 12, 1000, 3000) + \
         random_pairs(rng, 6, 2000, 5000, related=0.25) + [("A" * 700, "ACGT" * 150), ("ACGT" * 200, "T" * 40)]
+    # a symbol outside ACGT anywhere in the batch -> the int32 sweeps (8-bit compare) take the whole batch
     check_batch_against_oracle(gpu_lib, algo, sc, pairs)
+    assert _kernel_used(gpu_lib, algo, sc, pairs[:40]).endswith("_i32")
+    # ACGT only -> forward + reverse sweep packed as one s16x2 wavefront
+    clean = [p for p in pairs if set(p[0] + p[1]) <= set("ACGT")]
+    assert _kernel_used(gpu_lib, algo, sc, clean[:40]).endswith("_s16x2")
+    check_batch_against_oracle(gpu_lib, algo, sc, clean)
+    check_batch_against_oracle(gpu_lib, algo, sc, clean[-24:] + clean[:100], flags=capi.FLAG_FORCE_GENERIC)
     # 32-row blocks everywhere: every sweep becomes a deep row-block pipeline across warps (progress-flag protocol)
+    check_batch_against_oracle(gpu_lib, algo, sc, clean[-24:] + clean[:100], flags=capi.FLAG_LS_R1)
     check_batch_against_oracle(gpu_lib, algo, sc, pairs[-24:] + pairs[:100], flags=capi.FLAG_LS_R1)
 
 
 @pytest.mark.parametrize("algo,sc,n,lo,hi", [("hirschberg", S.linear(-1, 2, -1), 6, 9000, 20000),
-                                             ("myersmiller", S.affine(-3, -1, 1, -1), 6, 5000, 9000)])
+                                             ("myersmiller", S.affine(-3, -1, 1, -1), 6, 5000, 9000),
+                                             ("hirschberg", S.linear(-4, 9, -6), 4, 6000, 9000)])
 def test_linear_space_long_pairs(gpu_lib, algo, sc, n, lo, hi):
     """Sweeps tens of row blocks deep (the config-4 regime at a size the oracle finishes in seconds): unrelated and
-    related pairs (10 % substitutions + indels), bit-exact including the reference's sub-optimal splits."""
+    related pairs (10 % substitutions + indels), bit-exact including the reference's sub-optimal splits.  Scores
+    leave the 16-bit range (the packed sweeps re-base per 32-column chunk); both sweep kernels are checked."""
     rng = np.random.default_rng(31)
     pairs = random_pairs(rng, n // 2, lo, hi) + random_pairs(rng, n - n // 2, lo, hi, related=0.14)
     check_batch_against_oracle(gpu_lib, algo, sc, pairs)
+    check_batch_against_oracle(gpu_lib, algo, sc, pairs[:2] + pairs[-1:], flags=capi.FLAG_FORCE_GENERIC)
 
 
 @pytest.mark.parametrize("algo", ["sw", "nw"])
