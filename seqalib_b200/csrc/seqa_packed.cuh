@@ -23,6 +23,7 @@
 #include "seqa_common.cuh"
 
 #define PK_NULL 0xffffffffu
+#define PK_BND_AHEAD 8 /* column groups between the L2 prefetch of a global strip-boundary piece and its use */
 #define PK_BLOCK 128
 
 struct PkWarpJob {
@@ -192,6 +193,11 @@ __host__ __device__ inline uint64_t pk_trace_bytes(uint32_t nstrips, uint32_t Nw
 }
 
 #ifdef SEQA_EMU
+static inline void pk_prefetch_l2_line(const void *) {}
+#else
+__device__ __forceinline__ void pk_prefetch_l2_line(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+#ifdef SEQA_EMU
 static inline void pk_store_stream(uint4 *p, uint4 v) { *p = v; }
 static inline void pk_store_stream(uint2 *p, uint2 v) { *p = v; }
 #else
@@ -250,6 +256,8 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                     nb = prof[(uint64_t)(cg + 1) * 64 + 1];
                     if (GB && !first) nu = bnd[(uint64_t)(cg + 1) * 32];
                 }
+                // long pairs: the boundary rows of all resident warps outgrow the L2; pull mine back in well ahead
+                if (GB && !first && (lane & 7) == 0 && cg + PK_BND_AHEAD < Ng) pk_prefetch_l2_line(&bnd[(uint64_t)(cg + PK_BND_AHEAD) * 32]);
                 unsigned up[4];
                 if (GB) {
                     if (first) { // matrix row 0 (SW 0, NW j*gap: include/SANeedlemanWunsch.h:61-62)
@@ -350,14 +358,69 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
     }
 }
 
+// ---- walk helpers: fewer memory instructions per traceback step ------------------------------------------------------
+// A walk step touches the two sequences and the op slot; every lane has its own addresses, so each load / store
+// instruction costs one L1 access per lane.  Symbols are therefore read as aligned 32-bit words kept in a register
+// (one load per 4 steps along a sequence) and ops leave as 32-bit words (one store per 4 ops; the at most 3 head and
+// 3 tail bytes of a slot, which share words with the neighbouring pairs' slots, go out as single bytes).
+struct PkSymCache {
+    const uint8_t *base; // A.bases (4-byte aligned, 16 bytes of slack behind the last sequence)
+    uint64_t off;        // offset of the sequence
+    uint32_t key, word;
+    __device__ __forceinline__ void init(const uint8_t *b, uint64_t o)
+    {
+        base = b;
+        off = o;
+        key = 0xffffffffu;
+        word = 0;
+    }
+    __device__ __forceinline__ unsigned at(int idx) // symbol idx of the sequence
+    {
+        const uint64_t a = off + (uint64_t)idx;
+        const uint32_t k = (uint32_t)(a >> 2);
+        if (k != key) {
+            word = *reinterpret_cast<const uint32_t *>(base + ((uint64_t)k << 2));
+            key = k;
+        }
+        return (word >> ((unsigned)(a & 3u) * 8u)) & 0xffu;
+    }
+};
+
+struct PkOpWriter {
+    uint8_t *slots; // A.slots (4-byte aligned)
+    uint64_t pos;   // byte offset of the next op + 1 (ops are written back to front)
+    uint64_t atop;  // largest multiple of 4 <= end of the slot: bytes at or above it go out one by one
+    uint32_t acc;
+    __device__ __forceinline__ void init(uint8_t *s, uint64_t slot_end)
+    {
+        slots = s;
+        pos = slot_end;
+        atop = slot_end & ~(uint64_t)3;
+        acc = 0;
+    }
+    __device__ __forceinline__ void put(unsigned op)
+    {
+        const uint64_t a = --pos;
+        if (a >= atop) {
+            slots[a] = (uint8_t)op;
+        } else {
+            acc |= op << ((unsigned)(a & 3u) * 8u);
+            if ((a & 3u) == 0) {
+                *reinterpret_cast<uint32_t *>(slots + a) = acc;
+                acc = 0;
+            }
+        }
+    }
+    __device__ __forceinline__ void finish() // the bytes of the last, incomplete word
+    {
+        if (pos < atop)
+            for (uint64_t a = pos; (a & 3u) != 0; a++) slots[a] = (uint8_t)(acc >> ((unsigned)(a & 3u) * 8u));
+    }
+};
+
 // ---- walk -------------------------------------------------------------------------------------------------
 // One thread per pair.  Exact neighbour values are rebuilt from the stored low bits:
 // H(n) = H(c) + sext_TB(low(n) - low(H(c))) for any cell n adjacent to the current cell c.
-#ifdef SEQA_EMU
-static inline void pk_prefetch_l2_line(const void *) {}
-#else
-__device__ __forceinline__ void pk_prefetch_l2_line(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#endif
 
 template <bool LOCAL, int TB, int R>
 __global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A)
@@ -371,7 +434,9 @@ __global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A)
     const int M = (int)A.len1[p], N = (int)A.len2[p];
     const uint32_t Ng = (J.Nw + 3) >> 2;
     constexpr unsigned MASK = TB == 8 ? 0xffu : 0xfu;
-    const uint8_t *a = A.bases + A.off1[p], *b = A.bases + A.off2[p];
+    PkSymCache a, b;
+    a.init(A.bases, A.off1[p]);
+    b.init(A.bases, A.off2[p]);
     const int gap = A.gap;
     // 16-byte pieces (TB 8: 2 rows x 4 columns x 2 pairs; TB 4: 8 rows x 4 columns of this pair), see pk_fill_kernel;
     // two of them are kept in registers (one per row-group parity), so a step usually costs no load at all
@@ -408,8 +473,8 @@ __global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A)
         if (i == 0 || j == 0) return border(i, j);
         return hc + sext(low(i, j) - ((unsigned)hc & MASK));
     };
-    uint8_t *slot = A.slots + A.slot_off[p];
-    int k = M + N;
+    PkOpWriter out;
+    out.init(A.slots, A.slot_off[p] + (uint64_t)(M + N));
     int i, j, h;
     if (LOCAL) {
         // MaxCol: the last column of row MaxRow holding MaxScore (include/SASmithWaterman.h:177-182).  One 16-byte
@@ -448,29 +513,31 @@ __global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A)
     }
     while (i > 0 && j > 0) {
         if (LOCAL && h == 0) break; // include/SASmithWaterman.h:281-284
-        const bool eq = a[i - 1] == b[j - 1];
+        const bool eq = a.at(i - 1) == b.at(j - 1);
         const int hdg = near(h, i - 1, j - 1);
         if ((eq || A.allow) && h == hdg + (eq ? A.match : A.mismatch)) { // include/SANeedlemanWunsch.h:190
-            slot[--k] = 0;
+            out.put(0);
             i--; j--;
             h = hdg;
             continue;
         }
         const int hup = near(h, i - 1, j);
         if (h == hup + gap) { // include/SANeedlemanWunsch.h:216
-            slot[--k] = 1;
+            out.put(1);
             i--;
             h = hup;
         } else { // :223
             h = near(h, i, j - 1);
-            slot[--k] = 2;
+            out.put(2);
             j--;
         }
     }
     if (!LOCAL) { // borders: column 0 -> up, row 0 -> left
-        while (i > 0) { slot[--k] = 1; i--; }
-        while (j > 0) { slot[--k] = 2; j--; }
+        while (i > 0) { out.put(1); i--; }
+        while (j > 0) { out.put(2); j--; }
     }
+    out.finish();
+    const int k = (int)(out.pos - A.slot_off[p]);
     A.start_i[p] = (uint32_t)i;
     A.start_j[p] = (uint32_t)j;
     A.slot_start[p] = (uint32_t)k;

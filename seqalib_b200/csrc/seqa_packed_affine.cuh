@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
                         nu1 = bnd[(uint64_t)(cg + 1) * 64 + 1];
                     }
                 }
+                if (!first && (lane & 3) == 0 && cg + PK_BND_AHEAD < Ng) pk_prefetch_l2_line(&bnd[(uint64_t)(cg + PK_BND_AHEAD) * 64]);
                 unsigned outG[4], outX[4];
                 unsigned Wg[RP], Wx[RP], Wy[RP];
 #pragma unroll
@@ -205,7 +206,9 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
     const int lane = (int)((pos & 63) >> 1), half = (int)(pos & 1);
     const int M = (int)A.len1[p], N = (int)A.len2[p];
     const uint32_t NC = TB == 8 ? J.Nw : (J.Nw + 1) >> 1, RH = (uint32_t)(R / 8);
-    const uint8_t *a = A.bases + A.off1[p], *b = A.bases + A.off2[p];
+    PkSymCache a, b;
+    a.init(A.bases, A.off1[p]);
+    b.init(A.bases, A.off2[p]);
     const int go = A.go, ge = A.ge, gogo = go + ge;
     const uint4 *pieces = reinterpret_cast<const uint4 *>(A.trace + J.trace_off);
     uint4 cv0 = make_uint4(0, 0, 0, 0), cv1 = cv0, cv2 = cv0;
@@ -246,8 +249,8 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
         if (LOCAL || (i == 0 && j == 0)) return 0;
         return go + (i == 0 ? j : i) * ge;
     };
-    uint8_t *slot = A.slots + A.slot_off[p];
-    int k = M + N;
+    PkOpWriter out;
+    out.init(A.slots, A.slot_off[p] + (uint64_t)(M + N));
     int i, j, h, x = 0, y = 0, state = 0;
     if (LOCAL) {
         // MaxCol: the last column of row MaxRow holding MaxScore (include/SALocalGotoh.h:220-225); exact values are
@@ -274,18 +277,18 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
             if (i <= 0 || j <= 0) break; // include/SALocalGotoh.h:289
         } else {
             if (i == 0 && j == 0) break;
-            if (j == 0) { slot[--k] = 1; i--; continue; } // include/SAGlobalGotoh.h:312
-            if (i == 0) { slot[--k] = 2; j--; continue; } // :370
+            if (j == 0) { out.put(1); i--; continue; } // include/SAGlobalGotoh.h:312
+            if (i == 0) { out.put(2); j--; continue; } // :370
         }
         if (state == 0) {
             if (LOCAL && h == 0) break; // H == max(D,0) == 0 (include/SALocalGotoh.h:334)
-            const bool eq = a[i - 1] == b[j - 1];
+            const bool eq = a.at(i - 1) == b.at(j - 1);
             if (eq || A.allow) {
                 const int t = h - (eq ? A.match : A.mismatch); // H(i-1,j-1) if this cell came from the diagonal
                 const bool isd = (i == 1 || j == 1) ? (t == borderH(i - 1, j - 1))
                                                     : (lowG(i - 1, j - 1) == ((unsigned)(t + gogo) & MASK));
                 if (isd) { // include/SAGlobalGotoh.h:286
-                    slot[--k] = 0;
+                    out.put(0);
                     i--; j--;
                     h = t;
                     continue;
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
             }
         }
         if (state == 1) {
-            slot[--k] = 1;
+            out.put(1);
             const bool ext = (i == 1) ? (x == PKG_NEG + ge) : (lowX(i - 1, j) == ((unsigned)(x - ge) & MASK)); // :336 before :344
             if (ext) {
                 x -= ge;
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
             }
             i--;
         } else {
-            slot[--k] = 2;
+            out.put(2);
             const bool ext = (j == 1) ? (y == PKG_NEG + ge) : (lowY(i, j - 1) == ((unsigned)(y - ge) & MASK)); // :394 before :402
             if (ext) {
                 y -= ge;
@@ -321,6 +324,8 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
             j--;
         }
     }
+    out.finish();
+    const int k = (int)(out.pos - A.slot_off[p]);
     A.start_i[p] = (uint32_t)i;
     A.start_j[p] = (uint32_t)j;
     A.slot_start[p] = (uint32_t)k;
