@@ -20,6 +20,7 @@
 // recovers exact neighbour values from the low bytes and applies the reference's own equality tests and
 // priority (diag > up > left) -- bit-exact by construction, no direction derivation on the hot loop.
 #pragma once
+#include <type_traits>
 #include "seqa_common.cuh"
 
 #define PK_NULL 0xffffffffu
@@ -272,6 +273,10 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                 }
                 unsigned bot[4];
                 unsigned W[RP][TB == 8 ? 4 : 2];
+                // the 4 columns of the group; CAP = this group holds the corner column of one of my global alignments
+                // (twice per pair): only that rare variant carries the H(M,N) capture code
+                auto cols = [&](auto cap) {
+                constexpr bool CAP = decltype(cap)::value;
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const unsigned T0 = c == 0 ? ca.x : c == 1 ? ca.z : c == 2 ? cb.x : cb.z;
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                         bot[c] = hu;
                     else if (cg * 4 + c < Nw)
                         top[(cg * 4 + c) * PK_BLOCK + tid] = hu;
-                    if (!LOCAL) {
+                    if (!LOCAL && CAP) {
                         const int j = cg * 4 + c + 1;
                         if (j == N0 || j == N1) {
 #pragma unroll
@@ -313,6 +318,15 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                             }
                         }
                     }
+                }
+                };
+                {
+                    const bool hit = !LOCAL && (((unsigned)(M0 - 1 - i0) < (unsigned)R && (unsigned)(N0 - 1 - cg * 4) < 4u) ||
+                                                ((unsigned)(M1 - 1 - i0) < (unsigned)R && (unsigned)(N1 - 1 - cg * 4) < 4u));
+                    if (!LOCAL && __any_sync(SEQA_FULL, hit))
+                        cols(std::true_type());
+                    else
+                        cols(std::false_type());
                 }
                 if (GB && keep) bnd[(uint64_t)cg * 32] = make_uint4(bot[0], bot[1], bot[2], bot[3]);
                 if (TB == 8) {

@@ -92,6 +92,10 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
                 if (!first && (lane & 3) == 0 && cg + PK_BND_AHEAD < Ng) pk_prefetch_l2_line(&bnd[(uint64_t)(cg + PK_BND_AHEAD) * 64]);
                 unsigned outG[4], outX[4];
                 unsigned Wg[RP], Wx[RP], Wy[RP];
+                // CAP = this group holds the corner column of one of my global alignments: only that rare variant carries
+                // the H(M,N) capture code (seqa_packed.cuh)
+                auto cols = [&](auto cap) {
+                constexpr bool CAP = decltype(cap)::value;
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const int j = cg * 4 + c + 1;
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
                             pk_store_stream(&dst[(2 * RH + hf) * 32], make_uint4(Wy[hf * 4], Wy[hf * 4 + 1], Wy[hf * 4 + 2], Wy[hf * 4 + 3]));
                         }
                     }
-                    if (!LOCAL) {
+                    if (!LOCAL && CAP) {
                         if (j == N0 || j == N1) {
 #pragma unroll
                             for (int r = 0; r < R; r++) {
@@ -161,6 +165,15 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
                             }
                         }
                     }
+                }
+                };
+                {
+                    const bool hit = !LOCAL && (((unsigned)(M0 - 1 - i0) < (unsigned)R && (unsigned)(N0 - 1 - cg * 4) < 4u) ||
+                                                ((unsigned)(M1 - 1 - i0) < (unsigned)R && (unsigned)(N1 - 1 - cg * 4) < 4u));
+                    if (!LOCAL && __any_sync(SEQA_FULL, hit))
+                        cols(std::true_type());
+                    else
+                        cols(std::false_type());
                 }
                 if (keep) {
                     bnd[(uint64_t)cg * 64] = make_uint4(outG[0], outX[0], outG[1], outX[1]);

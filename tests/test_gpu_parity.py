@@ -211,6 +211,85 @@ def test_config2_full_size_properties(gpu_lib):
             (o["start_i"], o["start_j"], o["end_i"], o["end_j"]), p
 
 
+def _rescore_all_affine(bases, off1, off2, res, n, go, ge, match, mismatch):
+    """Vectorised re-scoring of every alignment of a batch under the affine model (a run of k gaps: go + k*ge)."""
+    ops_len = res.ops_len[:n].astype(np.int64)
+    ops_off = res.ops_off[:n].astype(np.int64)
+    tot = int(ops_len.sum())
+    ops = res.ops[:tot]
+    pair = np.repeat(np.arange(n), ops_len)
+    di = (ops != 2).astype(np.int64)
+    dj = (ops != 1).astype(np.int64)
+    ci = np.cumsum(di) - di
+    cj = np.cumsum(dj) - dj
+    first = ops_off[pair]
+    i = ci - ci[np.minimum(first, tot - 1)] * (ops_len[pair] > 0) + res.start_i[:n].astype(np.int64)[pair]
+    j = cj - cj[np.minimum(first, tot - 1)] * (ops_len[pair] > 0) + res.start_j[:n].astype(np.int64)[pair]
+    a = bases[(off1[:n].astype(np.int64)[pair] + i)]
+    b = bases[(off2[:n].astype(np.int64)[pair] + j)]
+    prev = np.empty_like(ops)
+    prev[0] = 255
+    prev[1:] = ops[:-1]
+    prev[ops_off[ops_len > 0]] = 255  # the first op of a pair has no predecessor
+    opens = (ops != 0) & (ops != prev)
+    s = np.where(ops == 0, np.where(a == b, match, mismatch), ge).astype(np.int64) + opens * go
+    score = np.zeros(n, dtype=np.int64)
+    np.add.at(score, pair, s)
+    return score, np.bincount(pair, weights=di, minlength=n).astype(np.int64), np.bincount(pair, weights=dj, minlength=n).astype(np.int64)
+
+
+@pytest.mark.parametrize("algo", ["ggotoh", "lgotoh"])
+def test_config3_large_batch_properties(gpu_lib, algo):
+    """BASELINE configs[2] shape at 1,000,000 x 250 bp (a tenth of the full 10 M: host memory for the numpy check):
+    every alignment re-scores, under the affine model, to the score the kernel reports; ops span [start,end);
+    a second run is identical; plus an oracle comparison of a 1,500-pair random sample."""
+    n = 1_000_000
+    sc = S.affine(-3, -1, 1, -1)
+    ctx = capi.Ctx(gpu_lib)
+    ctx.generate(scoring_to_params(algo, sc), synth.SEED, 20_000_000, n, 0, 250, 250)
+    ctx.run()
+    res = ctx.download(ops_capacity=n * 500)
+    assert ctx.last_kernel().startswith("pkg_fill")
+    bases, off1, off2, l1, l2 = ctx.download_inputs(n * 500)
+    score, ni, nj = _rescore_all_affine(bases, off1, off2, res, n, -3, -1, 1, -1)
+    assert np.array_equal(score, res.score[:n].astype(np.int64))
+    assert np.array_equal(ni, res.end_i[:n].astype(np.int64) - res.start_i[:n])
+    assert np.array_equal(nj, res.end_j[:n].astype(np.int64) - res.start_j[:n])
+    if algo == "ggotoh":
+        assert (res.start_i[:n] == 0).all() and (res.end_i[:n] == 250).all() and (res.end_j[:n] == 250).all()
+    ctx.run()
+    res2 = ctx.download(ops_capacity=n * 500)
+    assert np.array_equal(res.score[:n], res2.score[:n]) and res.c.ops_used == res2.c.ops_used
+    assert np.array_equal(res.ops[:res.c.ops_used], res2.ops[:res2.c.ops_used])
+    rng = np.random.default_rng(7)
+    for p in rng.integers(0, n, 1500):
+        p = int(p)
+        a = bytes(bases[int(off1[p]):int(off1[p]) + 250]).decode()
+        b = bytes(bases[int(off2[p]):int(off2[p]) + 250]).decode()
+        o = orc.oracle_align(algo, sc, a, b)
+        assert int(res.score[p]) == o["score"] and np.array_equal(res.pair_ops(p), o["ops"]), p
+
+
+def test_config4_full_length_pairs(gpu_lib):
+    """BASELINE configs[3] at its real pair length: 8 Hirschberg pairs of 100,000 x 100,000 bp (random DNA from the
+    shared generator) and 4 MyersMiller pairs of 30,000 bp, bit-exact against the oracle (one pair per host thread)."""
+    from concurrent.futures import ThreadPoolExecutor
+    for algo, sc, n, L in (("hirschberg", S.linear(-1, 2, -1), 8, 100_000), ("myersmiller", S.affine(-3, -1, 1, -1), 4, 30_000)):
+        ctx = capi.Ctx(gpu_lib)
+        ctx.generate(scoring_to_params(algo, sc), synth.SEED, 0, n, 0, L, L)
+        ctx.run()
+        res = ctx.download(ops_capacity=n * 2 * L)
+        assert ctx.last_kernel().endswith("_s16x2")
+        bases, off1, off2, l1, l2 = ctx.download_inputs(n * 2 * L)
+        seqs = [(bytes(bases[int(off1[p]):int(off1[p]) + L]).decode(), bytes(bases[int(off2[p]):int(off2[p]) + L]).decode())
+                for p in range(n)]
+        with ThreadPoolExecutor(max_workers=n) as ex:
+            outs = list(ex.map(lambda ab: orc.oracle_align(algo, sc, ab[0], ab[1]), seqs))
+        for p, o in enumerate(outs):
+            assert int(res.score[p]) == o["score"], (algo, p)
+            assert np.array_equal(res.pair_ops(p), o["ops"]), (algo, p)
+
+
 def test_mixed_length_batch(gpu_lib):
     """BASELINE configs[4] shape (independent U[50,1000] lengths, NW + SW over the same pairs), 3,000 pairs."""
     n = 3000
