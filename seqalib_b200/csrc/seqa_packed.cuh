@@ -433,12 +433,22 @@ struct PkOpWriter {
 };
 
 // ---- walk -------------------------------------------------------------------------------------------------
-// One thread per pair.  Exact neighbour values are rebuilt from the stored low bits:
-// H(n) = H(c) + sext_TB(low(n) - low(H(c))) for any cell n adjacent to the current cell c.
+// One thread per pair follows the reference's buildResult (include/SANeedlemanWunsch.h:155-231,
+// include/SASmithWaterman.h:220-339) on the stored low bits alone: neighbouring cells differ by less than 2^TB / 2
+// (host check), so  H(i,j) == H(i-1,j-1) + sim  <=>  low(i,j) - low(i-1,j-1) - sim == 0 (mod 2^TB)  -- the reference's
+// own equality tests, in its own order (diag, then up, else left), with no exact neighbour value ever rebuilt.  The
+// exact score is only tracked for SmithWaterman's stop test (H == 0) by subtracting each step's contribution.
+// Trace pieces (16 B) are cached in shared memory, 4 per thread, direct-mapped by the parity of the piece's row band
+// and column group: the 2 x 2 pieces around a cell never collide, and a lookup is a tag compare plus one LDS instead
+// of a register select tree.  Word w of slot s of thread t lives at pcw[s*4+w][t]: bank = t % 32, conflict-free.
+#define PK_WALK_TPB 256
 
 template <bool LOCAL, int TB, int R>
-__global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A)
+__global__ void __launch_bounds__(PK_WALK_TPB, 6) pk_walk_kernel(PkArgs A)
 {
+    __shared__ uint32_t pcw[16][PK_WALK_TPB];
+    __shared__ uint32_t tag[4][PK_WALK_TPB];
+    const int tid = threadIdx.x;
     const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= A.npos) return;
     const uint32_t p = A.perm[pos];
@@ -448,70 +458,81 @@ __global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A)
     const int M = (int)A.len1[p], N = (int)A.len2[p];
     const uint32_t Ng = (J.Nw + 3) >> 2;
     constexpr unsigned MASK = TB == 8 ? 0xffu : 0xfu;
+    constexpr int PRSH = TB == 8 ? 1 : 3; // rows per piece: 2 (TB 8: 2 rows x 4 columns x 2 pairs) or 8 (TB 4: this pair only)
+    constexpr uint32_t RG = (uint32_t)(R >> PRSH);
     PkSymCache a, b;
     a.init(A.bases, A.off1[p]);
     b.init(A.bases, A.off2[p]);
     const int gap = A.gap;
-    // 16-byte pieces (TB 8: 2 rows x 4 columns x 2 pairs; TB 4: 8 rows x 4 columns of this pair), see pk_fill_kernel;
-    // two of them are kept in registers (one per row-group parity), so a step usually costs no load at all
-    constexpr int PRSH = TB == 8 ? 1 : 3;
-    const uint32_t RG = (uint32_t)(R >> PRSH);
-    auto pkey = [&](int s, int cg, int r) -> uint32_t {
-        const uint32_t g = ((uint32_t)s * Ng + (uint32_t)cg) * RG + (uint32_t)(r >> PRSH);
-        return (TB == 8 ? g : g * 2u + (uint32_t)half) * 32u + (uint32_t)lane;
-    };
     const uint4 *pieces = reinterpret_cast<const uint4 *>(A.trace + J.trace_off);
-    uint4 cv[2];
-    uint32_t ck[2] = {0xffffffffu, 0xffffffffu};
-    auto pick = [&](const uint4 &v, int r, int c) -> unsigned { // low bits of (row r of the strip, column c of the group)
-        const int wsel = TB == 8 ? c : (((r & 7) >> 2) * 2 + (c >> 1));
-        const unsigned wv = wsel == 0 ? v.x : wsel == 1 ? v.y : wsel == 2 ? v.z : v.w;
-        return (wv >> (TB == 8 ? ((r & 1) * 2 + half) * 8 : (r & 3) * 8 + (c & 1) * 4)) & MASK;
-    };
-    auto low = [&](int i, int j) -> unsigned { // i >= 1, j >= 1
-        const int ii = i - 1, s = ii / R, r = ii - s * R, jj = j - 1;
-        const uint32_t key = pkey(s, jj >> 2, r);
-        const int e = (r >> PRSH) & 1;
-        const bool miss = e == 0 ? (ck[0] != key) : (ck[1] != key);
-        if (miss) {
-            if (e == 0) { cv[0] = pieces[key]; ck[0] = key; }
-            else { cv[1] = pieces[key]; ck[1] = key; }
+#pragma unroll
+    for (int q = 0; q < 4; q++) tag[q][tid] = 0xffffffffu;
+    // low TB bits of H(ii+1, jj+1) (0-based matrix cell ii, jj); see pk_fill_kernel for the piece layout
+    auto fetch = [&](int ii, int jj) -> unsigned {
+        const int s = ii / R, r = ii - s * R, cg = jj >> 2, c = jj & 3;
+        const uint32_t g = ((uint32_t)s * Ng + (uint32_t)cg) * RG + (uint32_t)(r >> PRSH);
+        const uint32_t key = (TB == 8 ? g : g * 2u + (uint32_t)half) * 32u + (uint32_t)lane;
+        const int slot = (((ii >> PRSH) & 1) << 1) | (cg & 1);
+        if (tag[slot][tid] != key) {
+            const uint4 v = pieces[key];
+            pcw[slot * 4 + 0][tid] = v.x;
+            pcw[slot * 4 + 1][tid] = v.y;
+            pcw[slot * 4 + 2][tid] = v.z;
+            pcw[slot * 4 + 3][tid] = v.w;
+            tag[slot][tid] = key;
         }
-        return pick(e == 0 ? cv[0] : cv[1], r, jj & 3);
+        const int w = TB == 8 ? c : (((r & 7) >> 2) * 2 + (c >> 1));
+        const int sh = TB == 8 ? ((r & 1) * 2 + half) * 8 : (r & 3) * 8 + (c & 1) * 4;
+        return (pcw[slot * 4 + w][tid] >> sh) & MASK;
     };
     auto sext = [&](unsigned d) -> int { // signed difference from its low TB bits
         return TB == 8 ? (int)(int8_t)(uint8_t)d : ((int)((d & 0xfu) ^ 8u) - 8);
     };
-    auto border = [&](int i, int j) -> int { return LOCAL ? 0 : (i == 0 ? j * gap : i * gap); };
-    auto near = [&](int hc, int i, int j) -> int { // exact H(i,j) given the exact value hc of an adjacent cell
-        if (i == 0 || j == 0) return border(i, j);
-        return hc + sext(low(i, j) - ((unsigned)hc & MASK));
+    auto border_low = [&](int i, int j) -> unsigned { // i == 0 or j == 0
+        return LOCAL ? 0u : (unsigned)((i == 0 ? j : i) * gap) & MASK;
     };
     PkOpWriter out;
     out.init(A.slots, A.slot_off[p] + (uint64_t)(M + N));
     int i, j, h;
     if (LOCAL) {
-        // MaxCol: the last column of row MaxRow holding MaxScore (include/SASmithWaterman.h:177-182).  One 16-byte
-        // load brings 4 (8) columns of the row; exact values are chained from H(i,0) = 0.
+        // MaxCol: the last column of row MaxRow holding MaxScore (include/SASmithWaterman.h:177-182); exact values are
+        // chained along the row from H(i,0) = 0 through the differences of neighbouring low bits
         const int best = A.score[p];
         i = (int)A.end_i[p];
         int e = 0, bj = N;
         if (i >= 1) {
-            const int ii = i - 1, s = ii / R, r = ii - s * R;
-            const int ng = (N + 3) >> 2;
-            for (int cg0 = 0; cg0 < ng; cg0 += 4) { // four independent piece loads in flight
+            // piece by piece (4 columns each), four independent 16-byte loads in flight, no cache bookkeeping
+            const int ii = i - 1, s = ii / R, r = ii - s * R, ng = (N + 3) >> 2;
+            const uint32_t g0 = (uint32_t)s * Ng * RG + (uint32_t)(r >> PRSH);
+            unsigned prev = 0;
+            for (int cg0 = 0; cg0 < ng; cg0 += 4) {
                 uint4 v4[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) v4[u] = pieces[pkey(s, min(cg0 + u, ng - 1), r)];
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t g = g0 + (uint32_t)min(cg0 + u, ng - 1) * RG;
+                    v4[u] = pieces[(TB == 8 ? g : g * 2u + (uint32_t)half) * 32u + (uint32_t)lane];
+                }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const int cg = cg0 + u;
+                    // the row's 4 columns of this piece -> nib[c]
+                    unsigned nib[4];
+                    if (TB == 8) {
+                        const int sh = ((r & 1) * 2 + half) * 8;
+                        nib[0] = (v4[u].x >> sh) & 0xffu; nib[1] = (v4[u].y >> sh) & 0xffu;
+                        nib[2] = (v4[u].z >> sh) & 0xffu; nib[3] = (v4[u].w >> sh) & 0xffu;
+                    } else {
+                        const bool hi = (r & 4) != 0;
+                        const int sh = (r & 3) * 8;
+                        const unsigned b01 = ((hi ? v4[u].z : v4[u].x) >> sh) & 0xffu, b23 = ((hi ? v4[u].w : v4[u].y) >> sh) & 0xffu;
+                        nib[0] = b01 & 0xfu; nib[1] = b01 >> 4; nib[2] = b23 & 0xfu; nib[3] = b23 >> 4;
+                    }
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
-                        const int jj = cg * 4 + c + 1;
-                        if (jj <= N) {
-                            e += sext(pick(v4[u], r, c) - ((unsigned)e & MASK));
-                            if (e == best) bj = jj;
+                        const int jj = (cg0 + u) * 4 + c;
+                        if (jj < N) {
+                            e += sext(nib[c] - prev);
+                            prev = nib[c];
+                            if (e == best) bj = jj + 1;
                         }
                     }
                 }
@@ -525,26 +546,30 @@ __global__ void __launch_bounds__(256, 6) pk_walk_kernel(PkArgs A)
         j = N;
         h = A.score[p];
     }
+    unsigned nc = (unsigned)h & MASK; // low bits of H(i,j)
     while (i > 0 && j > 0) {
         if (LOCAL && h == 0) break; // include/SASmithWaterman.h:281-284
         const bool eq = a.at(i - 1) == b.at(j - 1);
-        const int hdg = near(h, i - 1, j - 1);
-        if ((eq || A.allow) && h == hdg + (eq ? A.match : A.mismatch)) { // include/SANeedlemanWunsch.h:190
+        const int sim = eq ? A.match : A.mismatch;
+        const unsigned nd = (i == 1 || j == 1) ? border_low(i - 1, j - 1) : fetch(i - 2, j - 2);
+        if ((eq || A.allow) && ((nc - nd - (unsigned)sim) & MASK) == 0) { // H == H(i-1,j-1) + sim, include/SANeedlemanWunsch.h:190
             out.put(0);
             i--; j--;
-            h = hdg;
+            h -= sim;
+            nc = nd;
             continue;
         }
-        const int hup = near(h, i - 1, j);
-        if (h == hup + gap) { // include/SANeedlemanWunsch.h:216
+        const unsigned nu = i == 1 ? border_low(0, j) : fetch(i - 2, j - 1);
+        if (((nc - nu - (unsigned)gap) & MASK) == 0) { // H == H(i-1,j) + Gap, include/SANeedlemanWunsch.h:216
             out.put(1);
             i--;
-            h = hup;
+            nc = nu;
         } else { // :223
-            h = near(h, i, j - 1);
+            nc = j == 1 ? border_low(i, 0) : fetch(i - 1, j - 2);
             out.put(2);
             j--;
         }
+        h -= gap;
     }
     if (!LOCAL) { // borders: column 0 -> up, row 0 -> left
         while (i > 0) { out.put(1); i--; }
