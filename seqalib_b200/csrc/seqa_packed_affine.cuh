@@ -208,9 +208,14 @@ __global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
 // One thread per pair; state machine = reference buildResult (include/SAGlobalGotoh.h:235-422,
 // include/SALocalGotoh.h:275-473).  h / x / y are the EXACT values of H / Ix / Iy at the current cell.
 template <bool LOCAL, int R, int TB>
-__global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
+__global__ void __launch_bounds__(PK_WALK_TPB) pkg_walk_kernel(PkArgs A)
 {
     constexpr unsigned MASK = TB == 8 ? 0xffu : 0xfu;
+    // trace pieces cached in shared memory like pk_walk_kernel: per plane two slots, direct-mapped by the parity of
+    // the piece's row band (a step touches at most two bands of a plane); word w of slot q at pcw[q*4+w][thread]
+    __shared__ uint32_t pcw[24][PK_WALK_TPB];
+    __shared__ uint32_t tag[6][PK_WALK_TPB];
+    const int tid = threadIdx.x;
     const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= A.npos) return;
     const uint32_t p = A.perm[pos];
@@ -224,37 +229,28 @@ __global__ void __launch_bounds__(256) pkg_walk_kernel(PkArgs A)
     b.init(A.bases, A.off2[p]);
     const int go = A.go, ge = A.ge, gogo = go + ge;
     const uint4 *pieces = reinterpret_cast<const uint4 *>(A.trace + J.trace_off);
-    uint4 cv0 = make_uint4(0, 0, 0, 0), cv1 = cv0, cv2 = cv0;
-    uint32_t ck0 = 0xffffffffu, ck1 = 0xffffffffu, ck2 = 0xffffffffu;
-    auto pick = [&](const uint4 &v, int r, int j) -> unsigned {
-        const int wsel = (r & 7) >> 1;
-        const unsigned wv = wsel == 0 ? v.x : wsel == 1 ? v.y : wsel == 2 ? v.z : v.w;
-        return (wv >> (((r & 1) * 2 + half) * 8 + (TB == 4 ? ((j - 1) & 1) * 4 : 0))) & MASK;
-    };
-    auto key_of = [&](int plane, int i, int j, int &r) -> uint32_t { // i >= 1, j >= 1
-        const int ii = i - 1, s = ii / R;
-        r = ii - s * R;
+#pragma unroll
+    for (int q = 0; q < 6; q++) tag[q][tid] = 0xffffffffu;
+    // low TB bits of plane `plane` (0 G = H+go+ge, 1 Ix, 2 Iy) at matrix cell (i, j), i >= 1, j >= 1
+    auto low = [&](int plane, int i, int j) -> unsigned {
+        const int ii = i - 1, s = ii / R, r = ii - s * R;
         const uint32_t jc = TB == 8 ? (uint32_t)(j - 1) : (uint32_t)(j - 1) >> 1;
-        return ((((uint32_t)s * NC + jc) * 3u + (uint32_t)plane) * RH + (uint32_t)(r >> 3)) * 32u + (uint32_t)lane;
+        const uint32_t key = ((((uint32_t)s * NC + jc) * 3u + (uint32_t)plane) * RH + (uint32_t)(r >> 3)) * 32u + (uint32_t)lane;
+        const int slot = plane * 2 + ((ii >> 3) & 1);
+        if (tag[slot][tid] != key) {
+            const uint4 v = pieces[key];
+            pcw[slot * 4 + 0][tid] = v.x;
+            pcw[slot * 4 + 1][tid] = v.y;
+            pcw[slot * 4 + 2][tid] = v.z;
+            pcw[slot * 4 + 3][tid] = v.w;
+            tag[slot][tid] = key;
+        }
+        const int sh = ((r & 1) * 2 + half) * 8 + (TB == 4 ? ((j - 1) & 1) * 4 : 0);
+        return (pcw[slot * 4 + ((r & 7) >> 1)][tid] >> sh) & MASK;
     };
-    auto lowG = [&](int i, int j) -> unsigned {
-        int r;
-        const uint32_t k = key_of(0, i, j, r);
-        if (ck0 != k) { cv0 = pieces[k]; ck0 = k; }
-        return pick(cv0, r, j);
-    };
-    auto lowX = [&](int i, int j) -> unsigned {
-        int r;
-        const uint32_t k = key_of(1, i, j, r);
-        if (ck1 != k) { cv1 = pieces[k]; ck1 = k; }
-        return pick(cv1, r, j);
-    };
-    auto lowY = [&](int i, int j) -> unsigned {
-        int r;
-        const uint32_t k = key_of(2, i, j, r);
-        if (ck2 != k) { cv2 = pieces[k]; ck2 = k; }
-        return pick(cv2, r, j);
-    };
+    auto lowG = [&](int i, int j) -> unsigned { return low(0, i, j); };
+    auto lowX = [&](int i, int j) -> unsigned { return low(1, i, j); };
+    auto lowY = [&](int i, int j) -> unsigned { return low(2, i, j); };
     auto sext = [&](unsigned d) -> int { // signed difference from its low TB bits
         return TB == 8 ? (int)(int8_t)(uint8_t)d : ((int)((d & 0xfu) ^ 8u) - 8);
     };
