@@ -366,6 +366,31 @@ class StaticFuncs {
         AlignedSequence<Ty, Blank> Part = NW.getAlignment(V1, V2);
         Result.splice(Part);
     }
+
+    // Batched form of bridgeNW: the anchor-chaining aligners spend their DP time in many small
+    // NW calls between anchors (reference include/SAMummer.h:49,75,101, include/SABLAT.h:399).  Collect the windows
+    // of one or many alignments and submit them as ONE batch to the GPU path; Results[k] receives window k appended,
+    // exactly as bridgeNW(..., Windows[k]) would have.
+    struct Window {
+        int Idx1, Idx2, EndIdx1, EndIdx2;
+    };
+    static void bridgeNWBatch(ContainerType &Seq1, ContainerType &Seq2, const std::vector<Window> &Windows,
+                              std::vector<AlignedSequence<Ty, Blank>> &Results, ScoringSystem Scoring, MatchFnTy Match)
+    {
+        typedef ArrayView<ContainerType> View;
+        NeedlemanWunschSA<View, Ty, Blank, MatchFnTy> NW(Scoring, Match);
+        std::vector<std::pair<View, View>> Pairs;
+        Pairs.reserve(Windows.size());
+        for (const Window &W : Windows) {
+            View V1(Seq1), V2(Seq2);
+            V1.sliceWindow((size_t)W.Idx1, (size_t)W.EndIdx1);
+            V2.sliceWindow((size_t)W.Idx2, (size_t)W.EndIdx2);
+            Pairs.emplace_back(V1, V2);
+        }
+        std::vector<AlignedSequence<Ty, Blank>> Parts = NW.getAlignments(Pairs);
+        if (Results.size() < Windows.size()) Results.resize(Windows.size());
+        for (size_t K = 0; K < Windows.size(); K++) Results[K].splice(Parts[K]);
+    }
 };
 
 #endif // SEQA_SEQUENCE_ALIGNMENT_H

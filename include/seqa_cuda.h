@@ -160,6 +160,11 @@ int seqa_ctx_run(seqa_ctx *ctx);
 /* Copy the results of the last run to host buffers (synchronises the stream). */
 int seqa_ctx_download(seqa_ctx *ctx, seqa_batch_out *out);
 int seqa_ctx_sync(seqa_ctx *ctx);
+/* Device-resident results: fills `dev` with DEVICE pointers to the arrays of the last run
+ * (same layout and meaning as seqa_ctx_download would produce; ops are dense, ops_off relative to dev->ops) for a
+ * GPU consumer on the ctx stream.  Synchronises once (the packed path's bad-symbol check); the pointers stay valid
+ * until the next upload / generate / run on this ctx.  dev->ops_capacity and dev->ops_used receive the ops bytes. */
+int seqa_ctx_device_results(seqa_ctx *ctx, seqa_batch_out *dev);
 /* Number of kernels launched by this ctx since creation / sum(len1*len2) of the resident batch. */
 uint64_t seqa_ctx_launch_count(const seqa_ctx *ctx);
 uint64_t seqa_ctx_cells(const seqa_ctx *ctx);

@@ -23,7 +23,7 @@ ERR_NAMES = {0: "SEQA_OK", -1: "SEQA_ERR_INVALID", -2: "SEQA_ERR_UNSUPPORTED", -
 # every symbol include/seqa_cuda.h declares
 EXPORTS = ["seqa_cuda_align_batch", "seqa_cuda_last_error", "seqa_cuda_device_count", "seqa_cuda_abi_version",
            "seqa_ctx_create", "seqa_ctx_destroy", "seqa_ctx_upload", "seqa_ctx_generate", "seqa_ctx_run",
-           "seqa_ctx_download", "seqa_ctx_sync", "seqa_ctx_launch_count", "seqa_ctx_cells", "seqa_ctx_last_fill_ms",
+           "seqa_ctx_download", "seqa_ctx_device_results", "seqa_ctx_sync", "seqa_ctx_launch_count", "seqa_ctx_cells", "seqa_ctx_last_fill_ms",
            "seqa_ctx_last_kernel", "seqa_ctx_download_inputs", "seqa_cuda_int_peak", "seqa_cuda_trim"]
 
 
@@ -101,6 +101,7 @@ class Lib(object):
         L.seqa_ctx_run.argtypes = [C.c_void_p]
         L.seqa_ctx_sync.argtypes = [C.c_void_p]
         L.seqa_ctx_download.argtypes = [C.c_void_p, C.POINTER(BatchOut)]
+        L.seqa_ctx_device_results.argtypes = [C.c_void_p, C.POINTER(BatchOut)]
         L.seqa_ctx_launch_count.argtypes = [C.c_void_p]
         L.seqa_ctx_launch_count.restype = C.c_uint64
         L.seqa_ctx_cells.argtypes = [C.c_void_p]
@@ -177,6 +178,12 @@ class Ctx(object):
             results = Results(self.n, ops_capacity if ops_capacity is not None else self.slots)
         self.lib.check(self.lib.L.seqa_ctx_download(self.h, C.byref(results.c)))
         return results
+
+    def device_results(self):
+        """Device pointers of the last run's results (a BatchOut whose pointer fields are device addresses)."""
+        out = BatchOut()
+        self.lib.check(self.lib.L.seqa_ctx_device_results(self.h, C.byref(out)))
+        return out
 
     def download_inputs(self, total_bases):
         bases = np.zeros(max(total_bases, 1), dtype=np.uint8)

@@ -1034,6 +1034,25 @@ int seqa_ctx_sync(seqa_ctx *c)
     return ctx_resolve(c);
 }
 
+int seqa_ctx_device_results(seqa_ctx *c, seqa_batch_out *dev)
+{
+    if (!c || !dev) return fail(SEQA_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    if (!c->ran) return fail(SEQA_ERR_INVALID, "device results before run");
+    CKS(ctx_resolve(c));
+    dev->score = c->score.p;
+    dev->start_i = c->start_i.p;
+    dev->start_j = c->start_j.p;
+    dev->end_i = c->end_i.p;
+    dev->end_j = c->end_j.p;
+    dev->ops = c->dense.p;
+    dev->ops_off = c->ops_off.p;
+    dev->ops_len = c->ops_len.p;
+    dev->ops_used = c->n ? c->h_tail.p[0] : 0;
+    dev->ops_capacity = dev->ops_used;
+    return SEQA_OK;
+}
+
 int seqa_ctx_download(seqa_ctx *c, seqa_batch_out *out)
 {
     if (!c || !out) return fail(SEQA_ERR_INVALID, "NULL argument");

@@ -104,6 +104,23 @@ int main()
         expect("bridgeNW row1", R1, Q1);
         expect("bridgeNW row2", R2, Q2);
     }
+    { // StaticFuncs::bridgeNWBatch: the windows between anchors of a chaining aligner as ONE GPU batch
+        typedef StaticFuncs<std::string, char, '-'> SF;
+        std::string G1 = "ACGTACGTTTGACCAGTACGATCGATCGGCTA", G2 = "ACGTACGTTGACCAGTCGATCGGATCGGTTA";
+        std::vector<SF::Window> Ws = {{0, 0, 8, 8}, {8, 8, 16, 15}, {16, 15, 32, 31}, {3, 3, 3, 9}};
+        std::vector<AlignedSequence<char, '-'>> Batch;
+        SF::bridgeNWBatch(G1, G2, Ws, Batch, ScoringSystem(-1, 2, -1), nullptr);
+        for (size_t K = 0; K < Ws.size(); K++) {
+            AlignedSequence<char, '-'> One;
+            SF::bridgeNW(G1, G2, One, ScoringSystem(-1, 2, -1), Ws[K].Idx1, Ws[K].Idx2, Ws[K].EndIdx1, Ws[K].EndIdx2, nullptr);
+            std::string B1, B2, BF;
+            rows(Batch[K], B1, B2, BF);
+            rows(One, R1, R2, Fl);
+            expect("bridgeNWBatch row1", B1, R1);
+            expect("bridgeNWBatch row2", B2, R2);
+            expect("bridgeNWBatch flags", BF, Fl);
+        }
+    }
     { // a functor that is not equality is outside the GPU path
         bool Threw = false;
         try {

@@ -1,6 +1,8 @@
 """Parity tests proper: the CUDA path, called through the C ABI (seqa_cuda_align_batch / seqa_ctx_*), against the
 oracle on the same inputs -- bit-exact scores, end points and op strings -- plus the committed golden vectors of
 the unmodified reference and size-independent properties at the BASELINE batch size."""
+import os
+
 import numpy as np
 import pytest
 
@@ -316,6 +318,34 @@ def test_multi_device_split(gpu_lib):
     pairs = random_pairs(rng, 500, 1, 200)
     check_batch_against_oracle(gpu_lib, "sw", S.linear(-1, 1, -1), pairs, device_count=2)
     check_batch_against_oracle(gpu_lib, "ggotoh", S.affine(-3, -1, 1, -1), pairs, device_count=gpu_lib.device_count())
+
+
+def test_device_resident_results(gpu_lib):
+    """seqa_ctx_device_results: the arrays a GPU consumer would read equal what seqa_ctx_download copies out."""
+    import ctypes as C
+    import glob
+    import site
+    cands = ["/usr/local/cuda/lib64/libcudart.so"]
+    for sp in site.getsitepackages():
+        cands += glob.glob(os.path.join(sp, "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+    rt = C.CDLL([c for c in cands if os.path.exists(c)][-1])
+    n = 5000
+    ctx = capi.Ctx(gpu_lib)
+    ctx.generate(scoring_to_params("sw", S.linear(-1, 1, -1)), synth.SEED, 123, n, 0, 150, 150)
+    ctx.run()
+    dev = ctx.device_results()
+    res = ctx.download(ops_capacity=n * 300)
+    assert int(dev.ops_used) == int(res.c.ops_used) > 0
+
+    def d2h(ptr, nbytes, dtype):
+        out = np.zeros(nbytes // np.dtype(dtype).itemsize, dtype=dtype)
+        addr = int(ptr)
+        assert rt.cudaMemcpy(C.c_void_p(out.ctypes.data), C.c_void_p(addr), C.c_size_t(nbytes), 2) == 0
+        return out
+    assert np.array_equal(d2h(dev.score, n * 4, np.int32), res.score[:n])
+    assert np.array_equal(d2h(dev.ops_len, n * 4, np.uint32), res.ops_len[:n])
+    assert np.array_equal(d2h(dev.ops_off, n * 8, np.uint64), res.ops_off[:n])
+    assert np.array_equal(d2h(dev.ops, int(dev.ops_used), np.uint8), res.ops[:int(res.c.ops_used)])
 
 
 def test_int_peak_microbenchmark(gpu_lib):
