@@ -129,6 +129,29 @@ def cpu_reference_gcups(n_pairs, threads):
     return cells / sec / 1e9, kind, sec
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-GPU runs: keep this rank's threads and its pinned host buffers on the NUMA node its GPU hangs off
+    (torchrun does not place ranks; a remote node halves the PCIe copy rate of the end-to-end leg)."""
+    try:
+        q = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout.strip()
+        dom, bus, rest = q.lower().split(":")
+        node = int(open("/sys/bus/pci/devices/%s:%s:%s/numa_node" % (dom[-4:], bus, rest)).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -166,6 +189,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ["NCCL_DEBUG"] = os.environ.get("SEQA_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
@@ -297,7 +321,7 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2",
             "data": "synthetic",
             "config": {"workload": "SmithWatermanSA linear gap (-1,1,-1), %d random DNA pairs of %d bp per GPU, score+traceback" % (n, LEN),
-                       "pairs_per_gpu": n, "len": LEN, "parallelism": "pairs sharded statically over %d GPU(s), no collective" % world,
+                       "pairs_per_gpu": n, "len": LEN, "parallelism": "pairs sharded statically over %d GPU(s), no collective" % world, "numa_bound": numa is not None,
                        "l2": "no flush needed: every step streams %.1f GB of trace + %.0f MB of inputs through HBM (L2 is 126 MB)"
                              % (cells / 1e9 * 0.5 * 16 / 15 * 152 / 150, tot_bases / 1e6),
                        "result_checksum": checksum},
