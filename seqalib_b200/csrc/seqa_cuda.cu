@@ -661,7 +661,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
         const unsigned wpb = PK_BLOCK / 32;
         const unsigned full = (nj + wpb - 1) / wpb;
         const unsigned grid = std::min<unsigned>(full, (unsigned)(c->sms * bps));
-        LAUNCH(c, (pk_prep_kernel), std::min<unsigned>(full, (unsigned)c->sms * 16), PK_BLOCK, 0, A, PK_R);
+        LAUNCH(c, (pk_prep_kernel), full, PK_BLOCK, 0, A, PK_R); // one job per warp
         cudaEventRecord(next_event(c), c->stream);
         if (affine && local && tb == 4)
             LAUNCH(c, (pkg_fill_kernel<true, PK_R, 4>), grid, PK_BLOCK, 0, A);
