@@ -143,6 +143,8 @@ def oracle_lib():
                                                       C.c_void_p, C.c_int, C.POINTER(C.c_int * 5)]
         lib.oracle_bench.restype = C.c_double
         lib.oracle_bench.argtypes = [C.c_int] * 7 + [C.c_void_p] * 5 + [C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+        lib.oracle_align_batch.restype = C.c_int
+        lib.oracle_align_batch.argtypes = [C.c_int] * 7 + [C.c_void_p] * 5 + [C.c_uint64, C.c_int] + [C.c_void_p] * 8
         _orc = lib
     return _orc
 
@@ -160,6 +162,43 @@ def oracle_align(algo, sc, s1, s2):
     if n < 0:
         raise RuntimeError("oracle_align failed: %d" % n)
     return dict(score=meta[0], start_i=meta[1], start_j=meta[2], end_i=meta[3], end_j=meta[4], ops=ops[:n].copy())
+
+
+class OracleBatch:
+    """Results of oracle_align_batch in the C-ABI's array layout (ops of pair p at slot_off[p], length ops_len[p])."""
+
+    def pair_ops(self, p):
+        o = int(self.slot_off[p])
+        return self.ops[o:o + int(self.ops_len[p])]
+
+
+def oracle_align_batch(algo, sc, bases, off1, off2, len1, len2, threads=0):
+    """Threaded C-oracle run over a whole batch -> OracleBatch (for the >= 100 k-pair parity samples)."""
+    lib = oracle_lib()
+    a = ALGOS[algo] if isinstance(algo, str) else algo
+    _, gap, go, ge, m, x, allow = sc.astuple()
+    n = len(len1)
+    threads = threads or len(os.sched_getaffinity(0))
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    off1 = np.ascontiguousarray(off1, dtype=np.uint64)
+    off2 = np.ascontiguousarray(off2, dtype=np.uint64)
+    len1 = np.ascontiguousarray(len1, dtype=np.uint32)
+    len2 = np.ascontiguousarray(len2, dtype=np.uint32)
+    r = OracleBatch()
+    slots = len1.astype(np.uint64) + len2
+    r.slot_off = np.zeros(n, dtype=np.uint64)
+    if n > 1:
+        np.cumsum(slots[:-1], out=r.slot_off[1:])
+    r.score = np.zeros(n, dtype=np.int32)
+    r.start_i, r.start_j, r.end_i, r.end_j, r.ops_len = (np.zeros(n, dtype=np.uint32) for _ in range(5))
+    r.ops = np.zeros(int(slots.sum()) + 8, dtype=np.uint8)
+    rc = lib.oracle_align_batch(a, gap, go, ge, m, x, allow, bases.ctypes.data, off1.ctypes.data, off2.ctypes.data,
+                                len1.ctypes.data, len2.ctypes.data, n, threads, r.score.ctypes.data, r.start_i.ctypes.data,
+                                r.start_j.ctypes.data, r.end_i.ctypes.data, r.end_j.ctypes.data, r.ops_len.ctypes.data,
+                                r.slot_off.ctypes.data, r.ops.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("oracle_align_batch failed: %d" % rc)
+    return r
 
 
 def oracle_bench(algo, sc, bases, off1, off2, len1, len2, threads):

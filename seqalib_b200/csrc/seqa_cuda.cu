@@ -595,6 +595,16 @@ int run_generic(seqa_ctx *c, bool want_walk)
     return SEQA_OK;
 }
 
+static int env_int(const char *name, int dflt, int lo, int hi)
+{
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    const long x = strtol(v, nullptr, 10);
+    return (int)std::min<long>(hi, std::max<long>(lo, x));
+}
+// resident CTAs per SM of the packed affine fill (168 registers x 128 threads: 3 fit); SEQA_PKG_BPS overrides for A/B runs
+static int pkg_ctas_per_sm() { static const int v = env_int("SEQA_PKG_BPS", 3, 1, 3); return v; }
+
 int run_packed(seqa_ctx *c, bool want_walk)
 {
     if (c->jobs.empty()) return SEQA_OK;
@@ -610,7 +620,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
         CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const int bps = affine ? 2 : (int)std::max<size_t>(1, std::min<size_t>(3, (c->smem_optin + 1024) / std::max<size_t>(smem + 1024, 1)));
+    const int bps = affine ? pkg_ctas_per_sm() : (int)std::max<size_t>(1, std::min<size_t>(3, (c->smem_optin + 1024) / std::max<size_t>(smem + 1024, 1)));
     const uint64_t bound_stride = (uint64_t)((c->pk_max_nw + 3) / 4) * (affine ? 64 : 32);
     if (affine || gb) CKS(c->pk_bound.ensure((size_t)c->sms * bps * (PK_BLOCK / 32) * bound_stride));
     CK(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 4, c->stream));
@@ -1104,13 +1114,6 @@ int seqa_ctx_download_inputs(seqa_ctx *c, char *bases, uint64_t bases_len, uint6
 // in flight together; a device whose cached contexts are all busy gets a temporary one.
 #define SEQA_CACHE_SLOTS 8
 #define SEQA_WORKERS 2 /* default host threads per device; each double-buffers two contexts */
-static int env_int(const char *name, int dflt, int lo, int hi)
-{
-    const char *v = getenv(name);
-    if (!v || !*v) return dflt;
-    const long x = strtol(v, nullptr, 10);
-    return (int)std::min<long>(hi, std::max<long>(lo, x));
-}
 static std::mutex g_cache_mu;
 static cudaStream_t g_pipe_stream[64][4]; // per device: upload / kernel (even waves) / download / kernel (odd waves) streams of the pipelined one-shot call
 static seqa_ctx *g_cache[64][SEQA_CACHE_SLOTS];
@@ -1214,7 +1217,7 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
             }
             if (sms_cache[dev] > 0) {
                 const uint64_t per_cta = PK_BLOCK / 32 * 64;
-                const uint64_t cta_per_sm = packed_affine(*params) ? 2 : (l2[0] > PK_MAX_LEN ? 3 : std::max<uint64_t>(1, std::min<uint64_t>(3, (227 * 1024) / ((uint64_t)l2[0] * PK_BLOCK * 4 + 1024))));
+                const uint64_t cta_per_sm = packed_affine(*params) ? (uint64_t)pkg_ctas_per_sm() : (l2[0] > PK_MAX_LEN ? 3 : std::max<uint64_t>(1, std::min<uint64_t>(3, (227 * 1024) / ((uint64_t)l2[0] * PK_BLOCK * 4 + 1024))));
                 const uint64_t round = (uint64_t)sms_cache[dev] * cta_per_sm * per_cta;
                 const uint64_t round_cells = round * ((uint64_t)l1[0] * l2[0] + 1);
                 const uint64_t rounds = std::max<uint64_t>(1, (wave_cells + round_cells / 2) / round_cells);

@@ -34,7 +34,7 @@ __host__ __device__ inline uint64_t pkg_trace_bytes(uint32_t nstrips, uint32_t N
 // TB == 4 halves the HBM write stream that bounds the 8-bit variant; the host admits it when every difference the
 // walk tests stays below 16 (packed_affine_trace_bits in seqa_cuda.cu).
 template <bool LOCAL, int R, int TB>
-__global__ void __launch_bounds__(PK_BLOCK, 2) pkg_fill_kernel(PkArgs A)
+__global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
 {
     static_assert(TB == 4 || TB == 8, "trace bits");
     static_assert(R % 8 == 0, "strips are cut into 8-row trace pieces");

@@ -61,3 +61,34 @@ def check_batch_against_oracle(lib, algo, sc, pairs, flags=0, device_count=1, la
             raise AssertionError("%s %s %r pair %d (%s | %s): got %r ops %s, expected %r ops %s" % (
                 label, algo, sc, p, a, b, got, ops.tolist(), exp, o["ops"].tolist()))
     return len(pairs)
+
+
+def _ragged_equal(ops_a, off_a, ops_b, off_b, lens):
+    """Index of the first pair whose op strings differ (ops_x[off_x[p] : off_x[p]+lens[p]]), or -1.  Vectorised."""
+    lens = lens.astype(np.int64)
+    tot = int(lens.sum())
+    if tot == 0:
+        return -1
+    owner = np.repeat(np.arange(len(lens), dtype=np.int64), lens)
+    start = np.cumsum(lens) - lens
+    within = np.arange(tot, dtype=np.int64) - start[owner]
+    a = ops_a[off_a.astype(np.int64)[owner] + within]
+    b = ops_b[off_b.astype(np.int64)[owner] + within]
+    bad = np.nonzero(a != b)[0]
+    return int(owner[bad[0]]) if len(bad) else -1
+
+
+def compare_with_oracle_batch(res, algo, sc, bases, off1, off2, len1, len2, label=""):
+    """Every field of every pair of a GPU result (capi.Results) against the threaded C oracle, bit-exact.
+    Used for the >= 100 k-pair parity samples of SURVEY.md 8d.  Returns the number of pairs compared."""
+    o = orc.oracle_align_batch(algo, sc, bases, off1, off2, len1, len2)
+    n = len(len1)
+    for name in ("score", "start_i", "start_j", "end_i", "end_j", "ops_len"):
+        g, e = getattr(res, name)[:n], getattr(o, name)[:n]
+        bad = np.nonzero(g != e)[0]
+        assert len(bad) == 0, "%s %s %r: %s of pair %d is %d, oracle %d (%d pairs differ)" % (
+            label, algo, sc, name, bad[0], g[bad[0]], e[bad[0]], len(bad))
+    p = _ragged_equal(res.ops, res.ops_off[:n], o.ops, o.slot_off, o.ops_len)
+    assert p < 0, "%s %s %r: ops of pair %d differ: got %s, oracle %s" % (
+        label, algo, sc, p, res.pair_ops(p).tolist(), o.pair_ops(p).tolist())
+    return n

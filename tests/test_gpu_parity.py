@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from common import capi, check_batch_against_oracle, orc, random_pairs, scoring_to_params
+from common import capi, check_batch_against_oracle, compare_with_oracle_batch, orc, random_pairs, scoring_to_params
 from seqalib_b200 import synth
 from test_oracle_golden import sc_from
 
@@ -109,8 +109,9 @@ def test_linear_space_long_pairs(gpu_lib, algo, sc, n, lo, hi):
 
 @pytest.mark.parametrize("algo", ["sw", "nw"])
 def test_config2_shape_150bp(gpu_lib, algo):
-    """20,000 pairs of the BASELINE 150 bp workload (same generator and seed as bench.py) vs the oracle."""
-    n = 20000
+    """a 100,000-pair sample of the BASELINE 150 bp workload (same generator and seed as
+    bench.py), every field and every op bit-exact against the oracle."""
+    n = 100_000
     sc = S.linear(-1, 1, -1) if algo == "sw" else S.linear(-1, 2, -1)
     ctx = capi.Ctx(gpu_lib)
     ctx.generate(scoring_to_params(algo, sc), synth.SEED, 0, n, 0, 150, 150)
@@ -120,36 +121,22 @@ def test_config2_shape_150bp(gpu_lib, algo):
     bases, off1, off2, l1, l2 = ctx.download_inputs(n * 300)
     hb, _, _, _, _ = synth.batch(synth.SEED, 0, 64, 0, 150, 150)
     assert np.array_equal(hb, bases[:64 * 300])  # device generator == numpy generator
-    for p in range(n):
-        a = bytes(bases[int(off1[p]):int(off1[p]) + 150]).decode()
-        b = bytes(bases[int(off2[p]):int(off2[p]) + 150]).decode()
-        o = orc.oracle_align(algo, sc, a, b)
-        assert int(res.score[p]) == o["score"], p
-        assert (int(res.start_i[p]), int(res.start_j[p]), int(res.end_i[p]), int(res.end_j[p])) == \
-            (o["start_i"], o["start_j"], o["end_i"], o["end_j"]), p
-        assert np.array_equal(res.pair_ops(p), o["ops"]), p
+    assert compare_with_oracle_batch(res, algo, sc, bases, off1, off2, l1, l2, "config2") == n
 
 
 @pytest.mark.parametrize("algo,sc", [("ggotoh", S.affine(-3, -1, 1, -1)), ("lgotoh", S.affine(-3, -1, 1, -1)),
                                      ("ggotoh", S.affine(-3, -1, 1, -1, False)), ("lgotoh", S.affine(-3, -1, 1, -1, False))])
 def test_config3_shape_250bp(gpu_lib, algo, sc):
-    """6,000 pairs of the BASELINE config-3 workload (250 bp, Gotoh (-3,-1,1,-1), + the AllowMismatch=false variant)
-    through the packed affine kernels vs the oracle."""
-    n = 6000 if sc.allow else 2000
+    """a 100,000-pair sample of the 250 bp Gotoh (-3,-1,1,-1) workload per algorithm (+ 20,000
+    pairs of the AllowMismatch=false variant) through the packed affine kernels, bit-exact against the oracle."""
+    n = 100_000 if sc.allow else 20_000
     ctx = capi.Ctx(gpu_lib)
     ctx.generate(scoring_to_params(algo, sc), synth.SEED, 7_000_000, n, 0, 250, 250)
     ctx.run()
     res = ctx.download(ops_capacity=n * 500)
     assert ctx.last_kernel().startswith("pkg_fill")
     bases, off1, off2, l1, l2 = ctx.download_inputs(n * 500)
-    for p in range(n):
-        a = bytes(bases[int(off1[p]):int(off1[p]) + 250]).decode()
-        b = bytes(bases[int(off2[p]):int(off2[p]) + 250]).decode()
-        o = orc.oracle_align(algo, sc, a, b)
-        assert int(res.score[p]) == o["score"], p
-        assert (int(res.start_i[p]), int(res.start_j[p]), int(res.end_i[p]), int(res.end_j[p])) == \
-            (o["start_i"], o["start_j"], o["end_i"], o["end_j"]), p
-        assert np.array_equal(res.pair_ops(p), o["ops"]), p
+    assert compare_with_oracle_batch(res, algo, sc, bases, off1, off2, l1, l2, "config3") == n
 
 
 def _rescore_all(bases, off1, off2, res, n, gap, match, mismatch):
@@ -293,8 +280,9 @@ def test_config4_full_length_pairs(gpu_lib):
 
 
 def test_mixed_length_batch(gpu_lib):
-    """BASELINE configs[4] shape (independent U[50,1000] lengths, NW + SW over the same pairs), 3,000 pairs."""
-    n = 3000
+    """a 100,000-pair sample of the mixed-length workload (independent U[50,1000] lengths,
+    NW (-1,2,-1) and SW (-1,1,-1) over the same pairs, generated on the device and read back for the oracle)."""
+    n = 100_000
     for algo, sc in (("nw", S.linear(-1, 2, -1)), ("sw", S.linear(-1, 1, -1))):
         ctx = capi.Ctx(gpu_lib)
         ctx.generate(scoring_to_params(algo, sc), synth.SEED, 5_000_000, n, 1)
@@ -302,13 +290,11 @@ def test_mixed_length_batch(gpu_lib):
         l1, l2 = synth.lengths(synth.SEED, 5_000_000, n)
         tot = int(l1.sum() + l2.sum())
         res = ctx.download(ops_capacity=tot)
+        assert ctx.last_kernel().startswith("pk_fill")
         bases, off1, off2, d1, d2 = ctx.download_inputs(tot)
         assert np.array_equal(d1, l1) and np.array_equal(d2, l2)
-        for p in range(n):
-            a = bytes(bases[int(off1[p]):int(off1[p]) + int(l1[p])]).decode()
-            b = bytes(bases[int(off2[p]):int(off2[p]) + int(l2[p])]).decode()
-            o = orc.oracle_align(algo, sc, a, b)
-            assert int(res.score[p]) == o["score"] and np.array_equal(res.pair_ops(p), o["ops"]), (algo, p)
+        assert compare_with_oracle_batch(res, algo, sc, bases, off1, off2, l1, l2, "config5") == n
+        ctx.close()
 
 
 def test_multi_device_split(gpu_lib):

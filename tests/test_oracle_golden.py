@@ -109,3 +109,26 @@ def test_differential_fuzz_vs_reference(oracle_built, algo):
                 assert o["score"] == r["score"]
             n += 1
     assert n > 250
+
+
+def test_oracle_batch_entry_matches_single_pair_entry():
+    """oracle_align_batch (threaded, used for the 100 k-pair GPU parity samples) == oracle_align pair by pair,
+    and the vectorised comparison helper flags a single flipped op."""
+    from common import _ragged_equal
+    rng = np.random.default_rng(5)
+    pairs = random_pairs(rng, 150, 0, 90) + random_pairs(rng, 50, 1, 200, related=0.3) + [("", "ACGT"), ("ACGT", ""), ("", "")]
+    bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+    for algo, sc in (("nw", orc.Scoring.linear(-1, 2, -1)), ("sw", orc.Scoring.linear(-1, 1, -1)),
+                     ("ggotoh", orc.Scoring.affine(-3, -1, 1, -1)), ("lgotoh", orc.Scoring.affine(-3, -1, 1, -1, False)),
+                     ("hirschberg", orc.Scoring.linear(-1, 2, -1)), ("myersmiller", orc.Scoring.affine(-3, -1, 1, -1))):
+        r = orc.oracle_align_batch(algo, sc, bases, off1, off2, len1, len2, threads=3)
+        for p, (a, b) in enumerate(pairs):
+            o = orc.oracle_align(algo, sc, a, b)
+            assert (int(r.score[p]), int(r.start_i[p]), int(r.start_j[p]), int(r.end_i[p]), int(r.end_j[p])) == \
+                (o["score"], o["start_i"], o["start_j"], o["end_i"], o["end_j"]), (algo, p)
+            assert np.array_equal(r.pair_ops(p), o["ops"]), (algo, p)
+        assert _ragged_equal(r.ops, r.slot_off, r.ops, r.slot_off, r.ops_len) == -1
+        flipped = r.ops.copy()
+        victim = int(np.nonzero(r.ops_len > 3)[0][7])
+        flipped[int(r.slot_off[victim]) + 2] ^= 3
+        assert _ragged_equal(flipped, r.slot_off, r.ops, r.slot_off, r.ops_len) == victim
