@@ -418,8 +418,8 @@ int build_plan(seqa_ctx *c)
         std::fill(c->perm.p + pkl.size(), c->perm.p + njobs * 64, PK_NULL);
         c->jobs.resize(njobs);
         Chunk ch{0, 0, 0};
-        uint64_t tr = 0, pf = 0, rs = 0; // running offsets inside the chunk
-        auto chunk_bytes = [&](uint64_t t, uint64_t q, uint64_t r) { return t + q * 8 + r * 4 + 4096; };
+        uint64_t tr = 0, pf = 0, rs = 0, lc = 0; // running offsets inside the chunk
+        auto chunk_bytes = [&](uint64_t t, uint64_t q, uint64_t r, uint64_t l) { return t + q * 8 + r * 4 + l * 16 + 4096; };
         for (size_t w = 0; w < njobs; w++) {
             uint32_t Mw = 0, Nw = 0;
             if (fast) {
@@ -441,24 +441,27 @@ int build_plan(seqa_ctx *c)
             const uint64_t tbytes = packed_affine(prm) ? pkg_trace_bytes(J.nstrips, Nw, PK_R, packed_affine_trace_bits(prm))
                                                        : pk_trace_bytes(J.nstrips, Nw, PK_R, packed_trace_bits(prm));
             const uint64_t pelems = (uint64_t)((Nw + 3) / 4) * 128, relems = (uint64_t)J.nstrips * PK_R * 32;
-            if (ch.hi > ch.lo && chunk_bytes(tr + tbytes, pf + pelems, rs + relems) > budget) {
-                ch.scratch_bytes = chunk_bytes(tr, pf, rs);
+            const uint64_t lelems = (uint64_t)J.nstrips * (PK_R / 4) * 32; // last-column values (SW walk), uint4
+            if (ch.hi > ch.lo && chunk_bytes(tr + tbytes, pf + pelems, rs + relems, lc + lelems) > budget) {
+                ch.scratch_bytes = chunk_bytes(tr, pf, rs, lc);
                 c->pk_chunks.push_back(ch);
                 ch.lo = ch.hi;
-                tr = pf = rs = 0;
+                tr = pf = rs = lc = 0;
             }
             J.trace_off = tr;
             J.prof_off = pf;
             J.rowsel_off = rs;
+            J.last_off = lc;
             tr += tbytes;
             pf += pelems;
             rs += relems;
+            lc += lelems;
             ch.hi = (uint32_t)(w + 1);
             c->pk_max_nw = std::max(c->pk_max_nw, Nw);
         }
-        ch.scratch_bytes = chunk_bytes(tr, pf, rs);
+        ch.scratch_bytes = chunk_bytes(tr, pf, rs, lc);
         c->pk_chunks.push_back(ch);
-        // chunk-relative layout: [trace | prof (8 B) | rowsel (4 B)], offsets resolved at launch
+        // chunk-relative layout: [trace | prof (8 B) | rowsel (4 B) | lastcol (16 B)], offsets resolved at launch
         CKS(c->d_perm.ensure(c->perm_n));
         CKS(c->d_jobs.ensure(c->jobs.size()));
         CKS(c->jobs_pin.ensure(c->jobs.size()));
@@ -605,6 +608,16 @@ static int env_int(const char *name, int dflt, int lo, int hi)
 // resident CTAs per SM of the packed affine fill (168 registers x 128 threads: 3 fit); SEQA_PKG_BPS overrides for A/B runs
 static int pkg_ctas_per_sm() { static const int v = env_int("SEQA_PKG_BPS", 3, 1, 3); return v; }
 
+// resident CTAs per SM of the packed linear fill: its dynamic shared memory (one strip-boundary column per thread)
+// is the limit, plus the 1 KB the driver reserves per CTA.  Used by the launch AND by the wave sizing of the one-shot
+// call, which cuts waves at whole rounds of this kernel.
+static int pk_ctas_per_sm(size_t smem_optin, uint32_t cols)
+{
+    if (cols > PK_MAX_LEN) return 3; // strip boundaries in global memory: registers are the limit
+    const size_t smem = (size_t)cols * PK_BLOCK * 4;
+    return (int)std::max<size_t>(1, std::min<size_t>(3, (smem_optin + 1024) / (smem + 1024)));
+}
+
 int run_packed(seqa_ctx *c, bool want_walk)
 {
     if (c->jobs.empty()) return SEQA_OK;
@@ -620,18 +633,19 @@ int run_packed(seqa_ctx *c, bool want_walk)
         CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const int bps = affine ? pkg_ctas_per_sm() : (int)std::max<size_t>(1, std::min<size_t>(3, (c->smem_optin + 1024) / std::max<size_t>(smem + 1024, 1)));
+    const int bps = affine ? pkg_ctas_per_sm() : pk_ctas_per_sm(c->smem_optin, c->pk_max_nw);
     const uint64_t bound_stride = (uint64_t)((c->pk_max_nw + 3) / 4) * (affine ? 64 : 32);
     if (affine || gb) CKS(c->pk_bound.ensure((size_t)c->sms * bps * (PK_BLOCK / 32) * bound_stride));
     CK(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 4, c->stream));
     for (const Chunk &ch : c->pk_chunks) {
         const uint32_t nj = ch.hi - ch.lo;
-        // chunk layout: trace | prof | rowsel
-        uint64_t tr = 0, pf = 0;
+        // chunk layout: trace | prof | rowsel | lastcol
+        uint64_t tr = 0, pf = 0, rs = 0;
         {
             const PkWarpJob &L = c->jobs[ch.hi - 1];
             tr = L.trace_off + (affine ? pkg_trace_bytes(L.nstrips, L.Nw, PK_R, tb) : pk_trace_bytes(L.nstrips, L.Nw, PK_R, tb));
             pf = L.prof_off + (uint64_t)((L.Nw + 3) / 4) * 128;
+            rs = L.rowsel_off + (uint64_t)L.nstrips * PK_R * 32;
         }
         PkArgs A{};
         A.bases = c->bases.p;
@@ -645,6 +659,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
         A.trace = c->scratch.p;
         A.prof = reinterpret_cast<uint2 *>(c->scratch.p + ((tr + 255) / 256) * 256);
         A.rowsel = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(A.prof) + pf * 8);
+        A.lastcol = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(A.rowsel) + ((rs * 4 + 15) / 16) * 16);
         A.score = c->score.p;
         A.end_i = c->end_i.p;
         A.end_j = c->end_j.p;
@@ -1209,15 +1224,19 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
         // resident warp), otherwise every wave pays a mostly idle last round.
         if (uni && !linspace && n > 1 && packed_scoring_ok(*params) && packed_shape_ok(*params, l1[0], l2[0])) {
             static int sms_cache[64];
+            static size_t smem_cache[64];
             const int dev = first < 64 ? first : 0;
             if (!sms_cache[dev]) {
                 cudaDeviceProp prop;
-                if (cudaGetDeviceProperties(&prop, first) == cudaSuccess) sms_cache[dev] = prop.multiProcessorCount;
+                if (cudaGetDeviceProperties(&prop, first) == cudaSuccess) {
+                    smem_cache[dev] = prop.sharedMemPerBlockOptin;
+                    sms_cache[dev] = prop.multiProcessorCount;
+                }
                 (void)cudaGetLastError();
             }
             if (sms_cache[dev] > 0) {
                 const uint64_t per_cta = PK_BLOCK / 32 * 64;
-                const uint64_t cta_per_sm = packed_affine(*params) ? (uint64_t)pkg_ctas_per_sm() : (l2[0] > PK_MAX_LEN ? 3 : std::max<uint64_t>(1, std::min<uint64_t>(3, (227 * 1024) / ((uint64_t)l2[0] * PK_BLOCK * 4 + 1024))));
+                const uint64_t cta_per_sm = packed_affine(*params) ? (uint64_t)pkg_ctas_per_sm() : (uint64_t)pk_ctas_per_sm(smem_cache[dev], l2[0]);
                 const uint64_t round = (uint64_t)sms_cache[dev] * cta_per_sm * per_cta;
                 const uint64_t round_cells = round * ((uint64_t)l1[0] * l2[0] + 1);
                 const uint64_t rounds = std::max<uint64_t>(1, (wave_cells + round_cells / 2) / round_cells);

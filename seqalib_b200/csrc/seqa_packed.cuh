@@ -34,6 +34,7 @@ struct PkWarpJob {
     uint64_t trace_off;  // byte offset of the warp's trace region
     uint64_t prof_off;   // uint2 index of the column profile  [ceil(Nw/4)][32][4]
     uint64_t rowsel_off; // uint32 index of the row selectors  [nstrips*R][32]
+    uint64_t last_off;   // uint4 index of the last-column values (SmithWaterman) [nstrips][R/4][32]
 };
 
 struct PkArgs {
@@ -45,6 +46,7 @@ struct PkArgs {
     uint32_t njobs;
     uint2 *prof;
     uint32_t *rowsel;
+    uint4 *lastcol; // SW: exact H of every row in the last (padded) column, 4 rows x 2 pairs per uint4
     uint8_t *trace;
     int32_t *score;
     uint32_t *end_i, *end_j, *start_i, *start_j;
@@ -78,21 +80,23 @@ __device__ __forceinline__ bool pk_is_acgt(unsigned c) { return c == 'A' || c ==
 // ---- prep: column profiles + row selectors ----------------------------------------------------------------
 // Sequences are read as ALIGNED 32-bit words (one load per 4 symbols; a funnel shift restores the pair's own
 // alignment): a warp's lanes read 32 different sequences, so the number of load instructions, not bytes, is the
-// cost.  Words may reach 3 bytes before / after a sequence; `bases` is 4-byte aligned with 16 bytes of slack.
+// cost.  Words may reach 3 bytes before / 11 bytes after a sequence; `bases` is 4-byte aligned with 16 bytes of slack.
 struct PkSeqReader {
     const uint32_t *w; // aligned word pointer
     unsigned sh;       // bit shift of the first symbol inside *w
-    uint32_t carry;
+    uint32_t carry, ahead; // `ahead` is loaded one call early: the load of call k+1 overlaps the work of call k
     __device__ __forceinline__ void init(const uint8_t *base, const uint8_t *p)
     {
         const uint64_t o = (uint64_t)(p - base);
         w = reinterpret_cast<const uint32_t *>(base) + (o >> 2);
         sh = (unsigned)(o & 3u) * 8u;
-        carry = *w++;
+        carry = __ldg(w++);
+        ahead = __ldg(w++);
     }
     __device__ __forceinline__ uint32_t next4() // the next 4 symbols, first in the low byte
     {
-        const uint32_t hi = *w++;
+        const uint32_t hi = ahead;
+        ahead = __ldg(w++);
         const uint32_t v = sh ? ((carry >> sh) | (hi << (32u - sh))) : carry;
         carry = hi;
         return v;
@@ -349,6 +353,12 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                 }
             }
             if (LOCAL) {
+                // exact H of the strip's rows in the last stored column (4*Ng): the walk chains row MaxRow's low bits
+                // leftwards from it and stops at the first (= last, include/SASmithWaterman.h:177) column holding MaxScore
+                static_assert(R % 4 == 0, "last-column pieces hold 4 rows");
+                uint4 *lc = A.lastcol + J.last_off + (uint64_t)s * (R / 4) * 32 + lane;
+#pragma unroll
+                for (int q = 0; q < R / 4; q++) pk_store_stream(&lc[q * 32], make_uint4(H[4 * q], H[4 * q + 1], H[4 * q + 2], H[4 * q + 3]));
                 // last maximum in row-major order (include/SASmithWaterman.h:177): rows ascending, ">="
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -501,41 +511,45 @@ __global__ void __launch_bounds__(PK_WALK_TPB, 6) pk_walk_kernel(PkArgs A)
         i = (int)A.end_i[p];
         int e = 0, bj = N;
         if (i >= 1) {
-            // piece by piece (4 columns each), four independent 16-byte loads in flight, no cache bookkeeping
-            const int ii = i - 1, s = ii / R, r = ii - s * R, ng = (N + 3) >> 2;
+            // from the right: e = exact H(i, 4*ng) stored by the fill; one step left subtracts the signed difference of
+            // the neighbouring low bits.  The first hit is the last column holding MaxScore; for the near-global
+            // alignments of the linear-growth regime it sits within a few pieces of the right edge (two 16-byte loads
+            // in flight), and in the worst case the whole row is read once, as a left-to-right scan always would.
+            const int ii = i - 1, s = ii / R, r = ii - s * R, ng = (int)Ng;
             const uint32_t g0 = (uint32_t)s * Ng * RG + (uint32_t)(r >> PRSH);
-            unsigned prev = 0;
-            for (int cg0 = 0; cg0 < ng; cg0 += 4) {
-                uint4 v4[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t g = g0 + (uint32_t)min(cg0 + u, ng - 1) * RG;
-                    v4[u] = pieces[(TB == 8 ? g : g * 2u + (uint32_t)half) * 32u + (uint32_t)lane];
+            e = (int)reinterpret_cast<const int16_t *>(A.lastcol + J.last_off + ((uint64_t)s * (R / 4) + (uint64_t)(r >> 2)) * 32 + lane)[(r & 3) * 2 + half];
+            auto piece = [&](int cg) -> uint4 {
+                const uint32_t g = g0 + (uint32_t)max(cg, 0) * RG;
+                return pieces[(TB == 8 ? g : g * 2u + (uint32_t)half) * 32u + (uint32_t)lane];
+            };
+            auto nibbles = [&](const uint4 &v, unsigned *nib) { // the row's 4 columns of a piece
+                if (TB == 8) {
+                    const int sh = ((r & 1) * 2 + half) * 8;
+                    nib[0] = (v.x >> sh) & 0xffu; nib[1] = (v.y >> sh) & 0xffu;
+                    nib[2] = (v.z >> sh) & 0xffu; nib[3] = (v.w >> sh) & 0xffu;
+                } else {
+                    const bool hi = (r & 4) != 0;
+                    const int sh = (r & 3) * 8;
+                    const unsigned b01 = ((hi ? v.z : v.x) >> sh) & 0xffu, b23 = ((hi ? v.w : v.y) >> sh) & 0xffu;
+                    nib[0] = b01 & 0xfu; nib[1] = b01 >> 4; nib[2] = b23 & 0xfu; nib[3] = b23 >> 4;
                 }
+            };
+            bool found = false;
+            uint4 cur = piece(ng - 1), nxt = piece(ng - 2);
+            for (int cg = ng - 1; cg >= 0 && !found; cg--) {
+                const uint4 nn = piece(cg - 2); // in flight while this piece is examined
+                unsigned nib[4], left[4];
+                nibbles(cur, nib);
+                nibbles(nxt, left);
+                const unsigned before = cg > 0 ? left[3] : 0u; // column 0: H(i,0) = 0
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    // the row's 4 columns of this piece -> nib[c]
-                    unsigned nib[4];
-                    if (TB == 8) {
-                        const int sh = ((r & 1) * 2 + half) * 8;
-                        nib[0] = (v4[u].x >> sh) & 0xffu; nib[1] = (v4[u].y >> sh) & 0xffu;
-                        nib[2] = (v4[u].z >> sh) & 0xffu; nib[3] = (v4[u].w >> sh) & 0xffu;
-                    } else {
-                        const bool hi = (r & 4) != 0;
-                        const int sh = (r & 3) * 8;
-                        const unsigned b01 = ((hi ? v4[u].z : v4[u].x) >> sh) & 0xffu, b23 = ((hi ? v4[u].w : v4[u].y) >> sh) & 0xffu;
-                        nib[0] = b01 & 0xfu; nib[1] = b01 >> 4; nib[2] = b23 & 0xfu; nib[3] = b23 >> 4;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const int jj = (cg0 + u) * 4 + c;
-                        if (jj < N) {
-                            e += sext(nib[c] - prev);
-                            prev = nib[c];
-                            if (e == best) bj = jj + 1;
-                        }
-                    }
+                for (int c = 3; c >= 0; c--) {
+                    const int jj = cg * 4 + c; // 0-based column; e = H(i, jj+1)
+                    if (!found && jj < N && e == best) { bj = jj + 1; found = true; }
+                    e -= sext(nib[c] - (c > 0 ? nib[c - 1] : before));
                 }
+                cur = nxt;
+                nxt = nn;
             }
         }
         j = bj;

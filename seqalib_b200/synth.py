@@ -54,3 +54,59 @@ def batch(seed, first_pair, n, len_mode=0, len1=150, len2=150):
         bases[int(off1[p]):int(off1[p]) + int(l1[p])] = sequence(seed, first_pair + p, 0, int(l1[p]))
         bases[int(off2[p]):int(off2[p]) + int(l2[p])] = sequence(seed, first_pair + p, 1, int(l2[p]))
     return bases, off1, off2, l1, l2
+
+
+RELATED_SALT = 0x52454C41544544  # "RELATED"
+
+
+def related_sequence(seed, pair, length):
+    """Sequence 2 of the RELATED variant of config 4: sequence 1 of the pair with 10 % substitutions,
+    2 % insertions and 2 % deletions, every draw from the same counter-based generator.  Exact procedure, position by
+    position over sequence 1 (independent draws, so any position can be regenerated on its own):
+
+        r_i = splitmix64((key(seed, pair, 1) ^ RELATED_SALT) + i)           one draw per position i of sequence 1
+        u   = r_i % 100
+        u <  2        deletion:      emit nothing
+        2 <= u <  4   insertion:     emit seq1[i], then the base "ACGT"[(r_i >> 32) & 3]
+        4 <= u < 14   substitution:  emit "ACGT"[(code(seq1[i]) + 1 + (r_i >> 32) % 3) & 3]   (always a different base)
+        otherwise     copy:          emit seq1[i]
+
+    -> (seq1 bytes, seq2 bytes); len(seq2) is length * (1 + 0.02 - 0.02) on average."""
+    s1 = sequence(seed, pair, 0, length)
+    code = np.zeros(256, dtype=np.uint8)
+    code[np.frombuffer(b"ACGT", dtype=np.uint8)] = np.arange(4, dtype=np.uint8)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    with np.errstate(over="ignore"):
+        r = splitmix64((key(seed, pair, 1) ^ np.uint64(RELATED_SALT)) + np.arange(length, dtype=np.uint64))
+    u = (r % np.uint64(100)).astype(np.int64)
+    hi = (r >> np.uint64(32))
+    first = s1.copy()
+    sub = (u >= 4) & (u < 14)
+    first[sub] = acgt[(code[s1[sub]].astype(np.uint64) + np.uint64(1) + hi[sub] % np.uint64(3)) & np.uint64(3)]
+    second = acgt[(hi & np.uint64(3)).astype(np.int64)]
+    count = np.ones(length, dtype=np.int64)
+    count[u < 2] = 0
+    count[(u >= 2) & (u < 4)] = 2
+    out = np.repeat(first, count)
+    # the second symbol of every insertion is the inserted base
+    ends = np.cumsum(count) - 1
+    ins = np.nonzero(count == 2)[0]
+    out[ends[ins]] = second[ins]
+    return s1, out
+
+
+def related_batch(seed, first_pair, n, length):
+    """n related pairs (see related_sequence) in the C-ABI batch layout."""
+    seqs = [related_sequence(seed, first_pair + p, length) for p in range(n)]
+    l1 = np.array([len(a) for a, _ in seqs], dtype=np.uint32)
+    l2 = np.array([len(b) for _, b in seqs], dtype=np.uint32)
+    tot = l1.astype(np.uint64) + l2.astype(np.uint64)
+    off1 = np.zeros(n, dtype=np.uint64)
+    if n > 1:
+        off1[1:] = np.cumsum(tot)[:-1]
+    off2 = off1 + l1.astype(np.uint64)
+    bases = np.zeros(int(tot.sum()) if n else 0, dtype=np.uint8)
+    for p, (a, b) in enumerate(seqs):
+        bases[int(off1[p]):int(off1[p]) + len(a)] = a
+        bases[int(off2[p]):int(off2[p]) + len(b)] = b
+    return bases, off1, off2, l1, l2

@@ -28,11 +28,14 @@ def cpu_sample(algo, sc, n, len_mode, l1, l2, first=0):
     return float((a.astype(np.float64) * b).sum()) / sec / 1e9, threads, kind
 
 
-def run(lib, name, algo, sc, n, len_mode, l1, l2, cpu_n, reps=3):
+def run(lib, name, algo, sc, n, len_mode, l1, l2, cpu_n, reps=3, related=False):
     prm = capi.make_params(algo, gap=sc.gap, gap_open=sc.gap_open, gap_extend=sc.gap_extend, match=sc.match,
                            mismatch=sc.mismatch if sc.allow else 0, allow=sc.allow)
     ctx = capi.Ctx(lib)
-    ctx.generate(prm, synth.SEED, 0, n, len_mode, l1, l2)
+    if related:  # config 4's realism variant: seq2 derived from seq1 (synth.related_sequence), uploaded once
+        ctx.upload(prm, *synth.related_batch(synth.SEED, 0, n, l1))
+    else:
+        ctx.generate(prm, synth.SEED, 0, n, len_mode, l1, l2)
     ctx.run()
     ctx.sync()
     t0 = time.perf_counter()
@@ -78,6 +81,8 @@ def main():
     run(lib, "config4 Hirschberg 100kbp x8", "hirschberg", S.linear(-1, 2, -1), 8, 0, 100000, 100000, 0, reps=1)
     run(lib, "config4 Hirschberg 100kbp x64", "hirschberg", S.linear(-1, 2, -1), 64, 0, 100000, 100000, 0, reps=1)
     run(lib, "config4 MyersMiller 100kbp x64", "myersmiller", S.affine(-3, -1, 1, -1), 64, 0, 100000, 100000, 0, reps=1)
+    run(lib, "config4 related Hirschberg 100kbp x64", "hirschberg", S.linear(-1, 2, -1), 64, 0, 100000, 100000, 0, reps=1, related=True)
+    run(lib, "config4 related MyersMiller 100kbp x64", "myersmiller", S.affine(-3, -1, 1, -1), 64, 0, 100000, 100000, 0, reps=1, related=True)
 
 
 if __name__ == "__main__":

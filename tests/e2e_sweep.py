@@ -17,8 +17,8 @@ po2 = pinned(n, np.uint64); po2[:] = o2
 pl1 = pinned(n, np.uint32); pl1[:] = l1
 pl2 = pinned(n, np.uint32); pl2[:] = l2
 res = capi.Results(n, n * 300, pinned=pinned)
-for ring in (2, 3, 4):
-    for mcells in (750, 1500, 3000, 6000):
+for ring in (3, 4, 6):
+    for mcells in (2500, 5000, 7500):
         os.environ["SEQA_RING"] = str(ring); os.environ["SEQA_WAVE_MCELLS"] = str(mcells)
         ts = []
         for k in range(6):

@@ -279,6 +279,24 @@ def test_config4_full_length_pairs(gpu_lib):
             assert np.array_equal(res.pair_ops(p), o["ops"]), (algo, p)
 
 
+def test_config4_related_pairs(gpu_lib):
+    """BASELINE configs[3], realism variant: RELATED pairs -- sequence 2 = sequence 1 with 10 %
+    substitutions, 2 % insertions, 2 % deletions from the shared generator (seqalib_b200/synth.py: related_sequence
+    documents the exact procedure).  Long diagonal runs, a different split pattern, scores far beyond 16 bits
+    (the packed sweeps re-base): 4 Hirschberg pairs of 100,000 bp and 4 MyersMiller pairs of 30,000 bp, bit-exact."""
+    for algo, sc, n, L in (("hirschberg", S.linear(-1, 2, -1), 4, 100_000), ("myersmiller", S.affine(-3, -1, 1, -1), 4, 30_000)):
+        bases, off1, off2, l1, l2 = synth.related_batch(synth.SEED, 0, n, L)
+        ctx = capi.Ctx(gpu_lib)
+        ctx.upload(scoring_to_params(algo, sc), bases, off1, off2, l1, l2)
+        ctx.run()
+        res = ctx.download(ops_capacity=int(l1.sum() + l2.sum()))
+        assert ctx.last_kernel().endswith("_s16x2")
+        ctx.close()
+        assert compare_with_oracle_batch(res, algo, sc, bases, off1, off2, l1, l2, "config4 related") == n
+        ident = [(res.pair_ops(p) == 0).sum() / float(l1[p]) for p in range(n)]
+        assert min(ident) > 0.9  # the pairs really are related: > 90 % of sequence 1 sits on diagonal steps
+
+
 def test_mixed_length_batch(gpu_lib):
     """a 100,000-pair sample of the mixed-length workload (independent U[50,1000] lengths,
     NW (-1,2,-1) and SW (-1,1,-1) over the same pairs, generated on the device and read back for the oracle)."""
