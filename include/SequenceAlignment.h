@@ -127,8 +127,29 @@ struct PackedAlignments {
     std::vector<int32_t> Score;
     std::vector<uint32_t> StartI, StartJ, EndI, EndJ, OpsLen;
     std::vector<uint64_t> OpsOff;
-    std::vector<uint8_t> Ops; // 0 diagonal, 1 up (Seq1 symbol vs Blank), 2 left (Blank vs Seq2 symbol)
+    // 0 diagonal, 1 up (Seq1 symbol vs Blank), 2 left (Blank vs Seq2 symbol); in the 2-bit wire format
+    // (SEQA_FLAG_OPS_2BIT, what the aligners below request): 4 ops per byte, OpsOff in bytes, OpsLen in ops
+    std::vector<uint8_t> Ops;
+    bool TwoBit = false;
     size_t size() const { return Score.size(); }
+    // op K of pair P, whatever the wire format
+    unsigned op(size_t P, uint32_t K) const
+    {
+        return TwoBit ? (Ops[OpsOff[P] + (K >> 2)] >> (2 * (K & 3))) & 3u : Ops[OpsOff[P] + K];
+    }
+    // CIGAR-like run-length view of pair P: (op, run length) pairs in alignment order
+    std::vector<std::pair<uint8_t, uint32_t>> runs(size_t P) const
+    {
+        std::vector<std::pair<uint8_t, uint32_t>> R;
+        for (uint32_t K = 0; K < OpsLen[P]; K++) {
+            const uint8_t O = (uint8_t)op(P, K);
+            if (!R.empty() && R.back().first == O)
+                R.back().second++;
+            else
+                R.emplace_back(O, 1u);
+        }
+        return R;
+    }
 };
 
 namespace detail {
@@ -236,6 +257,7 @@ class SequenceAligner {
         Prm.mismatch = Scoring.getAllowMismatch() ? Scoring.getMismatchPenalty() : 0;
         Prm.device_first = 0;
         Prm.device_count = 0; // every visible device
+        Prm.flags = SEQA_FLAG_OPS_2BIT; // a quarter of the result bytes over PCIe and in host memory
         seqa_batch_in In{Bases.data(), Off1.data(), Off2.data(), Len1.data(), Len2.data(), (uint64_t)N, Total};
         seqa::PackedAlignments R;
         R.Score.resize(N);
@@ -245,12 +267,13 @@ class SequenceAligner {
         R.EndJ.resize(N);
         R.OpsLen.resize(N);
         R.OpsOff.resize(N);
-        R.Ops.resize(Total ? Total : 1);
+        R.Ops.resize(Total / 4 + N + 1);
+        R.TwoBit = true;
         seqa_batch_out Out{R.Score.data(), R.StartI.data(), R.StartJ.data(), R.EndI.data(), R.EndJ.data(), R.Ops.data(),
                            R.OpsOff.data(), R.OpsLen.data(), (uint64_t)R.Ops.size(), 0};
         if (seqa_cuda_align_batch(&Prm, &In, &Out) != SEQA_OK)
             throw std::runtime_error(std::string("seqa_cuda_align_batch: ") + seqa_cuda_last_error());
-        R.Ops.resize(Out.ops_used);
+        // no shrink: large batches are processed in waves whose op strings sit at each wave's own base offset
         LastScores.assign(R.Score.begin(), R.Score.end());
         return R;
     }
@@ -260,12 +283,12 @@ class SequenceAligner {
     {
         AlignedSequence<Ty, Blank> Res;
         size_t I = R.StartI[P], J = R.StartJ[P];
-        const uint8_t *Ops = R.Ops.data() + R.OpsOff[P];
         for (uint32_t K = 0; K < R.OpsLen[P]; K++) {
-            if (Ops[K] == SEQA_OP_DIAG) {
+            const unsigned Op = R.op(P, K);
+            if (Op == SEQA_OP_DIAG) {
                 Res.Data.emplace_back(Seq1[I], Seq2[J], Seq1[I] == Seq2[J]);
                 I++, J++;
-            } else if (Ops[K] == SEQA_OP_UP) {
+            } else if (Op == SEQA_OP_UP) {
                 Res.Data.emplace_back(Seq1[I], Blank, false);
                 I++;
             } else {

@@ -63,6 +63,10 @@ enum {
 #define SEQA_FLAG_SCORE_ONLY 0x1u  /* skip traceback/ops (scores and end positions only) */
 #define SEQA_FLAG_FORCE_GENERIC 0x2u /* use the generic int32 kernels even where a packed fast path applies */
 #define SEQA_FLAG_TRACE8 0x4u /* packed path: keep 8 trace bits per cell even where 4 suffice (testing) */
+#define SEQA_FLAG_OPS_2BIT 0x10u /* ops leave the device packed 4 per byte: op k of pair p sits in bits 2*(k%4) of byte
+                                   ops[ops_off[p] + k/4]; ops_off is in BYTES (every pair starts on a byte boundary), ops_len
+                                   in OPS; ops_capacity >= sum(len1+len2)/4 + n_pairs suffices.  A quarter of the PCIe bytes
+                                   of the default one-byte-per-op form ("2 bits each or one byte each (flag)") */
 #define SEQA_FLAG_LS_R1 0x8u /* linear-space path: 32-row blocks everywhere (testing: deep row-block pipelines on short pairs) */
 
 /*
@@ -106,6 +110,7 @@ typedef struct seqa_batch_in {
  * Results, one entry per pair (arrays of n_pairs elements; any of the start/end/ops arrays may be NULL when
  * SEQA_FLAG_SCORE_ONLY is set).  ops for pair p are ops[ops_off[p] .. ops_off[p]+ops_len[p]).
  * ops_capacity >= sum(len1+len2) always suffices.  ops_used receives the bytes written.
+ * With SEQA_FLAG_OPS_2BIT the same ops are packed 4 per byte (see the flag).
  * Replaces the AlignedSequence<Ty,Blank> return value (include/SequenceAlignment.h:13-80).
  * score: NW/GlobalGotoh H[M][N]; SW/LocalGotoh MaxScore (0 for an empty input); Hirschberg/MyersMiller
  * (which expose no score in the reference) the score of the returned alignment under the algorithm's

@@ -16,6 +16,7 @@ FLAG_SCORE_ONLY = 1
 FLAG_FORCE_GENERIC = 2
 FLAG_TRACE8 = 4
 FLAG_LS_R1 = 8
+FLAG_OPS_2BIT = 16  # ops packed 4 per byte on the wire (Results.pair_ops unpacks)
 OK = 0
 ERR_NAMES = {0: "SEQA_OK", -1: "SEQA_ERR_INVALID", -2: "SEQA_ERR_UNSUPPORTED", -3: "SEQA_ERR_NO_DEVICE",
              -4: "SEQA_ERR_CUDA", -5: "SEQA_ERR_CAPACITY", -6: "SEQA_ERR_NOMEM"}
@@ -75,8 +76,13 @@ class Results(object):
                           self.end_i.ctypes.data, self.end_j.ctypes.data, self.ops.ctypes.data,
                           self.ops_off.ctypes.data, self.ops_len.ctypes.data, int(ops_capacity), 0)
 
+    packed2 = False  # set by the call that filled this object when SEQA_FLAG_OPS_2BIT was on
+
     def pair_ops(self, p):
         o, l = int(self.ops_off[p]), int(self.ops_len[p])
+        if self.packed2:
+            b = self.ops[o:o + (l + 3) // 4]
+            return ((b[:, None] >> np.array([0, 2, 4, 6], dtype=np.uint8)[None, :]) & 3).reshape(-1)[:l].astype(np.uint8)
         return self.ops[o:o + l]
 
 
@@ -132,6 +138,7 @@ class Lib(object):
             results = Results(n, cap)
         bi = self.batch_in(bases, off1, off2, len1, len2)
         self.check(self.L.seqa_cuda_align_batch(C.byref(params), C.byref(bi), C.byref(results.c)))
+        results.packed2 = bool(params.flags & FLAG_OPS_2BIT)
         return results
 
 
@@ -159,11 +166,13 @@ class Ctx(object):
     def upload(self, params, bases, off1, off2, len1, len2):
         bi = Lib.batch_in(bases, off1, off2, len1, len2)
         self.lib.check(self.lib.L.seqa_ctx_upload(self.h, C.byref(params), C.byref(bi)))
+        self.flags = int(params.flags)
         self.n = len(len1)
         self.slots = int(len1.astype(np.uint64).sum() + len2.astype(np.uint64).sum())
 
     def generate(self, params, seed, first_pair, n_pairs, len_mode=0, len1=0, len2=0):
         self.lib.check(self.lib.L.seqa_ctx_generate(self.h, C.byref(params), seed, first_pair, n_pairs, len_mode, len1, len2))
+        self.flags = int(params.flags)
         self.n = n_pairs
         self.slots = None
 
@@ -177,6 +186,7 @@ class Ctx(object):
         if results is None:
             results = Results(self.n, ops_capacity if ops_capacity is not None else self.slots)
         self.lib.check(self.lib.L.seqa_ctx_download(self.h, C.byref(results.c)))
+        results.packed2 = bool(getattr(self, "flags", 0) & FLAG_OPS_2BIT)
         return results
 
     def device_results(self):

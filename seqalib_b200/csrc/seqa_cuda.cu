@@ -343,9 +343,9 @@ int build_plan(seqa_ctx *c)
         if (n) {
             const unsigned tiles = (unsigned)((n + SEQA_SCAN_TILE - 1) / SEQA_SCAN_TILE);
             LAUNCH(c, (lensum_kernel), (unsigned)((n + 255) / 256), 256, 0, c->len1.p, c->len2.p, c->ops_len.p, n);
-            LAUNCH(c, (scan_tile_sums_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p);
+            LAUNCH(c, (scan_tile_sums_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, 0);
             LAUNCH(c, (scan_spine_kernel), 1, 1024, 0, c->tile_sum.p, (uint64_t)tiles, c->total.p);
-            LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, c->slot_off.p);
+            LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, c->slot_off.p, 0);
         }
     }
     CKS(c->score.ensure(n));
@@ -751,9 +751,10 @@ int finish_ops(seqa_ctx *c)
     const uint64_t n = c->n;
     if (n == 0) return SEQA_OK;
     const unsigned tiles = (unsigned)((n + SEQA_SCAN_TILE - 1) / SEQA_SCAN_TILE);
-    LAUNCH(c, (scan_tile_sums_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p);
+    const int pack = (c->prm.flags & SEQA_FLAG_OPS_2BIT) ? 1 : 0; // dense ops: 4 per byte, offsets in bytes
+    LAUNCH(c, (scan_tile_sums_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, pack);
     LAUNCH(c, (scan_spine_kernel), 1, 1024, 0, c->tile_sum.p, (uint64_t)tiles, c->total.p);
-    LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, c->ops_off.p);
+    LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, c->ops_off.p, pack);
     GatherArgs G{};
     G.n_pairs = n;
     G.slots = c->slots.p;
@@ -762,6 +763,7 @@ int finish_ops(seqa_ctx *c)
     G.ops_len = c->ops_len.p;
     G.ops_off = c->ops_off.p;
     G.dense = c->dense.p;
+    G.pack = pack;
     const unsigned blocks = (unsigned)std::min<uint64_t>((n * 8 + 255) / 256, (uint64_t)c->sms * 32);
     LAUNCH(c, (gather_ops_kernel), blocks, 256, 0, G);
     CK(cudaGetLastError());
@@ -1280,7 +1282,11 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
     }
     const size_t nwaves = wave_lo.size() - 1;
     const uint64_t slots_total = wave_slots.back();
-    const bool sparse = out->ops_capacity >= slots_total || (params->flags & SEQA_FLAG_SCORE_ONLY);
+    // where a wave's ops start in the caller's buffer: behind the slots of all earlier pairs (one byte per op), or, in the
+    // 2-bit wire format, behind ceil(len/4) <= len/4 + 1 bytes per earlier pair
+    const bool ops2 = (params->flags & SEQA_FLAG_OPS_2BIT) != 0;
+    auto wave_ops_base = [&](size_t w) { return ops2 ? wave_slots[w] / 4 + wave_lo[w] : wave_slots[w]; };
+    const bool sparse = out->ops_capacity >= (ops2 ? slots_total / 4 + n : slots_total) || (params->flags & SEQA_FLAG_SCORE_ONLY);
     // waves -> devices: contiguous runs of waves with ~equal cells (SURVEY.md 8e static split)
     std::vector<size_t> dev_lo(nd + 1, nwaves);
     dev_lo[0] = 0;
@@ -1296,6 +1302,11 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
     std::vector<std::string> werr(nwaves);
     std::vector<uint64_t> wused(nwaves, 0);
     const bool dbg = getenv("SEQA_DEBUG_TIMING") != nullptr;
+    // SEQA_DEBUG_TIMING: per wave five events (H2D queued / H2D + planning done / kernels may start / kernels done /
+    // D2H done) against one base event per device, printed as a table when the call ends
+    struct WaveEv { cudaEvent_t e[5] = {}; int dev = -1; };
+    std::vector<WaveEv> wev(dbg ? nwaves : 0);
+    std::vector<cudaEvent_t> dbg_base(dbg ? nd : 0, nullptr);
     const auto t_start = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     // Per device a PRODUCER thread uploads, plans and launches wave after wave into a ring of contexts (each with its
@@ -1340,15 +1351,23 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
             }
             if (s == SEQA_OK && P.st[0]) P.c[slot]->stream = (k & 1) && !one_comp ? P.st[3] : P.st[1];
             if (dbg && s == SEQA_OK) {
-                for (auto &e : P.c[slot]->dbg_ev)
-                    if (!e) cudaEventCreate(&e);
-                cudaEventRecord(P.c[slot]->dbg_ev[0], P.c[slot]->stream);
+                cudaSetDevice(first + d);
+                for (auto &e : wev[w].e) cudaEventCreate(&e);
+                wev[w].dev = d;
+                if (!dbg_base[d]) {
+                    cudaEventCreate(&dbg_base[d]);
+                    cudaEventRecord(dbg_base[d], P.c[slot]->up);
+                }
+                cudaEventRecord(wev[w].e[0], P.c[slot]->up);
             }
             if (s == SEQA_OK) s = ctx_upload_range(P.c[slot], params, in, wave_lo[w], wave_lo[w + 1]);
-            if (dbg && s == SEQA_OK) cudaEventRecord(P.c[slot]->dbg_ev[1], P.c[slot]->stream);
+            if (dbg && s == SEQA_OK) {
+                cudaEventRecord(wev[w].e[1], P.c[slot]->up);
+                cudaEventRecord(wev[w].e[2], P.c[slot]->stream);
+            }
             const double t1 = since();
             if (s == SEQA_OK) s = ctx_run(P.c[slot]);
-            if (dbg && s == SEQA_OK) cudaEventRecord(P.c[slot]->dbg_ev[2], P.c[slot]->stream);
+            if (dbg && s == SEQA_OK) cudaEventRecord(wev[w].e[3], P.c[slot]->stream);
             if (dbg) fprintf(stderr, "[seqa] dev %d wave %zu: upload+plan %.2f..%.2f launched ..%.2f ms\n", d, w, t0, t1, since());
             std::lock_guard<std::mutex> lk(P.mu);
             if (s != SEQA_OK) {
@@ -1378,22 +1397,10 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
             const double t2 = since();
             int s = ctx_resolve(P.c[slot]);
             const double t3 = since();
-            if (s == SEQA_OK) s = ctx_download_into(P.c[slot], out, wave_lo[w], wave_slots[w], &wused[w]);
+            if (s == SEQA_OK) s = ctx_download_into(P.c[slot], out, wave_lo[w], wave_ops_base(w), &wused[w]);
             if (dbg) {
                 fprintf(stderr, "[seqa] dev %d wave %zu: wait %.2f..%.2f download ..%.2f ms\n", d, w, t2, t3, since());
-                if (s == SEQA_OK && P.c[0] && P.c[0]->dbg_ev[0]) {
-                    cudaEventRecord(P.c[slot]->dbg_ev[3], P.c[slot]->down);
-                    cudaEventSynchronize(P.c[slot]->dbg_ev[3]);
-                    float a = 0, b = 0, cc = 0, dd = 0;
-                    static thread_local cudaEvent_t base = nullptr;
-                    if (k == 0) base = P.c[0]->dbg_ev[0];
-                    // note: slot 0's first event is re-recorded when the ring wraps; times are then relative to that re-record
-                    cudaEventElapsedTime(&a, base, P.c[slot]->dbg_ev[0]);
-                    cudaEventElapsedTime(&b, base, P.c[slot]->dbg_ev[1]);
-                    cudaEventElapsedTime(&cc, base, P.c[slot]->dbg_ev[2]);
-                    cudaEventElapsedTime(&dd, base, P.c[slot]->dbg_ev[3]);
-                    fprintf(stderr, "[seqa]   device timeline wave %zu: start %.2f  H2D+plan done %.2f  kernels done %.2f  D2H done %.2f ms\n", w, a, b, cc, dd);
-                }
+                if (s == SEQA_OK && wev[w].e[4]) cudaEventRecord(wev[w].e[4], P.c[slot]->down);
             }
             std::lock_guard<std::mutex> lk(P.mu);
             if (s != SEQA_OK) {
@@ -1445,6 +1452,24 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
                 g_err = werr[w];
             }
             used += wused[w];
+        }
+        if (dbg) { // every stream was synchronised above: the events are complete
+            fprintf(stderr, "[seqa] device timeline (ms after the first upload was queued): wave pairs | H2D start..done | kernels start..done | D2H done\n");
+            for (size_t w = 0; w < nwaves; w++) {
+                if (wev[w].dev < 0 || !wev[w].e[4] || !dbg_base[wev[w].dev]) continue;
+                float t[5] = {0, 0, 0, 0, 0};
+                bool ok = true;
+                for (int q = 0; q < 5; q++) ok &= cudaEventElapsedTime(&t[q], dbg_base[wev[w].dev], wev[w].e[q]) == cudaSuccess;
+                (void)cudaGetLastError();
+                if (ok)
+                    fprintf(stderr, "[seqa]   dev %d wave %2zu %7llu | %6.2f .. %6.2f | %6.2f .. %6.2f | %6.2f\n", wev[w].dev, w,
+                            (unsigned long long)(wave_lo[w + 1] - wave_lo[w]), t[0], t[1], t[2], t[3], t[4]);
+            }
+            for (auto &we : wev)
+                for (auto e : we.e)
+                    if (e) cudaEventDestroy(e);
+            for (auto e : dbg_base)
+                if (e) cudaEventDestroy(e);
         }
     } else {
         // small caller buffer: waves one after another, ops packed densely in pair order

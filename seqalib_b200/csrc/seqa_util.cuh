@@ -10,19 +10,20 @@ __global__ void add_base_kernel(uint64_t *__restrict__ v, uint64_t n, uint64_t b
 }
 
 // ---- exclusive scan of uint32 -> uint64 (three launches; n up to 2^32) --------------------------------
+// `pack`: the scanned item is ceil(in/4) -- the bytes of an op string in the 2-bit wire format (SEQA_FLAG_OPS_2BIT)
 #define SEQA_SCAN_TPB 256
 #define SEQA_SCAN_IPT 8
 #define SEQA_SCAN_TILE (SEQA_SCAN_TPB * SEQA_SCAN_IPT)
 
 __global__ void __launch_bounds__(SEQA_SCAN_TPB) scan_tile_sums_kernel(const uint32_t *__restrict__ in, uint64_t n,
-                                                                      uint64_t *__restrict__ tile_sum)
+                                                                      uint64_t *__restrict__ tile_sum, int pack)
 {
     __shared__ uint64_t wsum[SEQA_SCAN_TPB / 32];
     const uint64_t base = (uint64_t)blockIdx.x * SEQA_SCAN_TILE;
     uint64_t s = 0;
     for (int k = 0; k < SEQA_SCAN_IPT; k++) {
         const uint64_t idx = base + (uint64_t)k * SEQA_SCAN_TPB + threadIdx.x;
-        if (idx < n) s += in[idx];
+        if (idx < n) s += pack ? (in[idx] + 3u) >> 2 : in[idx];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(SEQA_FULL, s, o);
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(1024) scan_spine_kernel(uint64_t *__restrict__
 
 __global__ void __launch_bounds__(SEQA_SCAN_TPB) scan_apply_kernel(const uint32_t *__restrict__ in, uint64_t n,
                                                                   const uint64_t *__restrict__ tile_off,
-                                                                  uint64_t *__restrict__ out)
+                                                                  uint64_t *__restrict__ out, int pack)
 {
     // thread t owns the IPT consecutive items [base + t*IPT, +IPT)
     __shared__ uint64_t wsum[SEQA_SCAN_TPB / 32];
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(SEQA_SCAN_TPB) scan_apply_kernel(const uint32_
 #pragma unroll
     for (int k = 0; k < SEQA_SCAN_IPT; k++) {
         v[k] = (base + k < n) ? in[base + k] : 0u;
+        if (pack) v[k] = (v[k] + 3u) >> 2;
         s += v[k];
     }
     // inclusive warp scan of s
@@ -124,6 +126,7 @@ struct GatherArgs {
     const uint32_t *ops_len;
     const uint64_t *ops_off; // exclusive scan of ops_len
     uint8_t *dense;
+    int pack; // SEQA_FLAG_OPS_2BIT: 4 ops per dense byte, ops_off in bytes
 };
 
 __global__ void __launch_bounds__(256) gather_ops_kernel(GatherArgs A)
@@ -136,7 +139,17 @@ __global__ void __launch_bounds__(256) gather_ops_kernel(GatherArgs A)
         const uint8_t *src = A.slots + A.slot_off[p] + A.slot_start[p];
         uint8_t *dst = A.dense + A.ops_off[p];
         const uint32_t len = A.ops_len[p];
-        for (uint32_t k = sub; k < len; k += 8) dst[k] = src[k];
+        if (A.pack) {
+            for (uint32_t b = sub; b * 4 < len; b += 8) {
+                unsigned v = 0;
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++)
+                    if (b * 4 + q < len) v |= (unsigned)(src[b * 4 + q] & 3u) << (2 * q);
+                dst[b] = (uint8_t)v;
+            }
+        } else {
+            for (uint32_t k = sub; k < len; k += 8) dst[k] = src[k];
+        }
     }
 }
 

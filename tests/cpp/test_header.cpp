@@ -92,6 +92,12 @@ int main()
             std::printf("FAIL packed accessor\n");
             Failures++;
         }
+        // README pair: AAA-GAATGCAT / AAAC---T-CAT  =  3 diag, 1 left, 3 up, 1 diag, 1 up, 3 diag (2-bit wire format)
+        const std::vector<std::pair<uint8_t, uint32_t>> Want = {{0, 3}, {2, 1}, {1, 3}, {0, 1}, {1, 1}, {0, 3}};
+        if (!Pk.TwoBit || Pk.runs(0) != Want || Pk.op(2, 7) != SEQA_OP_LEFT || Pk.runs(3).size() != 1) {
+            std::printf("FAIL packed runs / 2-bit ops\n");
+            Failures++;
+        }
     }
     { // StaticFuncs::bridgeNW appends NW of a window (reference include/StaticFuncs.h:27-39)
         AlignedSequence<char, '-'> Res;

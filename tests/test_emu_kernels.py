@@ -22,7 +22,7 @@ def test_matrix_algorithms(emu_lib, algo, sc):
     rng = np.random.default_rng(11)
     pairs = list(EDGE) + random_pairs(rng, 30, 1, 70) + random_pairs(rng, 8, 1, 50, "AC") + \
         random_pairs(rng, 6, 120, 180) + random_pairs(rng, 8, 1, 90, related=0.3)
-    for flags in (0, capi.FLAG_TRACE8, capi.FLAG_FORCE_GENERIC):
+    for flags in (0, capi.FLAG_TRACE8, capi.FLAG_FORCE_GENERIC, capi.FLAG_OPS_2BIT):  # OPS_2BIT: 4 ops per byte on the wire
         check_batch_against_oracle(emu_lib, algo, sc, pairs, flags=flags)
 
 
@@ -40,7 +40,7 @@ def test_linear_space_algorithms(emu_lib, algo, sc):
     check_batch_against_oracle(emu_lib, algo, sc, pairs[-12:], flags=capi.FLAG_LS_R1)
     clean = [p for p in pairs if set(p[0] + p[1]) <= set("ACGT")]  # packed forward+reverse s16x2 sweeps
     check_batch_against_oracle(emu_lib, algo, sc, clean)
-    check_batch_against_oracle(emu_lib, algo, sc, clean[-12:], flags=capi.FLAG_LS_R1)
+    check_batch_against_oracle(emu_lib, algo, sc, clean[-12:], flags=capi.FLAG_LS_R1 | capi.FLAG_OPS_2BIT)
 
 
 def test_packed_path_is_taken(emu_lib):

@@ -297,6 +297,36 @@ def test_config4_related_pairs(gpu_lib):
         assert min(ident) > 0.9  # the pairs really are related: > 90 % of sequence 1 sits on diagonal steps
 
 
+def test_two_bit_wire_format(gpu_lib):
+    """SEQA_FLAG_OPS_2BIT (4 ops per byte over PCIe): same alignments as the one-byte form, through the one-shot call
+    in several waves (300,000 pairs > one wave) and through the resident interface; sampled against the oracle."""
+    n = 300_000
+    sc = S.linear(-1, 1, -1)
+    bases, off1, off2, l1, l2 = None, None, None, None, None
+    ctx = capi.Ctx(gpu_lib)
+    ctx.generate(scoring_to_params("sw", sc, flags=capi.FLAG_OPS_2BIT), synth.SEED, 11_000_000, n, 0, 150, 150)
+    ctx.run()
+    r2 = ctx.download(ops_capacity=n * 76)
+    bases, off1, off2, l1, l2 = ctx.download_inputs(n * 300)
+    ctx.close()
+    assert r2.packed2 and int(r2.ops_off[-1]) < n * 76
+    plain = gpu_lib.align_batch(scoring_to_params("sw", sc), bases, off1, off2, l1, l2)
+    packed = gpu_lib.align_batch(scoring_to_params("sw", sc, flags=capi.FLAG_OPS_2BIT), bases, off1, off2, l1, l2,
+                                 capi.Results(n, n * 76))
+    for name in ("score", "start_i", "start_j", "end_i", "end_j", "ops_len"):
+        assert np.array_equal(getattr(plain, name), getattr(packed, name)), name
+        assert np.array_equal(getattr(plain, name), getattr(r2, name)), name
+    rng = np.random.default_rng(2)
+    for p in [0, 1, n - 1] + [int(x) for x in rng.integers(0, n, 3000)]:
+        assert np.array_equal(plain.pair_ops(p), packed.pair_ops(p)), p
+        assert np.array_equal(plain.pair_ops(p), r2.pair_ops(p)), p
+    idx = np.sort(rng.choice(n, 2000, replace=False))
+    for p in idx:
+        a = bytes(bases[int(off1[p]):int(off1[p]) + 150]).decode()
+        b = bytes(bases[int(off2[p]):int(off2[p]) + 150]).decode()
+        assert np.array_equal(packed.pair_ops(p), orc.oracle_align("sw", sc, a, b)["ops"]), p
+
+
 def test_mixed_length_batch(gpu_lib):
     """a 100,000-pair sample of the mixed-length workload (independent U[50,1000] lengths,
     NW (-1,2,-1) and SW (-1,1,-1) over the same pairs, generated on the device and read back for the oracle)."""
