@@ -88,7 +88,7 @@ class Results(object):
 
 class Lib(object):
     def __init__(self, path=None):
-        path = path or DEFAULT_SO
+        path = path or os.environ.get("SEQA_LIB") or DEFAULT_SO  # SEQA_LIB: an experimental build of the same library (A/B runs)
         if not os.path.exists(path):
             raise ImportError("%s is missing: run `make` (nvcc, sm_100a) at the repository root. "
                               "There is no CPU fallback for the alignment path." % path)

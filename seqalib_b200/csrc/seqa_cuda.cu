@@ -764,7 +764,7 @@ int finish_ops(seqa_ctx *c)
     G.ops_off = c->ops_off.p;
     G.dense = c->dense.p;
     G.pack = pack;
-    const unsigned blocks = (unsigned)std::min<uint64_t>((n * 8 + 255) / 256, (uint64_t)c->sms * 32);
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n * 32 + 255) / 256, (uint64_t)c->sms * 64);
     LAUNCH(c, (gather_ops_kernel), blocks, 256, 0, G);
     CK(cudaGetLastError());
     return SEQA_OK;
@@ -1313,7 +1313,7 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
     // own stream) and a CONSUMER thread, in the same order, waits for a wave and copies its results out: the host
     // planning of wave k+1, the kernels of wave k and the device->host copy of wave k-1 overlap, and the device
     // queue is fed in wave order.
-    const int ring = env_int("SEQA_RING", 3, 2, SEQA_CACHE_SLOTS);
+    const int ring = env_int("SEQA_RING", 4, 2, SEQA_CACHE_SLOTS);
     const bool one_comp = getenv("SEQA_ONE_COMPUTE_STREAM") != nullptr;
     struct DevPipe {
         std::mutex mu;

@@ -32,7 +32,7 @@ struct PkWarpJob {
     uint32_t Mw, Nw;  // max len1 / len2 over the 64 pairs
     uint32_t nstrips; // ceil(Mw / R)
     uint64_t trace_off;  // byte offset of the warp's trace region
-    uint64_t prof_off;   // uint2 index of the column profile  [ceil(Nw/4)][32][4]
+    uint64_t prof_off;   // uint2 index of the column profile: uint4 [ceil(Nw/4)][2][32] = {T0,T1} of columns (0,1) / (2,3) per lane
     uint64_t rowsel_off; // uint32 index of the row selectors  [nstrips*R][32]
     uint64_t last_off;   // uint4 index of the last-column values (SmithWaterman) [nstrips][R/4][32]
 };
@@ -121,53 +121,50 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
         b0.init(A.bases, p0 == PK_NULL ? A.bases : A.bases + A.off2[p0]);
         a1.init(A.bases, p1 == PK_NULL ? A.bases : A.bases + A.off1[p1]);
         b1.init(A.bases, p1 == PK_NULL ? A.bases : A.bases + A.off2[p1]);
-        bool bad = false;
+        // Four symbols per 32-bit word are handled together: codes4 = (w >> 1) & 0x03030303 (A0 C1 T2 G3 in every byte); the
+        // word is valid iff "ACTG"[code] gives back every byte (one PRMT table look-up + XOR); bytes behind the end of
+        // the sequence are masked out.
+        unsigned bad = 0;
         const uint32_t Ng = (J.Nw + 3) >> 2;
-        uint4 *pout = reinterpret_cast<uint4 *>(A.prof + J.prof_off) + lane * 2;
+        auto valid_mask = [](uint32_t have) { return have >= 4u ? 0xffffffffu : ((1u << (8u * have)) - 1u); }; // have = symbols left
+        auto check4 = [&](uint32_t w, uint32_t codes, uint32_t vmask) {
+            const unsigned x = codes | (codes >> 4);                    // byte 0: c0 | c1 << 4, byte 2: c2 | c3 << 4
+            const unsigned letters = seqa_prmt(0x47544341u, 0u, seqa_prmt(x, 0u, 0x4420)); // "ACTG"[c0..c3]
+            bad |= (letters ^ w) & vmask;
+        };
+        uint4 *pout = reinterpret_cast<uint4 *>(A.prof + J.prof_off) + lane; // [cg][half][lane]: every warp store / load is 512 contiguous bytes
         for (uint32_t cg = 0; cg < Ng; cg++) {
             const uint32_t j0 = cg * 4;
-            const uint32_t w0 = j0 < N0 ? b0.next4() : 0u, w1 = j0 < N1 ? b1.next4() : 0u;
+            const uint32_t h0 = j0 < N0 ? N0 - j0 : 0u, h1 = j0 < N1 ? N1 - j0 : 0u; // real columns left in this group
+            const uint32_t w0 = h0 ? b0.next4() : 0u, w1 = h1 ? b1.next4() : 0u;
+            const uint32_t k0 = (w0 >> 1) & 0x03030303u, k1 = (w1 >> 1) & 0x03030303u;
+            check4(w0, k0, valid_mask(h0));
+            check4(w1, k1, valid_mask(h1));
+            const uint32_t s0 = k0 << 3, s1 = k1 << 3; // 8 * code: the byte position of the matching row base in the profile
             unsigned t[8];
 #pragma unroll
             for (uint32_t c = 0; c < 4; c++) {
-                const uint32_t j = j0 + c;
-                unsigned t0 = 0x80808080u, t1 = 0x80808080u; // padded column: every score -128
-                if (j < N0) {
-                    const unsigned ch = (w0 >> (8 * c)) & 0xffu;
-                    bad |= !pk_is_acgt(ch);
-                    t0 = mm4 ^ (mx << (8 * pk_code(ch)));
-                }
-                if (j < N1) {
-                    const unsigned ch = (w1 >> (8 * c)) & 0xffu;
-                    bad |= !pk_is_acgt(ch);
-                    t1 = mm4 ^ (mx << (8 * pk_code(ch)));
-                }
-                t[2 * c] = t0;
-                t[2 * c + 1] = t1;
+                // padded column: every score -128
+                t[2 * c] = c < h0 ? mm4 ^ (mx << ((s0 >> (8 * c)) & 0xffu)) : 0x80808080u;
+                t[2 * c + 1] = c < h1 ? mm4 ^ (mx << ((s1 >> (8 * c)) & 0xffu)) : 0x80808080u;
             }
             pout[(uint64_t)cg * 64] = make_uint4(t[0], t[1], t[2], t[3]);
-            pout[(uint64_t)cg * 64 + 1] = make_uint4(t[4], t[5], t[6], t[7]);
+            pout[(uint64_t)cg * 64 + 32] = make_uint4(t[4], t[5], t[6], t[7]);
         }
         const uint32_t rows = J.nstrips * (uint32_t)R;
+        uint32_t *rout = A.rowsel + J.rowsel_off + lane;
         for (uint32_t i0 = 0; i0 < rows; i0 += 4) {
-            const uint32_t w0 = i0 < M0 ? a0.next4() : 0u, w1 = i0 < M1 ? a1.next4() : 0u;
+            const uint32_t h0 = i0 < M0 ? M0 - i0 : 0u, h1 = i0 < M1 ? M1 - i0 : 0u;
+            const uint32_t w0 = h0 ? a0.next4() : 0u, w1 = h1 ? a1.next4() : 0u;
+            const uint32_t v0 = valid_mask(h0), v1 = valid_mask(h1);
+            const uint32_t k0 = (w0 >> 1) & 0x03030303u & v0, k1 = (w1 >> 1) & 0x03030303u & v1; // rows behind the end: code 0
+            check4(w0, k0, v0);
+            check4(w1, k1, v1);
 #pragma unroll
             for (uint32_t c = 0; c < 4; c++) {
-                const uint32_t i = i0 + c;
-                unsigned c0 = 0, c1 = 0;
-                if (i < M0) {
-                    const unsigned ch = (w0 >> (8 * c)) & 0xffu;
-                    bad |= !pk_is_acgt(ch);
-                    c0 = pk_code(ch);
-                }
-                if (i < M1) {
-                    const unsigned ch = (w1 >> (8 * c)) & 0xffu;
-                    bad |= !pk_is_acgt(ch);
-                    c1 = pk_code(ch);
-                }
-                // nibble0: byte c0 of T0; nibble1: its sign; nibble2: byte 4+c1 (= T1); nibble3: its sign
-                const unsigned sel = c0 | ((8u | c0) << 4) | ((4u | c1) << 8) | ((12u | c1) << 12);
-                A.rowsel[J.rowsel_off + (uint64_t)i * 32 + lane] = sel;
+                const unsigned c0 = (k0 >> (8 * c)) & 3u, c1 = (k1 >> (8 * c)) & 3u;
+                // nibble0: byte c0 of T0; nibble1: its sign (8 | c0); nibble2: byte 4 + c1 (= T1); nibble3: its sign (12 | c1)
+                rout[(uint64_t)(i0 + c) * 32] = 0xC480u + c0 * 0x11u + c1 * 0x1100u;
             }
         }
         if (bad) *A.bad = 1;
@@ -192,9 +189,25 @@ __device__ __forceinline__ int pk_half(unsigned v, int k) { return (int)(int16_t
 // walk step usually stays inside the piece it already holds (thread-major 128-byte lines were measured 2x slower
 // in the fill: 32 lines per store instruction saturate the LSU).
 // The column profiles of the next 4-column group are prefetched into registers one group ahead.
+// PK_PAIR_PIECES (TB == 4 only): the pieces of column groups 2q and 2q+1 of one pair sit side by side in ONE 32-byte
+// sector (piece index ((((s*ceil(Ng/2) + cg/2)*(R/8) + hs)*2 + k)*32 + lane)*2 + cg%2): a diagonal walk then changes
+// sector every 8 columns instead of every 4.  The fill's warp stores become 32 half-sectors spread over 1 KB, completed
+// by the next column group.
+#ifndef PK_PAIR_PIECES
+#define PK_PAIR_PIECES 0
+#endif
 __host__ __device__ inline uint64_t pk_trace_bytes(uint32_t nstrips, uint32_t Nw, int R, int TB)
 {
-    return (uint64_t)nstrips * ((Nw + 3) / 4) * (uint64_t)(R * TB / 16) * 32ull * 16ull;
+    const uint32_t Ng = (Nw + 3) / 4;
+    const uint32_t Nge = (PK_PAIR_PIECES == 1 && TB == 4) ? (Ng + 1) / 2 * 2 : Ng;
+    return (uint64_t)nstrips * Nge * (uint64_t)(R * TB / 16) * 32ull * 16ull;
+}
+// 16-byte piece index of (strip s, column group cg, row band rb of the strip, pair half k, lane) for TB == 4
+__host__ __device__ inline uint32_t pk_piece4(uint32_t s, uint32_t Ng, uint32_t cg, uint32_t RG, uint32_t rb, uint32_t k, uint32_t lane)
+{
+    if (PK_PAIR_PIECES == 2) return ((s * Ng + cg) * 2u + k) * 32u * RG + lane * RG + rb; // the strip's row bands side by side
+    if (PK_PAIR_PIECES) return (((((s * ((Ng + 1) / 2) + (cg >> 1)) * RG + rb) * 2u + k) * 32u + lane) * 2u) + (cg & 1u);
+    return (((s * Ng + cg) * RG + rb) * 2u + k) * 32u + lane;
 }
 
 #ifdef SEQA_EMU
@@ -231,7 +244,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
         const int M0 = p0 == PK_NULL ? 0 : (int)A.len1[p0], N0 = p0 == PK_NULL ? 0 : (int)A.len2[p0];
         const int M1 = p1 == PK_NULL ? 0 : (int)A.len1[p1], N1 = p1 == PK_NULL ? 0 : (int)A.len2[p1];
         const int Ng = ((int)J.Nw + 3) >> 2, Nw = (int)J.Nw;
-        const uint4 *__restrict__ prof = reinterpret_cast<const uint4 *>(A.prof + J.prof_off) + lane * 2;
+        const uint4 *__restrict__ prof = reinterpret_cast<const uint4 *>(A.prof + J.prof_off) + lane;
         const uint32_t *__restrict__ rowsel = A.rowsel + J.rowsel_off + lane;
         uint8_t *__restrict__ trace = A.trace + J.trace_off + (uint64_t)lane * 16;
         int best0 = 0, best1 = 0, bi0 = 0, bi1 = 0; // SW: running (max, last row holding it)
@@ -250,15 +263,15 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                 rmax[r] = 0u;
             }
             unsigned diag = LOCAL ? 0u : pk_dup(i0 * A.gap);
-            uint8_t *__restrict__ tr = trace + (uint64_t)s * Ng * (R * TB / 16 * 512);
-            uint4 na = prof[0], nb = prof[1]; // profile of the next group: {T0,T1} x 4 columns
+            uint8_t *__restrict__ tr = trace + (uint64_t)s * ((PK_PAIR_PIECES == 1 && TB == 4) ? (Ng + 1) / 2 * 2 : Ng) * (R * TB / 16 * 512);
+            uint4 na = prof[0], nb = prof[32]; // profile of the next group: {T0,T1} x 4 columns
             uint4 nu = make_uint4(0, 0, 0, 0);  // GB: boundary of the next group
             if (GB && !first) nu = bnd[0];
             for (int cg = 0; cg < Ng; cg++) {
                 const uint4 ca = na, cb = nb, cu = nu;
                 if (cg + 1 < Ng) {
                     na = prof[(uint64_t)(cg + 1) * 64];
-                    nb = prof[(uint64_t)(cg + 1) * 64 + 1];
+                    nb = prof[(uint64_t)(cg + 1) * 64 + 32];
                     if (GB && !first) nu = bnd[(uint64_t)(cg + 1) * 32];
                 }
                 // long pairs: the boundary rows of all resident warps outgrow the L2; pull mine back in well ahead
@@ -339,15 +352,19 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                     for (int rp = 0; rp < RP; rp++) pk_store_stream(&dst[rp * 32], make_uint4(W[rp][0], W[rp][1], W[rp][2], W[rp][3]));
                 } else {
                     static_assert(TB == 8 || R % 8 == 0, "4-bit trace pieces hold 8 rows");
-                    uint4 *dst = reinterpret_cast<uint4 *>(tr + (uint64_t)cg * (R / 4 * 32 * 16));
+                    // trace already points at this lane's 16 bytes (lane * 16); PAIR_PIECES: lane * 32 + (cg % 2) * 16
+                    uint4 *dst = PK_PAIR_PIECES == 1 ? reinterpret_cast<uint4 *>(tr + (uint64_t)(cg >> 1) * (R / 4 * 32 * 32) + lane * 16 + (cg & 1) * 16)
+                                 : PK_PAIR_PIECES == 2 ? reinterpret_cast<uint4 *>(tr + (uint64_t)cg * (R / 4 * 32 * 16) + lane * 16 * (R / 8 - 1))
+                                                       : reinterpret_cast<uint4 *>(tr + (uint64_t)cg * (R / 4 * 32 * 16));
+                    constexpr int PS = PK_PAIR_PIECES == 1 ? 64 : 32; // uint4 stride between consecutive (hs, k) pieces
 #pragma unroll
                     for (int hs = 0; hs < R / 8; hs++) {
                         // W[rp][cc]: rows (2rp, 2rp+1) x pairs x column pair cc  ->  per pair: 4 rows per word
                         const unsigned a0 = W[4 * hs][0], a1 = W[4 * hs + 1][0], a2 = W[4 * hs + 2][0], a3 = W[4 * hs + 3][0];
                         const unsigned b0 = W[4 * hs][1], b1 = W[4 * hs + 1][1], b2 = W[4 * hs + 2][1], b3 = W[4 * hs + 3][1];
-                        pk_store_stream(&dst[(hs * 2 + 0) * 32], make_uint4(seqa_prmt(a0, a1, 0x6420), seqa_prmt(b0, b1, 0x6420),
+                        pk_store_stream(&dst[PK_PAIR_PIECES == 2 ? hs : (hs * 2 + 0) * PS], make_uint4(seqa_prmt(a0, a1, 0x6420), seqa_prmt(b0, b1, 0x6420),
                                                                             seqa_prmt(a2, a3, 0x6420), seqa_prmt(b2, b3, 0x6420)));
-                        pk_store_stream(&dst[(hs * 2 + 1) * 32], make_uint4(seqa_prmt(a0, a1, 0x7531), seqa_prmt(b0, b1, 0x7531),
+                        pk_store_stream(&dst[PK_PAIR_PIECES == 2 ? 32 * (R / 8) + hs : (hs * 2 + 1) * PS], make_uint4(seqa_prmt(a0, a1, 0x7531), seqa_prmt(b0, b1, 0x7531),
                                                                             seqa_prmt(a2, a3, 0x7531), seqa_prmt(b2, b3, 0x7531)));
                     }
                 }
@@ -481,7 +498,8 @@ __global__ void __launch_bounds__(PK_WALK_TPB, 6) pk_walk_kernel(PkArgs A)
     auto fetch = [&](int ii, int jj) -> unsigned {
         const int s = ii / R, r = ii - s * R, cg = jj >> 2, c = jj & 3;
         const uint32_t g = ((uint32_t)s * Ng + (uint32_t)cg) * RG + (uint32_t)(r >> PRSH);
-        const uint32_t key = (TB == 8 ? g : g * 2u + (uint32_t)half) * 32u + (uint32_t)lane;
+        const uint32_t key = TB == 8 ? g * 32u + (uint32_t)lane
+                                     : pk_piece4((uint32_t)s, Ng, (uint32_t)cg, RG, (uint32_t)(r >> PRSH), (uint32_t)half, (uint32_t)lane);
         const int slot = (((ii >> PRSH) & 1) << 1) | (cg & 1);
         if (tag[slot][tid] != key) {
             const uint4 v = pieces[key];
@@ -520,7 +538,8 @@ __global__ void __launch_bounds__(PK_WALK_TPB, 6) pk_walk_kernel(PkArgs A)
             e = (int)reinterpret_cast<const int16_t *>(A.lastcol + J.last_off + ((uint64_t)s * (R / 4) + (uint64_t)(r >> 2)) * 32 + lane)[(r & 3) * 2 + half];
             auto piece = [&](int cg) -> uint4 {
                 const uint32_t g = g0 + (uint32_t)max(cg, 0) * RG;
-                return pieces[(TB == 8 ? g : g * 2u + (uint32_t)half) * 32u + (uint32_t)lane];
+                return pieces[TB == 8 ? g * 32u + (uint32_t)lane
+                                      : pk_piece4((uint32_t)s, Ng, (uint32_t)max(cg, 0), RG, (uint32_t)(r >> PRSH), (uint32_t)half, (uint32_t)lane)];
             };
             auto nibbles = [&](const uint4 &v, unsigned *nib) { // the row's 4 columns of a piece
                 if (TB == 8) {

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
         const int M0 = p0 == PK_NULL ? 0 : (int)A.len1[p0], N0 = p0 == PK_NULL ? 0 : (int)A.len2[p0];
         const int M1 = p1 == PK_NULL ? 0 : (int)A.len1[p1], N1 = p1 == PK_NULL ? 0 : (int)A.len2[p1];
         const int Ng = ((int)J.Nw + 3) >> 2, Nw = (int)J.Nw;
-        const uint4 *__restrict__ prof = reinterpret_cast<const uint4 *>(A.prof + J.prof_off) + lane * 2;
+        const uint4 *__restrict__ prof = reinterpret_cast<const uint4 *>(A.prof + J.prof_off) + lane;
         const uint32_t *__restrict__ rowsel = A.rowsel + J.rowsel_off + lane;
         uint4 *__restrict__ trace = reinterpret_cast<uint4 *>(A.trace + J.trace_off) + lane;
         int best0 = 0, best1 = 0, bi0 = 0, bi1 = 0; // local: running (max, last row holding it)
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
             unsigned diag = pk_dup((LOCAL || i0 == 0 ? 0 : A.go + i0 * A.ge) + gogo); // G(i0, 0)
             const int NC = TB == 8 ? Nw : (Nw + 1) >> 1;
             uint4 *__restrict__ tr = trace + (uint64_t)s * NC * (3 * RH * 32);
-            uint4 na = prof[0], nb = prof[1];
+            uint4 na = prof[0], nb = prof[32];
             uint4 nu0 = make_uint4(0, 0, 0, 0), nu1 = nu0;
             if (!first) {
                 nu0 = bnd[0];
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
                 const uint4 ca = na, cb = nb, cu0 = nu0, cu1 = nu1;
                 if (cg + 1 < Ng) {
                     na = prof[(uint64_t)(cg + 1) * 64];
-                    nb = prof[(uint64_t)(cg + 1) * 64 + 1];
+                    nb = prof[(uint64_t)(cg + 1) * 64 + 32];
                     if (!first) {
                         nu0 = bnd[(uint64_t)(cg + 1) * 64];
                         nu1 = bnd[(uint64_t)(cg + 1) * 64 + 1];

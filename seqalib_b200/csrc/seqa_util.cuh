@@ -131,16 +131,19 @@ struct GatherArgs {
 
 __global__ void __launch_bounds__(256) gather_ops_kernel(GatherArgs A)
 {
-    // 8 lanes per pair: local alignments of short reads are a few dozen ops
-    const int sub = threadIdx.x & 7;
-    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const uint64_t ng = ((uint64_t)gridDim.x * blockDim.x) >> 3;
-    for (uint64_t p = g; p < A.n_pairs; p += ng) {
+    // one warp per pair (an op string of a short read is 100-300 bytes, i.e. a few coalesced warp accesses); batches with
+    // fewer pairs than warps (the 100 kbp linear-space pairs) spread every pair over `wpp` warps
+    const uint32_t sub = threadIdx.x & 31;
+    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t ng = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t wpp = A.n_pairs < ng ? ng / A.n_pairs : 1;
+    const uint32_t first = (uint32_t)(g % wpp) * 32u + sub, step = (uint32_t)wpp * 32u;
+    for (uint64_t p = g / wpp; p < A.n_pairs; p += (wpp > 1 ? A.n_pairs : ng)) {
         const uint8_t *src = A.slots + A.slot_off[p] + A.slot_start[p];
         uint8_t *dst = A.dense + A.ops_off[p];
         const uint32_t len = A.ops_len[p];
         if (A.pack) {
-            for (uint32_t b = sub; b * 4 < len; b += 8) {
+            for (uint32_t b = first; (uint64_t)b * 4 < len; b += step) {
                 unsigned v = 0;
 #pragma unroll
                 for (uint32_t q = 0; q < 4; q++)
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(256) gather_ops_kernel(GatherArgs A)
                 dst[b] = (uint8_t)v;
             }
         } else {
-            for (uint32_t k = sub; k < len; k += 8) dst[k] = src[k];
+            for (uint32_t k = first; k < len; k += step) dst[k] = src[k];
         }
     }
 }

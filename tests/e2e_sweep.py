@@ -6,6 +6,7 @@ from seqalib_b200 import capi, synth
 n = 1_000_000
 lib = capi.Lib()
 prm = capi.make_params("sw", gap=-1, match=1, mismatch=-1)
+prm2 = capi.make_params("sw", gap=-1, match=1, mismatch=-1, flags=capi.FLAG_OPS_2BIT)
 ctx = capi.Ctx(lib); ctx.generate(prm, synth.SEED, 0, n, 0, 150, 150)
 hb, o1, o2, l1, l2 = ctx.download_inputs(n * 300); ctx.close()
 def pinned(shape, dt):
@@ -17,8 +18,9 @@ po2 = pinned(n, np.uint64); po2[:] = o2
 pl1 = pinned(n, np.uint32); pl1[:] = l1
 pl2 = pinned(n, np.uint32); pl2[:] = l2
 res = capi.Results(n, n * 300, pinned=pinned)
-for ring in (3, 4, 6):
-    for mcells in (2500, 5000, 7500):
+prm = prm2
+for ring in (3, 4, 5):
+    for mcells in (2500, 5000):
         os.environ["SEQA_RING"] = str(ring); os.environ["SEQA_WAVE_MCELLS"] = str(mcells)
         ts = []
         for k in range(6):
