@@ -32,6 +32,25 @@ ALG_TRACE_BITS = 2    # algorithmic traceback bits per cell (linea
 METRIC = "GCUPS (score+traceback) batched 150bp SW/NW at 1/2/4/8 B200 vs host CPU"
 
 
+_JSON_OUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner, torch warnings)
+    is sent to stderr instead, and emit() writes to the saved descriptor."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def kernel_traffic(kernel, pairs):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu` capture of this same command
     (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), scaled by the pair count."""
@@ -174,7 +193,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -341,7 +360,7 @@ def run_ours(args):
                     "byte_ops": {"value": total_cells / (e2e_ms_b * 1e-3) / 1e9, "ms_per_step": e2e_ms_b, "d2h_bytes_per_step": d2h_b,
                                  "note": "same call with one byte per op (flags = 0)"}},
             "gpu_launches": int(launches), "clocks": clocks}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -356,6 +375,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

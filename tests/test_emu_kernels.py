@@ -107,3 +107,23 @@ def test_synthetic_generator_matches_spec(emu_lib):
             key = splitmix64(seed ^ (2 * (first + p) + w))
             exp = "".join("ACGT"[(splitmix64((key + pos // 32) & (2 ** 64 - 1)) >> (2 * (pos % 32))) & 3] for pos in range(ln))
             assert bytes(bases[int(off):int(off) + ln]).decode() == exp
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_measured_trace_layout_variants_stay_correct(oracle_built, tmp_path, variant):
+    """PK_PAIR_PIECES=1/2 (the sector-private trace layouts measured and rejected in profiles/r01_notes_walk_layout.md)
+    are kept behind a compile-time switch: build each for the emulator and check the packed NW/SW path still matches."""
+    import os
+    import subprocess
+    from common import ROOT
+    so = str(tmp_path / ("libseqa_emu_pp%d.so" % variant))
+    csrc = os.path.join(ROOT, "seqalib_b200", "csrc")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-DSEQA_EMU", "-DPK_PAIR_PIECES=%d" % variant,
+                           "-I" + os.path.join(ROOT, "tests", "emu"), "-I" + csrc, "-Wno-unknown-pragmas", "-x", "c++",
+                           os.path.join(csrc, "seqa_cuda.cu"), os.path.join(ROOT, "tests", "emu", "cuda_emu.cpp"), "-o", so])
+    lib = capi.Lib(so)
+    rng = np.random.default_rng(21)
+    pairs = random_pairs(rng, 40, 1, 70) + random_pairs(rng, 5, 120, 180) + random_pairs(rng, 8, 1, 90, related=0.3) + \
+        [("", ""), ("A", "C"), ("ACGT", "")]
+    for algo, sc in (("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("sw", S.linear(-2, 1, -1, False))):
+        check_batch_against_oracle(lib, algo, sc, pairs)
