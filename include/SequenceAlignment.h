@@ -24,10 +24,14 @@
 #ifndef SEQA_SEQUENCE_ALIGNMENT_H
 #define SEQA_SEQUENCE_ALIGNMENT_H
 
+#include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <functional>
 #include <limits>
 #include <list>
+#include <memory>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -123,14 +127,55 @@ template <typename ContainerType> class ArrayView {
 namespace seqa {
 
 // Raw results of a batch: what the C ABI returns, owned by vectors.
+// Grow-only block of page-locked host memory from the library (seqa_cuda_host_alloc): batch buffers in such memory
+// cross PCIe at full speed and are not page-faulted in on every call.
+struct PinnedBlock {
+    char *P = nullptr;
+    size_t Cap = 0;
+    PinnedBlock() = default;
+    PinnedBlock(const PinnedBlock &) = delete;
+    PinnedBlock &operator=(const PinnedBlock &) = delete;
+    ~PinnedBlock()
+    {
+        if (P) seqa_cuda_host_free(P);
+    }
+    void reserve(size_t Bytes)
+    {
+        if (Bytes <= Cap) return;
+        if (P) seqa_cuda_host_free(P);
+        P = nullptr;
+        Cap = 0;
+        const size_t Want = Bytes + Bytes / 8 + 4096;
+        P = static_cast<char *>(seqa_cuda_host_alloc(Want));
+        if (!P) throw std::runtime_error(std::string("seqa_cuda_host_alloc: ") + seqa_cuda_last_error());
+        Cap = Want;
+    }
+};
+
+// Non-owning array view with the vector accessors the result type needs.
+template <typename T> struct Span {
+    T *P = nullptr;
+    size_t N = 0;
+    size_t size() const { return N; }
+    bool empty() const { return N == 0; }
+    T *data() const { return P; }
+    T *begin() const { return P; }
+    T *end() const { return P + N; }
+    T &operator[](size_t I) const { return P[I]; }
+};
+
+// Scores + op strings of a batch without any std::list.  The arrays live in one block of
+// page-locked memory shared with (and recycled by) the aligner that produced them: copying a PackedAlignments is
+// cheap and keeps the block alive.
 struct PackedAlignments {
-    std::vector<int32_t> Score;
-    std::vector<uint32_t> StartI, StartJ, EndI, EndJ, OpsLen;
-    std::vector<uint64_t> OpsOff;
+    Span<int32_t> Score;
+    Span<uint32_t> StartI, StartJ, EndI, EndJ, OpsLen;
+    Span<uint64_t> OpsOff;
     // 0 diagonal, 1 up (Seq1 symbol vs Blank), 2 left (Blank vs Seq2 symbol); in the 2-bit wire format
     // (SEQA_FLAG_OPS_2BIT, what the aligners below request): 4 ops per byte, OpsOff in bytes, OpsLen in ops
-    std::vector<uint8_t> Ops;
+    Span<uint8_t> Ops;
     bool TwoBit = false;
+    std::shared_ptr<PinnedBlock> Store; // owns the memory behind the spans
     size_t size() const { return Score.size(); }
     // op K of pair P, whatever the wire format
     unsigned op(size_t P, uint32_t K) const
@@ -182,6 +227,9 @@ class SequenceAligner {
     ScoringSystem Scoring;
     MatchFnTy Match;
     int EqualityChecked = -1; // -1 unknown, 0 not equality, 1 equality / nullptr
+    // page-locked staging, reused from call to call: packed inputs (indices, symbols) and the result block, which is
+    // recycled only once the caller has dropped every PackedAlignments that still points into it
+    std::shared_ptr<seqa::PinnedBlock> IdxBlock, BasesBlock, OutBlock;
 
   public:
     using EntryType = typename AlignedSequence<Ty, Blank>::Entry;
@@ -231,8 +279,21 @@ class SequenceAligner {
         static_assert(sizeof(Ty) == 1, "seqalib_b200: the GPU path aligns 8-bit symbols (char); wider types are reference-only");
         requireGpuEligible();
         const size_t N = S1.size();
-        std::vector<uint64_t> Off1(N), Off2(N);
-        std::vector<uint32_t> Len1(N), Len2(N);
+        seqa::PackedAlignments R;
+        R.TwoBit = true;
+        if (N == 0) {
+            LastScores.clear();
+            return R;
+        }
+        auto Up = [](size_t X) { return (X + 63) / 64 * 64; };
+        // ---- inputs: indices and symbols packed into page-locked memory (symbols copied by a few host threads) ----
+        if (!IdxBlock) IdxBlock = std::make_shared<seqa::PinnedBlock>();
+        if (!BasesBlock) BasesBlock = std::make_shared<seqa::PinnedBlock>();
+        IdxBlock->reserve(Up(8 * N) * 2 + Up(4 * N) * 2);
+        uint64_t *Off1 = reinterpret_cast<uint64_t *>(IdxBlock->P);
+        uint64_t *Off2 = reinterpret_cast<uint64_t *>(IdxBlock->P + Up(8 * N));
+        uint32_t *Len1 = reinterpret_cast<uint32_t *>(IdxBlock->P + 2 * Up(8 * N));
+        uint32_t *Len2 = reinterpret_cast<uint32_t *>(IdxBlock->P + 2 * Up(8 * N) + Up(4 * N));
         uint64_t Total = 0;
         for (size_t P = 0; P < N; P++) {
             Len1[P] = (uint32_t)S1[P]->size();
@@ -241,11 +302,21 @@ class SequenceAligner {
             Off2[P] = Total + Len1[P];
             Total += (uint64_t)Len1[P] + Len2[P];
         }
-        std::string Bases;
-        Bases.resize(Total);
-        for (size_t P = 0; P < N; P++) {
-            Bases.replace(Off1[P], Len1[P], seqa::detail::bytes_of(*S1[P]), Len1[P]);
-            Bases.replace(Off2[P], Len2[P], seqa::detail::bytes_of(*S2[P]), Len2[P]);
+        BasesBlock->reserve(Total + 64);
+        char *Bases = BasesBlock->P;
+        auto CopyRange = [&](size_t Lo, size_t Hi) {
+            for (size_t P = Lo; P < Hi; P++) {
+                if (Len1[P]) std::memcpy(Bases + Off1[P], seqa::detail::bytes_of(*S1[P]), Len1[P]);
+                if (Len2[P]) std::memcpy(Bases + Off2[P], seqa::detail::bytes_of(*S2[P]), Len2[P]);
+            }
+        };
+        const size_t Threads = Total < (1u << 22) ? 1 : std::min<size_t>(16, std::max<size_t>(1, std::thread::hardware_concurrency()));
+        if (Threads <= 1) {
+            CopyRange(0, N);
+        } else {
+            std::vector<std::thread> Pool;
+            for (size_t T = 0; T < Threads; T++) Pool.emplace_back(CopyRange, N * T / Threads, N * (T + 1) / Threads);
+            for (std::thread &T : Pool) T.join();
         }
         seqa_params Prm{};
         Prm.algo = Algo;
@@ -258,22 +329,26 @@ class SequenceAligner {
         Prm.device_first = 0;
         Prm.device_count = 0; // every visible device
         Prm.flags = SEQA_FLAG_OPS_2BIT; // a quarter of the result bytes over PCIe and in host memory
-        seqa_batch_in In{Bases.data(), Off1.data(), Off2.data(), Len1.data(), Len2.data(), (uint64_t)N, Total};
-        seqa::PackedAlignments R;
-        R.Score.resize(N);
-        R.StartI.resize(N);
-        R.StartJ.resize(N);
-        R.EndI.resize(N);
-        R.EndJ.resize(N);
-        R.OpsLen.resize(N);
-        R.OpsOff.resize(N);
-        R.Ops.resize(Total / 4 + N + 1);
-        R.TwoBit = true;
+        seqa_batch_in In{Bases, Off1, Off2, Len1, Len2, (uint64_t)N, Total};
+        // ---- results: one page-locked block; the previous one is reused once nobody else holds it ----
+        const size_t OpsCap = (size_t)(Total / 4 + N + 1);
+        if (!OutBlock || OutBlock.use_count() > 1) OutBlock = std::make_shared<seqa::PinnedBlock>();
+        OutBlock->reserve(Up(4 * N) * 6 + Up(8 * N) + Up(OpsCap));
+        char *O = OutBlock->P;
+        R.Score = {reinterpret_cast<int32_t *>(O), N};
+        R.StartI = {reinterpret_cast<uint32_t *>(O + Up(4 * N)), N};
+        R.StartJ = {reinterpret_cast<uint32_t *>(O + 2 * Up(4 * N)), N};
+        R.EndI = {reinterpret_cast<uint32_t *>(O + 3 * Up(4 * N)), N};
+        R.EndJ = {reinterpret_cast<uint32_t *>(O + 4 * Up(4 * N)), N};
+        R.OpsLen = {reinterpret_cast<uint32_t *>(O + 5 * Up(4 * N)), N};
+        R.OpsOff = {reinterpret_cast<uint64_t *>(O + 6 * Up(4 * N)), N};
+        R.Ops = {reinterpret_cast<uint8_t *>(O + 6 * Up(4 * N) + Up(8 * N)), OpsCap};
+        R.Store = OutBlock;
         seqa_batch_out Out{R.Score.data(), R.StartI.data(), R.StartJ.data(), R.EndI.data(), R.EndJ.data(), R.Ops.data(),
-                           R.OpsOff.data(), R.OpsLen.data(), (uint64_t)R.Ops.size(), 0};
+                           R.OpsOff.data(), R.OpsLen.data(), (uint64_t)OpsCap, 0};
         if (seqa_cuda_align_batch(&Prm, &In, &Out) != SEQA_OK)
             throw std::runtime_error(std::string("seqa_cuda_align_batch: ") + seqa_cuda_last_error());
-        // no shrink: large batches are processed in waves whose op strings sit at each wave's own base offset
+        // (large batches are processed in waves whose op strings sit at each wave's own base offset inside Ops)
         LastScores.assign(R.Score.begin(), R.Score.end());
         return R;
     }

@@ -140,6 +140,13 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
  * calls -- the only hidden state of the library. */
 void seqa_cuda_trim(void);
 
+/* Page-locked host memory for the caller's batch buffers (cudaHostAlloc, portable across devices): transfers from / to
+ * such buffers run at PCIe speed and overlap with the kernels; pageable buffers work too but are staged by the
+ * driver at a fraction of that.  NULL on failure (message in seqa_cuda_last_error()).  include/SequenceAlignment.h
+ * keeps its packing buffers in memory from here. */
+void *seqa_cuda_host_alloc(uint64_t bytes);
+void seqa_cuda_host_free(void *ptr);
+
 const char *seqa_cuda_last_error(void);
 int seqa_cuda_device_count(void); /* number of visible CUDA devices, 0 if none / no driver */
 int seqa_cuda_abi_version(void);

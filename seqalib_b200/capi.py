@@ -25,7 +25,8 @@ ERR_NAMES = {0: "SEQA_OK", -1: "SEQA_ERR_INVALID", -2: "SEQA_ERR_UNSUPPORTED", -
 EXPORTS = ["seqa_cuda_align_batch", "seqa_cuda_last_error", "seqa_cuda_device_count", "seqa_cuda_abi_version",
            "seqa_ctx_create", "seqa_ctx_destroy", "seqa_ctx_upload", "seqa_ctx_generate", "seqa_ctx_run",
            "seqa_ctx_download", "seqa_ctx_device_results", "seqa_ctx_sync", "seqa_ctx_launch_count", "seqa_ctx_cells", "seqa_ctx_last_fill_ms",
-           "seqa_ctx_last_kernel", "seqa_ctx_download_inputs", "seqa_cuda_int_peak", "seqa_cuda_trim"]
+           "seqa_ctx_last_kernel", "seqa_ctx_download_inputs", "seqa_cuda_int_peak", "seqa_cuda_trim",
+           "seqa_cuda_host_alloc", "seqa_cuda_host_free"]
 
 
 class SeqaError(RuntimeError):
@@ -116,6 +117,10 @@ class Lib(object):
         L.seqa_ctx_download_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p]
         L.seqa_cuda_trim.restype = None
+        L.seqa_cuda_host_alloc.restype = C.c_void_p
+        L.seqa_cuda_host_alloc.argtypes = [C.c_uint64]
+        L.seqa_cuda_host_free.restype = None
+        L.seqa_cuda_host_free.argtypes = [C.c_void_p]
         L.seqa_cuda_int_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
 
     def check(self, rc):

@@ -1172,6 +1172,26 @@ static void cache_release(seqa_ctx *c, int cached)
     g_cache_busy[c->device][cached] = false;
 }
 
+void *seqa_cuda_host_alloc(uint64_t bytes)
+{
+    void *p = nullptr;
+    if (seqa_cuda_device_count() <= 0) {
+        fail(SEQA_ERR_NO_DEVICE, "no CUDA device is visible (there is no CPU fallback)");
+        return nullptr;
+    }
+    if (cudaHostAlloc(&p, bytes ? (size_t)bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        (void)cudaGetLastError();
+        fail(SEQA_ERR_NOMEM, "cudaHostAlloc(%llu bytes) failed", (unsigned long long)bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void seqa_cuda_host_free(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+}
+
 void seqa_cuda_trim(void)
 {
     std::lock_guard<std::mutex> lk(g_cache_mu);

@@ -10,7 +10,7 @@ from common import ROOT
 
 def _build_and_run(libdir, libname, tmp_path):
     exe = str(tmp_path / "test_header")
-    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "tests", "cpp", "test_header.cpp"), "-o", exe,
                            "-L", libdir, "-l" + libname, "-Wl,-rpath," + libdir])
     out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
