@@ -427,6 +427,45 @@ struct PkSymCache {
     }
 };
 
+// The same cache with 16-byte lines kept in shared memory (column `tid` of a [4][TPB] word array per sequence): one global
+// load per 16 steps along a sequence instead of one per 4.  The walk's L1 is thrashed by trace lines (1 % hit rate), so
+// every symbol word load is an L2 round trip on the serial path of a step.
+#ifndef PK_SYM16
+#define PK_SYM16 1
+#endif
+struct PkSymCache16 {
+    const uint8_t *base; // A.bases (256-byte aligned allocation, 16 bytes of slack behind the last sequence)
+    uint64_t off;
+    uint32_t key;
+    uint32_t *sm; // sm[w * stride]: word w of the cached 16-byte line
+    int stride;
+    __device__ __forceinline__ void init(const uint8_t *b, uint64_t o, uint32_t *column, int str)
+    {
+        base = b;
+        off = o;
+        key = 0xffffffffu;
+        sm = column;
+        stride = str;
+    }
+    // (Also measured: the current word kept in a register on top of the shared line -- one LDS per 4 steps instead of
+    // one per step.  Two more live registers under the walk's 40-register cap spill inside the loop; NW 150 bp
+    // 6.16 -> 6.50 ms per 1 M pairs, SW 6.64 -> 6.54 against 6.41 for this version.)
+    __device__ __forceinline__ unsigned at(int idx)
+    {
+        const uint64_t a = off + (uint64_t)idx;
+        const uint32_t k = (uint32_t)(a >> 4);
+        if (k != key) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(base + ((uint64_t)k << 4));
+            sm[0] = v.x;
+            sm[stride] = v.y;
+            sm[2 * stride] = v.z;
+            sm[3 * stride] = v.w;
+            key = k;
+        }
+        return (sm[(int)((a >> 2) & 3u) * stride] >> ((unsigned)(a & 3u) * 8u)) & 0xffu;
+    }
+};
+
 struct PkOpWriter {
     uint8_t *slots; // A.slots (4-byte aligned)
     uint64_t pos;   // byte offset of the next op + 1 (ops are written back to front)
@@ -487,9 +526,16 @@ __global__ void __launch_bounds__(PK_WALK_TPB, 6) pk_walk_kernel(PkArgs A)
     constexpr unsigned MASK = TB == 8 ? 0xffu : 0xfu;
     constexpr int PRSH = TB == 8 ? 1 : 3; // rows per piece: 2 (TB 8: 2 rows x 4 columns x 2 pairs) or 8 (TB 4: this pair only)
     constexpr uint32_t RG = (uint32_t)(R >> PRSH);
+#if PK_SYM16
+    __shared__ uint32_t symw[8][PK_WALK_TPB];
+    PkSymCache16 a, b;
+    a.init(A.bases, A.off1[p], &symw[0][tid], PK_WALK_TPB);
+    b.init(A.bases, A.off2[p], &symw[4][tid], PK_WALK_TPB);
+#else
     PkSymCache a, b;
     a.init(A.bases, A.off1[p]);
     b.init(A.bases, A.off2[p]);
+#endif
     const int gap = A.gap;
     const uint4 *pieces = reinterpret_cast<const uint4 *>(A.trace + J.trace_off);
 #pragma unroll

@@ -224,9 +224,16 @@ __global__ void __launch_bounds__(PK_WALK_TPB) pkg_walk_kernel(PkArgs A)
     const int lane = (int)((pos & 63) >> 1), half = (int)(pos & 1);
     const int M = (int)A.len1[p], N = (int)A.len2[p];
     const uint32_t NC = TB == 8 ? J.Nw : (J.Nw + 1) >> 1, RH = (uint32_t)(R / 8);
+#if PK_SYM16
+    __shared__ uint32_t symw[8][PK_WALK_TPB]; // 16-byte symbol lines of both sequences (PkSymCache16)
+    PkSymCache16 a, b;
+    a.init(A.bases, A.off1[p], &symw[0][tid], PK_WALK_TPB);
+    b.init(A.bases, A.off2[p], &symw[4][tid], PK_WALK_TPB);
+#else
     PkSymCache a, b;
     a.init(A.bases, A.off1[p]);
     b.init(A.bases, A.off2[p]);
+#endif
     const int go = A.go, ge = A.ge, gogo = go + ge;
     const uint4 *pieces = reinterpret_cast<const uint4 *>(A.trace + J.trace_off);
 #pragma unroll
