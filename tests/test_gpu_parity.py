@@ -283,8 +283,8 @@ def test_config4_related_pairs(gpu_lib):
     """BASELINE configs[3], realism variant: RELATED pairs -- sequence 2 = sequence 1 with 10 %
     substitutions, 2 % insertions, 2 % deletions from the shared generator (seqalib_b200/synth.py: related_sequence
     documents the exact procedure).  Long diagonal runs, a different split pattern, scores far beyond 16 bits
-    (the packed sweeps re-base): 4 Hirschberg pairs of 100,000 bp and 4 MyersMiller pairs of 30,000 bp, bit-exact."""
-    for algo, sc, n, L in (("hirschberg", S.linear(-1, 2, -1), 4, 100_000), ("myersmiller", S.affine(-3, -1, 1, -1), 4, 30_000)):
+    (the packed sweeps re-base): 8 Hirschberg pairs of 100,000 bp and 8 MyersMiller pairs of 30,000 bp, bit-exact."""
+    for algo, sc, n, L in (("hirschberg", S.linear(-1, 2, -1), 8, 100_000), ("myersmiller", S.affine(-3, -1, 1, -1), 8, 30_000)):
         bases, off1, off2, l1, l2 = synth.related_batch(synth.SEED, 0, n, L)
         ctx = capi.Ctx(gpu_lib)
         ctx.upload(scoring_to_params(algo, sc), bases, off1, off2, l1, l2)
@@ -325,6 +325,26 @@ def test_two_bit_wire_format(gpu_lib):
         a = bytes(bases[int(off1[p]):int(off1[p]) + 150]).decode()
         b = bytes(bases[int(off2[p]):int(off2[p]) + 150]).decode()
         assert np.array_equal(packed.pair_ops(p), orc.oracle_align("sw", sc, a, b)["ops"]), p
+
+
+def test_config4_myersmiller_full_length(gpu_lib):
+    """BASELINE configs[3] at its real pair length for MyersMiller too: 8 pairs of 100,000 x 100,000 bp (4 random, 4
+    related), bit-exact against the oracle (about a minute: one pair per host thread)."""
+    sc = S.affine(-3, -1, 1, -1)
+    L = 100_000
+    rb, ro1, ro2, rl1, rl2 = synth.batch(synth.SEED, 100, 4, 0, L, L)
+    qb, qo1, qo2, ql1, ql2 = synth.related_batch(synth.SEED, 200, 4, L)
+    bases = np.concatenate([rb, qb])
+    off1 = np.concatenate([ro1, qo1 + np.uint64(len(rb))])
+    off2 = np.concatenate([ro2, qo2 + np.uint64(len(rb))])
+    l1, l2 = np.concatenate([rl1, ql1]), np.concatenate([rl2, ql2])
+    ctx = capi.Ctx(gpu_lib)
+    ctx.upload(scoring_to_params("myersmiller", sc), bases, off1, off2, l1, l2)
+    ctx.run()
+    res = ctx.download(ops_capacity=int(l1.sum() + l2.sum()))
+    assert ctx.last_kernel().endswith("_s16x2")
+    ctx.close()
+    assert compare_with_oracle_batch(res, "myersmiller", sc, bases, off1, off2, l1, l2, "config4 MM 100 kbp") == 8
 
 
 def test_mixed_length_batch(gpu_lib):
