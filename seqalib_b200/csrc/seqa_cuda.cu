@@ -802,19 +802,22 @@ int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in
     c->hlen1.assign(in->len1 + pb, in->len1 + pe);
     c->hlen2.assign(in->len2 + pb, in->len2 + pe);
     uint64_t lo = UINT64_MAX, hi = 0, st_cells = 0, st_slots = 0;
-    bool st_uni = true;
+    bool st_uni = true, dense = true; // dense: seq1 then seq2 of every pair, pairs back to back from the first offset on
     const uint32_t M0 = n ? in->len1[pb] : 0, N0 = n ? in->len2[pb] : 0;
+    const uint64_t first_off = n ? in->off1[pb] : 0;
     for (uint64_t p = pb; p < pe; p++) {
         const uint64_t l1 = in->len1[p], l2 = in->len2[p];
         const uint64_t a0 = in->off1[p], a1 = a0 + l1, b0 = in->off2[p], b1 = b0 + l2;
         if (a1 > in->bases_len || b1 > in->bases_len)
             return fail(SEQA_ERR_INVALID, "pair %llu reaches past bases_len", (unsigned long long)p);
+        dense &= a0 == first_off + st_slots && b0 == a1;
         lo = std::min(lo, std::min(a0, b0));
         hi = std::max(hi, std::max(a1, b1));
         st_cells += l1 * l2;
         st_slots += l1 + l2;
         st_uni &= l1 == M0 && l2 == N0;
     }
+    if (getenv("SEQA_NO_DENSE_UPLOAD")) dense = false; // A/B switch: always send the offset / length arrays
     c->have_stats = true;
     c->st_cells = st_cells;
     c->st_slots = st_slots;
@@ -823,16 +826,26 @@ int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in
     c->bases_len = hi - lo;
     CKS(c->bases.ensure(c->bases_len + 16));
     if (hi > lo) CK(cudaMemcpyAsync(c->bases.p, in->bases + lo, hi - lo, cudaMemcpyHostToDevice, c->up));
+    const bool dev_lengths = dense && st_uni; // uniform: the device fills the length arrays itself
     if (n) {
-        CK(cudaMemcpyAsync(c->off1.p, in->off1 + pb, n * 8, cudaMemcpyHostToDevice, c->up));
-        CK(cudaMemcpyAsync(c->off2.p, in->off2 + pb, n * 8, cudaMemcpyHostToDevice, c->up));
-        CK(cudaMemcpyAsync(c->len1.p, in->len1 + pb, n * 4, cudaMemcpyHostToDevice, c->up));
-        CK(cudaMemcpyAsync(c->len2.p, in->len2 + pb, n * 4, cudaMemcpyHostToDevice, c->up));
+        // a dense batch sends no offsets (24 of its 324 bytes per 150 bp pair): the device derives them from the
+        // op-slot scan of build_plan, which has the same values (exclusive scan of len1 + len2)
+        if (!dense) {
+            CK(cudaMemcpyAsync(c->off1.p, in->off1 + pb, n * 8, cudaMemcpyHostToDevice, c->up));
+            CK(cudaMemcpyAsync(c->off2.p, in->off2 + pb, n * 8, cudaMemcpyHostToDevice, c->up));
+        }
+        if (!dev_lengths) {
+            CK(cudaMemcpyAsync(c->len1.p, in->len1 + pb, n * 4, cudaMemcpyHostToDevice, c->up));
+            CK(cudaMemcpyAsync(c->len2.p, in->len2 + pb, n * 4, cudaMemcpyHostToDevice, c->up));
+        }
         CKS(order_after(c, c->up, c->stream)); // the planning kernels read len1/len2/off
-        if (lo) LAUNCH(c, (rebase_kernel), (unsigned)((n + 255) / 256), 256, 0, c->off1.p, c->off2.p, n, lo);
+        if (dev_lengths) LAUNCH(c, (fill_lengths_kernel), (unsigned)((n + 255) / 256), 256, 0, c->len1.p, c->len2.p, n, M0, N0);
+        if (!dense && lo) LAUNCH(c, (rebase_kernel), (unsigned)((n + 255) / 256), 256, 0, c->off1.p, c->off2.p, n, lo);
     }
     const double t_up = ms_since(tu0);
-    const int rc = build_plan(c);
+    int rc = build_plan(c);
+    if (rc == SEQA_OK && n && dense) // slot_off is ready (stream-ordered) and equals off1 relative to the shard's first byte
+        LAUNCH(c, (dense_offsets_kernel), (unsigned)((n + 255) / 256), 256, 0, c->slot_off.p, c->len1.p, c->off1.p, c->off2.p, n);
     if (dbgt) fprintf(stderr, "[seqa]   upload %.3f ms, plan %.3f ms (%llu pairs)\n", t_up, ms_since(tu0) - t_up, (unsigned long long)n);
     return rc;
 }

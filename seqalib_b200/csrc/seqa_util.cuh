@@ -107,6 +107,29 @@ __global__ void __launch_bounds__(256) lensum_kernel(const uint32_t *__restrict_
     if (k < n) out[k] = a[k] + b[k];
 }
 
+// Dense batches (seq1 then seq2 of every pair, pairs back to back: what packers produce) need no offset arrays over
+// PCIe: off1 = exclusive scan of (len1 + len2) -- the same scan that places the op slots -- and off2 = off1 + len1.
+__global__ void __launch_bounds__(256) dense_offsets_kernel(const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ len1,
+                                                            uint64_t *__restrict__ off1, uint64_t *__restrict__ off2, uint64_t n)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        const uint64_t o = slot_off[k];
+        off1[k] = o;
+        off2[k] = o + len1[k];
+    }
+}
+
+// uniform batches do not need the length arrays either
+__global__ void __launch_bounds__(256) fill_lengths_kernel(uint32_t *__restrict__ len1, uint32_t *__restrict__ len2, uint64_t n, uint32_t a, uint32_t b)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        len1[k] = a;
+        len2[k] = b;
+    }
+}
+
 // device offsets are relative to the first byte the shard touches
 __global__ void __launch_bounds__(256) rebase_kernel(uint64_t *__restrict__ off1, uint64_t *__restrict__ off2, uint64_t n, uint64_t lo)
 {

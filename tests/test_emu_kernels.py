@@ -127,3 +127,31 @@ def test_measured_trace_layout_variants_stay_correct(oracle_built, tmp_path, var
         [("", ""), ("A", "C"), ("ACGT", "")]
     for algo, sc in (("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("sw", S.linear(-2, 1, -1, False))):
         check_batch_against_oracle(lib, algo, sc, pairs)
+
+
+def test_batch_layouts_dense_and_scattered(emu_lib):
+    """A dense batch (seq1, seq2, next pair ... back to back) sends no offset arrays -- the device derives them from the
+    op-slot scan -- and a uniform one no length arrays either; any other layout (gaps, reordered or shared sequences,
+    a dense run that does not start at byte 0) must give the same alignments."""
+    rng = np.random.default_rng(33)
+    sc = S.linear(-1, 1, -1)
+    for pairs in (random_pairs(rng, 80, 1, 90), [("ACGTACGTAC" * 3, "ACGTTCGTAC" * 3)] * 70):  # ragged / uniform
+        bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+        want = emu_lib.align_batch(scoring_to_params("sw", sc), bases, off1, off2, len1, len2)
+        # (1) dense, but behind 5 bytes of padding; (2) pairs stored in reverse order with a gap byte between sequences
+        pad = np.concatenate([np.frombuffer(b"NNNNN", dtype=np.uint8), bases])
+        layouts = [(pad, off1 + np.uint64(5), off2 + np.uint64(5))]
+        chunks, o1, o2, pos = [], np.zeros(len(pairs), np.uint64), np.zeros(len(pairs), np.uint64), 0
+        for p in reversed(range(len(pairs))):
+            a, b = pairs[p]
+            o2[p], o1[p] = pos, pos + len(b) + 1
+            chunks += [b.encode(), b"N", a.encode(), b"N"]
+            pos += len(a) + len(b) + 2
+        layouts.append((np.frombuffer(b"".join(chunks), dtype=np.uint8), o1, o2))
+        for lb, lo1, lo2 in layouts:
+            got = emu_lib.align_batch(scoring_to_params("sw", sc), np.ascontiguousarray(lb), lo1, lo2, len1, len2)
+            for name in ("score", "start_i", "start_j", "end_i", "end_j", "ops_len"):
+                assert np.array_equal(getattr(want, name), getattr(got, name)), name
+            for p in range(len(pairs)):
+                assert np.array_equal(want.pair_ops(p), got.pair_ops(p)), p
+        check_batch_against_oracle(emu_lib, "sw", sc, pairs)
