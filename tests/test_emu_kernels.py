@@ -86,6 +86,7 @@ def test_two_device_shards(emu_lib):
     pairs = random_pairs(rng, 41, 1, 60)
     check_batch_against_oracle(emu_lib, "nw", S.linear(-1, 2, -1), pairs, device_count=2)
     check_batch_against_oracle(emu_lib, "lgotoh", S.affine(-3, -1, 1, -1), pairs, device_count=2)
+    check_batch_against_oracle(emu_lib, "sw", S.linear(-1, 1, -1), pairs, flags=capi.FLAG_OPS_2BIT, device_count=2)
 
 
 def test_synthetic_generator_matches_spec(emu_lib):

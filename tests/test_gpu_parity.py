@@ -372,6 +372,8 @@ def test_multi_device_split(gpu_lib):
     pairs = random_pairs(rng, 500, 1, 200)
     check_batch_against_oracle(gpu_lib, "sw", S.linear(-1, 1, -1), pairs, device_count=2)
     check_batch_against_oracle(gpu_lib, "ggotoh", S.affine(-3, -1, 1, -1), pairs, device_count=gpu_lib.device_count())
+    # the 2-bit wire format places every wave behind ceil(len/4) bytes per earlier pair, on whichever device it ran
+    check_batch_against_oracle(gpu_lib, "nw", S.linear(-1, 2, -1), pairs, flags=capi.FLAG_OPS_2BIT, device_count=2)
 
 
 def test_device_resident_results(gpu_lib):
