@@ -764,7 +764,8 @@ int finish_ops(seqa_ctx *c)
     G.ops_off = c->ops_off.p;
     G.dense = c->dense.p;
     G.pack = pack;
-    const unsigned blocks = (unsigned)std::min<uint64_t>((n * 32 + 255) / 256, (uint64_t)c->sms * 64);
+    // 8 lanes per short pair; few long pairs get enough warps for their bytes (the kernel then spreads a pair over warps)
+    const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((n * 8 + 255) / 256, c->slots_total / 16384 + 1), (uint64_t)c->sms * 64);
     LAUNCH(c, (gather_ops_kernel), blocks, 256, 0, G);
     CK(cudaGetLastError());
     return SEQA_OK;

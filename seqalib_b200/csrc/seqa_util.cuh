@@ -154,14 +154,15 @@ struct GatherArgs {
 
 __global__ void __launch_bounds__(256) gather_ops_kernel(GatherArgs A)
 {
-    // one warp per pair (an op string of a short read is 100-300 bytes, i.e. a few coalesced warp accesses); batches with
-    // fewer pairs than warps (the 100 kbp linear-space pairs) spread every pair over `wpp` warps
-    const uint32_t sub = threadIdx.x & 31;
-    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t ng = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint64_t wpp = A.n_pairs < ng ? ng / A.n_pairs : 1;
-    const uint32_t first = (uint32_t)(g % wpp) * 32u + sub, step = (uint32_t)wpp * 32u;
-    for (uint64_t p = g / wpp; p < A.n_pairs; p += (wpp > 1 ? A.n_pairs : ng)) {
+    // Batches with fewer pairs than warps (the 100 kbp linear-space pairs): every pair is spread over `wpp` warps.
+    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    if (A.n_pairs < nw) {
+        const uint32_t sub = threadIdx.x & 31;
+        const uint64_t wpp = nw / A.n_pairs;
+        const uint64_t p = gw / wpp;
+        if (p >= A.n_pairs) return;
+        const uint32_t first = (uint32_t)(gw % wpp) * 32u + sub, step = (uint32_t)wpp * 32u;
         const uint8_t *src = A.slots + A.slot_off[p] + A.slot_start[p];
         uint8_t *dst = A.dense + A.ops_off[p];
         const uint32_t len = A.ops_len[p];
@@ -175,6 +176,50 @@ __global__ void __launch_bounds__(256) gather_ops_kernel(GatherArgs A)
             }
         } else {
             for (uint32_t k = first; k < len; k += step) dst[k] = src[k];
+        }
+        return;
+    }
+    // Many short pairs: 8 lanes per pair, every lane's loads of a 64-byte round issued before the first store, so a warp
+    // has four pairs and eight bytes per lane in flight (the kernel is bound by dependent-load latency, not by bytes).
+    const uint32_t sub = threadIdx.x & 7;
+    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const uint64_t ng = ((uint64_t)gridDim.x * blockDim.x) >> 3;
+    for (uint64_t p = g; p < A.n_pairs; p += ng) {
+        const uint8_t *src = A.slots + A.slot_off[p] + A.slot_start[p];
+        uint8_t *dst = A.dense + A.ops_off[p];
+        const uint32_t len = A.ops_len[p];
+        if (A.pack) {
+            const uint32_t nb = (len + 3u) >> 2; // output bytes
+            for (uint32_t base = 0; base < nb; base += 32) {
+                unsigned v[4];
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++) {
+                    const uint32_t b = base + sub + 8u * q;
+                    v[q] = 0;
+#pragma unroll
+                    for (uint32_t t = 0; t < 4; t++)
+                        if (b * 4 + t < len) v[q] |= (unsigned)(src[b * 4 + t] & 3u) << (2 * t);
+                }
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++) {
+                    const uint32_t b = base + sub + 8u * q;
+                    if (b < nb) dst[b] = (uint8_t)v[q];
+                }
+            }
+        } else {
+            for (uint32_t base = 0; base < len; base += 64) {
+                uint8_t v[8];
+#pragma unroll
+                for (uint32_t q = 0; q < 8; q++) {
+                    const uint32_t k = base + sub + 8u * q;
+                    v[q] = k < len ? src[k] : (uint8_t)0;
+                }
+#pragma unroll
+                for (uint32_t q = 0; q < 8; q++) {
+                    const uint32_t k = base + sub + 8u * q;
+                    if (k < len) dst[k] = v[q];
+                }
+            }
         }
     }
 }
