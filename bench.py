@@ -188,8 +188,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "SmithWatermanSA linear gap (-1,1,-1), %d bp x %d bp random DNA, score+traceback" % (LEN, LEN),
-                       "sample": sample},
+            # the same workload name as the GPU arm's line; the CPU arm times a bounded sample of it per step
+            "config": {"workload": "SmithWatermanSA linear gap (-1,1,-1), %d random DNA pairs of %d bp per GPU, score+traceback" % (args.pairs, LEN),
+                       "pairs_per_gpu": args.pairs, "len": LEN, "sample": sample},
             "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
