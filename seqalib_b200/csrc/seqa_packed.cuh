@@ -508,9 +508,12 @@ struct PkOpWriter {
 // and column group: the 2 x 2 pieces around a cell never collide, and a lookup is a tag compare plus one LDS instead
 // of a register select tree.  Word w of slot s of thread t lives at pcw[s*4+w][t]: bank = t % 32, conflict-free.
 #define PK_WALK_TPB 256
+#ifndef PK_WALK_MINB
+#define PK_WALK_MINB 6 /* resident CTAs per SM the walk is compiled for: 7 (36 registers) spills in the step loop -- measured, see notes */
+#endif
 
 template <bool LOCAL, int TB, int R>
-__global__ void __launch_bounds__(PK_WALK_TPB, 6) pk_walk_kernel(PkArgs A)
+__global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK_MINB) pk_walk_kernel(PkArgs A)
 {
     __shared__ uint32_t pcw[16][PK_WALK_TPB];
     __shared__ uint32_t tag[4][PK_WALK_TPB];
