@@ -52,14 +52,28 @@ def emit(line):
 
 
 def kernel_traffic(kernel, pairs):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu` capture of this same command
-    (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), scaled by the pair count."""
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
+    (profiles/r02_traffic.json, else r01: dram__bytes_read.sum + dram__bytes_write.sum), scaled by the pair count.
+    The contract allows the capture to be a separate run (a number printed under ncu is never a bench value)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)[kernel]
+            return float(t["dram_bytes_per_launch"]) * pairs / float(t["pairs"])
+        except Exception:
+            continue
+    return None
+
+
+def sass_alu_per_two_cells(kernel):
+    """ALU-pipe instructions per two cells in the hot loop of `kernel`, counted from the SASS of the committed build by
+    tests/sass_count.py (profiles/sass_counts.json).  Falls back to the hand count of seqa_packed.cuh (5.25)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "sass_counts.json")) as f:
             t = json.load(f)[kernel]
-        return float(t["dram_bytes_per_launch"]) * pairs / float(t["pairs"])
+        return float(t["alu_per_2_cells"]), "profiles/sass_counts.json (%s)" % t.get("function", kernel)
     except Exception:
-        return None
+        return 5.25, "hand count (seqa_packed.cuh header comment)"
 
 
 def measured_peaks():
@@ -97,12 +111,22 @@ class ClockSampler(object):
         return time.time()
 
     def stop(self, t0, t1):
+        out = self.window(t0, t1)
+        self.close()
+        return out
+
+    def close(self):
+        if self.proc:
+            self.proc.terminate()
+            self.proc = None
+
+    def window(self, t0, t1):
+        """clocks / throttle reasons of the samples taken between two mark()s (the sampler keeps running)"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
-        self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for (t, line) in self.rows:
+        for (t, line) in list(self.rows):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -129,6 +153,9 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+_CPU_BATCH = {}
+
+
 def cpu_reference_gcups(n_pairs, threads):
     """The reference's own CPU path (SmithWatermanSA::getAlignment with equal<char>, one aligner object per
     std::thread) on `n_pairs` pairs of the bench workload.  -> (gcups, kind, seconds)"""
@@ -136,7 +163,10 @@ def cpu_reference_gcups(n_pairs, threads):
     from seqalib_b200 import synth
     if not os.path.exists(orc.ORACLE_SO):
         orc.build()
-    bases, off1, off2, l1, l2 = synth.batch(SEED, 0, n_pairs, 0, LEN, LEN)
+    if _CPU_BATCH.get("n") != n_pairs:  # generated once (vectorised), reused by every step
+        _CPU_BATCH.clear()
+        _CPU_BATCH.update(n=n_pairs, arrays=synth.batch_uniform(SEED, 0, n_pairs, LEN, LEN))
+    bases, off1, off2, l1, l2 = _CPU_BATCH["arrays"]
     sc = orc.Scoring.linear(SCORING["gap"], SCORING["match"], SCORING["mismatch"])
     cells = float((l1.astype(np.float64) * l2).sum())
     if orc.have_ref():
@@ -176,7 +206,13 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = host_threads()
-    n = max(threads * 6000, 8000)  # ~1 s per step on all host threads at ~0.15 GCUPS/core
+    # the CPU arm on the FULL 1 M-pair set when the whole --steps/--warmup run still ends within a few
+    # minutes on this host (~0.18 GCUPS per thread), else a bounded sample of the same generator stream
+    per_step_s = args.pairs * LEN * LEN / (threads * 0.18e9)
+    if per_step_s * (args.steps + args.warmup) <= 330:
+        n = args.pairs
+    else:
+        n = max(8000, int(args.pairs * 330 / (per_step_s * (args.steps + args.warmup))))
     vals, kind = [], "port"
     for k in range(args.warmup + args.steps):
         g, kind, sec = cpu_reference_gcups(n, threads)
@@ -184,7 +220,8 @@ def run_reference(args):
             vals.append((g, sec))
     value = float(np.mean([v[0] for v in vals]))
     ms = float(np.mean([v[1] for v in vals])) * 1e3
-    sample = "%d pairs of %d bp per step (same generator/seed as the GPU arm)" % (n, LEN)
+    sample = ("the full %d pairs of %d bp per step (same generator/seed as the GPU arm)" if n == args.pairs else
+              "%d pairs of %d bp per step (same generator/seed as the GPU arm)") % (n, LEN)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
@@ -196,6 +233,210 @@ def run_reference(args):
             "gpu_launches": 0}
     emit(line)
     return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The other BASELINE configs (configs[2..4]) in the same JSON line: "configs": [...].  Strong scaling: the config's
+# whole workload is split over the N ranks (no collective on the data path), every rank times its own share with CUDA
+# events on its stream, the entry reports total cells / max-over-ranks time.
+W_OPS = {"nw": 7, "sw": 10, "ggotoh": 11, "lgotoh": 14, "hirschberg": 14, "myersmiller": 22}
+
+
+def _spot_check(ctx, algo, sc, seed, first_pair, seg_n, len_mode, l1, l2, want, rng):
+    """`want` pairs of the resident segment against the oracle (the checker, outside every timed region): the pair is
+    regenerated on the CPU from the shared counter-based generator, its results are read back with
+    seqa_ctx_download_range.  -> pairs checked (raises on any difference)."""
+    from oracle import pyoracle as orc
+    from seqalib_b200 import synth
+    if want <= 0 or seg_n == 0:
+        return 0
+    picks = sorted(set([0, seg_n - 1] + [int(x) for x in rng.integers(0, seg_n, max(want - 2, 0))]))[:want]
+    for k in picks:
+        pid = first_pair + k
+        if len_mode:
+            a_len, b_len = synth.lengths(seed, pid, 1)
+            a_len, b_len = int(a_len[0]), int(b_len[0])
+        else:
+            a_len, b_len = l1, l2
+        a = bytes(synth.sequence(seed, pid, 0, a_len)).decode()
+        b = bytes(synth.sequence(seed, pid, 1, b_len)).decode()
+        r = ctx.download_range(k, 1, a_len + b_len + 8)
+        o = orc.oracle_align(algo, sc, a, b)
+        got = (int(r.score[0]), int(r.start_i[0]), int(r.start_j[0]), int(r.end_i[0]), int(r.end_j[0]))
+        exp = (o["score"], o["start_i"], o["start_j"], o["end_i"], o["end_j"])
+        if got != exp or not np.array_equal(r.pair_ops(0), o["ops"]):
+            raise SystemExit("bench.py spot check FAILED: %s pair %d: got %r, oracle %r" % (algo, pid, got, exp))
+    return len(picks)
+
+
+def _resident_pass(lib, capi, torch, local, stream, algo, sc, seed, segments, len_mode, l1, l2, spot, fingerprints=None):
+    """One pass of `algo` over this rank's share, given as a list of (first_pair, n_pairs) segments that are generated
+    on the device one after another (a share larger than HBM is streamed through in segments; the host-side planning
+    of a segment is outside the timed region, like the resident `value` of the headline).  The first segment is run
+    once untimed (allocations, instruction cache).  -> dict(ms, fill_ms, cells, launches, kernel, checked)"""
+    prm = capi.make_params(algo, gap=sc.gap, gap_open=sc.gap_open, gap_extend=sc.gap_extend, match=sc.match,
+                           mismatch=sc.mismatch if sc.allow else 0, allow=sc.allow, device_first=local, device_count=1)
+    ctx = capi.Ctx(lib, local, stream.cuda_stream)
+    out = {"ms": 0.0, "fill_ms": 0.0, "cells": 0, "launches": 0, "kernel": "none", "checked": 0, "pairs": 0}
+    rng = np.random.default_rng(12345 + local)
+    warmed = False
+    for (first, n) in segments:
+        if n == 0:
+            continue
+        ctx.generate(prm, seed, first, n, len_mode, l1, l2)
+        if not warmed:
+            ctx.run()
+            ctx.sync()
+            warmed = True
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        ctx.run()
+        e1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        out["ms"] += e0.elapsed_time(e1)
+        fm, _ = ctx.last_fill_ms()
+        out["fill_ms"] += fm
+        out["cells"] += ctx.cells()
+        out["launches"] += ctx.launch_count() - l0
+        out["kernel"] = ctx.last_kernel()
+        out["pairs"] += n
+        if fingerprints is not None:  # every pair of the segment against committed oracle fingerprints (config 4)
+            import zlib
+            res = ctx.download(ops_capacity=n * (l1 + l2))
+            for k in range(n):
+                g = fingerprints[first + k]
+                ops = np.ascontiguousarray(res.pair_ops(k))
+                got = (int(res.score[k]), int(res.ops_len[k]), zlib.crc32(ops.tobytes()) & 0xffffffff)
+                if got != (g["score"], g["ops_len"], g["crc32"]):
+                    raise SystemExit("bench.py fingerprint check FAILED: %s pair %d: got %r, golden %r" % (algo, first + k, got, g))
+            out["checked"] += n
+        elif spot:
+            take = min(spot - out["checked"], max(2, spot // max(len(segments), 1) + 1))
+            out["checked"] += _spot_check(ctx, algo, sc, seed, first, n, len_mode, l1, l2, take, rng)
+    ctx.close()
+    return out
+
+
+def _config5_cuts(seed, n_total, world, block=16384, chunk=1 << 20):
+    """Static split of the mixed-length stream balanced by sum(len1*len2): cumulative cells per block of
+    16,384 pairs over the WHOLE stream (every rank computes the same numbers from the counter-based generator), cut at
+    the block boundaries nearest to k/N of the total.  -> (pair cut points [world+1], cells per rank)"""
+    from seqalib_b200 import synth
+    from concurrent.futures import ThreadPoolExecutor
+    nblocks = (n_total + block - 1) // block
+    cells = np.zeros(nblocks, dtype=np.float64)
+
+    def part(lo):
+        hi = min(n_total, lo + chunk)
+        a, b = synth.lengths(seed, lo, hi - lo)
+        idx = (np.arange(lo, hi) // block).astype(np.int64)
+        return np.bincount(idx, weights=a.astype(np.float64) * b, minlength=nblocks)
+    with ThreadPoolExecutor(max_workers=max(1, min(4, host_threads() // max(world, 1)))) as ex:  # numpy releases the GIL
+        for c in ex.map(part, range(0, n_total, chunk)):
+            cells += c
+    cum = np.concatenate([[0.0], np.cumsum(cells)])
+    ks = [0]
+    for r in range(1, world):
+        ks.append(max(ks[-1], int(np.argmin(np.abs(cum - cum[-1] * r / world)))))
+    ks.append(nblocks)
+    cuts = [min(k * block, n_total) for k in ks]
+    per_rank = [float(cum[ks[r + 1]] - cum[ks[r]]) for r in range(world)]
+    return cuts, per_rank
+
+
+def run_secondary_configs(args, lib, capi, torch, dist, local, rank, world, stream, sampler, f_max_mhz):
+    from oracle import pyoracle as orc  # the checker for the spot checks; never inside a timed region
+    from seqalib_b200 import shard
+    S = orc.Scoring
+
+    def gather(x):
+        if world == 1:
+            return [float(x)]
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        outl = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(outl, t)
+        return [float(v.item()) for v in outl]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    entries = []
+
+    def entry(name, algo, sc, segments, len_mode, l1, l2, spot, note, fingerprints=None, total_pairs=None):
+        barrier()
+        torch.cuda.synchronize()
+        t0 = sampler.mark()
+        r = _resident_pass(lib, capi, torch, local, stream, algo, sc, SEED, segments, len_mode, l1, l2, spot, fingerprints)
+        t1 = sampler.mark()
+        clocks = sampler.window(t0, t1)
+        barrier()
+        ms_all = gather(r["ms"])
+        fill_all = gather(r["fill_ms"])
+        cells_all = gather(r["cells"])
+        checked_all = gather(r["checked"])
+        launches = sum(gather(r["launches"]))
+        if rank != 0:
+            return
+        ms = max(ms_all)
+        tot_cells = sum(cells_all)
+        f_clk = (clocks.get("sm_mhz") or f_max_mhz) * 1e6
+        p_int = 148 * 128 * f_clk
+        gcups = tot_cells / (ms * 1e-3) / 1e9
+        fill_gcups = tot_cells / (max(fill_all) * 1e-3) / 1e9 if max(fill_all) > 0 else None
+        entries.append({"config": name, "algo": algo, "scoring": list(sc.astuple()), "pairs": int(total_pairs), "cells": tot_cells,
+                        "gcups": gcups, "ms": ms, "kernel": r["kernel"], "ops_per_cell": W_OPS[algo],
+                        "roofline_frac": gcups * 1e9 * W_OPS[algo] / p_int,
+                        "fill_gcups": fill_gcups, "fill_roofline_frac": (fill_gcups * 1e9 * W_OPS[algo] / p_int) if fill_gcups else None,
+                        "per_rank_ms": ms_all, "per_rank_cells": cells_all, "imbalance": ms / (sum(ms_all) / len(ms_all)),
+                        "oracle_checked_pairs": int(sum(checked_all)), "oracle_checked_per_rank": [int(c) for c in checked_all],
+                        "gpu_launches": int(launches), "scaling": "strong", "clocks": clocks, "note": note})
+
+    # ---- configs[2]: Global + Local Gotoh, 10 M pairs of 250 bp, contiguous static shard ----
+    n3 = args.config3_pairs
+    lo, hi = shard.shard_range(n3, rank, world)
+    seg = 2_500_000
+    segs3 = [(a, min(seg, hi - a)) for a in range(lo, hi, seg)]
+    for algo in ("ggotoh", "lgotoh"):
+        entry("configs[2] %s 250 bp x %d" % ("GlobalGotohSA" if algo == "ggotoh" else "LocalGotohSA", n3), algo, S.affine(-3, -1, 1, -1),
+              segs3, 0, 250, 250, 24,
+              "ScoringSystem(-3,-1,1,-1); %d pairs split contiguously over %d rank(s), streamed through HBM in segments of <= %d pairs; "
+              "score + traceback, inputs generated on the device" % (n3, world, seg), total_pairs=n3)
+
+    # ---- configs[3]: Hirschberg / MyersMiller, 64 pairs of 100 kbp, whole pairs per rank ----
+    n4, L4 = args.config4_pairs, 100_000
+    lo, hi = shard.shard_range(n4, rank, world)
+    gold = None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "config4_100kbp.json")) as f:
+            gold = json.load(f)
+    except Exception:
+        gold = None
+    for algo, sc in (("hirschberg", S.linear(-1, 2, -1)), ("myersmiller", S.affine(-3, -1, 1, -1))):
+        fp = None
+        if gold and algo in gold["algos"] and gold["len"] == L4 and gold["seed"] == SEED and n4 <= gold["pairs"]:
+            fp = gold["algos"][algo]["pairs"]
+        entry("configs[3] %s 100 kbp x %d" % ("HirschbergSA" if algo == "hirschberg" else "MyersMillerSA", n4), algo, sc,
+              [(lo, hi - lo)], 0, L4, L4, 0,
+              "whole pairs per rank (%d rank(s)); every pair checked against the committed oracle fingerprints "
+              "(tests/golden/config4_100kbp.json: score, ops_len, CRC-32 of the ops)" % world if fp else
+              "whole pairs per rank (%d rank(s)); fingerprints file missing: unchecked here" % world, fingerprints=fp, total_pairs=n4)
+
+    # ---- configs[4]: NW + SW over the mixed-length stream, shards balanced by sum(len1*len2), length-binned inside a device ----
+    n5 = args.config5_pairs
+    cuts, _ = _config5_cuts(SEED, n5, world)
+    lo, hi = cuts[rank], cuts[rank + 1]
+    seg = 4_000_000
+    segs5 = [(a, min(seg, hi - a)) for a in range(lo, hi, seg)]
+    for algo, sc in (("nw", S.linear(-1, 2, -1)), ("sw", S.linear(-1, 1, -1))):
+        entry("configs[4] %s mixed 50-1000 bp x %d" % ("NeedlemanWunschSA" if algo == "nw" else "SmithWatermanSA", n5), algo, sc,
+              segs5, 1, 0, 0, 24,
+              "independent U[50,1000] lengths; the stream is cut into %d contiguous shard(s) of equal sum(len1*len2); inside a device pairs are "
+              "binned by shape (sorted by (ceil(len1/16), len2), 64 similar pairs per warp job, largest jobs first) and streamed through HBM "
+              "in segments of <= %d pairs" % (world, seg), total_pairs=n5)
+    return entries
 
 
 def run_ours(args):
@@ -212,7 +453,7 @@ def run_ours(args):
     numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("SEQA_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # (NCCL_DEBUG is left to the caller: quiet_stdout() already keeps stdout to the one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -265,7 +506,7 @@ def run_ours(args):
     launches = ctx.launch_count() - l0
     fill_ms, fill_launches = ctx.last_fill_ms()  # CUDA events on the ctx stream around the last step's fill launches
     kernel = ctx.last_kernel()
-    clocks = sampler.stop(t0, t1)
+    clocks = sampler.window(t0, t1)
     ctx.sync()
     ms_step = ms_total / args.steps
     total_cells = sum_over_ranks(float(cells))
@@ -313,6 +554,14 @@ def run_ours(args):
     e2e_value = total_cells / (e2e_ms * 1e-3) / 1e9
     checksum = int(res.score[:n].astype(np.int64).sum())
     lib.L.seqa_cuda_trim()
+    del pb, po1, po2, pl1, pl2, res
+
+    # ---- the other BASELINE configs, sharded over the same ranks (strong scaling) ----
+    configs = None
+    if not args.no_configs:
+        _, f_max, _ = measured_peaks()
+        configs = run_secondary_configs(args, lib, capi, torch, dist, local, rank, world, stream, sampler, f_max)
+    sampler.close()
 
     if rank != 0:
         if world > 1:
@@ -326,14 +575,23 @@ def run_ours(args):
     cells_per_launch = cells / max(fill_launches, 1)
     achieved = cells_per_launch * W_OPS_PER_CELL / fill_s / 1e12
     trace_alg_bytes = cells_per_launch * ALG_TRACE_BITS / 8 + n * 2 * LEN / 4.0 / max(fill_launches, 1)
-    # what the kernel really issues: 5.25 ALU-pipe warp instructions per TWO cells (seqa_packed.cuh), against the
-    # ALU-pipe ceiling measured by tests/int_peak.py on this pool (63.8 lane-ops/clk/SM, profiles/r01_int_peak.json)
-    alu_ops = cells_per_launch / 2 * 5.25 / fill_s / 1e12
+    # what the kernel really issues: ALU-pipe warp instructions per TWO cells, COUNTED from the SASS of the hot loop of
+    # this build (tests/sass_count.py -> profiles/sass_counts.json), against the ALU-pipe ceiling measured by
+    # tests/int_peak.py on this pool (63.8 lane-ops/clk/SM, profiles/r01_int_peak.json)
+    alu_per_2cells, alu_src = sass_alu_per_two_cells(kernel)
+    alu_ops = cells_per_launch / 2 * alu_per_2cells / fill_s / 1e12
     alu_peak = 148 * 63.8 * f_clk / 1e12
+    step_achieved = value * 1e9 / max(world, 1) * W_OPS_PER_CELL / 1e12  # per GPU, whole step (prep + fill + walk + gather)
     roofline = {"bound": "int32_issue", "kernel": kernel, "achieved": achieved, "peak": p_int, "unit": "Tlane-op/s",
                 "frac": achieved / p_int, "traffic": kernel_traffic(kernel, n), "ops_per_cell": W_OPS_PER_CELL,
+                "frac_note": "achieved counts the W = 10 algorithmic int32 ops of a SW cell (SURVEY.md 8d); the kernel retires a "
+                             "cell in ~%.2f issued ALU-pipe instructions (two cells per s16x2 instruction, fused add-max), so the "
+                             "contract fraction can exceed 1; `alu_pipe.frac` is the hardware-bound figure" % (alu_per_2cells / 2),
+                "step_frac": step_achieved / p_int,
+                "step_note": "whole step per GPU (GCUPS x W / peak): the figure north_star's 'score+traceback >= 60 %' is about",
                 "alu_pipe": {"achieved": alu_ops, "peak": alu_peak, "unit": "Tlane-op/s", "frac": alu_ops / alu_peak,
-                             "note": "issued packed instructions (5.25 per 2 cells) vs the measured ALU-pipe rate"},
+                             "instr_per_2_cells": alu_per_2cells, "source": alu_src,
+                             "note": "issued ALU-pipe instructions vs the measured ALU-pipe rate (63.8 lane-ops/clk/SM)"},
                 "kernel_ms_per_launch": fill_s * 1e3, "kernel_gcups": cells_per_launch / fill_s / 1e9,
                 "peak_def": "148 SMs x 128 lane-ops/clk x SM clock observed under load (SURVEY.md 8d)",
                 "hbm": {"bound": "hbm", "achieved": trace_alg_bytes / fill_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -341,7 +599,9 @@ def run_ours(args):
                         "stored_bytes_per_cell": 0.5 * ((LEN + 15) // 16 * 16) * ((LEN + 3) // 4 * 4) / (LEN * LEN),
                         "stored_gbs": cells_per_launch * 0.5 * ((LEN + 15) // 16 * 16) * ((LEN + 3) // 4 * 4) / (LEN * LEN) / fill_s / 1e9}}
 
-    cpu = None
+    cpu = None if not args.no_cpu else {"skipped": "--no-cpu"}
+    if world > 1:
+        cpu = {"skipped": "cpu_baseline is timed at N=1 only (the contract: rank 0 at N=1); see the --impl reference arm for every N"}
     if world == 1 and not args.no_cpu:
         threads = host_threads()
         sample_pairs = min(n, max(threads * 40000, 50000))  # ~5-15 s of CPU work on all host threads
@@ -362,7 +622,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms, "api": "seqa_cuda_align_batch (pinned host buffers, SEQA_FLAG_OPS_2BIT: ops packed 4 per byte, the format include/SequenceAlignment.h requests)",
                     "byte_ops": {"value": total_cells / (e2e_ms_b * 1e-3) / 1e9, "ms_per_step": e2e_ms_b, "d2h_bytes_per_step": d2h_b,
                                  "note": "same call with one byte per op (flags = 0)"}},
-            "gpu_launches": int(launches), "clocks": clocks}
+            "gpu_launches": int(launches), "clocks": clocks, "configs": configs}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -377,6 +637,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configs (configs[2..4])")
+    ap.add_argument("--config3-pairs", type=int, default=10_000_000, help="configs[2]: total Gotoh pairs of 250 bp (split over the ranks)")
+    ap.add_argument("--config4-pairs", type=int, default=64, help="configs[3]: total pairs of 100 kbp (split over the ranks)")
+    ap.add_argument("--config5-pairs", type=int, default=100_000_000, help="configs[4]: total mixed-length pairs (split over the ranks)")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":

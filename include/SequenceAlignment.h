@@ -186,6 +186,7 @@ struct PackedAlignments {
     std::vector<std::pair<uint8_t, uint32_t>> runs(size_t P) const
     {
         std::vector<std::pair<uint8_t, uint32_t>> R;
+        if (OpsLen[P] == SEQA_PAIR_UNSUPPORTED) return R;
         for (uint32_t K = 0; K < OpsLen[P]; K++) {
             const uint8_t O = (uint8_t)op(P, K);
             if (!R.empty() && R.back().first == O)
@@ -245,6 +246,10 @@ class SequenceAligner {
 
     // Scores of the most recent getAlignment / getAlignments call (the reference exposes none).
     std::vector<int> LastScores;
+    // Pairs of the most recent batch call that the GPU path rejected one by one (ops_len == SEQA_PAIR_UNSUPPORTED: the
+    // three LocalGotoh shapes that are undefined behaviour in the reference, include/SALocalGotoh.h:484-488).  Their
+    // AlignedSequence is empty; getAlignment (one pair) throws std::invalid_argument instead.
+    std::vector<size_t> LastUnsupported;
 
     virtual AlignedSequence<Ty, Blank> getAlignment(ContainerType &Seq0, ContainerType &Seq1) = 0;
 
@@ -350,6 +355,9 @@ class SequenceAligner {
             throw std::runtime_error(std::string("seqa_cuda_align_batch: ") + seqa_cuda_last_error());
         // (large batches are processed in waves whose op strings sit at each wave's own base offset inside Ops)
         LastScores.assign(R.Score.begin(), R.Score.end());
+        LastUnsupported.clear();
+        for (size_t P = 0; P < N; P++)
+            if (R.OpsLen[P] == SEQA_PAIR_UNSUPPORTED) LastUnsupported.push_back(P);
         return R;
     }
 
@@ -357,6 +365,7 @@ class SequenceAligner {
     AlignedSequence<Ty, Blank> expand(const seqa::PackedAlignments &R, size_t P, ContainerType &Seq1, ContainerType &Seq2, bool Local)
     {
         AlignedSequence<Ty, Blank> Res;
+        if (R.OpsLen[P] == SEQA_PAIR_UNSUPPORTED) return Res; // rejected pair: see LastUnsupported
         size_t I = R.StartI[P], J = R.StartJ[P];
         for (uint32_t K = 0; K < R.OpsLen[P]; K++) {
             const unsigned Op = R.op(P, K);
@@ -379,6 +388,9 @@ class SequenceAligner {
     {
         std::vector<const ContainerType *> A{&Seq1}, B{&Seq2};
         seqa::PackedAlignments R = runBatch(Algo, A, B);
+        if (!LastUnsupported.empty())
+            throw std::invalid_argument("seqalib_b200: this (len1,len2) shape is undefined behaviour in the reference's LocalGotohSA "
+                                        "(include/SALocalGotoh.h:484-488) and is not aligned on the GPU path");
         return expand(R, 0, Seq1, Seq2, Local);
     }
 
@@ -437,10 +449,13 @@ class SequenceAligner {
 // include/SAGlobalGotoh.h:441, include/SALocalGotoh.h:509, include/SAHirschberg.h:165-168, include/SAMyersMiller.h:406
 SEQA_DEFINE_ALIGNER(NeedlemanWunschSA, SEQA_NW, false, ScoringSystem(-1, 2, -1))
 SEQA_DEFINE_ALIGNER(SmithWatermanSA, SEQA_SW, true, ScoringSystem(-1, 1, -1))
-SEQA_DEFINE_ALIGNER(GlobalGotohSA, SEQA_GLOBAL_GOTOH, false, ScoringSystem(-1, 2, -1))
-SEQA_DEFINE_ALIGNER(LocalGotohSA, SEQA_LOCAL_GOTOH, true, ScoringSystem(-1, 2, -1))
+// The three affine aligners: the reference's default, ScoringSystem(-1, 2, -1), leaves GapOpen / GapExtend
+// uninitialised (it reads indeterminate values: no behaviour to match).  Here a default-constructed affine aligner is
+// DEFINED: GapOpen = -1, GapExtend = -1, Match = 2, Mismatch = -1 (the same match / mismatch, a gap of k costs -1 - k).
+SEQA_DEFINE_ALIGNER(GlobalGotohSA, SEQA_GLOBAL_GOTOH, false, ScoringSystem(-1, -1, 2, -1, true))
+SEQA_DEFINE_ALIGNER(LocalGotohSA, SEQA_LOCAL_GOTOH, true, ScoringSystem(-1, -1, 2, -1, true))
 SEQA_DEFINE_ALIGNER(HirschbergSA, SEQA_HIRSCHBERG, false, ScoringSystem(-1, 2, -1))
-SEQA_DEFINE_ALIGNER(MyersMillerSA, SEQA_MYERS_MILLER, false, ScoringSystem(-1, 2, -1))
+SEQA_DEFINE_ALIGNER(MyersMillerSA, SEQA_MYERS_MILLER, false, ScoringSystem(-1, -1, 2, -1, true))
 #undef SEQA_DEFINE_ALIGNER
 
 // Hooks by which the reference's heuristic aligners (BLAT, MUMmer, LocalGotoh) reach the NW hot path

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SEQA_ABI_VERSION 1
+#define SEQA_ABI_VERSION 2
 
 typedef enum seqa_algo {
     SEQA_NW = 0,          /* NeedlemanWunschSA   reference include/SANeedlemanWunsch.h:40-231 */
@@ -76,8 +76,11 @@ enum {
  * allow_mismatch != 0.  allow_mismatch == 0 reproduces the reference's "mismatch = INT_MIN constant"
  * behaviour (include/SANeedlemanWunsch.h:55-57,138); `mismatch` is then ignored.
  * LocalGotoh shapes (314,288), (60,57), (61,58) hit undefined behaviour in the reference
- * (include/SALocalGotoh.h:484-488) and are rejected with SEQA_ERR_UNSUPPORTED.
+ * (include/SALocalGotoh.h:484-488: the result is replaced by NeedlemanWunsch with an uninitialised Gap) and are
+ * rejected PER PAIR: the call succeeds, the pair comes back with ops_len = SEQA_PAIR_UNSUPPORTED, score = INT32_MIN,
+ * start = end = (0,0) and no ops; every other pair of the batch is aligned normally.
  */
+#define SEQA_PAIR_UNSUPPORTED 0xffffffffu /* seqa_batch_out.ops_len of a pair the GPU path rejects */
 typedef struct seqa_params {
     int32_t algo; /* seqa_algo */
     int32_t gap;
@@ -147,6 +150,11 @@ void seqa_cuda_trim(void);
 void *seqa_cuda_host_alloc(uint64_t bytes);
 void seqa_cuda_host_free(void *ptr);
 
+/* How the calling thread's last seqa_cuda_align_batch split its batch: sum(len1*len2 + 1) per device of the range
+ * (the static split of SURVEY.md 8e, balanced by cells).  Returns the number of devices used; fills at most
+ * `capacity` entries. */
+int seqa_cuda_last_split(uint64_t *cells_per_device, int32_t capacity);
+
 const char *seqa_cuda_last_error(void);
 int seqa_cuda_device_count(void); /* number of visible CUDA devices, 0 if none / no driver */
 int seqa_cuda_abi_version(void);
@@ -171,6 +179,10 @@ int seqa_ctx_generate(seqa_ctx *ctx, const seqa_params *params, uint64_t seed, u
 int seqa_ctx_run(seqa_ctx *ctx);
 /* Copy the results of the last run to host buffers (synchronises the stream). */
 int seqa_ctx_download(seqa_ctx *ctx, seqa_batch_out *out);
+/* Results of pairs [first, first + count) of the last run only (arrays of `count` elements; ops_off rebased so that
+ * the slice's first op string starts at out->ops[0]; ops_capacity >= sum(len1+len2) of the slice suffices): a
+ * consumer that samples or streams the results of a large resident batch.  Synchronises the stream. */
+int seqa_ctx_download_range(seqa_ctx *ctx, uint64_t first, uint64_t count, seqa_batch_out *out);
 int seqa_ctx_sync(seqa_ctx *ctx);
 /* Device-resident results: fills `dev` with DEVICE pointers to the arrays of the last run
  * (same layout and meaning as seqa_ctx_download would produce; ops are dense, ops_off relative to dev->ops) for a

@@ -17,6 +17,7 @@ FLAG_FORCE_GENERIC = 2
 FLAG_TRACE8 = 4
 FLAG_LS_R1 = 8
 FLAG_OPS_2BIT = 16  # ops packed 4 per byte on the wire (Results.pair_ops unpacks)
+PAIR_UNSUPPORTED = 0xFFFFFFFF  # Results.ops_len of a pair the GPU path rejects (SEQA_PAIR_UNSUPPORTED)
 OK = 0
 ERR_NAMES = {0: "SEQA_OK", -1: "SEQA_ERR_INVALID", -2: "SEQA_ERR_UNSUPPORTED", -3: "SEQA_ERR_NO_DEVICE",
              -4: "SEQA_ERR_CUDA", -5: "SEQA_ERR_CAPACITY", -6: "SEQA_ERR_NOMEM"}
@@ -26,7 +27,7 @@ EXPORTS = ["seqa_cuda_align_batch", "seqa_cuda_last_error", "seqa_cuda_device_co
            "seqa_ctx_create", "seqa_ctx_destroy", "seqa_ctx_upload", "seqa_ctx_generate", "seqa_ctx_run",
            "seqa_ctx_download", "seqa_ctx_device_results", "seqa_ctx_sync", "seqa_ctx_launch_count", "seqa_ctx_cells", "seqa_ctx_last_fill_ms",
            "seqa_ctx_last_kernel", "seqa_ctx_download_inputs", "seqa_cuda_int_peak", "seqa_cuda_trim",
-           "seqa_cuda_host_alloc", "seqa_cuda_host_free"]
+           "seqa_cuda_host_alloc", "seqa_cuda_host_free", "seqa_ctx_download_range", "seqa_cuda_last_split"]
 
 
 class SeqaError(RuntimeError):
@@ -109,6 +110,8 @@ class Lib(object):
         L.seqa_ctx_sync.argtypes = [C.c_void_p]
         L.seqa_ctx_download.argtypes = [C.c_void_p, C.POINTER(BatchOut)]
         L.seqa_ctx_device_results.argtypes = [C.c_void_p, C.POINTER(BatchOut)]
+        L.seqa_ctx_download_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(BatchOut)]
+        L.seqa_cuda_last_split.argtypes = [C.c_void_p, C.c_int32]
         L.seqa_ctx_launch_count.argtypes = [C.c_void_p]
         L.seqa_ctx_launch_count.restype = C.c_uint64
         L.seqa_ctx_cells.argtypes = [C.c_void_p]
@@ -129,6 +132,12 @@ class Lib(object):
 
     def device_count(self):
         return self.L.seqa_cuda_device_count()
+
+    def last_split(self):
+        """cells per device of this thread's last align_batch call (seqa_cuda_last_split)."""
+        buf = np.zeros(64, dtype=np.uint64)
+        nd = self.L.seqa_cuda_last_split(buf.ctypes.data, 64)
+        return buf[:nd].copy()
 
     @staticmethod
     def batch_in(bases, off1, off2, len1, len2):
@@ -191,6 +200,13 @@ class Ctx(object):
         if results is None:
             results = Results(self.n, ops_capacity if ops_capacity is not None else self.slots)
         self.lib.check(self.lib.L.seqa_ctx_download(self.h, C.byref(results.c)))
+        results.packed2 = bool(getattr(self, "flags", 0) & FLAG_OPS_2BIT)
+        return results
+
+    def download_range(self, first, count, ops_capacity):
+        """Results of pairs [first, first+count) of the last run (seqa_ctx_download_range)."""
+        results = Results(count, ops_capacity)
+        self.lib.check(self.lib.L.seqa_ctx_download_range(self.h, first, count, C.byref(results.c)))
         results.packed2 = bool(getattr(self, "flags", 0) & FLAG_OPS_2BIT)
         return results
 

@@ -28,6 +28,7 @@
 namespace {
 
 thread_local std::string g_err;
+thread_local std::vector<uint64_t> g_last_split; // cells per device of this thread's last seqa_cuda_align_batch call
 
 int fail(int code, const char *fmt, ...)
 {
@@ -117,8 +118,8 @@ struct Chunk {
 struct seqa_ctx;
 namespace {
 // linear-space algorithms (seqa_linspace_host.inl)
-int ls_plan(LsState &ls, const seqa_params &prm, const std::vector<uint32_t> &len1, const std::vector<uint32_t> &len2,
-            const std::vector<uint32_t> &idx, bool myers_miller, int sms);
+int ls_plan(seqa_ctx *c, const std::vector<uint32_t> &len1, const std::vector<uint32_t> &len2,
+            const std::vector<uint32_t> &idx, bool myers_miller);
 int ls_run(seqa_ctx *c, bool want_ops);
 void ls_release(LsState &ls);
 } // namespace
@@ -178,6 +179,13 @@ struct seqa_ctx {
     // linear-space plan
     std::vector<uint32_t> lidx;
     LsState ls;
+    HBuf<uint64_t> ls_rowoff_pin;
+    HBuf<uint32_t> ls_roww_pin, ls_idx_pin;
+
+    // pairs rejected one by one (LocalGotoh shapes that are undefined behaviour in the reference)
+    std::vector<uint32_t> ub_idx;
+    HBuf<uint32_t> ub_pin;
+    DBuf<uint32_t> d_ub;
 
     DBuf<uint8_t> scratch; // trace / direction matrices (+ profiles) of one chunk
     bool generic_rerun = false;
@@ -292,13 +300,14 @@ bool packed_shape_ok(const seqa_params &p, uint32_t M, uint32_t N)
     return lo < 30000 && hi < 30000;
 }
 
-// scratch budget of one context (trace / direction matrices of one chunk): a quarter of the device, so that the
-// three contexts of a pipelined call and a resident context fit together; queried once per context
-size_t free_budget()
+// scratch budget of one context (trace / direction matrices of one chunk): 80 % of the device shared by `sharers` + 1
+// contexts -- a quarter of the device for a resident context, 0.8 / (ring + 1) for the contexts of a pipelined one-shot
+// call (the producer lowers c->budget when it takes a context into its ring); queried once per context
+size_t free_budget(int sharers = 3)
 {
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (size_t)1 << 30;
-    return (size_t)std::min((double)fr * 0.8, (double)tot * 0.25);
+    return (size_t)std::min((double)fr * 0.8, (double)tot * 0.8 / (sharers + 1));
 }
 
 int order_after(seqa_ctx *c, cudaStream_t from, cudaStream_t to);
@@ -364,14 +373,30 @@ int build_plan(seqa_ctx *c)
     if (prm.algo == SEQA_HIRSCHBERG || prm.algo == SEQA_MYERS_MILLER) {
         c->lidx.resize(n);
         std::iota(c->lidx.begin(), c->lidx.end(), 0u);
-        return ls_plan(c->ls, prm, c->hlen1, c->hlen2, c->lidx, prm.algo == SEQA_MYERS_MILLER, c->sms);
+        return ls_plan(c, c->hlen1, c->hlen2, c->lidx, prm.algo == SEQA_MYERS_MILLER);
     }
+    // LocalGotoh shapes the reference routes into NW with an uninitialised Gap (SALocalGotoh.h:484-488, undefined
+    // behaviour): rejected PER PAIR -- the pair is skipped and reported with ops_len = SEQA_PAIR_UNSUPPORTED, the rest
+    // of the batch is aligned normally
+    c->ub_idx.clear();
+    auto ub_shape = [&](uint32_t M, uint32_t N) {
+        return prm.algo == SEQA_LOCAL_GOTOH && ((M == 314 && N == 288) || (M == 60 && N == 57) || (M == 61 && N == 58));
+    };
     if (prm.algo == SEQA_LOCAL_GOTOH) {
-        for (uint64_t p = 0; p < (c->st_uniform ? std::min<uint64_t>(n, 1) : n); p++) {
-            const uint32_t M = c->hlen1[p], N = c->hlen2[p];
-            if ((M == 314 && N == 288) || (M == 60 && N == 57) || (M == 61 && N == 58))
-                return fail(SEQA_ERR_UNSUPPORTED,
-                            "LocalGotoh shape (%u,%u) is undefined behaviour in the reference (SALocalGotoh.h:484-488)", M, N);
+        if (c->st_uniform) {
+            if (n && ub_shape(c->hlen1[0], c->hlen2[0])) {
+                c->ub_idx.resize(n);
+                std::iota(c->ub_idx.begin(), c->ub_idx.end(), 0u);
+            }
+        } else {
+            for (uint64_t p = 0; p < n; p++)
+                if (ub_shape(c->hlen1[p], c->hlen2[p])) c->ub_idx.push_back((uint32_t)p);
+        }
+        if (!c->ub_idx.empty()) {
+            CKS(c->d_ub.ensure(c->ub_idx.size()));
+            CKS(c->ub_pin.ensure(c->ub_idx.size()));
+            std::copy(c->ub_idx.begin(), c->ub_idx.end(), c->ub_pin.p);
+            CK(cudaMemcpyAsync(c->d_ub.p, c->ub_pin.p, c->ub_idx.size() * 4, cudaMemcpyHostToDevice, c->up));
         }
     }
 
@@ -380,7 +405,7 @@ int build_plan(seqa_ctx *c)
     pkl.clear();
     bool uniform = true;
     // uniform batch (every pair the same shape): one eligibility test, identity permutation, identical jobs
-    const bool fast = c->st_uniform && n > 0 && pk && packed_shape_ok(prm, c->hlen1[0], c->hlen2[0]);
+    const bool fast = c->st_uniform && n > 0 && pk && packed_shape_ok(prm, c->hlen1[0], c->hlen2[0]) && c->ub_idx.empty();
     if (fast) {
         pkl.resize(n);
         std::iota(pkl.begin(), pkl.end(), 0u);
@@ -388,6 +413,7 @@ int build_plan(seqa_ctx *c)
         if (pk) pkl.reserve(n);
         for (uint64_t p = 0; p < n; p++) {
             const uint32_t M = c->hlen1[p], N = c->hlen2[p];
+            if (ub_shape(M, N)) continue;
             if (pk && packed_shape_ok(prm, M, N)) {
                 if (!pkl.empty() && (M != c->hlen1[pkl[0]] || N != c->hlen2[pkl[0]])) uniform = false;
                 pkl.push_back((uint32_t)p);
@@ -809,7 +835,7 @@ int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in
     for (uint64_t p = pb; p < pe; p++) {
         const uint64_t l1 = in->len1[p], l2 = in->len2[p];
         const uint64_t a0 = in->off1[p], a1 = a0 + l1, b0 = in->off2[p], b1 = b0 + l2;
-        if (a1 > in->bases_len || b1 > in->bases_len)
+        if (a0 > in->bases_len || l1 > in->bases_len - a0 || b0 > in->bases_len || l2 > in->bases_len - b0) // no wrap-around
             return fail(SEQA_ERR_INVALID, "pair %llu reaches past bases_len", (unsigned long long)p);
         dense &= a0 == first_off + st_slots && b0 == a1;
         lo = std::min(lo, std::min(a0, b0));
@@ -865,7 +891,13 @@ int ctx_run(seqa_ctx *c)
         CKS(run_packed(c, want_walk));
         CKS(run_generic(c, want_walk));
     }
+    if (!c->ub_idx.empty()) // rejected pairs: no ops, neutral fields (the walk kernels never saw them)
+        LAUNCH(c, (mark_pairs_kernel), (unsigned)((c->ub_idx.size() + 255) / 256), 256, 0, c->d_ub.p, (uint64_t)c->ub_idx.size(), c->score.p,
+               c->start_i.p, c->start_j.p, c->end_i.p, c->end_j.p, c->ops_len.p, c->slot_start.p, 0u);
     CKS(finish_ops(c));
+    if (!c->ub_idx.empty()) // ... and, once the op strings are gathered, the per-pair status the caller sees
+        LAUNCH(c, (mark_pairs_kernel), (unsigned)((c->ub_idx.size() + 255) / 256), 256, 0, c->d_ub.p, (uint64_t)c->ub_idx.size(), c->score.p,
+               c->start_i.p, c->start_j.p, c->end_i.p, c->end_j.p, c->ops_len.p, c->slot_start.p, (uint32_t)SEQA_PAIR_UNSUPPORTED);
     CK(cudaEventRecord(c->ev_run, c->stream)); // downloads are ordered behind this (ctx_resolve)
     c->ran = true;
     return SEQA_OK;
@@ -1008,8 +1040,9 @@ void seqa_ctx_destroy(seqa_ctx *c)
     c->ops_len.release(); c->slot_start.release(); c->slot_off.release(); c->ops_off.release();
     c->slots.release(); c->dense.release(); c->tile_sum.release(); c->total.release(); c->flags.release();
     c->perm.release(); c->jobs_pin.release(); c->h_tail.release(); c->gidx_pin.release(); c->gdir_pin.release();
+    c->ls_rowoff_pin.release(); c->ls_roww_pin.release(); c->ls_idx_pin.release();
     c->d_perm.release(); c->d_jobs.release(); c->pk_bound.release(); c->d_gidx.release(); c->d_gdir_off.release(); c->bound.release();
-    c->scratch.release();
+    c->scratch.release(); c->ub_pin.release(); c->d_ub.release();
     ls_release(c->ls);
     for (auto e : c->ev) cudaEventDestroy(e);
     if (c->ev_up) cudaEventDestroy(c->ev_up);
@@ -1103,6 +1136,47 @@ int seqa_ctx_download(seqa_ctx *c, seqa_batch_out *out)
     return SEQA_OK;
 }
 
+// Results of pairs [first, first + count) of the last run: the same arrays seqa_ctx_download fills, for a slice of a
+// resident batch (a consumer that samples or streams results; bench.py's per-rank spot checks).  ops_off is
+// rebased so that the slice's first op string starts at out->ops[0].
+int seqa_ctx_download_range(seqa_ctx *c, uint64_t first, uint64_t count, seqa_batch_out *out)
+{
+    if (!c || !out) return fail(SEQA_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    if (!c->ran) return fail(SEQA_ERR_INVALID, "download before run");
+    if (first > c->n || count > c->n - first) return fail(SEQA_ERR_INVALID, "pair range [%llu,+%llu) outside the batch of %llu",
+                                                          (unsigned long long)first, (unsigned long long)count, (unsigned long long)c->n);
+    CKS(ctx_resolve(c));
+    out->ops_used = 0;
+    if (count == 0) return SEQA_OK;
+    if (!out->score) return fail(SEQA_ERR_INVALID, "out->score is NULL");
+    const bool score_only = (c->prm.flags & SEQA_FLAG_SCORE_ONLY) != 0;
+    CK(cudaMemcpyAsync(out->score, c->score.p + first, count * 4, cudaMemcpyDeviceToHost, c->down));
+    if (out->end_i) CK(cudaMemcpyAsync(out->end_i, c->end_i.p + first, count * 4, cudaMemcpyDeviceToHost, c->down));
+    if (out->end_j) CK(cudaMemcpyAsync(out->end_j, c->end_j.p + first, count * 4, cudaMemcpyDeviceToHost, c->down));
+    if (score_only) {
+        CK(cudaStreamSynchronize(c->down));
+        return SEQA_OK;
+    }
+    if (!out->start_i || !out->start_j || !out->end_i || !out->end_j || !out->ops || !out->ops_off || !out->ops_len)
+        return fail(SEQA_ERR_INVALID, "output arrays are NULL (only allowed with SEQA_FLAG_SCORE_ONLY)");
+    CK(cudaMemcpyAsync(out->start_i, c->start_i.p + first, count * 4, cudaMemcpyDeviceToHost, c->down));
+    CK(cudaMemcpyAsync(out->start_j, c->start_j.p + first, count * 4, cudaMemcpyDeviceToHost, c->down));
+    CK(cudaMemcpyAsync(out->ops_len, c->ops_len.p + first, count * 4, cudaMemcpyDeviceToHost, c->down));
+    CK(cudaMemcpyAsync(out->ops_off, c->ops_off.p + first, count * 8, cudaMemcpyDeviceToHost, c->down));
+    uint64_t end = c->h_tail.p[0]; // dense bytes of the whole batch (ctx_resolve fetched it)
+    if (first + count < c->n) CK(cudaMemcpyAsync(&end, c->ops_off.p + first + count, 8, cudaMemcpyDeviceToHost, c->down));
+    CK(cudaStreamSynchronize(c->down));
+    const uint64_t base = out->ops_off[0], bytes = end - base;
+    if (bytes > out->ops_capacity)
+        return fail(SEQA_ERR_CAPACITY, "ops_capacity %llu < %llu needed", (unsigned long long)out->ops_capacity, (unsigned long long)bytes);
+    if (bytes) CK(cudaMemcpyAsync(out->ops, c->dense.p + base, bytes, cudaMemcpyDeviceToHost, c->down));
+    for (uint64_t k = 0; k < count; k++) out->ops_off[k] -= base;
+    CK(cudaStreamSynchronize(c->down));
+    out->ops_used = bytes;
+    return SEQA_OK;
+}
+
 uint64_t seqa_ctx_launch_count(const seqa_ctx *c) { return c ? c->launches : 0; }
 uint64_t seqa_ctx_cells(const seqa_ctx *c) { return c ? c->cells : 0; }
 const char *seqa_ctx_last_kernel(const seqa_ctx *c) { return c ? c->last_kernel : "none"; }
@@ -1184,6 +1258,13 @@ static void cache_release(seqa_ctx *c, int cached)
     }
     std::lock_guard<std::mutex> lk(g_cache_mu);
     g_cache_busy[c->device][cached] = false;
+}
+
+int seqa_cuda_last_split(uint64_t *cells_per_device, int32_t capacity)
+{
+    for (int32_t d = 0; d < capacity && d < (int32_t)g_last_split.size(); d++)
+        if (cells_per_device) cells_per_device[d] = g_last_split[d];
+    return (int)g_last_split.size();
 }
 
 void *seqa_cuda_host_alloc(uint64_t bytes)
@@ -1276,7 +1357,10 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
                 const uint64_t round = (uint64_t)sms_cache[dev] * cta_per_sm * per_cta;
                 const uint64_t round_cells = round * ((uint64_t)l1[0] * l2[0] + 1);
                 const uint64_t rounds = std::max<uint64_t>(1, (wave_cells + round_cells / 2) / round_cells);
-                if (round * rounds * 2 <= n) maxcnt = std::min<uint64_t>(n, round * rounds);
+                // whole rounds per wave only while every device still gets at least two waves (upload / kernels /
+                // download of consecutive waves overlap); else keep the per-device cap, cut down to whole rounds
+                if (round * rounds * 2 * (uint64_t)nd <= n) maxcnt = std::min<uint64_t>(n, round * rounds);
+                else if (nd > 1 && maxcnt > round) maxcnt = maxcnt / round * round;
             }
         }
         wave_lo.push_back(0);
@@ -1332,6 +1416,9 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
             if ((long double)run >= (long double)tot * d / nd) dev_lo[d++] = w + 1;
         }
     }
+    g_last_split.assign(nd, 0);
+    for (int d = 0; d < nd; d++)
+        for (size_t w = dev_lo[d]; w < dev_lo[d + 1]; w++) g_last_split[d] += wave_cellsum[w];
     std::vector<int> wstatus(nwaves, SEQA_OK);
     std::vector<std::string> werr(nwaves);
     std::vector<uint64_t> wused(nwaves, 0);
@@ -1376,6 +1463,10 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
             const double t0 = since();
             if (!P.c[slot]) {
                 s = cache_acquire(first + d, &P.c[slot], &P.cached[slot]);
+                if (s == SEQA_OK) {
+                    const size_t b = free_budget(ring);
+                    if (!P.c[slot]->budget || P.c[slot]->budget > b) P.c[slot]->budget = b;
+                }
                 if (s == SEQA_OK && P.st[0]) {
                     seqa_ctx *cx = P.c[slot];
                     P.saved[slot] = cx->stream;

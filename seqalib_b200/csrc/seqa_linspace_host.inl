@@ -28,9 +28,12 @@ void ls_release(LsState &ls)
     ls = LsState();
 }
 
-int ls_plan(LsState &ls, const seqa_params &prm, const std::vector<uint32_t> &len1, const std::vector<uint32_t> &len2,
-            const std::vector<uint32_t> &idx, bool myers_miller, int sms)
+int ls_plan(seqa_ctx *c, const std::vector<uint32_t> &len1, const std::vector<uint32_t> &len2,
+            const std::vector<uint32_t> &idx, bool myers_miller)
 {
+    LsState &ls = c->ls;
+    const seqa_params &prm = c->prm;
+    const int sms = c->sms;
     const uint64_t n = idx.size();
     ls.mm = myers_miller;
     ls.roots.resize(n);
@@ -107,9 +110,18 @@ int ls_plan(LsState &ls, const seqa_params &prm, const std::vector<uint32_t> &le
 #endif
     }
     if (n) {
-        CK(cudaMemcpy(ls.d_row_off, ls.row_off.data(), len1.size() * 8, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(ls.d_row_w, ls.row_w.data(), len1.size() * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(ls.d_idx, idx.data(), n * 4, cudaMemcpyHostToDevice));
+        // staged in pinned memory and copied on the ctx's upload stream (ordered before the kernels), like the packed
+        // plan's perm / jobs: no legacy-stream copy that would synchronise with the caller's other streams
+        CKS(c->ls_rowoff_pin.ensure(len1.size()));
+        CKS(c->ls_roww_pin.ensure(len1.size()));
+        CKS(c->ls_idx_pin.ensure(n));
+        std::copy(ls.row_off.begin(), ls.row_off.end(), c->ls_rowoff_pin.p);
+        std::copy(ls.row_w.begin(), ls.row_w.end(), c->ls_roww_pin.p);
+        std::copy(idx.begin(), idx.end(), c->ls_idx_pin.p);
+        CK(cudaMemcpyAsync(ls.d_row_off, c->ls_rowoff_pin.p, len1.size() * 8, cudaMemcpyHostToDevice, c->up));
+        CK(cudaMemcpyAsync(ls.d_row_w, c->ls_roww_pin.p, len1.size() * 4, cudaMemcpyHostToDevice, c->up));
+        CK(cudaMemcpyAsync(ls.d_idx, c->ls_idx_pin.p, n * 4, cudaMemcpyHostToDevice, c->up));
+        CKS(order_after(c, c->up, c->stream));
     }
     return SEQA_OK;
 }
@@ -195,7 +207,8 @@ int ls_run(seqa_ctx *c, bool want_ops)
     }
     cudaEventRecord(next_event(c), c->stream);
     int ovf = 0;
-    CK(cudaMemcpy(&ovf, ls.d_overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(&ovf, ls.d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     if (ovf) return fail(SEQA_ERR_CUDA, "internal: node / task list overflow");
     LsFinishArgs F{};
     F.bases = c->bases.p;

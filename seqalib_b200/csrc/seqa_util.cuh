@@ -107,6 +107,22 @@ __global__ void __launch_bounds__(256) lensum_kernel(const uint32_t *__restrict_
     if (k < n) out[k] = a[k] + b[k];
 }
 
+// Pairs rejected one by one (seqa_cuda.h: SEQA_PAIR_UNSUPPORTED): neutral result fields and the given ops_len
+// (0 before the op strings are gathered, the status marker after).
+__global__ void __launch_bounds__(256) mark_pairs_kernel(const uint32_t *__restrict__ idx, uint64_t n, int32_t *__restrict__ score,
+                                                         uint32_t *__restrict__ start_i, uint32_t *__restrict__ start_j,
+                                                         uint32_t *__restrict__ end_i, uint32_t *__restrict__ end_j,
+                                                         uint32_t *__restrict__ ops_len, uint32_t *__restrict__ slot_start, uint32_t len_value)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t p = idx[k];
+    score[p] = INT32_MIN;
+    start_i[p] = start_j[p] = end_i[p] = end_j[p] = 0u;
+    slot_start[p] = 0u;
+    ops_len[p] = len_value;
+}
+
 // Dense batches (seq1 then seq2 of every pair, pairs back to back: what packers produce) need no offset arrays over
 // PCIe: off1 = exclusive scan of (len1 + len2) -- the same scan that places the op slots -- and off2 = off1 + len1.
 __global__ void __launch_bounds__(256) dense_offsets_kernel(const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ len1,

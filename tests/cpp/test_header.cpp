@@ -127,6 +127,40 @@ int main()
             expect("bridgeNWBatch flags", BF, Fl);
         }
     }
+    { // default-constructed affine aligners are defined here: GapOpen = -1, GapExtend = -1, Match = 2, Mismatch = -1
+        GlobalGotohSA<std::string, char, '-'> D;
+        GlobalGotohSA<std::string, char, '-'> E(ScoringSystem(-1, -1, 2, -1));
+        AlignedSequence<char, '-'> A = D.getAlignment(S1, S2), B = E.getAlignment(S1, S2);
+        std::string Q1, Q2, QF;
+        rows(A, R1, R2, Fl);
+        rows(B, Q1, Q2, QF);
+        expect("default GlobalGotoh row1", R1, Q1);
+        expect("default GlobalGotoh row2", R2, Q2);
+        LocalGotohSA<std::string, char, '-'> DL;
+        MyersMillerSA<std::string, char, '-'> DM;
+        if (DL.getAlignment(S1, S2).size() < S1.size() || DM.getAlignment(S1, S2).size() < S1.size()) {
+            std::printf("FAIL default-constructed LocalGotoh / MyersMiller\n");
+            Failures++;
+        }
+    }
+    { // LocalGotoh shapes that are undefined behaviour in the reference (SALocalGotoh.h:484-488): rejected per pair
+        std::string U1(60, 'A'), U2(57, 'C');
+        LocalGotohSA<std::string, char, '-'> LG(ScoringSystem(-3, -1, 1, -1));
+        bool Threw = false;
+        try {
+            LG.getAlignment(U1, U2);
+        } catch (const std::invalid_argument &) {
+            Threw = true;
+        }
+        std::vector<std::pair<std::string, std::string>> Pairs = {{S1, S2}, {U1, U2}, {S1, S2}};
+        auto All = LG.getAlignments(Pairs);
+        rows(All[2], R1, R2, Fl);
+        if (!Threw || All.size() != 3 || All[1].size() != 0 || LG.LastUnsupported != std::vector<size_t>{1} || All[0].size() != All[2].size()) {
+            std::printf("FAIL per-pair rejection of LocalGotoh UB shapes\n");
+            Failures++;
+        }
+        expect("LocalGotoh batch beside a rejected pair", R2, "--------AAACTCAT");
+    }
     { // a functor that is not equality is outside the GPU path
         bool Threw = false;
         try {

@@ -18,6 +18,28 @@ def _build_and_run(libdir, libname, tmp_path):
     assert "AAA-GAATGCAT\n|||    | |||\nAAAC---T-CAT" in out.stdout  # reference README.md:34-37
 
 
+def _bridge_vs_oracle(libdir, libname, tmp_path):
+    """StaticFuncs::bridgeNWBatch on anchor windows (as MUMmer / BLAT cut them) against oracle_align("nw") on the
+    substrings -- the C++ test links the C oracle (test infrastructure) beside the library under test."""
+    exe = str(tmp_path / "test_bridge_oracle")
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_bridge_oracle.cpp"), "-o", exe,
+                           "-L", libdir, "-l" + libname, "-L", odir, "-lseqa_oracle", "-Wl,-rpath," + libdir, "-Wl,-rpath," + odir])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert out.returncode == 0 and out.stdout.strip().startswith("OK"), out.stdout
+    assert int(out.stdout.split()[1]) > 100
+
+
+def test_bridge_windows_against_oracle_emulated(emu_lib, tmp_path):
+    _bridge_vs_oracle(os.path.join(ROOT, "tests", "emu"), "seqa_emu", tmp_path)
+
+
+@pytest.mark.gpu
+def test_bridge_windows_against_oracle_on_gpu(gpu_lib, tmp_path):
+    _bridge_vs_oracle(os.path.join(ROOT, "seqalib_b200"), "seqa_cuda", tmp_path)
+
+
 def test_header_against_emulated_kernels(emu_lib, tmp_path):
     _build_and_run(os.path.join(ROOT, "tests", "emu"), "seqa_emu", tmp_path)
 
