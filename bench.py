@@ -178,6 +178,28 @@ def cpu_reference_gcups(n_pairs, threads):
     return cells / sec / 1e9, kind, sec
 
 
+def header_api_bench(pairs):
+    """e2e.api_packed / e2e.api_list: tests/cpp/bench_header.cpp (the reference's own class templates from
+    include/SequenceAlignment.h, std::string pairs in pageable memory) compiled against the in-tree library and run as a
+    separate process on this GPU.  -> {"packed": {...}, "list": {...}, "note": ...} or {"note": why not}"""
+    import tempfile
+    exe = os.path.join(tempfile.mkdtemp(prefix="seqa_bench_"), "bench_header")
+    libdir = os.path.join(ROOT, "seqalib_b200")
+    try:
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"),
+                               os.path.join(ROOT, "tests", "cpp", "bench_header.cpp"), "-o", exe, "-L", libdir, "-lseqa_cuda",
+                               "-Wl,-rpath," + libdir], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=300)
+        out = subprocess.run([exe, str(pairs), "3", str(min(pairs, 200000))], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+        d = json.loads(line)
+        d["note"] = ("getAlignmentsPacked on %d and getAlignments on %d std::string pairs of %d bp, best of 3 / 2 calls after a warm-up call, "
+                     "%d host threads; packing, PCIe and (list) std::list construction inside the timed call"
+                     % (d["packed"]["pairs"], d["list"]["pairs"], LEN, d.get("host_threads", 0)))
+        return d
+    except Exception as e:  # no compiler on the box, ...
+        return {"note": "template-API legs unavailable: %r" % (e,)}
+
+
 def bind_to_gpu_numa_node(index):
     """Multi-GPU runs: keep this rank's threads and its pinned host buffers on the NUMA node its GPU hangs off
     (torchrun does not place ranks; a remote node halves the PCIe copy rate of the end-to-end leg)."""
@@ -532,29 +554,48 @@ def run_ours(args):
     # offsets and lengths on the device (SEQA_NO_DENSE_UPLOAD=1 sends all five arrays: + 24 bytes per pair)
     h2d = int(pb.nbytes) if not os.environ.get("SEQA_NO_DENSE_UPLOAD") else int(pb.nbytes + po1.nbytes + po2.nbytes + pl1.nbytes + pl2.nbytes)
 
+    # the 2-bit input wire format (SEQA_FLAG_BASES_2BIT): what a caller that keeps its reads packed hands over -- 4 symbols
+    # per byte, every sequence byte-aligned; packed here once, outside the timed region (it is the caller's storage format)
+    packed_len = n * 2 * ((LEN + 3) // 4)
+    pk = pinned(packed_len, np.uint8)
+    _, pk1, pk2 = capi.pack_bases_2bit(pb, po1, po2, pl1, pl2, out=pk)
+    pp1 = pinned(n, np.uint64); pp1[:] = pk1
+    pp2 = pinned(n, np.uint64); pp2[:] = pk2
+
     def e2e_leg(flags):
         """the one-shot C-ABI call on pinned host buffers: H2D, kernels and D2H all inside the timed region"""
         p = capi.make_params("sw", gap=SCORING["gap"], match=SCORING["match"], mismatch=SCORING["mismatch"], allow=True,
                              device_first=local, device_count=1, flags=flags)
+        ins = (pk, pp1, pp2, pl1, pl2) if flags & capi.FLAG_BASES_2BIT else (pb, po1, po2, pl1, pl2)
         for _ in range(2):
-            lib.align_batch(p, pb, po1, po2, pl1, pl2, res)
+            lib.align_batch(p, *ins, res)
         barrier()
         w0 = time.perf_counter()
         for _ in range(e2e_steps):
-            lib.align_batch(p, pb, po1, po2, pl1, pl2, res)
+            lib.align_batch(p, *ins, res)
         torch.cuda.synchronize()
         w1 = time.perf_counter()
         ms = max_over_ranks((w1 - w0) * 1e3 / e2e_steps)
-        return ms, int(res.score.nbytes * 6 + res.ops_off.nbytes + int(res.c.ops_used))
+        return ms, int(res.score.nbytes * 6 + res.ops_off.nbytes + int(res.c.ops_used)), int(res.score[:n].astype(np.int64).sum())
 
-    # headline: the wire format the C++ host header requests (SEQA_FLAG_OPS_2BIT, 4 ops per byte); the one-byte-per-op
-    # form of the same call is reported next to it
-    e2e_ms_b, d2h_b = e2e_leg(0)
-    e2e_ms, d2h = e2e_leg(capi.FLAG_OPS_2BIT)
+    # headline: both wire formats packed (2-bit symbols in, 2-bit ops out: what include/SequenceAlignment.h sends for ACGT
+    # input); next to it the same call with the reference's own 8-bit symbols in, and with one byte per op out
+    e2e_ms_b, d2h_b, ck_b = e2e_leg(0)
+    e2e_ms_8, d2h_8, ck_8 = e2e_leg(capi.FLAG_OPS_2BIT)
+    e2e_ms, d2h, ck_2 = e2e_leg(capi.FLAG_OPS_2BIT | capi.FLAG_BASES_2BIT)
+    if not (ck_b == ck_8 == ck_2):
+        raise SystemExit("bench.py: the wire formats disagree (score checksums %d / %d / %d)" % (ck_b, ck_8, ck_2))
+    h2d_8 = h2d
+    h2d = int(pk.nbytes) if not os.environ.get("SEQA_NO_DENSE_UPLOAD") else int(pk.nbytes + pp1.nbytes + pp2.nbytes + pl1.nbytes + pl2.nbytes)
     e2e_value = total_cells / (e2e_ms * 1e-3) / 1e9
     checksum = int(res.score[:n].astype(np.int64).sum())
     lib.L.seqa_cuda_trim()
-    del pb, po1, po2, pl1, pl2, res
+    del pb, po1, po2, pl1, pl2, res, pk, pp1, pp2
+
+    # ---- the template API itself (include/SequenceAlignment.h), rank 0 at N=1: compiled here, run as its own process ----
+    api = None
+    if world == 1 and not args.no_api:
+        api = header_api_bench(n)
 
     # ---- the other BASELINE configs, sharded over the same ranks (strong scaling) ----
     configs = None
@@ -619,9 +660,14 @@ def run_ours(args):
                        "result_checksum": checksum},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "api": "seqa_cuda_align_batch (pinned host buffers, SEQA_FLAG_OPS_2BIT: ops packed 4 per byte, the format include/SequenceAlignment.h requests)",
-                    "byte_ops": {"value": total_cells / (e2e_ms_b * 1e-3) / 1e9, "ms_per_step": e2e_ms_b, "d2h_bytes_per_step": d2h_b,
-                                 "note": "same call with one byte per op (flags = 0)"}},
+                    "ms_per_step": e2e_ms, "api": "seqa_cuda_align_batch (pinned host buffers; SEQA_FLAG_BASES_2BIT | SEQA_FLAG_OPS_2BIT: symbols in and ops out "
+                                                  "packed 4 per byte, the wire formats include/SequenceAlignment.h uses for ACGT input)",
+                    "byte_bases": {"value": total_cells / (e2e_ms_8 * 1e-3) / 1e9, "ms_per_step": e2e_ms_8, "h2d_bytes_per_step": h2d_8,
+                                   "d2h_bytes_per_step": d2h_8, "note": "same call with the reference's 8-bit symbols in (SEQA_FLAG_OPS_2BIT only: round 1's headline)"},
+                    "byte_ops": {"value": total_cells / (e2e_ms_b * 1e-3) / 1e9, "ms_per_step": e2e_ms_b, "h2d_bytes_per_step": h2d_8,
+                                 "d2h_bytes_per_step": d2h_b, "note": "8-bit symbols in, one byte per op out (flags = 0)"},
+                    "api_packed": (api or {}).get("packed"), "api_list": (api or {}).get("list"),
+                    "api_note": (api or {}).get("note", "template-API legs run at N=1 only")},
             "gpu_launches": int(launches), "clocks": clocks, "configs": configs}
     emit(line)
     if world > 1:
@@ -637,6 +683,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-api", action="store_true", help="skip the C++ template-API legs (e2e.api_packed / e2e.api_list)")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configs (configs[2..4])")
     ap.add_argument("--config3-pairs", type=int, default=10_000_000, help="configs[2]: total Gotoh pairs of 250 bp (split over the ranks)")
     ap.add_argument("--config4-pairs", type=int, default=64, help="configs[3]: total pairs of 100 kbp (split over the ranks)")

@@ -214,6 +214,56 @@ template <typename Ty, typename Fn> inline bool is_equality_on_bytes(Fn &F)
     return true;
 }
 
+// Runs Body(Lo, Hi, T) over [0, N) cut into contiguous ranges, one per host thread (the calling thread takes the
+// first); small N runs inline.  The header's packing, offset prefix and list expansion all go through this.
+inline size_t hostThreads(size_t Work, size_t MinPerThread)
+{
+    const size_t Hw = std::max<size_t>(1, std::thread::hardware_concurrency());
+    return std::max<size_t>(1, std::min<size_t>(std::min<size_t>(Hw, 32), Work / std::max<size_t>(MinPerThread, 1)));
+}
+template <typename BodyTy> inline void parallelFor(size_t N, size_t Threads, BodyTy Body)
+{
+    if (Threads <= 1 || N == 0) {
+        Body((size_t)0, N, (size_t)0);
+        return;
+    }
+    std::vector<std::thread> Pool;
+    Pool.reserve(Threads - 1);
+    for (size_t T = 1; T < Threads; T++) Pool.emplace_back(Body, N * T / Threads, N * (T + 1) / Threads, T);
+    Body((size_t)0, N / Threads, (size_t)0);
+    for (std::thread &Th : Pool) Th.join();
+}
+
+// 2-bit packing of one sequence for SEQA_FLAG_BASES_2BIT (4 symbols per byte, A0 C1 T2 G3 = (letter >> 1) & 3), eight
+// symbols per step.  Returns false when a symbol outside ACGT is met (the batch then goes out as 8-bit symbols).
+inline bool pack2bit(const char *S, size_t Len, uint8_t *Dst)
+{
+    uint64_t Bad = 0;
+    size_t K = 0;
+    for (; K + 8 <= Len; K += 8) {
+        uint64_t X;
+        std::memcpy(&X, S + K, 8);
+        const uint64_t C = (X >> 1) & 0x0303030303030303ull;
+        // the letter every code stands for, rebuilt bit by bit, must give back the input
+        const uint64_t B0 = C & 0x0101010101010101ull, B1 = (C >> 1) & 0x0101010101010101ull, T = B1 & ~B0;
+        Bad |= X ^ 0x4141414141414141ull ^ (T | (B0 << 1) | (B1 << 2) | (T << 4));
+        uint64_t Y = (C | (C >> 6)) & 0x000F000F000F000Full; // 16-bit lanes: c0 | c1 << 2
+        Y = (Y | (Y >> 12)) & 0x000000FF000000FFull;          // 32-bit lanes: four codes per byte
+        const uint16_t Out = (uint16_t)(Y | (Y >> 24));
+        std::memcpy(Dst + (K >> 2), &Out, 2);
+    }
+    for (; K < Len; K += 4) {
+        unsigned V = 0;
+        for (size_t Q = 0; Q < 4 && K + Q < Len; Q++) {
+            const unsigned Ch = (unsigned char)S[K + Q], Code = (Ch >> 1) & 3u;
+            Bad |= (uint64_t)(Ch ^ (unsigned char)"ACTG"[Code]);
+            V |= Code << (2 * Q);
+        }
+        Dst[K >> 2] = (uint8_t)V;
+    }
+    return Bad == 0;
+}
+
 template <typename Fn> inline bool is_null_functor(const Fn &) { return false; }
 template <typename R, typename... A> inline bool is_null_functor(const std::function<R(A...)> &F) { return !F; }
 template <typename R, typename... A> inline bool is_null_functor(R (*F)(A...)) { return F == nullptr; }
@@ -250,6 +300,9 @@ class SequenceAligner {
     // three LocalGotoh shapes that are undefined behaviour in the reference, include/SALocalGotoh.h:484-488).  Their
     // AlignedSequence is empty; getAlignment (one pair) throws std::invalid_argument instead.
     std::vector<size_t> LastUnsupported;
+    // Input wire format of the most recent call: true = 2-bit symbols (every symbol was one of ACGT), false = 8-bit.
+    // ForceByteInputs = true keeps the 8-bit form always (A/B measurements).
+    bool LastInputsTwoBit = false, ForceByteInputs = false;
 
     virtual AlignedSequence<Ty, Blank> getAlignment(ContainerType &Seq0, ContainerType &Seq1) = 0;
 
@@ -291,7 +344,8 @@ class SequenceAligner {
             return R;
         }
         auto Up = [](size_t X) { return (X + 63) / 64 * 64; };
-        // ---- inputs: indices and symbols packed into page-locked memory (symbols copied by a few host threads) ----
+        // ---- inputs: lengths / offsets and symbols packed into page-locked memory by the host threads.  Symbols go out
+        // 2-bit packed (SEQA_FLAG_BASES_2BIT: a quarter of the PCIe bytes) when every symbol is one of ACGT, else 8-bit ----
         if (!IdxBlock) IdxBlock = std::make_shared<seqa::PinnedBlock>();
         if (!BasesBlock) BasesBlock = std::make_shared<seqa::PinnedBlock>();
         IdxBlock->reserve(Up(8 * N) * 2 + Up(4 * N) * 2);
@@ -299,30 +353,57 @@ class SequenceAligner {
         uint64_t *Off2 = reinterpret_cast<uint64_t *>(IdxBlock->P + Up(8 * N));
         uint32_t *Len1 = reinterpret_cast<uint32_t *>(IdxBlock->P + 2 * Up(8 * N));
         uint32_t *Len2 = reinterpret_cast<uint32_t *>(IdxBlock->P + 2 * Up(8 * N) + Up(4 * N));
-        uint64_t Total = 0;
-        for (size_t P = 0; P < N; P++) {
-            Len1[P] = (uint32_t)S1[P]->size();
-            Len2[P] = (uint32_t)S2[P]->size();
-            Off1[P] = Total;
-            Off2[P] = Total + Len1[P];
-            Total += (uint64_t)Len1[P] + Len2[P];
-        }
-        BasesBlock->reserve(Total + 64);
-        char *Bases = BasesBlock->P;
-        auto CopyRange = [&](size_t Lo, size_t Hi) {
+        const size_t Threads = seqa::detail::hostThreads(N, 8192);
+        std::vector<uint64_t> PartSyms(Threads + 1, 0), PartBytes(Threads + 1, 0);
+        seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) { // lengths + per-thread totals
+            uint64_t Syms = 0, Bytes = 0;
             for (size_t P = Lo; P < Hi; P++) {
-                if (Len1[P]) std::memcpy(Bases + Off1[P], seqa::detail::bytes_of(*S1[P]), Len1[P]);
-                if (Len2[P]) std::memcpy(Bases + Off2[P], seqa::detail::bytes_of(*S2[P]), Len2[P]);
+                const uint32_t A = (uint32_t)S1[P]->size(), B = (uint32_t)S2[P]->size();
+                Len1[P] = A;
+                Len2[P] = B;
+                Syms += (uint64_t)A + B;
+                Bytes += (uint64_t)((A + 3) >> 2) + ((B + 3) >> 2);
             }
-        };
-        const size_t Threads = Total < (1u << 22) ? 1 : std::min<size_t>(16, std::max<size_t>(1, std::thread::hardware_concurrency()));
-        if (Threads <= 1) {
-            CopyRange(0, N);
-        } else {
-            std::vector<std::thread> Pool;
-            for (size_t T = 0; T < Threads; T++) Pool.emplace_back(CopyRange, N * T / Threads, N * (T + 1) / Threads);
-            for (std::thread &T : Pool) T.join();
+            PartSyms[T + 1] = Syms;
+            PartBytes[T + 1] = Bytes;
+        });
+        for (size_t T = 0; T < Threads; T++) {
+            PartSyms[T + 1] += PartSyms[T];
+            PartBytes[T + 1] += PartBytes[T];
         }
+        const uint64_t Total = PartSyms[Threads], TotalPacked = PartBytes[Threads];
+        BasesBlock->reserve(Total + 64); // large enough for either wire format
+        char *Bases = BasesBlock->P;
+        std::vector<char> ThreadOk(Threads, 1);
+        bool TwoBitIn = !ForceByteInputs;
+        if (TwoBitIn) {
+            seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) { // byte offsets + packed symbols
+                uint64_t Run = PartBytes[T];
+                bool Ok = true;
+                for (size_t P = Lo; P < Hi && Ok; P++) {
+                    Off1[P] = Run;
+                    Off2[P] = Run + ((Len1[P] + 3) >> 2);
+                    Ok = seqa::detail::pack2bit(seqa::detail::bytes_of(*S1[P]), Len1[P], reinterpret_cast<uint8_t *>(Bases) + Off1[P]) &&
+                         seqa::detail::pack2bit(seqa::detail::bytes_of(*S2[P]), Len2[P], reinterpret_cast<uint8_t *>(Bases) + Off2[P]);
+                    Run = Off2[P] + ((Len2[P] + 3) >> 2);
+                }
+                ThreadOk[T] = Ok ? 1 : 0;
+            });
+            for (char Ok : ThreadOk) TwoBitIn = TwoBitIn && Ok != 0;
+        }
+        if (!TwoBitIn) {
+            seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) { // symbol offsets + 8-bit symbols
+                uint64_t Run = PartSyms[T];
+                for (size_t P = Lo; P < Hi; P++) {
+                    Off1[P] = Run;
+                    Off2[P] = Run + Len1[P];
+                    if (Len1[P]) std::memcpy(Bases + Off1[P], seqa::detail::bytes_of(*S1[P]), Len1[P]);
+                    if (Len2[P]) std::memcpy(Bases + Off2[P], seqa::detail::bytes_of(*S2[P]), Len2[P]);
+                    Run = Off2[P] + Len2[P];
+                }
+            });
+        }
+        LastInputsTwoBit = TwoBitIn;
         seqa_params Prm{};
         Prm.algo = Algo;
         Prm.gap = Scoring.getGapPenalty();
@@ -333,8 +414,8 @@ class SequenceAligner {
         Prm.mismatch = Scoring.getAllowMismatch() ? Scoring.getMismatchPenalty() : 0;
         Prm.device_first = 0;
         Prm.device_count = 0; // every visible device
-        Prm.flags = SEQA_FLAG_OPS_2BIT; // a quarter of the result bytes over PCIe and in host memory
-        seqa_batch_in In{Bases, Off1, Off2, Len1, Len2, (uint64_t)N, Total};
+        Prm.flags = SEQA_FLAG_OPS_2BIT | (TwoBitIn ? SEQA_FLAG_BASES_2BIT : 0u); // a quarter of the bytes over PCIe, both ways
+        seqa_batch_in In{Bases, Off1, Off2, Len1, Len2, (uint64_t)N, TwoBitIn ? TotalPacked : Total};
         // ---- results: one page-locked block; the previous one is reused once nobody else holds it ----
         const size_t OpsCap = (size_t)(Total / 4 + N + 1);
         if (!OutBlock || OutBlock.use_count() > 1) OutBlock = std::make_shared<seqa::PinnedBlock>();
@@ -402,9 +483,12 @@ class SequenceAligner {
             B[P] = &Pairs[P].second;
         }
         seqa::PackedAlignments R = runBatch(Algo, A, B);
-        std::vector<AlignedSequence<Ty, Blank>> Out;
-        Out.reserve(Pairs.size());
-        for (size_t P = 0; P < Pairs.size(); P++) Out.push_back(expand(R, P, Pairs[P].first, Pairs[P].second, Local));
+        // std::list materialisation (one heap node per aligned column: the reference's own result type is the cost,
+        // SURVEY.md 8 a1): every host thread expands a contiguous range of pairs into the pre-sized vector
+        std::vector<AlignedSequence<Ty, Blank>> Out(Pairs.size());
+        seqa::detail::parallelFor(Pairs.size(), seqa::detail::hostThreads(Pairs.size(), 256), [&](size_t Lo, size_t Hi, size_t) {
+            for (size_t P = Lo; P < Hi; P++) Out[P] = expand(R, P, Pairs[P].first, Pairs[P].second, Local);
+        });
         return Out;
     }
 

@@ -67,6 +67,13 @@ enum {
                                    ops[ops_off[p] + k/4]; ops_off is in BYTES (every pair starts on a byte boundary), ops_len
                                    in OPS; ops_capacity >= sum(len1+len2)/4 + n_pairs suffices.  A quarter of the PCIe bytes
                                    of the default one-byte-per-op form ("2 bits each or one byte each (flag)") */
+#define SEQA_FLAG_BASES_2BIT 0x20u /* INPUT wire format: seqa_batch_in.bases holds 2-bit symbols, 4 per byte (symbol k of a
+                                     sequence in bits 2*(k%4) of its byte k/4), code A = 0, C = 1, T = 2, G = 3 (= (letter >> 1) & 3);
+                                     every sequence starts on a byte boundary; off1 / off2 are BYTE offsets into the packed
+                                     buffer, len1 / len2 count symbols, bases_len counts bytes.  A quarter of the bytes cross
+                                     PCIe; the device expands them once.  Only the letters ACGT have a code: a caller whose
+                                     sequences hold anything else sends 8-bit symbols (flag clear).  north_star: "sequences
+                                     packed 2-bit/8-bit"; replaces the same (Seq1, Seq2) arguments as the 8-bit form */
 #define SEQA_FLAG_LS_R1 0x8u /* linear-space path: 32-row blocks everywhere (testing: deep row-block pipelines on short pairs) */
 
 /*

@@ -143,6 +143,8 @@ struct seqa_ctx {
     uint64_t st_cells = 0, st_slots = 0;
 
     DBuf<uint8_t> bases;
+    DBuf<uint8_t> packed_in;      // SEQA_FLAG_BASES_2BIT: the packed bytes as they crossed PCIe (unpacked into `bases`)
+    DBuf<uint64_t> poff1, poff2;  // ... and their byte offsets when the batch is not dense
     DBuf<uint64_t> off1, off2;
     DBuf<uint32_t> len1, len2;
 
@@ -813,6 +815,90 @@ int ctx_set_inputs_common(seqa_ctx *c, const seqa_params *params, uint64_t n)
     return SEQA_OK;
 }
 
+// SEQA_FLAG_BASES_2BIT: `in->bases` holds 2-bit symbols (4 per byte, A0 C1 T2 G3, every sequence on a byte boundary;
+// off1 / off2 are BYTE offsets into it, len1 / len2 count symbols).  A quarter of the bytes cross PCIe; the device
+// expands them once into the one-byte-per-symbol dense layout every kernel reads (unpack2_kernel).
+int ctx_upload_range_2bit(seqa_ctx *c, const seqa_params *params, const seqa_batch_in *in, uint64_t pb, uint64_t pe)
+{
+    const uint64_t n = pe - pb;
+    CKS(ctx_set_inputs_common(c, params, n));
+    c->hlen1.assign(in->len1 + pb, in->len1 + pe);
+    c->hlen2.assign(in->len2 + pb, in->len2 + pe);
+    uint64_t lo = UINT64_MAX, hi = 0, st_cells = 0, st_slots = 0, run_bytes = 0;
+    bool st_uni = true, dense = true; // dense: seq1 then seq2 of every pair, byte-aligned, pairs back to back
+    const uint32_t M0 = n ? in->len1[pb] : 0, N0 = n ? in->len2[pb] : 0;
+    const uint64_t first_off = n ? in->off1[pb] : 0;
+    for (uint64_t p = pb; p < pe; p++) {
+        const uint64_t l1 = in->len1[p], l2 = in->len2[p], B1 = (l1 + 3) >> 2, B2 = (l2 + 3) >> 2;
+        const uint64_t a0 = in->off1[p], b0 = in->off2[p];
+        if (a0 > in->bases_len || B1 > in->bases_len - a0 || b0 > in->bases_len || B2 > in->bases_len - b0)
+            return fail(SEQA_ERR_INVALID, "pair %llu reaches past bases_len", (unsigned long long)p);
+        dense &= a0 == first_off + run_bytes && b0 == a0 + B1;
+        lo = std::min(lo, std::min(a0, b0));
+        hi = std::max(hi, std::max(a0 + B1, b0 + B2));
+        run_bytes += B1 + B2;
+        st_cells += l1 * l2;
+        st_slots += l1 + l2;
+        st_uni &= l1 == M0 && l2 == N0;
+    }
+    if (getenv("SEQA_NO_DENSE_UPLOAD")) dense = false;
+    c->have_stats = true;
+    c->st_cells = st_cells;
+    c->st_slots = st_slots;
+    c->st_uniform = st_uni;
+    if (n == 0 || hi < lo) lo = hi = 0;
+    c->bases_len = st_slots; // the unpacked copy is dense whatever the layout of the packed bytes
+    CKS(c->bases.ensure(c->bases_len + 16));
+    CKS(c->packed_in.ensure(hi - lo + 16));
+    if (hi > lo) CK(cudaMemcpyAsync(c->packed_in.p, in->bases + lo, hi - lo, cudaMemcpyHostToDevice, c->up));
+    if (n) {
+        if (!dense) {
+            CKS(c->poff1.ensure(n));
+            CKS(c->poff2.ensure(n));
+            CK(cudaMemcpyAsync(c->poff1.p, in->off1 + pb, n * 8, cudaMemcpyHostToDevice, c->up));
+            CK(cudaMemcpyAsync(c->poff2.p, in->off2 + pb, n * 8, cudaMemcpyHostToDevice, c->up));
+        }
+        if (!st_uni) {
+            CK(cudaMemcpyAsync(c->len1.p, in->len1 + pb, n * 4, cudaMemcpyHostToDevice, c->up));
+            CK(cudaMemcpyAsync(c->len2.p, in->len2 + pb, n * 4, cudaMemcpyHostToDevice, c->up));
+        }
+        CKS(order_after(c, c->up, c->stream));
+        if (st_uni) LAUNCH(c, (fill_lengths_kernel), (unsigned)((n + 255) / 256), 256, 0, c->len1.p, c->len2.p, n, M0, N0);
+        if (!dense && lo) LAUNCH(c, (rebase_kernel), (unsigned)((n + 255) / 256), 256, 0, c->poff1.p, c->poff2.p, n, lo);
+    }
+    int rc = build_plan(c);
+    if (rc != SEQA_OK || n == 0) return rc;
+    // unpacked offsets = the op-slot scan (exclusive scan of len1 + len2), as for a dense 8-bit batch
+    LAUNCH(c, (dense_offsets_kernel), (unsigned)((n + 255) / 256), 256, 0, c->slot_off.p, c->len1.p, c->off1.p, c->off2.p, n);
+    Unpack2Args U{};
+    U.packed = c->packed_in.p;
+    U.len1 = c->len1.p;
+    U.len2 = c->len2.p;
+    U.off1 = c->off1.p;
+    U.off2 = c->off2.p;
+    U.bases = c->bases.p;
+    U.n = n;
+    if (!dense) {
+        U.poff1 = c->poff1.p;
+        U.poff2 = c->poff2.p;
+    } else if (st_uni && ((uint64_t)((M0 + 3) >> 2) + ((N0 + 3) >> 2)) > 0) {
+        U.uniform_stride = (uint64_t)((M0 + 3) >> 2) + ((N0 + 3) >> 2);
+    } else {
+        // dense ragged batch: packed offsets = exclusive scan of ceil(len1/4) + ceil(len2/4), computed on the device
+        CKS(c->poff1.ensure(n));
+        const unsigned tiles = (unsigned)((n + SEQA_SCAN_TILE - 1) / SEQA_SCAN_TILE);
+        LAUNCH(c, (packed_bytes_kernel), (unsigned)((n + 255) / 256), 256, 0, c->len1.p, c->len2.p, c->start_i.p, n); // start_i: scratch until the walk
+        LAUNCH(c, (scan_tile_sums_kernel), tiles, SEQA_SCAN_TPB, 0, c->start_i.p, n, c->tile_sum.p, 0);
+        LAUNCH(c, (scan_spine_kernel), 1, 1024, 0, c->tile_sum.p, (uint64_t)tiles, c->total.p);
+        LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->start_i.p, n, c->tile_sum.p, c->poff1.p, 0);
+        U.poff1 = c->poff1.p;
+    }
+    const unsigned blocks = (unsigned)std::min<uint64_t>((2 * n * 32 + 255) / 256, (uint64_t)c->sms * 64);
+    LAUNCH(c, (unpack2_kernel), blocks, 256, 0, U);
+    CK(cudaGetLastError());
+    return SEQA_OK;
+}
+
 // upload pairs [pb, pe) of `in`; device offsets are rebased to the byte range the shard touches
 int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in *in, uint64_t pb, uint64_t pe)
 {
@@ -822,6 +908,7 @@ int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in
         return fail(SEQA_ERR_INVALID, "batch has NULL arrays");
     if (n > 0xfffffff0ull) return fail(SEQA_ERR_UNSUPPORTED, "more than 2^32-16 pairs per device shard");
     CK(cudaSetDevice(c->device));
+    if (params && (params->flags & SEQA_FLAG_BASES_2BIT)) return ctx_upload_range_2bit(c, params, in, pb, pe);
     const bool dbgt = getenv("SEQA_DEBUG_TIMING") != nullptr;
     const auto tu0 = std::chrono::steady_clock::now();
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
@@ -1035,7 +1122,7 @@ void seqa_ctx_destroy(seqa_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->bases.release(); c->off1.release(); c->off2.release(); c->len1.release(); c->len2.release();
+    c->bases.release(); c->packed_in.release(); c->poff1.release(); c->poff2.release(); c->off1.release(); c->off2.release(); c->len1.release(); c->len2.release();
     c->score.release(); c->start_i.release(); c->start_j.release(); c->end_i.release(); c->end_j.release();
     c->ops_len.release(); c->slot_start.release(); c->slot_off.release(); c->ops_off.release();
     c->slots.release(); c->dense.release(); c->tile_sum.release(); c->total.release(); c->flags.release();

@@ -156,6 +156,58 @@ __global__ void __launch_bounds__(256) rebase_kernel(uint64_t *__restrict__ off1
     }
 }
 
+// ---- SEQA_FLAG_BASES_2BIT: 2-bit symbols over PCIe, unpacked on the device -------------------------------------------
+// Wire format: 4 symbols per byte (symbol k of a sequence in bits 2*(k%4) of byte k/4), code A0 C1 T2 G3 = (letter >> 1) & 3,
+// every sequence on a byte boundary.  The unpacked copy (one byte per symbol, seq1 then seq2 per pair, dense) is what
+// every kernel of the path reads, exactly as if the caller had sent 8-bit symbols: a quarter of the PCIe bytes for one
+// streaming pass over HBM (0.4 GB per 1 M x 150 bp pairs).
+__global__ void __launch_bounds__(256) packed_bytes_kernel(const uint32_t *__restrict__ len1, const uint32_t *__restrict__ len2,
+                                                           uint32_t *__restrict__ out, uint64_t n)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = ((len1[k] + 3u) >> 2) + ((len2[k] + 3u) >> 2);
+}
+
+struct Unpack2Args {
+    const uint8_t *packed;           // the shard's packed bytes
+    const uint64_t *poff1, *poff2;   // packed byte offsets; poff2 == nullptr: sequence 2 follows sequence 1 (dense)
+    uint64_t uniform_stride;         // != 0: poff1[p] = p * uniform_stride (uniform dense batch, no offset array at all)
+    const uint32_t *len1, *len2;
+    const uint64_t *off1, *off2;     // unpacked offsets
+    uint8_t *bases;
+    uint64_t n;
+};
+
+__global__ void __launch_bounds__(256) unpack2_kernel(Unpack2Args A)
+{
+    // one warp per sequence; lane l expands packed bytes l, l + 32, ... (4 symbols each)
+    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t q = gw; q < 2 * A.n; q += nw) {
+        const uint64_t p = q >> 1;
+        const bool second = (q & 1) != 0;
+        const uint32_t l1 = A.len1[p], len = second ? A.len2[p] : l1;
+        uint64_t po = A.uniform_stride ? p * A.uniform_stride : A.poff1[p];
+        if (second) po = A.poff2 ? A.poff2[p] : po + ((l1 + 3u) >> 2);
+        uint8_t *dst = A.bases + (second ? A.off2[p] : A.off1[p]);
+        const uint32_t nb = (len + 3u) >> 2;
+        for (uint32_t b = lane; b < nb; b += 32) {
+            const unsigned v = A.packed[po + b];
+            // "ACTG"[code] for the four codes of the byte
+            const unsigned w = ((0x47544341u >> (8u * (v & 3u))) & 0xffu) | (((0x47544341u >> (8u * ((v >> 2) & 3u))) & 0xffu) << 8) |
+                               (((0x47544341u >> (8u * ((v >> 4) & 3u))) & 0xffu) << 16) | (((0x47544341u >> (8u * ((v >> 6) & 3u))) & 0xffu) << 24);
+            uint8_t *d = dst + 4u * b;
+            const uint32_t have = len - 4u * b;
+            if (have >= 4u && (reinterpret_cast<uintptr_t>(d) & 3u) == 0) {
+                *reinterpret_cast<uint32_t *>(d) = w;
+            } else {
+                for (uint32_t t = 0; t < 4u && t < have; t++) d[t] = (uint8_t)(w >> (8u * t));
+            }
+        }
+    }
+}
+
 // ---- gather the per-pair op slots (written back-to-front by the walk kernels) into the dense buffer ----
 struct GatherArgs {
     uint64_t n_pairs;

@@ -161,6 +161,37 @@ int main()
         }
         expect("LocalGotoh batch beside a rejected pair", R2, "--------AAACTCAT");
     }
+    { // input wire format: 2-bit symbols when everything is ACGT, 8-bit otherwise -- same alignments either way
+        std::vector<std::pair<std::string, std::string>> Clean, Dirty;
+        for (int K = 0; K < 40; K++) {
+            std::string A, B;
+            for (int I = 0; I < 5 + 7 * K % 90; I++) A.push_back("ACGT"[(I * 7 + K * 3 + I / 5) & 3]);
+            for (int I = 0; I < 3 + 11 * K % 70; I++) B.push_back("ACGT"[(I * 5 + K + I / 3) & 3]);
+            Clean.emplace_back(A, B);
+        }
+        Dirty = Clean;
+        Dirty[7].first[2] = 'N';
+        NeedlemanWunschSA<std::string, char, '-'> NW(ScoringSystem(-1, 2, -1));
+        auto Two = NW.getAlignments(Clean);
+        const bool WasTwo = NW.LastInputsTwoBit;
+        NW.ForceByteInputs = true;
+        auto Byte = NW.getAlignments(Clean);
+        const bool WasByte = !NW.LastInputsTwoBit;
+        NW.ForceByteInputs = false;
+        NW.getAlignments(Dirty);
+        if (!WasTwo || !WasByte || NW.LastInputsTwoBit) {
+            std::printf("FAIL input wire format selection\n");
+            Failures++;
+        }
+        for (size_t K = 0; K < Clean.size(); K++) {
+            std::string Q1, Q2, QF;
+            rows(Two[K], R1, R2, Fl);
+            rows(Byte[K], Q1, Q2, QF);
+            expect("2-bit vs 8-bit inputs row1", R1, Q1);
+            expect("2-bit vs 8-bit inputs row2", R2, Q2);
+            expect("2-bit vs 8-bit inputs flags", Fl, QF);
+        }
+    }
     { // a functor that is not equality is outside the GPU path
         bool Threw = false;
         try {

@@ -156,3 +156,58 @@ def test_batch_layouts_dense_and_scattered(emu_lib):
             for p in range(len(pairs)):
                 assert np.array_equal(want.pair_ops(p), got.pair_ops(p)), p
         check_batch_against_oracle(emu_lib, "sw", sc, pairs)
+
+
+def _same_results(want, got, n):
+    for name in ("score", "start_i", "start_j", "end_i", "end_j", "ops_len"):
+        assert np.array_equal(getattr(want, name)[:n], getattr(got, name)[:n]), name
+    for p in range(n):
+        assert np.array_equal(want.pair_ops(p), got.pair_ops(p)), p
+
+
+def shuffled_2bit_layout(pk, p1, p2, len1, len2):
+    """the same packed sequences in a NON-dense layout: junk in front, pairs in reverse order, sequence 2 before
+    sequence 1, a junk byte between them (exercises the offset-array path of SEQA_FLAG_BASES_2BIT)"""
+    n = len(len1)
+    chunks, q1, q2, pos = [b"\xff\xff\xff"], np.zeros(n, np.uint64), np.zeros(n, np.uint64), 3
+    for p in reversed(range(n)):
+        b1, b2 = (int(len1[p]) + 3) // 4, (int(len2[p]) + 3) // 4
+        q2[p] = pos
+        chunks += [pk[int(p2[p]):int(p2[p]) + b2].tobytes(), b"\xaa"]
+        pos += b2 + 1
+        q1[p] = pos
+        chunks.append(pk[int(p1[p]):int(p1[p]) + b1].tobytes())
+        pos += b1
+    return np.frombuffer(b"".join(chunks), dtype=np.uint8).copy(), q1, q2
+
+
+@pytest.mark.parametrize("algo,sc", [("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("ggotoh", S.affine(-3, -1, 1, -1)),
+                                     ("lgotoh", S.affine(-3, -1, 1, -1)), ("hirschberg", S.linear(-1, 2, -1)),
+                                     ("myersmiller", S.affine(-3, -1, 1, -1))])
+def test_two_bit_input_wire_format(emu_lib, algo, sc):
+    """SEQA_FLAG_BASES_2BIT: 2-bit symbols in (dense ragged, dense uniform and scattered layouts; several devices) give
+    exactly the results of the 8-bit form, which is checked against the oracle."""
+    rng = np.random.default_rng(5)
+    ragged = random_pairs(rng, 16, 1, 50) + [("", "ACGT"), ("ACGT", ""), ("", ""), ("A", "C")] + random_pairs(rng, 2, 90, 130)
+    if algo == "lgotoh":
+        ragged = [p for p in ragged if p[0] and p[1]]
+    uniform = [("ACGTACGTACGTTGCAAC", "ACGTTCGTACGGGTTGCAATCA")] * 66
+    check_batch_against_oracle(emu_lib, algo, sc, ragged)
+    for pairs in (ragged, uniform):
+        bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+        pk, p1, p2 = capi.pack_bases_2bit(bases, off1, off2, len1, len2)
+        for flags, dc in ((0, 1), (capi.FLAG_OPS_2BIT | capi.FLAG_FORCE_GENERIC, 2)):
+            want = emu_lib.align_batch(scoring_to_params(algo, sc, flags=flags, device_count=dc), bases, off1, off2, len1, len2)
+            got = emu_lib.align_batch(scoring_to_params(algo, sc, flags=flags | capi.FLAG_BASES_2BIT, device_count=dc), pk, p1, p2, len1, len2)
+            _same_results(want, got, len(pairs))
+        spk, q1, q2 = shuffled_2bit_layout(pk, p1, p2, len1, len2)
+        want = emu_lib.align_batch(scoring_to_params(algo, sc), bases, off1, off2, len1, len2)
+        got = emu_lib.align_batch(scoring_to_params(algo, sc, flags=capi.FLAG_BASES_2BIT), spk, q1, q2, len1, len2)
+        _same_results(want, got, len(pairs))
+    with pytest.raises(ValueError):
+        capi.pack_bases_2bit(*orc.batch_arrays([("ACGNT", "ACGT")]))
+    # a packed buffer that is too short for its offsets is refused
+    bases, off1, off2, len1, len2 = orc.batch_arrays(ragged)
+    pk, p1, p2 = capi.pack_bases_2bit(bases, off1, off2, len1, len2)
+    with pytest.raises(capi.SeqaError):
+        emu_lib.align_batch(scoring_to_params(algo, sc, flags=capi.FLAG_BASES_2BIT), pk[:len(pk) // 2].copy(), p1, p2, len1, len2)

@@ -20,6 +20,16 @@ def _seq(rng, n, alphabet="ACGT"):
     return "".join(alphabet[k] for k in rng.integers(0, len(alphabet), n))
 
 
+UB_SHAPES = ((314, 288), (60, 57), (61, 58))  # LocalGotoh: undefined behaviour in the reference, rejected per pair
+
+
+def _defined(algo, pairs):
+    """drop what the reference leaves undefined for LocalGotoh (the three UB shapes, empty inputs)"""
+    if algo != "lgotoh":
+        return pairs
+    return [p for p in pairs if (len(p[0]), len(p[1])) not in UB_SHAPES and p[0] and p[1]]
+
+
 def _kernel_used(lib, algo, sc, pairs, flags=0):
     bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
     ctx = capi.Ctx(lib)
@@ -45,8 +55,7 @@ def test_cuda_against_compiled_reference(gpu_lib, algo, sc):
         pytest.skip("oracle/_ref/libseqa_ref.so was not prebuilt (needs /root/reference at build time)")
     rng = np.random.default_rng(2024)
     pairs = random_pairs(rng, 1200, 1, 200) + random_pairs(rng, 300, 1, 120, "AC") + random_pairs(rng, 500, 20, 250, related=0.3)
-    if algo == "lgotoh":
-        pairs = [p for p in pairs if (len(p[0]), len(p[1])) not in ((314, 288), (60, 57), (61, 58))]
+    pairs = _defined(algo, pairs)
     bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
     res = gpu_lib.align_batch(scoring_to_params(algo, sc), bases, off1, off2, len1, len2)
     for p, (a, b) in enumerate(pairs):
@@ -77,7 +86,7 @@ def test_trace_width_threshold_affine(gpu_lib):
         for sc, want in ((S.affine(-2, -1, 4, -2), "_t4"), (S.affine(-2, -1, 4, -3), "_t8"), (S.affine(-3, -1, 3, -1), "_t4"),
                          (S.affine(-3, -1, 4, -1), "_t8"), (S.affine(0, -1, 6, -4), "_t4"), (S.affine(0, -1, 7, -1), "_t8")):
             assert _kernel_used(gpu_lib, algo, sc, pairs[:70]).endswith(want), (algo, sc)
-            check_batch_against_oracle(gpu_lib, algo, sc, pairs, label="affine-tb-threshold")
+            check_batch_against_oracle(gpu_lib, algo, sc, _defined(algo, pairs), label="affine-tb-threshold")
 
 
 def test_packed_versus_generic_scoring_threshold(gpu_lib):
@@ -92,7 +101,7 @@ def test_packed_versus_generic_scoring_threshold(gpu_lib):
                              ("sw", S.linear(-1, 100, -1), True), ("sw", S.linear(-1, 101, -1), False)):
         k = _kernel_used(gpu_lib, algo, sc, short[:70])
         assert k.startswith("pk") == packed, (algo, sc, k)
-        check_batch_against_oracle(gpu_lib, algo, sc, short, label="packed-threshold")
+        check_batch_against_oracle(gpu_lib, algo, sc, _defined(algo, short), label="packed-threshold")
 
 
 def test_packed_score_range_limit(gpu_lib):
@@ -108,7 +117,7 @@ def test_packed_score_range_limit(gpu_lib):
     check_batch_against_oracle(gpu_lib, "sw", S.linear(-1, 100, -1), tall + filler, label="hi-limit")
     aff = [(_seq(rng, 733), _seq(rng, 732)), (_seq(rng, 733), _seq(rng, 733)), (_seq(rng, 700), _seq(rng, 766))] + random_pairs(rng, 3, 720, 740, related=0.2)
     for algo in ("ggotoh", "lgotoh"):
-        check_batch_against_oracle(gpu_lib, algo, S.affine(-3, -1, 1, -1), aff + filler, label="affine-range-limit")
+        check_batch_against_oracle(gpu_lib, algo, S.affine(-3, -1, 1, -1), _defined(algo, aff + filler), label="affine-range-limit")
 
 
 # ---- (c) shared-memory / global strip boundary, packed length cap, long pairs in mixed batches ---------------------
@@ -172,7 +181,7 @@ def test_score_only_flag(gpu_lib, algo, sc):
     ops arrays may be NULL; packed and generic kernels."""
     import ctypes as C
     rng = np.random.default_rng(9)
-    pairs = random_pairs(rng, 400, 1, 250) + random_pairs(rng, 40, 1, 100, "AC")
+    pairs = _defined(algo, random_pairs(rng, 400, 1, 250) + random_pairs(rng, 40, 1, 100, "AC"))
     for flags in (capi.FLAG_SCORE_ONLY, capi.FLAG_SCORE_ONLY | capi.FLAG_FORCE_GENERIC):
         bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
         n = len(pairs)
@@ -285,3 +294,44 @@ def test_multi_device_uniform_batch_is_balanced(gpu_lib):
     assert np.array_equal(res.score, one.score) and np.array_equal(res.ops_len, one.ops_len)
     for p in (0, 1, n // 2, n - 1):
         assert np.array_equal(res.pair_ops(p), one.pair_ops(p))
+
+
+@pytest.mark.parametrize("algo,sc", [("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("ggotoh", S.affine(-3, -1, 1, -1)),
+                                     ("lgotoh", S.affine(-3, -1, 1, -1)), ("hirschberg", S.linear(-1, 2, -1)),
+                                     ("myersmiller", S.affine(-3, -1, 1, -1))])
+def test_two_bit_input_wire_format(gpu_lib, algo, sc):
+    """SEQA_FLAG_BASES_2BIT (north_star: "sequences packed 2-bit/8-bit"): a ragged batch against the oracle, and dense /
+    scattered packed layouts against the 8-bit form of the same call."""
+    from test_emu_kernels import _same_results, shuffled_2bit_layout
+    rng = np.random.default_rng(12)
+    pairs = _defined(algo, random_pairs(rng, 600, 1, 300) + random_pairs(rng, 100, 1, 120, "AC") + random_pairs(rng, 6, 1500, 2500))
+    bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+    pk, p1, p2 = capi.pack_bases_2bit(bases, off1, off2, len1, len2)
+    got = gpu_lib.align_batch(scoring_to_params(algo, sc, flags=capi.FLAG_BASES_2BIT), pk, p1, p2, len1, len2)
+    assert compare_with_oracle_batch(got, algo, sc, bases, off1, off2, len1, len2, "2-bit in") == len(pairs)
+    spk, q1, q2 = shuffled_2bit_layout(pk, p1, p2, len1, len2)
+    got2 = gpu_lib.align_batch(scoring_to_params(algo, sc, flags=capi.FLAG_BASES_2BIT | capi.FLAG_OPS_2BIT), spk, q1, q2, len1, len2)
+    want2 = gpu_lib.align_batch(scoring_to_params(algo, sc, flags=capi.FLAG_OPS_2BIT), bases, off1, off2, len1, len2)
+    _same_results(want2, got2, len(pairs))
+
+
+def test_two_bit_inputs_large_uniform_batch(gpu_lib):
+    """300,000 x 150 bp through the one-shot call in several waves: 2-bit symbols in == 8-bit symbols in, both wire
+    formats of the ops; the packed form moves 76 bytes per pair instead of 300."""
+    n = 300_000
+    sc = S.linear(-1, 1, -1)
+    bases, off1, off2, l1, l2 = synth.batch_uniform(synth.SEED, 31_000_000, n, 150, 150)
+    pk, p1, p2 = capi.pack_bases_2bit(bases, off1, off2, l1, l2)
+    assert len(pk) == n * 76
+    want = gpu_lib.align_batch(scoring_to_params("sw", sc, flags=capi.FLAG_OPS_2BIT), bases, off1, off2, l1, l2, capi.Results(n, n * 76))
+    got = gpu_lib.align_batch(scoring_to_params("sw", sc, flags=capi.FLAG_OPS_2BIT | capi.FLAG_BASES_2BIT), pk, p1, p2, l1, l2, capi.Results(n, n * 76))
+    for name in ("score", "start_i", "start_j", "end_i", "end_j", "ops_len", "ops_off"):
+        assert np.array_equal(getattr(want, name), getattr(got, name)), name
+    assert want.c.ops_used == got.c.ops_used and np.array_equal(want.ops[:want.c.ops_used], got.ops[:got.c.ops_used])
+    rng = np.random.default_rng(3)
+    for p in rng.integers(0, n, 300):
+        p = int(p)
+        a = bytes(bases[int(off1[p]):int(off1[p]) + 150]).decode()
+        b = bytes(bases[int(off2[p]):int(off2[p]) + 150]).decode()
+        o = orc.oracle_align("sw", sc, a, b)
+        assert int(got.score[p]) == o["score"] and np.array_equal(got.pair_ops(p), o["ops"]), p
