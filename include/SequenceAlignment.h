@@ -331,12 +331,11 @@ class SequenceAligner {
                                         "reference-only (see include/SequenceAlignment.h)");
     }
 
-    seqa::PackedAlignments runBatch(int Algo, const std::vector<const ContainerType *> &S1,
-                                    const std::vector<const ContainerType *> &S2)
+    // First(P) / Second(P) return the two sequences of pair P (no pointer vectors are built for a million pairs)
+    template <typename FirstFn, typename SecondFn> seqa::PackedAlignments runBatch(int Algo, size_t N, FirstFn First, SecondFn Second)
     {
         static_assert(sizeof(Ty) == 1, "seqalib_b200: the GPU path aligns 8-bit symbols (char); wider types are reference-only");
         requireGpuEligible();
-        const size_t N = S1.size();
         seqa::PackedAlignments R;
         R.TwoBit = true;
         if (N == 0) {
@@ -358,7 +357,7 @@ class SequenceAligner {
         seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) { // lengths + per-thread totals
             uint64_t Syms = 0, Bytes = 0;
             for (size_t P = Lo; P < Hi; P++) {
-                const uint32_t A = (uint32_t)S1[P]->size(), B = (uint32_t)S2[P]->size();
+                const uint32_t A = (uint32_t)First(P).size(), B = (uint32_t)Second(P).size();
                 Len1[P] = A;
                 Len2[P] = B;
                 Syms += (uint64_t)A + B;
@@ -383,8 +382,8 @@ class SequenceAligner {
                 for (size_t P = Lo; P < Hi && Ok; P++) {
                     Off1[P] = Run;
                     Off2[P] = Run + ((Len1[P] + 3) >> 2);
-                    Ok = seqa::detail::pack2bit(seqa::detail::bytes_of(*S1[P]), Len1[P], reinterpret_cast<uint8_t *>(Bases) + Off1[P]) &&
-                         seqa::detail::pack2bit(seqa::detail::bytes_of(*S2[P]), Len2[P], reinterpret_cast<uint8_t *>(Bases) + Off2[P]);
+                    Ok = seqa::detail::pack2bit(seqa::detail::bytes_of(First(P)), Len1[P], reinterpret_cast<uint8_t *>(Bases) + Off1[P]) &&
+                         seqa::detail::pack2bit(seqa::detail::bytes_of(Second(P)), Len2[P], reinterpret_cast<uint8_t *>(Bases) + Off2[P]);
                     Run = Off2[P] + ((Len2[P] + 3) >> 2);
                 }
                 ThreadOk[T] = Ok ? 1 : 0;
@@ -397,8 +396,8 @@ class SequenceAligner {
                 for (size_t P = Lo; P < Hi; P++) {
                     Off1[P] = Run;
                     Off2[P] = Run + Len1[P];
-                    if (Len1[P]) std::memcpy(Bases + Off1[P], seqa::detail::bytes_of(*S1[P]), Len1[P]);
-                    if (Len2[P]) std::memcpy(Bases + Off2[P], seqa::detail::bytes_of(*S2[P]), Len2[P]);
+                    if (Len1[P]) std::memcpy(Bases + Off1[P], seqa::detail::bytes_of(First(P)), Len1[P]);
+                    if (Len2[P]) std::memcpy(Bases + Off2[P], seqa::detail::bytes_of(Second(P)), Len2[P]);
                     Run = Off2[P] + Len2[P];
                 }
             });
@@ -435,10 +434,15 @@ class SequenceAligner {
         if (seqa_cuda_align_batch(&Prm, &In, &Out) != SEQA_OK)
             throw std::runtime_error(std::string("seqa_cuda_align_batch: ") + seqa_cuda_last_error());
         // (large batches are processed in waves whose op strings sit at each wave's own base offset inside Ops)
-        LastScores.assign(R.Score.begin(), R.Score.end());
+        LastScores.resize(N);
         LastUnsupported.clear();
-        for (size_t P = 0; P < N; P++)
-            if (R.OpsLen[P] == SEQA_PAIR_UNSUPPORTED) LastUnsupported.push_back(P);
+        std::vector<std::vector<size_t>> Rejected(Threads);
+        seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) {
+            std::memcpy(LastScores.data() + Lo, R.Score.data() + Lo, (Hi - Lo) * sizeof(int));
+            for (size_t P = Lo; P < Hi; P++)
+                if (R.OpsLen[P] == SEQA_PAIR_UNSUPPORTED) Rejected[T].push_back(P);
+        });
+        for (const std::vector<size_t> &V : Rejected) LastUnsupported.insert(LastUnsupported.end(), V.begin(), V.end());
         return R;
     }
 
@@ -467,8 +471,8 @@ class SequenceAligner {
 
     AlignedSequence<Ty, Blank> alignOne(int Algo, bool Local, ContainerType &Seq1, ContainerType &Seq2)
     {
-        std::vector<const ContainerType *> A{&Seq1}, B{&Seq2};
-        seqa::PackedAlignments R = runBatch(Algo, A, B);
+        seqa::PackedAlignments R = runBatch(Algo, 1, [&](size_t) -> const ContainerType & { return Seq1; },
+                                            [&](size_t) -> const ContainerType & { return Seq2; });
         if (!LastUnsupported.empty())
             throw std::invalid_argument("seqalib_b200: this (len1,len2) shape is undefined behaviour in the reference's LocalGotohSA "
                                         "(include/SALocalGotoh.h:484-488) and is not aligned on the GPU path");
@@ -477,12 +481,7 @@ class SequenceAligner {
 
     std::vector<AlignedSequence<Ty, Blank>> alignMany(int Algo, bool Local, std::vector<PairType> &Pairs)
     {
-        std::vector<const ContainerType *> A(Pairs.size()), B(Pairs.size());
-        for (size_t P = 0; P < Pairs.size(); P++) {
-            A[P] = &Pairs[P].first;
-            B[P] = &Pairs[P].second;
-        }
-        seqa::PackedAlignments R = runBatch(Algo, A, B);
+        seqa::PackedAlignments R = packMany(Algo, Pairs);
         // std::list materialisation (one heap node per aligned column: the reference's own result type is the cost,
         // SURVEY.md 8 a1): every host thread expands a contiguous range of pairs into the pre-sized vector
         std::vector<AlignedSequence<Ty, Blank>> Out(Pairs.size());
@@ -494,12 +493,8 @@ class SequenceAligner {
 
     seqa::PackedAlignments packMany(int Algo, std::vector<PairType> &Pairs)
     {
-        std::vector<const ContainerType *> A(Pairs.size()), B(Pairs.size());
-        for (size_t P = 0; P < Pairs.size(); P++) {
-            A[P] = &Pairs[P].first;
-            B[P] = &Pairs[P].second;
-        }
-        return runBatch(Algo, A, B);
+        return runBatch(Algo, Pairs.size(), [&](size_t P) -> const ContainerType & { return Pairs[P].first; },
+                        [&](size_t P) -> const ContainerType & { return Pairs[P].second; });
     }
 };
 

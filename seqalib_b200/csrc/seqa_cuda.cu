@@ -192,6 +192,7 @@ struct seqa_ctx {
     DBuf<uint8_t> scratch; // trace / direction matrices (+ profiles) of one chunk
     bool generic_rerun = false;
 
+    uint64_t ops_base = 0, ops_base_applied = 0; // offset added to ops_off by the next run / by the last run
     uint64_t launches = 0;
     cudaEvent_t dbg_ev[4] = {nullptr, nullptr, nullptr, nullptr}; // SEQA_DEBUG_TIMING: upload start / H2D done / kernels done / D2H done
     std::vector<cudaEvent_t> ev; // pairs of events around the DP fill launches of the last run
@@ -311,6 +312,20 @@ size_t free_budget(int sharers = 3)
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (size_t)1 << 30;
     return (size_t)std::min((double)fr * 0.8, (double)tot * 0.8 / (sharers + 1));
 }
+// the same cap from the device's total memory alone: cudaMemGetInfo costs ~1 ms, too much for the per-wave path of the
+// one-shot call (the total is queried once per device and process)
+size_t ring_budget(int device, int ring)
+{
+    static size_t total[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    const int d = device >= 0 && device < 64 ? device : 0;
+    if (!total[d]) {
+        size_t fr = 0, tot = 0;
+        total[d] = cudaMemGetInfo(&fr, &tot) == cudaSuccess ? tot : ((size_t)8 << 30);
+    }
+    return (size_t)((double)total[d] * 0.8 / (ring + 1));
+}
 
 int order_after(seqa_ctx *c, cudaStream_t from, cudaStream_t to);
 
@@ -356,7 +371,7 @@ int build_plan(seqa_ctx *c)
             LAUNCH(c, (lensum_kernel), (unsigned)((n + 255) / 256), 256, 0, c->len1.p, c->len2.p, c->ops_len.p, n);
             LAUNCH(c, (scan_tile_sums_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, 0);
             LAUNCH(c, (scan_spine_kernel), 1, 1024, 0, c->tile_sum.p, (uint64_t)tiles, c->total.p);
-            LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, c->slot_off.p, 0);
+            LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, c->slot_off.p, 0, (uint64_t)0);
         }
     }
     CKS(c->score.ensure(n));
@@ -782,7 +797,10 @@ int finish_ops(seqa_ctx *c)
     const int pack = (c->prm.flags & SEQA_FLAG_OPS_2BIT) ? 1 : 0; // dense ops: 4 per byte, offsets in bytes
     LAUNCH(c, (scan_tile_sums_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, pack);
     LAUNCH(c, (scan_spine_kernel), 1, 1024, 0, c->tile_sum.p, (uint64_t)tiles, c->total.p);
-    LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, c->ops_off.p, pack);
+    // ops_off leaves the device already shifted by the wave's base inside the caller's ops buffer (one-shot pipeline): no
+    // fix-up kernel on the download stream, where it would queue behind the next wave's persistent fill
+    c->ops_base_applied = c->ops_base;
+    LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->ops_len.p, n, c->tile_sum.p, c->ops_off.p, pack, c->ops_base);
     GatherArgs G{};
     G.n_pairs = n;
     G.slots = c->slots.p;
@@ -790,7 +808,7 @@ int finish_ops(seqa_ctx *c)
     G.slot_start = c->slot_start.p;
     G.ops_len = c->ops_len.p;
     G.ops_off = c->ops_off.p;
-    G.dense = c->dense.p;
+    G.dense = c->dense.p - c->ops_base; // dense index = ops_off - base
     G.pack = pack;
     // 8 lanes per short pair; few long pairs get enough warps for their bytes (the kernel then spreads a pair over warps)
     const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>((n * 8 + 255) / 256, c->slots_total / 16384 + 1), (uint64_t)c->sms * 64);
@@ -807,6 +825,7 @@ int ctx_set_inputs_common(seqa_ctx *c, const seqa_params *params, uint64_t n)
     c->ran = false;
     c->generic_rerun = false;
     c->have_stats = false;
+    c->ops_base = 0;
     set_scoring(c);
     CKS(c->off1.ensure(n));
     CKS(c->off2.ensure(n));
@@ -815,10 +834,55 @@ int ctx_set_inputs_common(seqa_ctx *c, const seqa_params *params, uint64_t n)
     return SEQA_OK;
 }
 
+// What one pass over a whole batch establishes, so that the waves of the one-shot call need no per-pair host loops of
+// their own: every pair has the same shape, sequences lie back to back (seq1, seq2, next pair ...; byte-aligned sequences
+// in the 2-bit wire format), and the last pair ends inside `bases`.
+struct BatchFacts {
+    bool uniform = false, dense = false, in_bounds = false;
+};
+
+BatchFacts scan_batch_facts(const seqa_batch_in *in, bool two_bit)
+{
+    BatchFacts f;
+    const uint64_t n = in->n_pairs;
+    if (n == 0 || !in->off1 || !in->off2 || !in->len1 || !in->len2) return f;
+    const uint32_t M0 = in->len1[0], N0 = in->len2[0];
+    const uint64_t s1 = two_bit ? (uint64_t)((M0 + 3) >> 2) : (uint64_t)M0, s2 = two_bit ? (uint64_t)((N0 + 3) >> 2) : (uint64_t)N0;
+    const uint64_t first = in->off1[0], stride = s1 + s2;
+    const int threads = (int)std::min<uint64_t>(8, std::max<uint64_t>(1, n / 131072));
+    std::vector<char> ok((size_t)threads, 1);
+    auto part = [&](int t) {
+        const uint64_t lo = n * t / threads, hi = n * (t + 1) / threads;
+        unsigned diff = 0;
+        uint64_t bad = 0;
+        for (uint64_t p = lo; p < hi; p++) {
+            diff |= (in->len1[p] ^ M0) | (in->len2[p] ^ N0);
+            bad |= (in->off1[p] ^ (first + p * stride)) | (in->off2[p] ^ (first + p * stride + s1));
+        }
+        ok[(size_t)t] = (char)((diff == 0 ? 1 : 0) | (bad == 0 ? 2 : 0));
+    };
+    if (threads == 1) {
+        part(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < threads; t++) th.emplace_back(part, t);
+        part(0);
+        for (auto &x : th) x.join();
+    }
+    f.uniform = f.dense = true;
+    for (char v : ok) {
+        f.uniform &= (v & 1) != 0;
+        f.dense &= (v & 2) != 0;
+    }
+    f.dense &= f.uniform; // the closed form above only describes a uniform batch
+    f.in_bounds = first <= in->bases_len && n * stride <= in->bases_len - first;
+    return f;
+}
+
 // SEQA_FLAG_BASES_2BIT: `in->bases` holds 2-bit symbols (4 per byte, A0 C1 T2 G3, every sequence on a byte boundary;
 // off1 / off2 are BYTE offsets into it, len1 / len2 count symbols).  A quarter of the bytes cross PCIe; the device
 // expands them once into the one-byte-per-symbol dense layout every kernel reads (unpack2_kernel).
-int ctx_upload_range_2bit(seqa_ctx *c, const seqa_params *params, const seqa_batch_in *in, uint64_t pb, uint64_t pe)
+int ctx_upload_range_2bit(seqa_ctx *c, const seqa_params *params, const seqa_batch_in *in, uint64_t pb, uint64_t pe, const BatchFacts *facts)
 {
     const uint64_t n = pe - pb;
     CKS(ctx_set_inputs_common(c, params, n));
@@ -828,7 +892,15 @@ int ctx_upload_range_2bit(seqa_ctx *c, const seqa_params *params, const seqa_bat
     bool st_uni = true, dense = true; // dense: seq1 then seq2 of every pair, byte-aligned, pairs back to back
     const uint32_t M0 = n ? in->len1[pb] : 0, N0 = n ? in->len2[pb] : 0;
     const uint64_t first_off = n ? in->off1[pb] : 0;
-    for (uint64_t p = pb; p < pe; p++) {
+    const bool known = facts && facts->uniform && facts->dense && facts->in_bounds && n > 0; // established once for the whole batch
+    if (known) {
+        const uint64_t stride = (uint64_t)((M0 + 3) >> 2) + ((N0 + 3) >> 2);
+        lo = first_off;
+        hi = first_off + n * stride;
+        st_cells = n * (uint64_t)M0 * N0;
+        st_slots = n * ((uint64_t)M0 + N0);
+    }
+    for (uint64_t p = pb; p < pe && !known; p++) {
         const uint64_t l1 = in->len1[p], l2 = in->len2[p], B1 = (l1 + 3) >> 2, B2 = (l2 + 3) >> 2;
         const uint64_t a0 = in->off1[p], b0 = in->off2[p];
         if (a0 > in->bases_len || B1 > in->bases_len - a0 || b0 > in->bases_len || B2 > in->bases_len - b0)
@@ -890,7 +962,7 @@ int ctx_upload_range_2bit(seqa_ctx *c, const seqa_params *params, const seqa_bat
         LAUNCH(c, (packed_bytes_kernel), (unsigned)((n + 255) / 256), 256, 0, c->len1.p, c->len2.p, c->start_i.p, n); // start_i: scratch until the walk
         LAUNCH(c, (scan_tile_sums_kernel), tiles, SEQA_SCAN_TPB, 0, c->start_i.p, n, c->tile_sum.p, 0);
         LAUNCH(c, (scan_spine_kernel), 1, 1024, 0, c->tile_sum.p, (uint64_t)tiles, c->total.p);
-        LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->start_i.p, n, c->tile_sum.p, c->poff1.p, 0);
+        LAUNCH(c, (scan_apply_kernel), tiles, SEQA_SCAN_TPB, 0, c->start_i.p, n, c->tile_sum.p, c->poff1.p, 0, (uint64_t)0);
         U.poff1 = c->poff1.p;
     }
     const unsigned blocks = (unsigned)std::min<uint64_t>((2 * n * 32 + 255) / 256, (uint64_t)c->sms * 64);
@@ -900,7 +972,7 @@ int ctx_upload_range_2bit(seqa_ctx *c, const seqa_params *params, const seqa_bat
 }
 
 // upload pairs [pb, pe) of `in`; device offsets are rebased to the byte range the shard touches
-int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in *in, uint64_t pb, uint64_t pe)
+int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in *in, uint64_t pb, uint64_t pe, const BatchFacts *facts = nullptr)
 {
     if (!in) return fail(SEQA_ERR_INVALID, "batch is NULL");
     const uint64_t n = pe - pb;
@@ -908,7 +980,25 @@ int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in
         return fail(SEQA_ERR_INVALID, "batch has NULL arrays");
     if (n > 0xfffffff0ull) return fail(SEQA_ERR_UNSUPPORTED, "more than 2^32-16 pairs per device shard");
     CK(cudaSetDevice(c->device));
-    if (params && (params->flags & SEQA_FLAG_BASES_2BIT)) return ctx_upload_range_2bit(c, params, in, pb, pe);
+    // Pipelined one-shot call: the planning kernels (length sums, scans, offsets, 2-bit unpack) go to the UPLOAD stream,
+    // behind the copies they read, so that they run beside the previous wave's kernels instead of between two waves on
+    // the compute stream; the compute stream waits once for everything (order_after below).
+    struct PlanOnUploadStream {
+        seqa_ctx *c;
+        cudaStream_t saved;
+        explicit PlanOnUploadStream(seqa_ctx *cx) : c(cx), saved(cx->stream) { c->stream = c->up; }
+        ~PlanOnUploadStream() { c->stream = saved; }
+    };
+    if (c->up != c->stream) {
+        int rc;
+        {
+            PlanOnUploadStream swap(c);
+            rc = ctx_upload_range(c, params, in, pb, pe, facts);
+        }
+        if (rc == SEQA_OK) rc = order_after(c, c->up, c->stream);
+        return rc;
+    }
+    if (params && (params->flags & SEQA_FLAG_BASES_2BIT)) return ctx_upload_range_2bit(c, params, in, pb, pe, facts);
     const bool dbgt = getenv("SEQA_DEBUG_TIMING") != nullptr;
     const auto tu0 = std::chrono::steady_clock::now();
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
@@ -919,7 +1009,14 @@ int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in
     bool st_uni = true, dense = true; // dense: seq1 then seq2 of every pair, pairs back to back from the first offset on
     const uint32_t M0 = n ? in->len1[pb] : 0, N0 = n ? in->len2[pb] : 0;
     const uint64_t first_off = n ? in->off1[pb] : 0;
-    for (uint64_t p = pb; p < pe; p++) {
+    const bool known = facts && facts->uniform && facts->dense && facts->in_bounds && n > 0; // established once for the whole batch
+    if (known) {
+        lo = first_off;
+        hi = first_off + n * ((uint64_t)M0 + N0);
+        st_cells = n * (uint64_t)M0 * N0;
+        st_slots = n * ((uint64_t)M0 + N0);
+    }
+    for (uint64_t p = pb; p < pe && !known; p++) {
         const uint64_t l1 = in->len1[p], l2 = in->len2[p];
         const uint64_t a0 = in->off1[p], a1 = a0 + l1, b0 = in->off2[p], b1 = b0 + l2;
         if (a0 > in->bases_len || l1 > in->bases_len - a0 || b0 > in->bases_len || l2 > in->bases_len - b0) // no wrap-around
@@ -1044,13 +1141,14 @@ int ctx_download_into(seqa_ctx *c, seqa_batch_out *out, uint64_t pb, uint64_t op
     if (ops_base + total > out->ops_capacity)
         return fail(SEQA_ERR_CAPACITY, "ops_capacity %llu < %llu needed", (unsigned long long)out->ops_capacity,
                     (unsigned long long)(ops_base + total));
-    if (ops_base) { c->launches++; SEQA_LAUNCH((add_base_kernel), (unsigned)((n + 255) / 256), 256, 0, c->down, c->ops_off.p, n, ops_base); }
+    const uint64_t delta = ops_base - c->ops_base_applied; // 0 when the run already placed ops_off (one-shot pipeline)
+    if (delta) { c->launches++; SEQA_LAUNCH((add_base_kernel), (unsigned)((n + 255) / 256), 256, 0, c->down, c->ops_off.p, n, delta); }
     CK(cudaMemcpyAsync(out->start_i + pb, c->start_i.p, n * 4, cudaMemcpyDeviceToHost, c->down));
     CK(cudaMemcpyAsync(out->start_j + pb, c->start_j.p, n * 4, cudaMemcpyDeviceToHost, c->down));
     CK(cudaMemcpyAsync(out->ops_len + pb, c->ops_len.p, n * 4, cudaMemcpyDeviceToHost, c->down));
     CK(cudaMemcpyAsync(out->ops_off + pb, c->ops_off.p, n * 8, cudaMemcpyDeviceToHost, c->down));
     if (total) CK(cudaMemcpyAsync(out->ops + ops_base, c->dense.p, total, cudaMemcpyDeviceToHost, c->down));
-    if (ops_base) { c->launches++; SEQA_LAUNCH((add_base_kernel), (unsigned)((n + 255) / 256), 256, 0, c->down, c->ops_off.p, n, (uint64_t)0 - ops_base); } // restore: a second download stays valid
+    if (delta) { c->launches++; SEQA_LAUNCH((add_base_kernel), (unsigned)((n + 255) / 256), 256, 0, c->down, c->ops_off.p, n, (uint64_t)0 - delta); } // restore: a second download stays valid
     CK(cudaStreamSynchronize(c->down));
     *ops_used = total;
     return SEQA_OK;
@@ -1254,10 +1352,11 @@ int seqa_ctx_download_range(seqa_ctx *c, uint64_t first, uint64_t count, seqa_ba
     uint64_t end = c->h_tail.p[0]; // dense bytes of the whole batch (ctx_resolve fetched it)
     if (first + count < c->n) CK(cudaMemcpyAsync(&end, c->ops_off.p + first + count, 8, cudaMemcpyDeviceToHost, c->down));
     CK(cudaStreamSynchronize(c->down));
+    if (first + count == c->n) end += c->ops_base_applied;
     const uint64_t base = out->ops_off[0], bytes = end - base;
     if (bytes > out->ops_capacity)
         return fail(SEQA_ERR_CAPACITY, "ops_capacity %llu < %llu needed", (unsigned long long)out->ops_capacity, (unsigned long long)bytes);
-    if (bytes) CK(cudaMemcpyAsync(out->ops, c->dense.p + base, bytes, cudaMemcpyDeviceToHost, c->down));
+    if (bytes) CK(cudaMemcpyAsync(out->ops, c->dense.p + (base - c->ops_base_applied), bytes, cudaMemcpyDeviceToHost, c->down));
     for (uint64_t k = 0; k < count; k++) out->ops_off[k] -= base;
     CK(cudaStreamSynchronize(c->down));
     out->ops_used = bytes;
@@ -1407,6 +1506,8 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
     if (!in->len1 || !in->len2) return fail(SEQA_ERR_INVALID, "batch has NULL arrays");
     if ((uint64_t)nd > n) nd = (int)n;
 
+    // one (threaded) pass over the index arrays: uniform shape? dense layout? inside `bases`?  The waves then skip their own loops
+    const BatchFacts facts = scan_batch_facts(in, (params->flags & SEQA_FLAG_BASES_2BIT) != 0);
     // waves: contiguous, ~3e9 cells or 256k pairs each; linear-space pairs (huge sweeps) go one wave per 4e10 cells
     const bool linspace = params->algo == SEQA_HIRSCHBERG || params->algo == SEQA_MYERS_MILLER;
     const uint64_t wave_cells = linspace ? 40000000000ull : (uint64_t)env_int("SEQA_WAVE_MCELLS", 3000, 10, 100000) * 1000000ull;
@@ -1414,16 +1515,11 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
     uint64_t tot = 0;
     {
         uint64_t acc = 0, slots = 0, cnt = 0;
+        std::vector<uint64_t> sched; // explicit wave sizes (uniform packed batch on one device), else empty
         // several devices: at least two waves per device even for small batches
         uint64_t maxcnt = nd > 1 ? std::min<uint64_t>(262144, std::max<uint64_t>(1, (n + 2 * nd - 1) / (2 * nd))) : 262144;
         const uint32_t *l1 = in->len1, *l2 = in->len2;
-        bool uni = true; // every pair the same shape: one cheap pass, then the waves are plain arithmetic
-        {
-            const uint32_t M0 = l1[0], N0 = l2[0];
-            unsigned diff = 0;
-            for (uint64_t p = 0; p < n; p++) diff |= (l1[p] ^ M0) | (l2[p] ^ N0);
-            uni = diff == 0;
-        }
+        const bool uni = facts.uniform; // every pair the same shape: the waves are plain arithmetic
         // Uniform batch on the packed kernels: cut waves at whole "rounds" of the fill kernel (one 64-pair job per
         // resident warp), otherwise every wave pays a mostly idle last round.
         if (uni && !linspace && n > 1 && packed_scoring_ok(*params) && packed_shape_ok(*params, l1[0], l2[0])) {
@@ -1448,6 +1544,22 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
                 // download of consecutive waves overlap); else keep the per-device cap, cut down to whole rounds
                 if (round * rounds * 2 * (uint64_t)nd <= n) maxcnt = std::min<uint64_t>(n, round * rounds);
                 else if (nd > 1 && maxcnt > round) maxcnt = maxcnt / round * round;
+                // One device, several rounds, no explicit SEQA_WAVE_MCELLS: a ONE-round first wave (its upload is all that
+                // delays the first kernel), then waves of SEQA_WAVE_ROUNDS rounds (default 2: two rounds of the fill are exactly
+                // one full wave of walk CTAs -- three leave the walk a half-empty second wave, measured 8.6 against 8.35 ms per
+                // 1 M x 150 bp) -- per-wave costs and the half-empty walk of one-round waves shrink; the last wave's walk,
+                // gather and download are the tail.
+                if (nd == 1 && !getenv("SEQA_WAVE_MCELLS") && n > 2 * round) {
+                    const uint64_t mid = (uint64_t)env_int("SEQA_WAVE_ROUNDS", 2, 1, 64);
+                    uint64_t left = n - std::min(n, round);
+                    sched.push_back(std::min(n, round));
+                    while (left > 0) {
+                        uint64_t take = std::min(left, mid * round);
+                        if (left - take > 0 && left - take < round / 2) take = left; // no sliver at the end
+                        sched.push_back(take);
+                        left -= take;
+                    }
+                }
             }
         }
         wave_lo.push_back(0);
@@ -1455,7 +1567,9 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
         if (uni) {
             const uint64_t cells1 = (uint64_t)l1[0] * l2[0] + 1, slots1 = (uint64_t)l1[0] + l2[0];
             uint64_t per = maxcnt < 262144 ? maxcnt : std::min<uint64_t>(maxcnt, std::max<uint64_t>(1, (wave_cells + cells1 - 1) / cells1));
+            size_t k = 0;
             for (uint64_t p = 0; p < n; p += per) {
+                if (!sched.empty()) per = sched[std::min(k++, sched.size() - 1)];
                 const uint64_t q = std::min(n, p + per);
                 if (p) {
                     wave_lo.push_back(p);
@@ -1522,7 +1636,10 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
     // planning of wave k+1, the kernels of wave k and the device->host copy of wave k-1 overlap, and the device
     // queue is fed in wave order.
     const int ring = env_int("SEQA_RING", 4, 2, SEQA_CACHE_SLOTS);
-    const bool one_comp = getenv("SEQA_ONE_COMPUTE_STREAM") != nullptr;
+    // kernels of consecutive waves on ONE stream by default: with two, the next wave's persistent fill and this wave's
+    // walk fight for the same SMs and both lose (measured: 7.6 ms of kernel time per 1 M x 150 bp pairs against 6.6 ms
+    // back to back, profiles/r02_e2e_timelines.txt); SEQA_TWO_COMPUTE_STREAMS=1 restores the even/odd streams
+    const bool one_comp = getenv("SEQA_TWO_COMPUTE_STREAMS") == nullptr;
     struct DevPipe {
         std::mutex mu;
         std::condition_variable cv;
@@ -1551,7 +1668,7 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
             if (!P.c[slot]) {
                 s = cache_acquire(first + d, &P.c[slot], &P.cached[slot]);
                 if (s == SEQA_OK) {
-                    const size_t b = free_budget(ring);
+                    const size_t b = ring_budget(first + d, ring);
                     if (!P.c[slot]->budget || P.c[slot]->budget > b) P.c[slot]->budget = b;
                 }
                 if (s == SEQA_OK && P.st[0]) {
@@ -1572,12 +1689,13 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
                 }
                 cudaEventRecord(wev[w].e[0], P.c[slot]->up);
             }
-            if (s == SEQA_OK) s = ctx_upload_range(P.c[slot], params, in, wave_lo[w], wave_lo[w + 1]);
+            if (s == SEQA_OK) s = ctx_upload_range(P.c[slot], params, in, wave_lo[w], wave_lo[w + 1], &facts);
             if (dbg && s == SEQA_OK) {
                 cudaEventRecord(wev[w].e[1], P.c[slot]->up);
                 cudaEventRecord(wev[w].e[2], P.c[slot]->stream);
             }
             const double t1 = since();
+            if (s == SEQA_OK) P.c[slot]->ops_base = wave_ops_base(w);
             if (s == SEQA_OK) s = ctx_run(P.c[slot]);
             if (dbg && s == SEQA_OK) cudaEventRecord(wev[w].e[3], P.c[slot]->stream);
             if (dbg) fprintf(stderr, "[seqa] dev %d wave %zu: upload+plan %.2f..%.2f launched ..%.2f ms\n", d, w, t0, t1, since());
@@ -1691,7 +1809,7 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
             rc = cache_acquire(first + d, &c, &cached);
             for (size_t w = dev_lo[d]; w < dev_lo[d + 1] && rc == SEQA_OK; w++) {
                 uint64_t u = 0;
-                rc = ctx_upload_range(c, params, in, wave_lo[w], wave_lo[w + 1]);
+                rc = ctx_upload_range(c, params, in, wave_lo[w], wave_lo[w + 1], &facts);
                 if (rc == SEQA_OK) rc = ctx_run(c);
                 if (rc == SEQA_OK) rc = ctx_download_into(c, out, wave_lo[w], used, &u);
                 used += u;

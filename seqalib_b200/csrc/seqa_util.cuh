@@ -67,9 +67,10 @@ __global__ void __launch_bounds__(1024) scan_spine_kernel(uint64_t *__restrict__
 
 __global__ void __launch_bounds__(SEQA_SCAN_TPB) scan_apply_kernel(const uint32_t *__restrict__ in, uint64_t n,
                                                                   const uint64_t *__restrict__ tile_off,
-                                                                  uint64_t *__restrict__ out, int pack)
+                                                                  uint64_t *__restrict__ out, int pack, uint64_t add)
 {
-    // thread t owns the IPT consecutive items [base + t*IPT, +IPT)
+    // thread t owns the IPT consecutive items [base + t*IPT, +IPT); `add` is added to every output (a wave's base offset
+    // inside the caller's ops buffer)
     __shared__ uint64_t wsum[SEQA_SCAN_TPB / 32];
     const uint64_t base = (uint64_t)blockIdx.x * SEQA_SCAN_TILE + (uint64_t)threadIdx.x * SEQA_SCAN_IPT;
     uint32_t v[SEQA_SCAN_IPT];
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(SEQA_SCAN_TPB) scan_apply_kernel(const uint32_
     __syncthreads();
     uint64_t woff = 0;
     for (int w = 0; w < warp; w++) woff += wsum[w];
-    uint64_t run = tile_off[blockIdx.x] + woff + inc - s;
+    uint64_t run = tile_off[blockIdx.x] + woff + inc - s + add;
 #pragma unroll
     for (int k = 0; k < SEQA_SCAN_IPT; k++) {
         if (base + k < n) out[base + k] = run;

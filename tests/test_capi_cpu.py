@@ -138,3 +138,31 @@ def test_multi_device_split_is_balanced(emu_lib):
     assert split.max() / split.mean() < 1.10, split
     o = orc.oracle_align("sw", orc.Scoring.linear(-1, 1, -1), *pairs[0])
     assert (res.score[:n] == o["score"]).all()
+
+
+def test_wave_schedule_of_uniform_batches(emu_lib, monkeypatch):
+    """One-shot call on a uniform batch larger than two rounds of the fill kernel (emulator: 1,536 pairs per round): a
+    one-round first wave, multi-round waves behind it, ops of every wave at its own base offset -- results must not
+    depend on the schedule (SEQA_WAVE_ROUNDS 1 / default, both wire formats, explicit SEQA_WAVE_MCELLS)."""
+    rng = np.random.default_rng(77)
+    n, L = 5000, 10
+    codes = rng.integers(0, 4, (n, 2 * L))
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)[codes].reshape(-1).copy()
+    off1 = np.arange(n, dtype=np.uint64) * np.uint64(2 * L)
+    off2 = off1 + np.uint64(L)
+    l1 = np.full(n, L, np.uint32)
+    l2 = np.full(n, L, np.uint32)
+    sc = orc.Scoring.linear(-1, 1, -1)
+    want = orc.oracle_align_batch("sw", sc, bases, off1, off2, l1, l2)
+    pk, p1, p2 = capi.pack_bases_2bit(bases, off1, off2, l1, l2)
+    for env in ({}, {"SEQA_WAVE_ROUNDS": "1"}, {"SEQA_WAVE_MCELLS": "10"}, {"SEQA_TWO_COMPUTE_STREAMS": "1"}):
+        for k in ("SEQA_WAVE_ROUNDS", "SEQA_WAVE_MCELLS", "SEQA_TWO_COMPUTE_STREAMS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for flags, ins in ((0, (bases, off1, off2, l1, l2)), (capi.FLAG_OPS_2BIT | capi.FLAG_BASES_2BIT, (pk, p1, p2, l1, l2))):
+            got = emu_lib.align_batch(scoring_to_params("sw", sc, flags=flags), *ins)
+            for name in ("score", "start_i", "start_j", "end_i", "end_j", "ops_len"):
+                assert np.array_equal(getattr(got, name)[:n], getattr(want, name)[:n]), (env, flags, name)
+            for p in list(range(0, n, 97)) + [1535, 1536, 1537, n - 1]:
+                assert np.array_equal(got.pair_ops(p), want.pair_ops(p)), (env, flags, p)
