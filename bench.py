@@ -405,7 +405,7 @@ def run_secondary_configs(args, lib, capi, torch, dist, local, rank, world, stre
         ms = max(ms_all)
         tot_cells = sum(cells_all)
         f_clk = (clocks.get("sm_mhz") or f_max_mhz) * 1e6
-        p_int = 148 * 128 * f_clk
+        p_int = 148 * 128 * f_clk * world  # the N GPUs of the job
         gcups = tot_cells / (ms * 1e-3) / 1e9
         fill_gcups = tot_cells / (max(fill_all) * 1e-3) / 1e9 if max(fill_all) > 0 else None
         entries.append({"config": name, "algo": algo, "scoring": list(sc.astuple()), "pairs": int(total_pairs), "cells": tot_cells,
