@@ -697,7 +697,7 @@ struct LsState {
     LsTask *d_tasks = nullptr;
     int *d_prog = nullptr;
     uint64_t task_cap = 0, sum_blocks = 0, cap_tasks = 0;
-    int sweep_blocks = 0, sweep2_blocks = 0;
+    int sweep_blocks = 0, sweep2_blocks = 0, sweep2_blocks_hb = 0;
     int *d_rows = nullptr;
     uint64_t *d_row_off = nullptr;
     uint32_t *d_row_w = nullptr;

@@ -98,7 +98,7 @@ int ls_plan(seqa_ctx *c, const std::vector<uint32_t> &len1, const std::vector<ui
     if (!ls.d_overflow) CKS(ls_alloc(&ls.d_overflow, 1));
     if (!ls.sweep_blocks) {
 #ifdef SEQA_EMU
-        ls.sweep_blocks = ls.sweep2_blocks = sms;
+        ls.sweep_blocks = ls.sweep2_blocks = ls.sweep2_blocks_hb = sms;
 #else
         int nb_hb = 0, nb_mm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_hb, ls_sweep_kernel<false>, LS_BLOCK, 0));
@@ -106,7 +106,11 @@ int ls_plan(seqa_ctx *c, const std::vector<uint32_t> &len1, const std::vector<ui
         ls.sweep_blocks = sms * std::max(1, std::min(nb_hb, nb_mm));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_hb, ls_sweep2_kernel<false>, LS_BLOCK, 0));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_mm, ls_sweep2_kernel<true>, LS_BLOCK, 0));
-        ls.sweep2_blocks = sms * std::max(1, std::min(nb_hb, nb_mm));
+        // per variant: Hirschberg's 72-80 registers leave room for more resident warps than MyersMiller's 96-116
+        // (round 1 launched both with the smaller of the two: 16 warps per SM, 23 % of the slots)
+        const int bps = env_int("SEQA_LS_BPS", 0, 0, 16);
+        ls.sweep2_blocks_hb = sms * std::max(1, bps ? bps : nb_hb);
+        ls.sweep2_blocks = sms * std::max(1, bps ? bps : nb_mm);
 #endif
     }
     if (n) {
@@ -194,7 +198,7 @@ int ls_run(seqa_ctx *c, bool want_ops)
         } else {
             LAUNCH(c, (ls_expand_kernel<false>), egrid, 128, 0, A);
             if (A.packed)
-                LAUNCH(c, (ls_sweep2_kernel<false>), (unsigned)ls.sweep2_blocks, LS_BLOCK, 0, A);
+                LAUNCH(c, (ls_sweep2_kernel<false>), (unsigned)ls.sweep2_blocks_hb, LS_BLOCK, 0, A);
             else
                 LAUNCH(c, (ls_sweep_kernel<false>), (unsigned)ls.sweep_blocks, LS_BLOCK, 0, A);
             LAUNCH(c, (ls_split_kernel<false>), egrid, 128, 0, A);

@@ -283,8 +283,15 @@ __device__ __forceinline__ void ls_run_task2(const LsArgs &A, const LsSweep &S, 
                                outXr, out_prog, sm);
 }
 
+// resident CTAs per SM the two variants are compiled for (register caps 65536 / (LS_BLOCK * n)); measured, DESIGN.md 4.5
+#ifndef LS2_MINB_HB
+#define LS2_MINB_HB 6
+#endif
+#ifndef LS2_MINB_MM
+#define LS2_MINB_MM 4
+#endif
 template <bool MM>
-__global__ void __launch_bounds__(LS_BLOCK) ls_sweep2_kernel(LsArgs A)
+__global__ void __launch_bounds__(LS_BLOCK, MM ? LS2_MINB_MM : LS2_MINB_HB) ls_sweep2_kernel(LsArgs A)
 {
     __shared__ uint2 smem[LS_BLOCK / 32][LS2_SMEM_INTS / 2]; // uint2: the profile ring needs 8-byte alignment
     const int lane = threadIdx.x & 31;
