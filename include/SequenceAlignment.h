@@ -264,6 +264,54 @@ inline bool pack2bit(const char *S, size_t Len, uint8_t *Dst)
     return Bad == 0;
 }
 
+// Is the matching functor an EQUIVALENCE on the 8-bit symbols -- F(a,b) == (class[a] == class[b]), with symbols that do not
+// even match themselves in a "matches nothing" class?  Then it is table-driven equality (seqa_batch_in.sym_class) and runs
+// on the GPU path: case-insensitive comparison, purine / pyrimidine, amino-acid groups, 'N' that matches nothing...
+// Checked exhaustively (65,536 + at most 65,536 calls, once per aligner).  Returns 0 (no), 1 (plain equality: no table
+// needed) or 2 (Table holds the classes).
+template <typename Ty, typename Fn> inline int classify_functor(Fn &F, std::vector<uint8_t> &Table)
+{
+    auto Sym = [](int V) { return static_cast<Ty>(static_cast<unsigned char>(V)); };
+    Table.assign(256, 0);
+    int Rep[256], Classes = 0;
+    bool Identity = true;
+    for (int A = 0; A < 256; A++) {
+        if (!F(Sym(A), Sym(A))) {
+            Table[A] = (uint8_t)SEQA_CLASS_NEVER;
+            Identity = false;
+            continue;
+        }
+        int K = -1;
+        for (int C = 0; C < Classes && K < 0; C++)
+            if (F(Sym(A), Sym(Rep[C]))) K = C;
+        if (K < 0) {
+            if (Classes == 254) { // more classes than ids: only plain equality has that many
+                K = Classes; // keep counting to tell equality apart below
+            } else {
+                Rep[Classes] = A;
+                K = Classes++;
+            }
+        } else {
+            Identity = false;
+        }
+        if (K >= 254) {
+            if (!Identity) return 0;
+            continue;
+        }
+        Table[A] = (uint8_t)K;
+    }
+    if (Identity) { // candidates: every symbol alone in its class -> must be == on all pairs
+        for (int A = 0; A < 256; A++)
+            for (int B = 0; B < 256; B++)
+                if (F(Sym(A), Sym(B)) != (A == B)) return 0;
+        return 1;
+    }
+    for (int A = 0; A < 256; A++)
+        for (int B = 0; B < 256; B++)
+            if (F(Sym(A), Sym(B)) != (Table[A] == Table[B] && Table[A] != (uint8_t)SEQA_CLASS_NEVER)) return 0;
+    return 2;
+}
+
 template <typename Fn> inline bool is_null_functor(const Fn &) { return false; }
 template <typename R, typename... A> inline bool is_null_functor(const std::function<R(A...)> &F) { return !F; }
 template <typename R, typename... A> inline bool is_null_functor(R (*F)(A...)) { return F == nullptr; }
@@ -277,7 +325,8 @@ template <typename ContainerType, typename Ty = typename ContainerType::value_ty
 class SequenceAligner {
     ScoringSystem Scoring;
     MatchFnTy Match;
-    int EqualityChecked = -1; // -1 unknown, 0 not equality, 1 equality / nullptr
+    int EqualityChecked = -1;        // -1 unknown, 0 not usable on the GPU path, 1 equality / nullptr, 2 class table
+    std::vector<uint8_t> ClassTable; // EqualityChecked == 2: seqa_batch_in.sym_class
     // page-locked staging, reused from call to call: packed inputs (indices, symbols) and the result block, which is
     // recycled only once the caller has dropped every PackedAlignments that still points into it
     std::shared_ptr<seqa::PinnedBlock> IdxBlock, BasesBlock, OutBlock;
@@ -325,10 +374,11 @@ class SequenceAligner {
     void requireGpuEligible()
     {
         if (EqualityChecked < 0)
-            EqualityChecked = (seqa::detail::is_null_functor(Match) || seqa::detail::is_equality_on_bytes<Ty>(Match)) ? 1 : 0;
+            EqualityChecked = seqa::detail::is_null_functor(Match) ? 1 : seqa::detail::classify_functor<Ty>(Match, ClassTable);
         if (!EqualityChecked)
-            throw std::invalid_argument("seqalib_b200: the GPU path compares symbols with ==; custom matching functors are "
-                                        "reference-only (see include/SequenceAlignment.h)");
+            throw std::invalid_argument("seqalib_b200: the GPU path compares symbols with == or through a class table; matching "
+                                        "functors that are not an equivalence on the 8-bit symbols are reference-only (see "
+                                        "include/SequenceAlignment.h)");
     }
 
     // First(P) / Second(P) return the two sequences of pair P (no pointer vectors are built for a million pairs)
@@ -374,7 +424,7 @@ class SequenceAligner {
         BasesBlock->reserve(Total + 64); // large enough for either wire format
         char *Bases = BasesBlock->P;
         std::vector<char> ThreadOk(Threads, 1);
-        bool TwoBitIn = !ForceByteInputs;
+        bool TwoBitIn = !ForceByteInputs && EqualityChecked != 2; // a class table is applied to 8-bit symbols
         if (TwoBitIn) {
             seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) { // byte offsets + packed symbols
                 uint64_t Run = PartBytes[T];
@@ -414,7 +464,8 @@ class SequenceAligner {
         Prm.device_first = 0;
         Prm.device_count = 0; // every visible device
         Prm.flags = SEQA_FLAG_OPS_2BIT | (TwoBitIn ? SEQA_FLAG_BASES_2BIT : 0u); // a quarter of the bytes over PCIe, both ways
-        seqa_batch_in In{Bases, Off1, Off2, Len1, Len2, (uint64_t)N, TwoBitIn ? TotalPacked : Total};
+        seqa_batch_in In{Bases, Off1, Off2, Len1, Len2, (uint64_t)N, TwoBitIn ? TotalPacked : Total,
+                         EqualityChecked == 2 ? ClassTable.data() : nullptr};
         // ---- results: one page-locked block; the previous one is reused once nobody else holds it ----
         const size_t OpsCap = (size_t)(Total / 4 + N + 1);
         if (!OutBlock || OutBlock.use_count() > 1) OutBlock = std::make_shared<seqa::PinnedBlock>();
@@ -455,7 +506,7 @@ class SequenceAligner {
         for (uint32_t K = 0; K < R.OpsLen[P]; K++) {
             const unsigned Op = R.op(P, K);
             if (Op == SEQA_OP_DIAG) {
-                Res.Data.emplace_back(Seq1[I], Seq2[J], Seq1[I] == Seq2[J]);
+                Res.Data.emplace_back(Seq1[I], Seq2[J], EqualityChecked == 2 ? (bool)Match(Seq1[I], Seq2[J]) : Seq1[I] == Seq2[J]);
                 I++, J++;
             } else if (Op == SEQA_OP_UP) {
                 Res.Data.emplace_back(Seq1[I], Blank, false);

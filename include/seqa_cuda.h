@@ -114,7 +114,16 @@ typedef struct seqa_batch_in {
     const uint32_t *len2;
     uint64_t n_pairs;
     uint64_t bases_len; /* total bytes addressable through `bases` */
+    /* Table-driven symbol equality, optional: NULL = symbols match iff they are the same byte.
+     * Else 256 entries: two symbols a, b match iff sym_class[a] == sym_class[b] and that class is not SEQA_CLASS_NEVER --
+     * the matching functors that ARE an equivalence on bytes (case-insensitive letters, purine / pyrimidine, amino-acid
+     * groups; 'N' that matches nothing: SEQA_CLASS_NEVER) without a functor call per cell (the reference evaluates
+     * match(a, b) per cell, include/SequenceAlignment.h:147 and e.g. include/SANeedlemanWunsch.h:22-38).  Class ids are
+     * 0..253.  The device replaces every symbol by a representative of its class once; the classes of 'A', 'C', 'G', 'T'
+     * keep the packed s16x2 kernels, pairs holding any other class run on the 8-bit kernels (pair by pair). */
+    const uint8_t *sym_class;
 } seqa_batch_in;
+#define SEQA_CLASS_NEVER 255u
 
 /*
  * Results, one entry per pair (arrays of n_pairs elements; any of the start/end/ops arrays may be NULL when

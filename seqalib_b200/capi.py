@@ -98,7 +98,7 @@ class Params(C.Structure):
 
 class BatchIn(C.Structure):
     _fields_ = [("bases", C.c_void_p), ("off1", C.c_void_p), ("off2", C.c_void_p), ("len1", C.c_void_p),
-                ("len2", C.c_void_p), ("n_pairs", C.c_uint64), ("bases_len", C.c_uint64)]
+                ("len2", C.c_void_p), ("n_pairs", C.c_uint64), ("bases_len", C.c_uint64), ("sym_class", C.c_void_p)]
 
 
 class BatchOut(C.Structure):
@@ -194,17 +194,18 @@ class Lib(object):
         return buf[:nd].copy()
 
     @staticmethod
-    def batch_in(bases, off1, off2, len1, len2):
+    def batch_in(bases, off1, off2, len1, len2, sym_class=None):
+        """sym_class: optional uint8[256] class table (seqa_batch_in.sym_class); the caller keeps it alive during the call"""
         return BatchIn(bases.ctypes.data, off1.ctypes.data, off2.ctypes.data, len1.ctypes.data, len2.ctypes.data,
-                       len(len1), len(bases))
+                       len(len1), len(bases), sym_class.ctypes.data if sym_class is not None else None)
 
-    def align_batch(self, params, bases, off1, off2, len1, len2, results=None):
+    def align_batch(self, params, bases, off1, off2, len1, len2, results=None, sym_class=None):
         """seqa_cuda_align_batch: host arrays in (numpy, C-contiguous), Results out."""
         n = len(len1)
         if results is None:
             cap = int(len1.astype(np.uint64).sum() + len2.astype(np.uint64).sum())
             results = Results(n, cap)
-        bi = self.batch_in(bases, off1, off2, len1, len2)
+        bi = self.batch_in(bases, off1, off2, len1, len2, sym_class)
         self.check(self.L.seqa_cuda_align_batch(C.byref(params), C.byref(bi), C.byref(results.c)))
         results.packed2 = bool(params.flags & FLAG_OPS_2BIT)
         return results
@@ -231,8 +232,8 @@ class Ctx(object):
         except Exception:
             pass
 
-    def upload(self, params, bases, off1, off2, len1, len2):
-        bi = Lib.batch_in(bases, off1, off2, len1, len2)
+    def upload(self, params, bases, off1, off2, len1, len2, sym_class=None):
+        bi = Lib.batch_in(bases, off1, off2, len1, len2, sym_class)
         self.lib.check(self.lib.L.seqa_ctx_upload(self.h, C.byref(params), C.byref(bi)))
         self.flags = int(params.flags)
         self.n = len(len1)

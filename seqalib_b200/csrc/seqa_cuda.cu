@@ -190,7 +190,14 @@ struct seqa_ctx {
     DBuf<uint32_t> d_ub;
 
     DBuf<uint8_t> scratch; // trace / direction matrices (+ profiles) of one chunk
-    bool generic_rerun = false;
+    // pairs the packed path met a non-ACGT symbol in: flagged by pk_prep_kernel, re-run on the 8-bit kernels one by one
+    // and kept off the packed path for later runs of the same resident batch
+    DBuf<uint8_t> badpair;
+    DBuf<uint32_t> d_badidx, d_badcnt;
+    std::vector<uint8_t> forced_generic; // per pair, empty = none
+    bool resolved = false;               // the last run's flagged pairs have been dealt with
+    bool replan = false;                 // build_plan is re-planning a batch whose slots / result arrays exist already
+    bool all_generic = false;            // linear-space path only: the batch holds non-ACGT symbols
 
     uint64_t ops_base = 0, ops_base_applied = 0; // offset added to ops_off by the next run / by the last run
     uint64_t launches = 0;
@@ -329,6 +336,50 @@ size_t ring_budget(int device, int ring)
 
 int order_after(seqa_ctx *c, cudaStream_t from, cudaStream_t to);
 
+// generic jobs (one warp per pair) for the pairs listed in c->gidx: direction-matrix offsets, chunks, uploads
+int plan_generic(seqa_ctx *c)
+{
+    const seqa_params &prm = c->prm;
+    const size_t budget = c->budget;
+    c->gdir_off.clear();
+    c->g_chunks.clear();
+    c->g_max_n = 0;
+    if (!c->gidx.empty()) {
+        const bool affine = prm.algo == SEQA_GLOBAL_GOTOH || prm.algo == SEQA_LOCAL_GOTOH;
+        c->gdir_off.resize(c->gidx.size());
+        Chunk ch{0, 0, 0};
+        uint64_t words = 0;
+        for (size_t k = 0; k < c->gidx.size(); k++) {
+            const uint32_t p = c->gidx[k];
+            const uint64_t wds = dir_words((int)c->hlen1[p], (int)c->hlen2[p], GEN_R, affine);
+            if (wds * 4 > budget)
+                return fail(SEQA_ERR_NOMEM, "pair %u (%u x %u) needs a %llu-byte direction matrix: use Hirschberg/MyersMiller",
+                            p, c->hlen1[p], c->hlen2[p], (unsigned long long)(wds * 4));
+            if (ch.hi > ch.lo && (words + wds) * 4 > budget) {
+                ch.scratch_bytes = words * 4;
+                c->g_chunks.push_back(ch);
+                ch.lo = ch.hi;
+                words = 0;
+            }
+            c->gdir_off[k] = words;
+            words += wds;
+            ch.hi = (uint32_t)(k + 1);
+            c->g_max_n = std::max(c->g_max_n, c->hlen2[p]);
+        }
+        ch.scratch_bytes = words * 4;
+        c->g_chunks.push_back(ch);
+        CKS(c->d_gidx.ensure(c->gidx.size()));
+        CKS(c->d_gdir_off.ensure(c->gidx.size()));
+        CKS(c->gidx_pin.ensure(c->gidx.size()));
+        CKS(c->gdir_pin.ensure(c->gidx.size()));
+        std::copy(c->gidx.begin(), c->gidx.end(), c->gidx_pin.p);
+        std::copy(c->gdir_off.begin(), c->gdir_off.end(), c->gdir_pin.p);
+        CK(cudaMemcpyAsync(c->d_gidx.p, c->gidx_pin.p, c->gidx.size() * 4, cudaMemcpyHostToDevice, c->up));
+        CK(cudaMemcpyAsync(c->d_gdir_off.p, c->gdir_pin.p, c->gidx.size() * 8, cudaMemcpyHostToDevice, c->up));
+    }
+    return SEQA_OK;
+}
+
 int build_plan(seqa_ctx *c)
 {
     const uint64_t n = c->n;
@@ -358,7 +409,8 @@ int build_plan(seqa_ctx *c)
     c->cells = c->st_cells;
 
     // per-pair op slots: len1+len2 bytes each (an alignment never has more columns); offsets by a device scan
-    {
+    // (a re-plan of the same resident batch keeps them: ops_len holds results by then)
+    if (!c->replan) {
         const uint64_t run = c->st_slots;
         c->slots_total = run;
         CKS(c->slot_off.ensure(n));
@@ -417,12 +469,13 @@ int build_plan(seqa_ctx *c)
         }
     }
 
-    const bool pk = packed_scoring_ok(prm) && !c->generic_rerun;
+    const bool pk = packed_scoring_ok(prm);
+    const bool forced = !c->forced_generic.empty(); // pairs taken off the packed path (non-ACGT symbols seen by an earlier run)
     std::vector<uint32_t> &pkl = c->pkl;
     pkl.clear();
     bool uniform = true;
     // uniform batch (every pair the same shape): one eligibility test, identity permutation, identical jobs
-    const bool fast = c->st_uniform && n > 0 && pk && packed_shape_ok(prm, c->hlen1[0], c->hlen2[0]) && c->ub_idx.empty();
+    const bool fast = c->st_uniform && n > 0 && pk && packed_shape_ok(prm, c->hlen1[0], c->hlen2[0]) && c->ub_idx.empty() && !forced;
     if (fast) {
         pkl.resize(n);
         std::iota(pkl.begin(), pkl.end(), 0u);
@@ -431,7 +484,7 @@ int build_plan(seqa_ctx *c)
         for (uint64_t p = 0; p < n; p++) {
             const uint32_t M = c->hlen1[p], N = c->hlen2[p];
             if (ub_shape(M, N)) continue;
-            if (pk && packed_shape_ok(prm, M, N)) {
+            if (pk && packed_shape_ok(prm, M, N) && !(forced && c->forced_generic[p])) {
                 if (!pkl.empty() && (M != c->hlen1[pkl[0]] || N != c->hlen2[pkl[0]])) uniform = false;
                 pkl.push_back((uint32_t)p);
             } else {
@@ -513,40 +566,7 @@ int build_plan(seqa_ctx *c)
         CK(cudaMemcpyAsync(c->d_jobs.p, c->jobs_pin.p, c->jobs.size() * sizeof(PkWarpJob), cudaMemcpyHostToDevice, c->up));
     }
 
-    // ---- generic jobs: one warp per pair ----
-    if (!c->gidx.empty()) {
-        const bool affine = prm.algo == SEQA_GLOBAL_GOTOH || prm.algo == SEQA_LOCAL_GOTOH;
-        c->gdir_off.resize(c->gidx.size());
-        Chunk ch{0, 0, 0};
-        uint64_t words = 0;
-        for (size_t k = 0; k < c->gidx.size(); k++) {
-            const uint32_t p = c->gidx[k];
-            const uint64_t wds = dir_words((int)c->hlen1[p], (int)c->hlen2[p], GEN_R, affine);
-            if (wds * 4 > budget)
-                return fail(SEQA_ERR_NOMEM, "pair %u (%u x %u) needs a %llu-byte direction matrix: use Hirschberg/MyersMiller",
-                            p, c->hlen1[p], c->hlen2[p], (unsigned long long)(wds * 4));
-            if (ch.hi > ch.lo && (words + wds) * 4 > budget) {
-                ch.scratch_bytes = words * 4;
-                c->g_chunks.push_back(ch);
-                ch.lo = ch.hi;
-                words = 0;
-            }
-            c->gdir_off[k] = words;
-            words += wds;
-            ch.hi = (uint32_t)(k + 1);
-            c->g_max_n = std::max(c->g_max_n, c->hlen2[p]);
-        }
-        ch.scratch_bytes = words * 4;
-        c->g_chunks.push_back(ch);
-        CKS(c->d_gidx.ensure(c->gidx.size()));
-        CKS(c->d_gdir_off.ensure(c->gidx.size()));
-        CKS(c->gidx_pin.ensure(c->gidx.size()));
-        CKS(c->gdir_pin.ensure(c->gidx.size()));
-        std::copy(c->gidx.begin(), c->gidx.end(), c->gidx_pin.p);
-        std::copy(c->gdir_off.begin(), c->gdir_off.end(), c->gdir_pin.p);
-        CK(cudaMemcpyAsync(c->d_gidx.p, c->gidx_pin.p, c->gidx.size() * 4, cudaMemcpyHostToDevice, c->up));
-        CK(cudaMemcpyAsync(c->d_gdir_off.p, c->gdir_pin.p, c->gidx.size() * 8, cudaMemcpyHostToDevice, c->up));
-    }
+    CKS(plan_generic(c));
     uint64_t need = 16;
     for (auto &ch : c->pk_chunks) need = std::max(need, ch.scratch_bytes);
     for (auto &ch : c->g_chunks) need = std::max(need, ch.scratch_bytes);
@@ -680,6 +700,8 @@ int run_packed(seqa_ctx *c, bool want_walk)
     const uint64_t bound_stride = (uint64_t)((c->pk_max_nw + 3) / 4) * (affine ? 64 : 32);
     if (affine || gb) CKS(c->pk_bound.ensure((size_t)c->sms * bps * (PK_BLOCK / 32) * bound_stride));
     CK(cudaMemsetAsync(c->flags.p, 0, sizeof(int) * 4, c->stream));
+    CKS(c->badpair.ensure(c->n));
+    CK(cudaMemsetAsync(c->badpair.p, 0, c->n, c->stream));
     for (const Chunk &ch : c->pk_chunks) {
         const uint32_t nj = ch.hi - ch.lo;
         // chunk layout: trace | prof | rowsel | lastcol
@@ -713,6 +735,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
         A.slot_start = c->slot_start.p;
         A.ops_len = c->ops_len.p;
         A.bad = c->flags.p;
+        A.badpair = c->badpair.p;
         A.gap = c->prm.gap;
         A.match = c->prm.match;
         A.mismatch = c->prm.mismatch;
@@ -823,7 +846,8 @@ int ctx_set_inputs_common(seqa_ctx *c, const seqa_params *params, uint64_t n)
     c->prm = *params;
     c->n = n;
     c->ran = false;
-    c->generic_rerun = false;
+    c->forced_generic.clear();
+    c->replan = false;
     c->have_stats = false;
     c->ops_base = 0;
     set_scoring(c);
@@ -831,6 +855,53 @@ int ctx_set_inputs_common(seqa_ctx *c, const seqa_params *params, uint64_t n)
     CKS(c->off2.ensure(n));
     CKS(c->len1.ensure(n));
     CKS(c->len2.ensure(n));
+    return SEQA_OK;
+}
+
+// seqa_batch_in.sym_class -> the two 256-entry translation tables of translate_kernel: every class gets ONE representative
+// byte (the classes of 'A', 'C', 'G', 'T' keep those letters, so that they stay on the packed 2-bit-code kernels; every
+// other class a byte outside ACGT); the "matches nothing" class becomes 254 in sequence 1 and 255 in sequence 2, which
+// never compare equal.  After this, byte equality IS the caller's match relation.
+int build_class_tables(const uint8_t *cls, uint8_t *tab1, uint8_t *tab2)
+{
+    int rep[256];
+    for (int &r : rep) r = -1;
+    for (const char *l = "ACGT"; *l; l++) {
+        const unsigned k = cls[(unsigned char)*l];
+        if (k != SEQA_CLASS_NEVER && k < 254 && rep[k] < 0) rep[k] = (unsigned char)*l;
+    }
+    int next = 0;
+    for (int ch = 0; ch < 256; ch++) {
+        const unsigned k = cls[ch];
+        if (k == SEQA_CLASS_NEVER) continue;
+        if (k > 253) return fail(SEQA_ERR_INVALID, "sym_class[%d] = %u: class ids are 0..253 (255 = matches nothing)", ch, k);
+        if (rep[k] < 0) {
+            while (next == 'A' || next == 'C' || next == 'G' || next == 'T') next++;
+            rep[k] = next++; // at most 250 such classes, 250 bytes outside {A,C,G,T,254,255}
+        }
+    }
+    for (int ch = 0; ch < 256; ch++) {
+        const unsigned k = cls[ch];
+        tab1[ch] = k == SEQA_CLASS_NEVER ? (uint8_t)254 : (uint8_t)rep[k];
+        tab2[ch] = k == SEQA_CLASS_NEVER ? (uint8_t)255 : (uint8_t)rep[k];
+    }
+    return SEQA_OK;
+}
+
+int translate_classes(seqa_ctx *c, const uint8_t *cls)
+{
+    if (!cls || c->n == 0) return SEQA_OK;
+    TranslateArgs T{};
+    CKS(build_class_tables(cls, T.tab1, T.tab2));
+    T.bases = c->bases.p;
+    T.off1 = c->off1.p;
+    T.off2 = c->off2.p;
+    T.len1 = c->len1.p;
+    T.len2 = c->len2.p;
+    T.n = c->n;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((2 * c->n * 32 + 255) / 256, (uint64_t)c->sms * 64);
+    LAUNCH(c, (translate_kernel), blocks, 256, 0, T);
+    CK(cudaGetLastError());
     return SEQA_OK;
 }
 
@@ -968,7 +1039,7 @@ int ctx_upload_range_2bit(seqa_ctx *c, const seqa_params *params, const seqa_bat
     const unsigned blocks = (unsigned)std::min<uint64_t>((2 * n * 32 + 255) / 256, (uint64_t)c->sms * 64);
     LAUNCH(c, (unpack2_kernel), blocks, 256, 0, U);
     CK(cudaGetLastError());
-    return SEQA_OK;
+    return translate_classes(c, in->sym_class);
 }
 
 // upload pairs [pb, pe) of `in`; device offsets are rebased to the byte range the shard touches
@@ -1058,7 +1129,22 @@ int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in
     if (rc == SEQA_OK && n && dense) // slot_off is ready (stream-ordered) and equals off1 relative to the shard's first byte
         LAUNCH(c, (dense_offsets_kernel), (unsigned)((n + 255) / 256), 256, 0, c->slot_off.p, c->len1.p, c->off1.p, c->off2.p, n);
     if (dbgt) fprintf(stderr, "[seqa]   upload %.3f ms, plan %.3f ms (%llu pairs)\n", t_up, ms_since(tu0) - t_up, (unsigned long long)n);
+    if (rc == SEQA_OK) rc = translate_classes(c, in->sym_class); // off1 / off2 are final here (uploaded or derived)
     return rc;
+}
+
+// op strings gathered, per-pair status of rejected pairs set, downloads may follow
+int finish_run(seqa_ctx *c)
+{
+    if (!c->ub_idx.empty()) // rejected pairs: no ops, neutral fields (the walk kernels never saw them)
+        LAUNCH(c, (mark_pairs_kernel), (unsigned)((c->ub_idx.size() + 255) / 256), 256, 0, c->d_ub.p, (uint64_t)c->ub_idx.size(), c->score.p,
+               c->start_i.p, c->start_j.p, c->end_i.p, c->end_j.p, c->ops_len.p, c->slot_start.p, 0u);
+    CKS(finish_ops(c));
+    if (!c->ub_idx.empty()) // ... and, once the op strings are gathered, the per-pair status the caller sees
+        LAUNCH(c, (mark_pairs_kernel), (unsigned)((c->ub_idx.size() + 255) / 256), 256, 0, c->d_ub.p, (uint64_t)c->ub_idx.size(), c->score.p,
+               c->start_i.p, c->start_j.p, c->end_i.p, c->end_j.p, c->ops_len.p, c->slot_start.p, (uint32_t)SEQA_PAIR_UNSUPPORTED);
+    CK(cudaEventRecord(c->ev_run, c->stream)); // downloads are ordered behind this (ctx_resolve)
+    return SEQA_OK;
 }
 
 int ctx_run(seqa_ctx *c)
@@ -1075,20 +1161,14 @@ int ctx_run(seqa_ctx *c)
         CKS(run_packed(c, want_walk));
         CKS(run_generic(c, want_walk));
     }
-    if (!c->ub_idx.empty()) // rejected pairs: no ops, neutral fields (the walk kernels never saw them)
-        LAUNCH(c, (mark_pairs_kernel), (unsigned)((c->ub_idx.size() + 255) / 256), 256, 0, c->d_ub.p, (uint64_t)c->ub_idx.size(), c->score.p,
-               c->start_i.p, c->start_j.p, c->end_i.p, c->end_j.p, c->ops_len.p, c->slot_start.p, 0u);
-    CKS(finish_ops(c));
-    if (!c->ub_idx.empty()) // ... and, once the op strings are gathered, the per-pair status the caller sees
-        LAUNCH(c, (mark_pairs_kernel), (unsigned)((c->ub_idx.size() + 255) / 256), 256, 0, c->d_ub.p, (uint64_t)c->ub_idx.size(), c->score.p,
-               c->start_i.p, c->start_j.p, c->end_i.p, c->end_j.p, c->ops_len.p, c->slot_start.p, (uint32_t)SEQA_PAIR_UNSUPPORTED);
-    CK(cudaEventRecord(c->ev_run, c->stream)); // downloads are ordered behind this (ctx_resolve)
+    CKS(finish_run(c));
     c->ran = true;
+    c->resolved = false;
     return SEQA_OK;
 }
 
-// If the packed path met a base outside ACGT its results are void: re-plan everything onto the generic
-// (8-bit compare) kernels and run again.  Called at the first synchronisation point after a run.
+// The first synchronisation point after a run: fetch what the host must know (ctx_fetch_tail) and, if the packed path
+// flagged pairs that hold a symbol outside ACGT, run exactly those pairs on the 8-bit kernels (ctx_resolve).
 int ctx_fetch_tail(seqa_ctx *c)
 {
     // what the host must know before it can fetch results (dense ops bytes, the packed path's "bad symbol" flag):
@@ -1109,14 +1189,43 @@ int ctx_resolve(seqa_ctx *c)
         return SEQA_OK;
     }
     CKS(ctx_fetch_tail(c));
-    if (c->jobs.empty() || c->generic_rerun) return SEQA_OK;
+    if (c->resolved || c->jobs.empty()) return SEQA_OK;
+    c->resolved = true;
     const int bad = (int)(c->h_tail.p[1] & 0xffffffffu);
     if (!bad) return SEQA_OK;
-    c->generic_rerun = true;
-    CKS(build_plan(c));
-    CKS(ctx_run(c));
+    // Pairs with a symbol outside ACGT: their packed results are void.  Collect them, run THEM on the 8-bit kernels (the
+    // other pairs keep their results), gather the op strings again, and keep them off the packed path for later runs.
+    const uint64_t n = c->n;
+    CKS(c->d_badidx.ensure(n));
+    CKS(c->d_badcnt.ensure(1));
+    CK(cudaMemsetAsync(c->d_badcnt.p, 0, 4, c->stream));
+    LAUNCH(c, (collect_flagged_kernel), (unsigned)((n + 255) / 256), 256, 0, c->badpair.p, n, c->d_badidx.p, c->d_badcnt.p);
+    uint32_t cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, c->d_badcnt.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<uint32_t> flagged(cnt);
+    if (cnt) {
+        CK(cudaMemcpyAsync(flagged.data(), c->d_badidx.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    std::sort(flagged.begin(), flagged.end());
+    if (c->forced_generic.empty()) c->forced_generic.assign(n, 0);
+    for (uint32_t p : flagged) c->forced_generic[p] = 1;
+    c->gidx = flagged; // temporary plan: only the flagged pairs
+    CKS(plan_generic(c));
+    uint64_t need = 16;
+    for (auto &ch : c->g_chunks) need = std::max(need, ch.scratch_bytes);
+    CKS(c->scratch.ensure(std::max<uint64_t>(need, c->scratch.cap)));
+    CKS(order_after(c, c->up, c->stream));
+    const char *kernel = c->last_kernel;
+    CKS(run_generic(c, !(c->prm.flags & SEQA_FLAG_SCORE_ONLY)));
+    c->last_kernel = kernel; // the batch's dominant kernel stays the packed one
+    CKS(finish_run(c));
     CKS(ctx_fetch_tail(c));
-    return SEQA_OK;
+    c->replan = true; // later runs of this resident batch: the flagged pairs are planned onto the 8-bit kernels from the start
+    const int rc = build_plan(c);
+    c->replan = false;
+    return rc;
 }
 
 int ctx_download_into(seqa_ctx *c, seqa_batch_out *out, uint64_t pb, uint64_t ops_base, uint64_t *ops_used)
@@ -1227,7 +1336,7 @@ void seqa_ctx_destroy(seqa_ctx *c)
     c->perm.release(); c->jobs_pin.release(); c->h_tail.release(); c->gidx_pin.release(); c->gdir_pin.release();
     c->ls_rowoff_pin.release(); c->ls_roww_pin.release(); c->ls_idx_pin.release();
     c->d_perm.release(); c->d_jobs.release(); c->pk_bound.release(); c->d_gidx.release(); c->d_gdir_off.release(); c->bound.release();
-    c->scratch.release(); c->ub_pin.release(); c->d_ub.release();
+    c->scratch.release(); c->ub_pin.release(); c->d_ub.release(); c->badpair.release(); c->d_badidx.release(); c->d_badcnt.release();
     ls_release(c->ls);
     for (auto e : c->ev) cudaEventDestroy(e);
     if (c->ev_up) cudaEventDestroy(c->ev_up);

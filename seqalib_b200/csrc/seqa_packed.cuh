@@ -54,6 +54,7 @@ struct PkArgs {
     const uint64_t *slot_off;
     uint32_t *slot_start, *ops_len;
     int *bad; // set when a base outside ACGT is met
+    uint8_t *badpair; // ... and per pair: badpair[p] = 1 (the pair is re-run on the 8-bit kernels, the rest of the batch stays)
     int gap, match, mismatch, allow;
     uint32_t smem_cols; // columns of shared boundary storage per thread
     uint64_t npos;      // njobs * 64
@@ -124,10 +125,10 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
         // Four symbols per 32-bit word are handled together: codes4 = (w >> 1) & 0x03030303 (A0 C1 T2 G3 in every byte); the
         // word is valid iff "ACTG"[code] gives back every byte (one PRMT table look-up + XOR); bytes behind the end of
         // the sequence are masked out.
-        unsigned bad = 0;
+        unsigned bad0 = 0, bad1 = 0; // pair p0 / pair p1 met a symbol outside ACGT
         const uint32_t Ng = (J.Nw + 3) >> 2;
         auto valid_mask = [](uint32_t have) { return have >= 4u ? 0xffffffffu : ((1u << (8u * have)) - 1u); }; // have = symbols left
-        auto check4 = [&](uint32_t w, uint32_t codes, uint32_t vmask) {
+        auto check4 = [&](uint32_t w, uint32_t codes, uint32_t vmask, unsigned &bad) {
             const unsigned x = codes | (codes >> 4);                    // byte 0: c0 | c1 << 4, byte 2: c2 | c3 << 4
             const unsigned letters = seqa_prmt(0x47544341u, 0u, seqa_prmt(x, 0u, 0x4420)); // "ACTG"[c0..c3]
             bad |= (letters ^ w) & vmask;
@@ -138,8 +139,8 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
             const uint32_t h0 = j0 < N0 ? N0 - j0 : 0u, h1 = j0 < N1 ? N1 - j0 : 0u; // real columns left in this group
             const uint32_t w0 = h0 ? b0.next4() : 0u, w1 = h1 ? b1.next4() : 0u;
             const uint32_t k0 = (w0 >> 1) & 0x03030303u, k1 = (w1 >> 1) & 0x03030303u;
-            check4(w0, k0, valid_mask(h0));
-            check4(w1, k1, valid_mask(h1));
+            check4(w0, k0, valid_mask(h0), bad0);
+            check4(w1, k1, valid_mask(h1), bad1);
             const uint32_t s0 = k0 << 3, s1 = k1 << 3; // 8 * code: the byte position of the matching row base in the profile
             unsigned t[8];
 #pragma unroll
@@ -158,8 +159,8 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
             const uint32_t w0 = h0 ? a0.next4() : 0u, w1 = h1 ? a1.next4() : 0u;
             const uint32_t v0 = valid_mask(h0), v1 = valid_mask(h1);
             const uint32_t k0 = (w0 >> 1) & 0x03030303u & v0, k1 = (w1 >> 1) & 0x03030303u & v1; // rows behind the end: code 0
-            check4(w0, k0, v0);
-            check4(w1, k1, v1);
+            check4(w0, k0, v0, bad0);
+            check4(w1, k1, v1, bad1);
 #pragma unroll
             for (uint32_t c = 0; c < 4; c++) {
                 const unsigned c0 = (k0 >> (8 * c)) & 3u, c1 = (k1 >> (8 * c)) & 3u;
@@ -167,7 +168,9 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
                 rout[(uint64_t)(i0 + c) * 32] = 0xC480u + c0 * 0x11u + c1 * 0x1100u;
             }
         }
-        if (bad) *A.bad = 1;
+        if (bad0 | bad1) *A.bad = 1;
+        if (bad0 && p0 != PK_NULL) A.badpair[p0] = 1;
+        if (bad1 && p1 != PK_NULL) A.badpair[p1] = 1;
     }
 }
 

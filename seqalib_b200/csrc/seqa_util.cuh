@@ -157,6 +157,44 @@ __global__ void __launch_bounds__(256) rebase_kernel(uint64_t *__restrict__ off1
     }
 }
 
+// Pairs the packed path flagged (a symbol outside ACGT): their indices, in any order, behind a counter.
+__global__ void __launch_bounds__(256) collect_flagged_kernel(const uint8_t *__restrict__ flag, uint64_t n, uint32_t *__restrict__ idx,
+                                                              uint32_t *__restrict__ count)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n && flag[k]) idx[atomicAdd(count, 1u)] = (uint32_t)k;
+}
+
+// seqa_batch_in.sym_class: every symbol is replaced by a representative of its class, once, so that every kernel of the
+// path keeps comparing bytes with == .  tab1 / tab2 translate sequence 1 / sequence 2 (they differ only for the
+// "matches nothing" class, which maps to two different bytes).  One warp per sequence.
+struct TranslateArgs {
+    uint8_t *bases;
+    const uint64_t *off1, *off2;
+    const uint32_t *len1, *len2;
+    uint64_t n;
+    uint8_t tab1[256], tab2[256];
+};
+
+__global__ void __launch_bounds__(256) translate_kernel(TranslateArgs A)
+{
+    __shared__ uint8_t t1[256], t2[256];
+    t1[threadIdx.x] = A.tab1[threadIdx.x];
+    t2[threadIdx.x] = A.tab2[threadIdx.x];
+    __syncthreads();
+    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t q = gw; q < 2 * A.n; q += nw) {
+        const uint64_t p = q >> 1;
+        const bool second = (q & 1) != 0;
+        const uint32_t len = second ? A.len2[p] : A.len1[p];
+        uint8_t *s = A.bases + (second ? A.off2[p] : A.off1[p]);
+        const uint8_t *t = second ? t2 : t1;
+        for (uint32_t k = lane; k < len; k += 32) s[k] = t[s[k]];
+    }
+}
+
 // ---- SEQA_FLAG_BASES_2BIT: 2-bit symbols over PCIe, unpacked on the device -------------------------------------------
 // Wire format: 4 symbols per byte (symbol k of a sequence in bits 2*(k%4) of byte k/4), code A0 C1 T2 G3 = (letter >> 1) & 3,
 // every sequence on a byte boundary.  The unpacked copy (one byte per symbol, seq1 then seq2 per pair, dense) is what

@@ -30,6 +30,9 @@ static void expect(const char *What, const std::string &Got, const std::string &
 }
 static bool equalChar(char A, char B) { return A == B; }
 static bool fuzzyChar(char A, char B) { return A == B || A == 'N' || B == 'N'; }
+static char upperOf(char C) { return (C >= 'a' && C <= 'z') ? (char)(C - 32) : C; }
+static bool caseless(char A, char B) { return upperOf(A) == upperOf(B); }                         // an equivalence: table-driven
+static bool nNever(char A, char B) { return upperOf(A) == upperOf(B) && upperOf(A) != 'N'; }      // 'N' matches nothing, not even 'N'
 
 int main()
 {
@@ -190,6 +193,27 @@ int main()
             expect("2-bit vs 8-bit inputs row1", R1, Q1);
             expect("2-bit vs 8-bit inputs row2", R2, Q2);
             expect("2-bit vs 8-bit inputs flags", Fl, QF);
+        }
+    }
+    { // table-driven equality: functors that are an equivalence on bytes run on the GPU path
+        std::string L1 = "aaagaATGCat", L2 = "AAACtcAT", U1 = "AAAGAATGCAT", U2 = "AAACTCAT";
+        NeedlemanWunschSA<std::string, char, '-'> CL(ScoringSystem(-1, 2), caseless), EQ(ScoringSystem(-1, 2));
+        AlignedSequence<char, '-'> A = CL.getAlignment(L1, L2), B = EQ.getAlignment(U1, U2);
+        std::string Q1, Q2, QF;
+        rows(A, R1, R2, Fl);
+        rows(B, Q1, Q2, QF);
+        expect("caseless flags", Fl, QF);
+        expect("caseless row1 keeps the caller's symbols", R1, "aaa-gaATGCat");
+        expect("caseless row2", R2, "AAAC---t-cAT");
+        // 'N' matches nothing: an N column scores as a mismatch even against another N
+        std::string N1 = "ACGTNNACGT", N2 = "ACGTNNACGT";
+        SmithWatermanSA<std::string, char, '-'> NN(ScoringSystem(-2, 1, -1), nNever);
+        AlignedSequence<char, '-'> C = NN.getAlignment(N1, N2);
+        rows(C, R1, R2, Fl);
+        expect("N-never flags", Fl, "||||  ||||");
+        if (NN.LastScores.empty() || NN.LastScores[0] != 6) { // 4 + 4 - 1 - 1
+            std::printf("FAIL N-never score %d\n", NN.LastScores.empty() ? -999 : NN.LastScores[0]);
+            Failures++;
         }
     }
     { // a functor that is not equality is outside the GPU path

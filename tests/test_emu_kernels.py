@@ -53,9 +53,26 @@ def test_packed_path_is_taken(emu_lib):
     ctx.sync()
     assert ctx.last_kernel() == "pk_fill_sw_s16x2_t4"
     assert ctx.cells() == int((len1.astype(np.int64) * len2).sum())
-    # a non-ACGT base voids the packed result: the batch is re-planned onto the 8-bit generic kernels
+    # a non-ACGT base voids the packed result of ITS pair only: that pair is re-run on the 8-bit kernels, the others keep
+    # their packed results; later runs of the resident batch plan it onto the 8-bit kernels from the start
     pairs[5] = (pairs[5][0][:10] + "N" + pairs[5][0][10:], pairs[5][1])
-    check_batch_against_oracle(emu_lib, "sw", S.linear(-1, 1, -1), pairs)
+    pairs[66] = (pairs[66][0], "n" + pairs[66][1])
+    for algo, sc in (("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("ggotoh", S.affine(-3, -1, 1, -1))):
+        check_batch_against_oracle(emu_lib, algo, sc, pairs)
+        check_batch_against_oracle(emu_lib, algo, sc, pairs, flags=capi.FLAG_OPS_2BIT, device_count=2)
+        bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+        ctx = capi.Ctx(emu_lib)
+        ctx.upload(scoring_to_params(algo, sc), bases, off1, off2, len1, len2)
+        ctx.run()
+        first = ctx.download()
+        assert ctx.last_kernel().startswith("pk")  # the batch stayed on the packed kernels
+        ctx.run()
+        second = ctx.download()
+        ctx.close()
+        for p, (a, b) in enumerate(pairs):
+            o = orc.oracle_align(algo, sc, a, b)
+            for res in (first, second):
+                assert int(res.score[p]) == o["score"] and np.array_equal(res.pair_ops(p), o["ops"]), (algo, p)
 
 
 def test_golden_through_emulated_kernels(emu_lib, golden):
@@ -211,3 +228,60 @@ def test_two_bit_input_wire_format(emu_lib, algo, sc):
     pk, p1, p2 = capi.pack_bases_2bit(bases, off1, off2, len1, len2)
     with pytest.raises(capi.SeqaError):
         emu_lib.align_batch(scoring_to_params(algo, sc, flags=capi.FLAG_BASES_2BIT), pk[:len(pk) // 2].copy(), p1, p2, len1, len2)
+
+
+def class_table_cases():
+    """(name, sym_class uint8[256]) -- case-insensitive DNA with 'N' / 'n' matching nothing; purine / pyrimidine; a
+    20-letter protein alphabet folded into 6 groups (everything else: matches nothing)."""
+    ident = np.arange(256, dtype=np.uint8)
+    dna = np.full(256, 255, dtype=np.uint8)
+    for k, (u, l) in enumerate(zip(b"ACGT", b"acgt")):
+        dna[u] = dna[l] = k
+    for k, ch in enumerate(b"RYKMSW"):  # IUPAC codes: each its own class here
+        dna[ch] = 4 + k
+    ry = np.full(256, 255, dtype=np.uint8)
+    for ch in b"AGag":
+        ry[ch] = 0
+    for ch in b"CTct":
+        ry[ch] = 1
+    prot = np.full(256, 255, dtype=np.uint8)
+    for k, grp in enumerate((b"AVLIMC", b"FWYH", b"STNQ", b"KR", b"DE", b"GP")):
+        for ch in grp:
+            prot[ch] = k
+    ident2 = ident.copy()
+    ident2[254] = ident2[255] = 253  # ids must stay below 254: fold the two top bytes into one class
+    return [("dna-caseless-N-never", dna), ("purine-pyrimidine", ry), ("protein-groups", prot), ("near-identity", ident2)]
+
+
+def translate_for_oracle(table, s, which):
+    """the string the oracle aligns with == to reproduce the class table: class ids as bytes, the 'matches nothing'
+    class as two different bytes in the two sequences"""
+    return bytes((254 + which) if table[c] == 255 else int(table[c]) for c in s.encode("latin1")).decode("latin1")
+
+
+def check_class_table(lib, algo, sc, pairs, table, flags=0, device_count=1):
+    bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+    res = lib.align_batch(scoring_to_params(algo, sc, flags=flags, device_count=device_count), bases, off1, off2, len1, len2, sym_class=table)
+    for p, (a, b) in enumerate(pairs):
+        o = orc.oracle_align(algo, sc, translate_for_oracle(table, a, 0), translate_for_oracle(table, b, 1))
+        got = (int(res.score[p]), int(res.start_i[p]), int(res.start_j[p]), int(res.end_i[p]), int(res.end_j[p]))
+        assert got == (o["score"], o["start_i"], o["start_j"], o["end_i"], o["end_j"]), (algo, p, a, b, got, o)
+        assert np.array_equal(res.pair_ops(p), o["ops"]), (algo, p, a, b)
+
+
+@pytest.mark.parametrize("algo,sc", [("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("lgotoh", S.affine(-3, -1, 1, -1)),
+                                     ("hirschberg", S.linear(-1, 2, -1)), ("myersmiller", S.affine(-3, -1, 1, -1))])
+def test_table_driven_symbol_equality(emu_lib, algo, sc):
+    """seqa_batch_in.sym_class: equivalent to aligning the class-id strings with ==."""
+    rng = np.random.default_rng(41)
+    for name, table in class_table_cases():
+        alphabet = {"dna-caseless-N-never": "ACGTacgtNnR", "purine-pyrimidine": "ACGTacgtN", "protein-groups": "AVLFWSTKRDEGPX",
+                    "near-identity": "ACGT\xfe\xff#"}[name]
+        few = algo in ("hirschberg", "myersmiller")  # the emulated recursion is slow
+        pairs = random_pairs(rng, 6 if few else 24, 1, 60, alphabet) + random_pairs(rng, 1 if few else 4, 70, 120, alphabet, related=0.3)
+        check_class_table(emu_lib, algo, sc, pairs, table)
+    check_class_table(emu_lib, algo, sc, pairs, table, flags=capi.FLAG_OPS_2BIT, device_count=2)
+    bad = np.zeros(256, dtype=np.uint8)
+    bad[65] = 254
+    with pytest.raises(capi.SeqaError):
+        emu_lib.align_batch(scoring_to_params(algo, sc), *orc.batch_arrays([("ACGT", "ACGA")]), sym_class=bad)

@@ -335,3 +335,34 @@ def test_two_bit_inputs_large_uniform_batch(gpu_lib):
         b = bytes(bases[int(off2[p]):int(off2[p]) + 150]).decode()
         o = orc.oracle_align("sw", sc, a, b)
         assert int(got.score[p]) == o["score"] and np.array_equal(got.pair_ops(p), o["ops"]), p
+
+
+@pytest.mark.parametrize("algo,sc", [("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("ggotoh", S.affine(-3, -1, 1, -1)),
+                                     ("lgotoh", S.affine(-3, -1, 1, -1)), ("hirschberg", S.linear(-1, 2, -1)),
+                                     ("myersmiller", S.affine(-3, -1, 1, -1))])
+def test_table_driven_symbol_equality(gpu_lib, algo, sc):
+    """seqa_batch_in.sym_class: case-insensitive DNA with N matching nothing, purine / pyrimidine,
+    protein groups -- identical to the oracle aligning the class-id strings with == (the reference's match(a, b) with the
+    corresponding functor, include/SequenceAlignment.h:147).  A batch of mostly ACGT/acgt pairs stays on the packed
+    kernels; only the pairs that hold another class run on the 8-bit kernels."""
+    from test_emu_kernels import check_class_table, class_table_cases
+    rng = np.random.default_rng(43)
+    tables = dict(class_table_cases())
+    for name, alphabet in (("dna-caseless-N-never", "ACGTacgtNnR"), ("purine-pyrimidine", "ACGTacgtN"), ("protein-groups", "AVLFWSTKRDEGPX"),
+                           ("near-identity", "ACGT\xfe\xff#")):
+        pairs = _defined(algo, random_pairs(rng, 300, 1, 250, alphabet) + random_pairs(rng, 60, 50, 300, alphabet, related=0.3))
+        check_class_table(gpu_lib, algo, sc, pairs, tables[name])
+    # mostly clean DNA in mixed case + a few pairs with N: the packed kernels take the batch, the N pairs are re-run one by one
+    dna = tables["dna-caseless-N-never"]
+    pairs = _defined(algo, random_pairs(rng, 400, 20, 200, "ACGTacgt"))
+    for k in (3, 77, 200):
+        pairs[k] = (pairs[k][0] + "N", "n" + pairs[k][1])
+    check_class_table(gpu_lib, algo, sc, pairs, dna)
+    if algo in ("sw", "nw", "ggotoh", "lgotoh"):
+        bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+        ctx = capi.Ctx(gpu_lib)
+        ctx.upload(scoring_to_params(algo, sc), bases, off1, off2, len1, len2, sym_class=dna)
+        ctx.run()
+        ctx.sync()
+        assert ctx.last_kernel().startswith("pk"), ctx.last_kernel()
+        ctx.close()
