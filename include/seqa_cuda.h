@@ -62,7 +62,8 @@ enum {
 /* seqa_params.flags */
 #define SEQA_FLAG_SCORE_ONLY 0x1u  /* skip traceback/ops (scores and end positions only) */
 #define SEQA_FLAG_FORCE_GENERIC 0x2u /* use the generic int32 kernels even where a packed fast path applies */
-#define SEQA_FLAG_TRACE8 0x4u /* packed path: keep 8 trace bits per cell even where 4 suffice (testing) */
+#define SEQA_FLAG_TRACE8 0x4u /* packed path: keep 8 trace bits per cell even where 4 or 2 suffice (testing) */
+#define SEQA_FLAG_TRACE4 0x40u /* packed linear path: at least 4 trace bits per cell even where 2 suffice (testing) */
 #define SEQA_FLAG_OPS_2BIT 0x10u /* ops leave the device packed 4 per byte: op k of pair p sits in bits 2*(k%4) of byte
                                    ops[ops_off[p] + k/4]; ops_off is in BYTES (every pair starts on a byte boundary), ops_len
                                    in OPS; ops_capacity >= sum(len1+len2)/4 + n_pairs suffices.  A quarter of the PCIe bytes

@@ -15,6 +15,7 @@ ALGOS = {"nw": 0, "sw": 1, "ggotoh": 2, "lgotoh": 3, "hirschberg": 4, "myersmill
 FLAG_SCORE_ONLY = 1
 FLAG_FORCE_GENERIC = 2
 FLAG_TRACE8 = 4
+FLAG_TRACE4 = 64  # packed linear path: no 2-bit trace (testing)
 FLAG_LS_R1 = 8
 FLAG_OPS_2BIT = 16  # ops packed 4 per byte on the wire (Results.pair_ops unpacks)
 FLAG_BASES_2BIT = 32  # INPUT symbols packed 4 per byte (A0 C1 T2 G3), see pack_bases_2bit

@@ -282,11 +282,19 @@ bool packed_scoring_ok(const seqa_params &p)
     if (m + x + 2 * g > 120) return false; // neighbouring cells must differ by < 128
     return true;
 }
-// 4 trace bits per cell suffice when neighbouring cells differ by less than 8 (seqa_packed.cuh)
+// Trace bits per cell of the packed linear path (seqa_packed.cuh): the walk's equality tests are exact modulo 2^TB when
+// every difference it can meet lies in a window of at most 2^TB values that contains the tested constant.
+//   8 bits: always (differences below 128: packed_scoring_ok);  4 bits: Match + |Mismatch| + 2|Gap| <= 7;
+//   2 bits -- the algorithmic minimum -- for Match = 1, Gap = -1, Mismatch >= -2 (or no mismatches): the default
+//   SmithWatermanSA scoring (-1, 1, -1).  Then H(i,j) - H(i-1,j-1) lies in [-2, 1] (tested against +1 / Mismatch),
+//   H(i,j) - H(i-1,j) and H(i,j) - H(i,j-1) in [-1, 2] (tested against -1; the row scan decodes the window [-1, 2]);
+//   NeedlemanWunsch's column-normalised K shifts the three windows by +1 / 0 / +1 and the constants with them.
 int packed_trace_bits(const seqa_params &p)
 {
     const int g = -p.gap, m = p.match, x = p.allow_mismatch ? -p.mismatch : 0;
-    return (m + x + 2 * g <= 7 && !(p.flags & SEQA_FLAG_TRACE8)) ? 4 : 8;
+    if (p.flags & SEQA_FLAG_TRACE8) return 8;
+    if (m == 1 && g == 1 && x <= 2 && !(p.flags & SEQA_FLAG_TRACE4)) return 2;
+    return m + x + 2 * g <= 7 ? 4 : 8;
 }
 // affine packed path: 4 trace bits per plane suffice when every difference the walk tests on low bits stays below 16
 // (and the row scan of the local aligner inside [-8, 7]); bounds: seqa_packed_affine.cuh / DESIGN.md 4.3
@@ -306,7 +314,9 @@ bool packed_shape_ok(const seqa_params &p, uint32_t M, uint32_t N)
     }
     if (M == 0 || N == 0 || M > PKG_MAX_LEN || N > PKG_MAX_LEN) return false;
     const int64_t g = -p.gap, m = p.match;
-    const int64_t lo = (int64_t)(M + N + 2 * PK_R + 2) * g + 300, hi = (int64_t)std::min(M, N) * m + 300;
+    // NeedlemanWunsch keeps K = H - j*gap (seqa_packed.cuh): up to (N + padding) * |gap| above H
+    const int64_t lo = (int64_t)(M + N + 2 * PK_R + 2) * g + 300;
+    const int64_t hi = (int64_t)std::min(M, N) * m + (p.algo == SEQA_NW ? (int64_t)(N + 2 * PK_R + 2) * g : 0) + 300;
     return lo < 30000 && hi < 30000;
 }
 
@@ -691,6 +701,8 @@ int run_packed(seqa_ctx *c, bool want_walk)
     const size_t smem = (affine || gb) ? 0 : (size_t)c->pk_max_nw * PK_BLOCK * 4;
     if (smem > c->smem_optin) return fail(SEQA_ERR_UNSUPPORTED, "internal: packed kernel shared memory %zu", smem);
     if (smem) {
+        CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(pk_fill_kernel<true, PK_R, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(pk_fill_kernel<false, PK_R, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -744,7 +756,8 @@ int run_packed(seqa_ctx *c, bool want_walk)
         A.npos = (uint64_t)nj * 64;
         A.go = c->prm.gap_open;
         A.ge = c->prm.gap_extend;
-        A.prof_bias = affine ? c->prm.gap_open + c->prm.gap_extend : 0;
+        // subtracted from every profile score: affine G = H + go + ge; NeedlemanWunsch column-normalised (K = H - j*gap)
+        A.prof_bias = affine ? c->prm.gap_open + c->prm.gap_extend : (local ? 0 : c->prm.gap);
         A.bound = c->pk_bound.p;
         A.bound_stride = bound_stride;
         A.ticket = reinterpret_cast<uint32_t *>(c->flags.p + 1);
@@ -762,6 +775,14 @@ int run_packed(seqa_ctx *c, bool want_walk)
             LAUNCH(c, (pkg_fill_kernel<false, PK_R, 4>), grid, PK_BLOCK, 0, A);
         else if (affine)
             LAUNCH(c, (pkg_fill_kernel<false, PK_R, 8>), grid, PK_BLOCK, 0, A);
+        else if (gb && local && tb == 2)
+            LAUNCH(c, (pk_fill_kernel<true, PK_R, 2, true>), grid, PK_BLOCK, 0, A);
+        else if (gb && tb == 2)
+            LAUNCH(c, (pk_fill_kernel<false, PK_R, 2, true>), grid, PK_BLOCK, 0, A);
+        else if (local && tb == 2)
+            LAUNCH(c, (pk_fill_kernel<true, PK_R, 2, false>), grid, PK_BLOCK, smem, A);
+        else if (tb == 2)
+            LAUNCH(c, (pk_fill_kernel<false, PK_R, 2, false>), grid, PK_BLOCK, smem, A);
         else if (gb && local && tb == 4)
             LAUNCH(c, (pk_fill_kernel<true, PK_R, 4, true>), grid, PK_BLOCK, 0, A);
         else if (gb && local)
@@ -793,6 +814,10 @@ int run_packed(seqa_ctx *c, bool want_walk)
                 LAUNCH(c, (pkg_walk_kernel<false, PK_R, 4>), wgrid, 256, 0, Wk);
             else if (affine)
                 LAUNCH(c, (pkg_walk_kernel<false, PK_R, 8>), wgrid, 256, 0, Wk);
+            else if (local && tb == 2)
+                LAUNCH(c, (pk_walk_kernel<true, 2, PK_R>), wgrid, 256, 0, Wk);
+            else if (tb == 2)
+                LAUNCH(c, (pk_walk_kernel<false, 2, PK_R>), wgrid, 256, 0, Wk);
             else if (local && tb == 4)
                 LAUNCH(c, (pk_walk_kernel<true, 4, PK_R>), wgrid, 256, 0, Wk);
             else if (local)
@@ -808,7 +833,8 @@ int run_packed(seqa_ctx *c, bool want_walk)
         c->last_kernel = local ? (tb == 4 ? "pkg_fill_lgotoh_s16x2_t4" : "pkg_fill_lgotoh_s16x2_t8")
                                : (tb == 4 ? "pkg_fill_ggotoh_s16x2_t4" : "pkg_fill_ggotoh_s16x2_t8");
     else
-        c->last_kernel = local ? (tb == 4 ? "pk_fill_sw_s16x2_t4" : "pk_fill_sw_s16x2_t8") : (tb == 4 ? "pk_fill_nw_s16x2_t4" : "pk_fill_nw_s16x2_t8");
+        c->last_kernel = local ? (tb == 2 ? "pk_fill_sw_s16x2_t2" : tb == 4 ? "pk_fill_sw_s16x2_t4" : "pk_fill_sw_s16x2_t8")
+                               : (tb == 2 ? "pk_fill_nw_s16x2_t2" : tb == 4 ? "pk_fill_nw_s16x2_t4" : "pk_fill_nw_s16x2_t8");
     return SEQA_OK;
 }
 

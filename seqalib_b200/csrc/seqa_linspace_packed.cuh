@@ -3,7 +3,10 @@
 // differ by at most one, so a task is "row block rb of both sweeps", and a cell pair costs what the inter-sequence
 // kernels pay (seqa_packed.cuh / seqa_packed_affine.cuh):
 //
-//   Hirschberg  PRMT (both sims from the two column profiles), VIADD.16x2, 2 x VIADDMNMX.S16x2        = 4 per 2 cells
+//   Hirschberg  PRMT (both sims from the two column profiles), 2 x VIADDMNMX.S16x2                    = 3 per 2 cells
+//               (column-normalised like the packed NeedlemanWunsch fill: K(i,j) = H(i,j) - j*gap makes the left
+//               candidate K(i,j-1) itself; the boundary rows in global memory stay absolute H, converted when a
+//               chunk is staged / flushed)
 //   MyersMiller PRMT, 3 x VIADDMNMX.S16x2, VIMNMX.S16x2, VIADD.16x2 (G = H + go + ge kept, not H)     = 6 per 2 cells
 //
 // against 5 / 8 int32 instructions per ONE cell.  100 kbp scores do not fit 16 bits, so every lane keeps its values
@@ -44,8 +47,10 @@ __device__ __forceinline__ void ls_block2(const DevScoring &sc, const Borders &b
     const int nactf = PARTIAL ? min(max(mf - row0, 0), R) : R, nactr = PARTIAL ? min(max(mr - row0, 0), R) : R;
     const int gogo = AFFINE ? sc.go + sc.ge : 0; // affine: registers hold G = H + go + ge
     const unsigned gap2 = pk_dup(sc.gap), ge2 = pk_dup(sc.ge), gogo2 = pk_dup(gogo);
-    const unsigned mmb = sc.allow ? ((unsigned)(sc.mismatch - gogo) & 0xffu) : 0x80u; // -128: never (seqa_packed.cuh)
-    const unsigned mm4 = mmb * 0x01010101u, mx = ((unsigned)(sc.match - gogo) & 0xffu) ^ mmb;
+    const int pbias = AFFINE ? gogo : sc.gap; // profile bias: affine G = H + go + ge; linear K = H - j*gap
+    const int cnorm = AFFINE ? 0 : sc.gap;    // column normalisation of the linear sweeps
+    const unsigned mmb = sc.allow ? ((unsigned)(sc.mismatch - pbias) & 0xffu) : 0x80u; // -128: never (seqa_packed.cuh)
+    const unsigned mm4 = mmb * 0x01010101u, mx = ((unsigned)(sc.match - pbias) & 0xffu) ^ mmb;
     unsigned h[R], f[R], sel[R], amask[R];
     int basef = bf.hcolA + (row0 + 1) * bf.hcolB, baser = br.hcolA + (row0 + 1) * br.hcolB;
 #pragma unroll
@@ -84,8 +89,8 @@ __device__ __forceinline__ void ls_block2(const DevScoring &sc, const Borders &b
             const bool prev = ((c + 30) >> 5) != ((j31 + 30) >> 5); // lane 31 finished this column in the previous chunk
             const int b31f = sm31[prev ? 2 : 0], b31r = sm31[prev ? 3 : 1];
             const unsigned v = (unsigned)smOutH[lane];
-            outHf[c] = b31f + ls2_lo(v) - gogo;
-            outHr[c] = b31r + ls2_hi(v) - gogo;
+            outHf[c] = b31f + ls2_lo(v) - gogo + cnorm * c; // back to absolute H
+            outHr[c] = b31r + ls2_hi(v) - gogo + cnorm * c;
             if (AFFINE) {
                 const unsigned x = (unsigned)smOutX[lane];
                 outXf[c] = b31f + ls2_lo(x);
@@ -119,7 +124,7 @@ __device__ __forceinline__ void ls_block2(const DevScoring &sc, const Borders &b
                 const unsigned sim = seqa_prmt(T.x, T.y, sel[r]);
                 unsigned hv, ix = ux;
                 if (!AFFINE) {
-                    const unsigned tl = __viaddmax_s16x2(dg, sim, __vadd2(left, gap2)); // max(D, L)
+                    const unsigned tl = __viaddmax_s16x2(dg, sim, left); // max(D, L): K(i-1,j-1) + sim - gap, K(i,j-1)
                     hv = __viaddmax_s16x2(uh, gap2, tl);                                 // max(U, .)
                 } else { // registers hold G = H + go + ge: seqa_packed_affine.cuh
                     ix = __viaddmax_s16x2(ux, ge2, uh);
@@ -203,7 +208,7 @@ __device__ __forceinline__ void ls_block2(const DevScoring &sc, const Borders &b
             const int b0f = __shfl_sync(SEQA_FULL, basef, 0), b0r = __shfl_sync(SEQA_FULL, baser, 0);
             const int jj = t0 + 1 + lane; // stage the row above and the profiles of columns t0+1 .. t0+32
             const int hf = rb > 0 ? nHf : border_hrow(bf, jj), hr = rb > 0 ? nHr : border_hrow(br, jj);
-            smInH[lane] = (int)ls2_pack(hf + gogo - b0f, hr + gogo - b0r);
+            smInH[lane] = (int)ls2_pack(hf + gogo - b0f - cnorm * jj, hr + gogo - b0r - cnorm * jj);
             if (AFFINE) {
                 const int xf = rb > 0 ? nXf : bf.ixA + jj * bf.ixB, xr = rb > 0 ? nXr : br.ixA + jj * br.ixB;
                 smInX[lane] = (int)ls2_pack(xf - b0f, xr - b0r);

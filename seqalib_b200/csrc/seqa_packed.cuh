@@ -8,6 +8,12 @@
 //     t    = VIADDMNMX.S16x2[.RELU](Hdiag, sim, lg)   max(Hdiag+sim, Hleft+gap [,0])
 //     H    = VIADDMNMX.S16x2(Hup, gap, t)             max(Hup+gap, t)          <- the only serial op per row
 //
+// NeedlemanWunsch runs COLUMN-NORMALISED, K(i,j) = H(i,j) - j*gap: the left candidate H(i,j-1)+gap becomes K(i,j-1) itself,
+// the diagonal one K(i-1,j-1) + (sim - gap) (the profile is biased by -gap), the upper one K(i-1,j) + gap -- the VIADD
+// disappears and a cell pair costs PRMT + 2 VIADDMNMX.  (SmithWaterman's clamp at 0 would become a clamp at -j*gap, one
+// more instruction: it stays in H-space with the RELU form.)  The trace holds the low bits of K and the walk tests the
+// same three equalities, shifted by the same constants; H(M,N) = K(M,N) + N*gap.
+//
 // T0_j/T1_j are the "column profile" of the two pairs (4 int8 scores, one per possible row base) and sel_i is
 // a per-row PRMT selector (row base of pair 0 in nibble 0, of pair 1 in nibble 2, sign-extension nibbles 1/3),
 // both precomputed once per batch by pk_prep_kernel, so no per-cell base comparison exists at all.
@@ -174,6 +180,17 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
     }
 }
 
+// bits of x under mask m inserted into w: ONE LOP3 (w, x, m -> (w & ~m) | (x & m), LUT 0xd8 with inputs a = w, b = x, c = m)
+#ifdef SEQA_EMU
+static inline unsigned pk_insert(unsigned w, unsigned x, unsigned m) { return (w & ~m) | (x & m); }
+#else
+__device__ __forceinline__ unsigned pk_insert(unsigned w, unsigned x, unsigned m)
+{
+    unsigned r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xd8;" : "=r"(r) : "r"(w), "r"(x), "r"(m)); // a&~c | b&c: a=0xf0, b=0xcc, c=0xaa -> (0xf0 & 0x55) | (0xcc & 0xaa) = 0x50 | 0x88
+    return r;
+}
+#endif
 __device__ __forceinline__ unsigned pk_dup(int v) { return ((unsigned)v & 0xffffu) * 0x00010001u; }
 __device__ __forceinline__ int pk_half(unsigned v, int k) { return (int)(int16_t)(k ? (v >> 16) : (v & 0xffffu)); }
 
@@ -232,7 +249,8 @@ template <bool LOCAL, int R, int TB, bool GB>
 __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
 {
     static_assert(R % 2 == 0, "R must be even");
-    static_assert(TB == 4 || TB == 8, "trace bits");
+    static_assert(TB == 2 || TB == 4 || TB == 8, "trace bits");
+    static_assert(TB != 2 || PK_PAIR_PIECES == 0, "the 2-bit trace has one layout");
     SEQA_DYN_SMEM(unsigned, top);
     constexpr int RP = R / 2;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -254,7 +272,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
         int corner0 = 0, corner1 = 0;               // NW: H(M,N)
         // row 0 of the matrix = first strip's upper boundary (SW 0, NW j*gap: include/SANeedlemanWunsch.h:61-62)
         if (!GB)
-            for (int jj = 0; jj < Nw; jj++) top[jj * PK_BLOCK + tid] = LOCAL ? 0u : pk_dup((jj + 1) * A.gap);
+            for (int jj = 0; jj < Nw; jj++) top[jj * PK_BLOCK + tid] = 0u; // SW: H(0,j) = 0; NW: K(0,j) = j*gap - j*gap = 0
         for (int s = 0; s < (int)J.nstrips; s++) {
             const int i0 = s * R;
             const bool first = s == 0, keep = s + 1 < (int)J.nstrips;
@@ -281,9 +299,9 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                 if (GB && !first && (lane & 7) == 0 && cg + PK_BND_AHEAD < Ng) pk_prefetch_l2_line(&bnd[(uint64_t)(cg + PK_BND_AHEAD) * 32]);
                 unsigned up[4];
                 if (GB) {
-                    if (first) { // matrix row 0 (SW 0, NW j*gap: include/SANeedlemanWunsch.h:61-62)
+                    if (first) { // matrix row 0 (SW 0; NW H(0,j) = j*gap, include/SANeedlemanWunsch.h:61-62, i.e. K(0,j) = 0)
 #pragma unroll
-                        for (int c = 0; c < 4; c++) up[c] = LOCAL ? 0u : pk_dup((cg * 4 + c + 1) * A.gap);
+                        for (int c = 0; c < 4; c++) up[c] = 0u;
                     } else {
                         up[0] = cu.x; up[1] = cu.y; up[2] = cu.z; up[3] = cu.w;
                     }
@@ -292,7 +310,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                     for (int c = 0; c < 4; c++) up[c] = (cg * 4 + c < Nw) ? top[(cg * 4 + c) * PK_BLOCK + tid] : 0u; // padded columns: no boundary
                 }
                 unsigned bot[4];
-                unsigned W[RP][TB == 8 ? 4 : 2];
+                unsigned W[RP][TB == 8 ? 4 : TB == 4 ? 2 : 1];
                 // the 4 columns of the group; CAP = this group holds the corner column of one of my global alignments
                 // (twice per pair): only that rare variant carries the H(M,N) capture code
                 auto cols = [&](auto cap) {
@@ -307,17 +325,20 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                     for (int r = 0; r < R; r++) {
                         const unsigned sim = seqa_prmt(T0, T1, sel[r]);
                         const unsigned hold = H[r];
-                        const unsigned lg = __vadd2(hold, gap2);
-                        const unsigned t = LOCAL ? __viaddmax_s16x2_relu(hd, sim, lg) : __viaddmax_s16x2(hd, sim, lg);
+                        // SW: max(H(i-1,j-1) + sim, H(i,j-1) + gap, 0); NW (column-normalised): max(K(i-1,j-1) + sim - gap, K(i,j-1))
+                        const unsigned t = LOCAL ? __viaddmax_s16x2_relu(hd, sim, __vadd2(hold, gap2)) : __viaddmax_s16x2(hd, sim, hold);
                         const unsigned hn = __viaddmax_s16x2(hu, gap2, t);
                         if (r & 1) {
                             const unsigned w8 = seqa_prmt(H[r - 1], hn, 0x6420); // low bytes: [p0 r-1, p1 r-1, p0 r, p1 r]
                             if (TB == 8)
                                 W[r >> 1][c] = w8;
-                            else if ((c & 1) == 0)
+                            else if (TB == 2) { // four columns per byte: column c's two bits inserted at 2c (one LOP3 each)
+                                const unsigned M = 0x03030303u << (2 * c);
+                                W[r >> 1][0] = c == 0 ? w8 : pk_insert(W[r >> 1][0], w8 << (2 * c), M);
+                            } else if ((c & 1) == 0)
                                 W[r >> 1][c >> 1] = w8;
                             else // low nibbles of column c-1, high nibbles from column c
-                                W[r >> 1][c >> 1] = (W[r >> 1][c >> 1] & 0x0f0f0f0fu) | ((w8 << 4) & 0xf0f0f0f0u);
+                                W[r >> 1][c >> 1] = pk_insert(W[r >> 1][c >> 1], w8 << 4, 0xf0f0f0f0u);
                         }
                         H[r] = hn;
                         hu = hn;
@@ -333,8 +354,8 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                         if (j == N0 || j == N1) {
 #pragma unroll
                             for (int r = 0; r < R; r++) {
-                                if (j == N0 && i0 + r + 1 == M0) corner0 = pk_half(H[r], 0);
-                                if (j == N1 && i0 + r + 1 == M1) corner1 = pk_half(H[r], 1);
+                                if (j == N0 && i0 + r + 1 == M0) corner0 = pk_half(H[r], 0) + N0 * A.gap; // H = K + j*gap
+                                if (j == N1 && i0 + r + 1 == M1) corner1 = pk_half(H[r], 1) + N1 * A.gap;
                             }
                         }
                     }
@@ -353,6 +374,14 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                     uint4 *dst = reinterpret_cast<uint4 *>(tr + (uint64_t)cg * (RP * 32 * 16));
 #pragma unroll
                     for (int rp = 0; rp < RP; rp++) pk_store_stream(&dst[rp * 32], make_uint4(W[rp][0], W[rp][1], W[rp][2], W[rp][3]));
+                } else if (TB == 2) {
+                    // one 16-byte piece per pair and column group: 16 rows x 4 columns x 2 bits, byte r = row r
+                    static_assert(TB != 2 || R == 16, "2-bit trace pieces hold 16 rows");
+                    uint4 *dst = reinterpret_cast<uint4 *>(tr + (uint64_t)cg * (2 * 32 * 16));
+                    pk_store_stream(&dst[0], make_uint4(seqa_prmt(W[0][0], W[1][0], 0x6420), seqa_prmt(W[2][0], W[3][0], 0x6420),
+                                                         seqa_prmt(W[4][0], W[5][0], 0x6420), seqa_prmt(W[6][0], W[7][0], 0x6420)));
+                    pk_store_stream(&dst[32], make_uint4(seqa_prmt(W[0][0], W[1][0], 0x7531), seqa_prmt(W[2][0], W[3][0], 0x7531),
+                                                          seqa_prmt(W[4][0], W[5][0], 0x7531), seqa_prmt(W[6][0], W[7][0], 0x7531)));
                 } else {
                     static_assert(TB == 8 || R % 8 == 0, "4-bit trace pieces hold 8 rows");
                     // trace already points at this lane's 16 bytes (lane * 16); PAIR_PIECES: lane * 32 + (cg % 2) * 16
@@ -529,8 +558,9 @@ __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK_MINB) pk_walk_kernel(PkAr
     const int lane = (int)((pos & 63) >> 1), half = (int)(pos & 1);
     const int M = (int)A.len1[p], N = (int)A.len2[p];
     const uint32_t Ng = (J.Nw + 3) >> 2;
-    constexpr unsigned MASK = TB == 8 ? 0xffu : 0xfu;
-    constexpr int PRSH = TB == 8 ? 1 : 3; // rows per piece: 2 (TB 8: 2 rows x 4 columns x 2 pairs) or 8 (TB 4: this pair only)
+    constexpr unsigned MASK = TB == 8 ? 0xffu : TB == 4 ? 0xfu : 0x3u;
+    // rows per piece: 2 (TB 8: 2 rows x 4 columns x 2 pairs), 8 (TB 4: this pair only) or 16 (TB 2: this pair only)
+    constexpr int PRSH = TB == 8 ? 1 : TB == 4 ? 3 : 4;
     constexpr uint32_t RG = (uint32_t)(R >> PRSH);
 #if PK_SYM16
     __shared__ uint32_t symw[8][PK_WALK_TPB];
@@ -561,15 +591,16 @@ __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK_MINB) pk_walk_kernel(PkAr
             pcw[slot * 4 + 3][tid] = v.w;
             tag[slot][tid] = key;
         }
-        const int w = TB == 8 ? c : (((r & 7) >> 2) * 2 + (c >> 1));
-        const int sh = TB == 8 ? ((r & 1) * 2 + half) * 8 : (r & 3) * 8 + (c & 1) * 4;
+        const int w = TB == 8 ? c : TB == 4 ? (((r & 7) >> 2) * 2 + (c >> 1)) : (r >> 2);
+        const int sh = TB == 8 ? ((r & 1) * 2 + half) * 8 : TB == 4 ? (r & 3) * 8 + (c & 1) * 4 : (r & 3) * 8 + c * 2;
         return (pcw[slot * 4 + w][tid] >> sh) & MASK;
     };
-    auto sext = [&](unsigned d) -> int { // signed difference from its low TB bits
-        return TB == 8 ? (int)(int8_t)(uint8_t)d : ((int)((d & 0xfu) ^ 8u) - 8);
+    auto sext = [&](unsigned d) -> int { // signed difference from its low TB bits (TB 2: the window is [-1, 2], see packed_trace_bits)
+        return TB == 8 ? (int)(int8_t)(uint8_t)d : TB == 4 ? ((int)((d & 0xfu) ^ 8u) - 8) : ((int)((d + 1u) & 3u) - 1);
     };
-    auto border_low = [&](int i, int j) -> unsigned { // i == 0 or j == 0
-        return LOCAL ? 0u : (unsigned)((i == 0 ? j : i) * gap) & MASK;
+    auto border_low = [&](int i, int j) -> unsigned { // i == 0 or j == 0; NW: K(0,j) = 0, K(i,0) = i*gap
+        (void)j;
+        return LOCAL ? 0u : (unsigned)(i * gap) & MASK;
     };
     PkOpWriter out;
     out.init(A.slots, A.slot_off[p] + (uint64_t)(M + N));
@@ -598,11 +629,15 @@ __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK_MINB) pk_walk_kernel(PkAr
                     const int sh = ((r & 1) * 2 + half) * 8;
                     nib[0] = (v.x >> sh) & 0xffu; nib[1] = (v.y >> sh) & 0xffu;
                     nib[2] = (v.z >> sh) & 0xffu; nib[3] = (v.w >> sh) & 0xffu;
-                } else {
+                } else if (TB == 4) {
                     const bool hi = (r & 4) != 0;
                     const int sh = (r & 3) * 8;
                     const unsigned b01 = ((hi ? v.z : v.x) >> sh) & 0xffu, b23 = ((hi ? v.w : v.y) >> sh) & 0xffu;
                     nib[0] = b01 & 0xfu; nib[1] = b01 >> 4; nib[2] = b23 & 0xfu; nib[3] = b23 >> 4;
+                } else { // byte r of the piece: four columns x 2 bits
+                    const int q = r >> 2;
+                    const unsigned b = ((q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w) >> ((r & 3) * 8)) & 0xffu;
+                    nib[0] = b & 3u; nib[1] = (b >> 2) & 3u; nib[2] = (b >> 4) & 3u; nib[3] = b >> 6;
                 }
             };
             bool found = false;
@@ -629,13 +664,14 @@ __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK_MINB) pk_walk_kernel(PkAr
     } else {
         i = M;
         j = N;
-        h = A.score[p];
+        h = A.score[p] - N * gap; // NW: the trace holds K = H - j*gap
     }
-    unsigned nc = (unsigned)h & MASK; // low bits of H(i,j)
+    const int dbias = LOCAL ? 0 : gap; // NW: K(i,j) - K(i-1,j-1) = sim - gap on a diagonal step
+    unsigned nc = (unsigned)h & MASK; // low bits of H(i,j) / K(i,j)
     while (i > 0 && j > 0) {
         if (LOCAL && h == 0) break; // include/SASmithWaterman.h:281-284
         const bool eq = a.at(i - 1) == b.at(j - 1);
-        const int sim = eq ? A.match : A.mismatch;
+        const int sim = (eq ? A.match : A.mismatch) - dbias;
         const unsigned nd = (i == 1 || j == 1) ? border_low(i - 1, j - 1) : fetch(i - 2, j - 2);
         if ((eq || A.allow) && ((nc - nd - (unsigned)sim) & MASK) == 0) { // H == H(i-1,j-1) + sim, include/SANeedlemanWunsch.h:190
             out.put(0);

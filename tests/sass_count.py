@@ -22,6 +22,8 @@ SO = os.path.join(ROOT, "seqalib_b200", "libseqa_cuda.so")
 
 # bench.py's kernel names -> mangled functions, cells per hot-loop iteration
 KERNELS = {
+    "pk_fill_sw_s16x2_t2": ("_Z14pk_fill_kernelILb1ELi16ELi2ELb0EEv6PkArgs", 128),
+    "pk_fill_nw_s16x2_t2": ("_Z14pk_fill_kernelILb0ELi16ELi2ELb0EEv6PkArgs", 128),
     "pk_fill_sw_s16x2_t4": ("_Z14pk_fill_kernelILb1ELi16ELi4ELb0EEv6PkArgs", 128),
     "pk_fill_nw_s16x2_t4": ("_Z14pk_fill_kernelILb0ELi16ELi4ELb0EEv6PkArgs", 128),
     "pk_fill_sw_s16x2_t8": ("_Z14pk_fill_kernelILb1ELi16ELi8ELb0EEv6PkArgs", 128),
@@ -150,7 +152,7 @@ def main():
                      "cells_per_iteration": cells, "classes": classes,
                      "alu_per_2_cells": classes["alu"] * 2.0 / cells, "issued_per_cell": len(loop) / float(cells),
                      "mix": dict(sorted(mix.items(), key=lambda kv: -kv[1]))}
-        if name in ("pk_fill_sw_s16x2_t4", "pkg_fill_ggotoh_s16x2_t4"):
+        if name in ("pk_fill_sw_s16x2_t2", "pk_fill_sw_s16x2_t4", "pkg_fill_ggotoh_s16x2_t4"):
             with open(os.path.join(ROOT, "profiles", "r02_sass_%s.txt" % name), "w") as f:
                 f.write("# hot loop of %s (%s): one iteration = one 4-column group x 16 rows x 2 pairs = %d cells\n" % (name, fn, cells))
                 f.write("# %d instructions; classes %r; ALU-pipe instructions per 2 cells = %.3f\n" % (len(loop), classes, classes["alu"] * 2.0 / cells))
