@@ -225,6 +225,7 @@ __host__ __device__ inline uint64_t pk_trace_bytes(uint32_t nstrips, uint32_t Nw
 // 16-byte piece index of (strip s, column group cg, row band rb of the strip, pair half k, lane) for TB == 4
 __host__ __device__ inline uint32_t pk_piece4(uint32_t s, uint32_t Ng, uint32_t cg, uint32_t RG, uint32_t rb, uint32_t k, uint32_t lane)
 {
+    if (RG == 1) return ((s * Ng + cg) * 2u + k) * 32u + lane; // TB == 2: one 16-row piece per strip and column group, one layout
     if (PK_PAIR_PIECES == 2) return ((s * Ng + cg) * 2u + k) * 32u * RG + lane * RG + rb; // the strip's row bands side by side
     if (PK_PAIR_PIECES) return (((((s * ((Ng + 1) / 2) + (cg >> 1)) * RG + rb) * 2u + k) * 32u + lane) * 2u) + (cg & 1u);
     return (((s * Ng + cg) * RG + rb) * 2u + k) * 32u + lane;
@@ -250,7 +251,6 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
 {
     static_assert(R % 2 == 0, "R must be even");
     static_assert(TB == 2 || TB == 4 || TB == 8, "trace bits");
-    static_assert(TB != 2 || PK_PAIR_PIECES == 0, "the 2-bit trace has one layout");
     SEQA_DYN_SMEM(unsigned, top);
     constexpr int RP = R / 2;
     const int tid = threadIdx.x, lane = tid & 31;

@@ -51,7 +51,7 @@ def test_packed_path_is_taken(emu_lib):
     ctx.upload(scoring_to_params("sw", S.linear(-1, 1, -1)), bases, off1, off2, len1, len2)
     ctx.run()
     ctx.sync()
-    assert ctx.last_kernel() == "pk_fill_sw_s16x2_t4"
+    assert ctx.last_kernel() == "pk_fill_sw_s16x2_t2"  # default SW scoring: 2 trace bits per cell
     assert ctx.cells() == int((len1.astype(np.int64) * len2).sum())
     # a non-ACGT base voids the packed result of ITS pair only: that pair is re-run on the 8-bit kernels, the others keep
     # their packed results; later runs of the resident batch plan it onto the 8-bit kernels from the start
