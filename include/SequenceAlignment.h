@@ -25,7 +25,10 @@
 #define SEQA_SEQUENCE_ALIGNMENT_H
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -39,6 +42,11 @@
 #include <vector>
 
 #include "seqa_cuda.h"
+
+#if defined(__GNUC__) && defined(__x86_64__)
+#include <immintrin.h>
+#define SEQA_HAVE_AVX2_DISPATCH 1
+#endif
 
 #define ScoreSystemType int
 
@@ -234,12 +242,41 @@ template <typename BodyTy> inline void parallelFor(size_t N, size_t Threads, Bod
     for (std::thread &Th : Pool) Th.join();
 }
 
+#ifdef SEQA_HAVE_AVX2_DISPATCH
+// 32 symbols per step where the CPU has AVX2 (checked at run time; the header itself needs no -mavx2): codes by shift + and,
+// validity by a byte shuffle through "ACTG", four codes per byte by two multiply-adds (1,4 then 1,16).  Packs the first
+// Len / 32 * 32 symbols and returns how many it packed; *Bad collects symbol ^ letter-of-its-code.
+__attribute__((target("avx2"))) inline size_t pack2bit_avx2(const char *S, size_t Len, uint8_t *Dst, uint64_t *Bad)
+{
+    const __m256i Lut = _mm256_setr_epi8('A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 'A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i Three = _mm256_set1_epi8(3), W1 = _mm256_set1_epi16(0x0401), W2 = _mm256_set1_epi32(0x00100001);
+    const __m256i Pick = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    __m256i Acc = _mm256_setzero_si256();
+    size_t K = 0;
+    for (; K + 32 <= Len; K += 32) {
+        const __m256i X = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(S + K));
+        const __m256i C = _mm256_and_si256(_mm256_srli_epi16(X, 1), Three);
+        Acc = _mm256_or_si256(Acc, _mm256_xor_si256(_mm256_shuffle_epi8(Lut, C), X));
+        const __m256i P = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(C, W1), W2), Pick);
+        const uint32_t Lo = (uint32_t)_mm256_extract_epi32(P, 0), Hi = (uint32_t)_mm256_extract_epi32(P, 4);
+        std::memcpy(Dst + (K >> 2), &Lo, 4);
+        std::memcpy(Dst + (K >> 2) + 4, &Hi, 4);
+    }
+    if (!_mm256_testz_si256(Acc, Acc)) *Bad |= 1;
+    return K;
+}
+#endif
+
 // 2-bit packing of one sequence for SEQA_FLAG_BASES_2BIT (4 symbols per byte, A0 C1 T2 G3 = (letter >> 1) & 3), eight
-// symbols per step.  Returns false when a symbol outside ACGT is met (the batch then goes out as 8-bit symbols).
+// symbols per step (32 with AVX2).  Returns false when a symbol outside ACGT is met (the batch then goes out as 8-bit symbols).
 inline bool pack2bit(const char *S, size_t Len, uint8_t *Dst)
 {
     uint64_t Bad = 0;
     size_t K = 0;
+#ifdef SEQA_HAVE_AVX2_DISPATCH
+    static const bool HasAvx2 = __builtin_cpu_supports("avx2");
+    if (HasAvx2 && Len >= 32) K = pack2bit_avx2(S, Len, Dst, &Bad);
+#endif
     for (; K + 8 <= Len; K += 8) {
         uint64_t X;
         std::memcpy(&X, S + K, 8);
@@ -393,6 +430,10 @@ class SequenceAligner {
             return R;
         }
         auto Up = [](size_t X) { return (X + 63) / 64 * 64; };
+        const bool Timing = std::getenv("SEQA_API_TIMING") != nullptr; // phase times of this call on stderr
+        const auto T0 = std::chrono::steady_clock::now();
+        auto Since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count(); };
+        double TLen = 0, TPack = 0, TGpu = 0;
         // ---- inputs: lengths / offsets and symbols packed into page-locked memory by the host threads.  Symbols go out
         // 2-bit packed (SEQA_FLAG_BASES_2BIT: a quarter of the PCIe bytes) when every symbol is one of ACGT, else 8-bit ----
         if (!IdxBlock) IdxBlock = std::make_shared<seqa::PinnedBlock>();
@@ -421,6 +462,7 @@ class SequenceAligner {
             PartBytes[T + 1] += PartBytes[T];
         }
         const uint64_t Total = PartSyms[Threads], TotalPacked = PartBytes[Threads];
+        TLen = Since();
         BasesBlock->reserve(Total + 64); // large enough for either wire format
         char *Bases = BasesBlock->P;
         std::vector<char> ThreadOk(Threads, 1);
@@ -453,6 +495,7 @@ class SequenceAligner {
             });
         }
         LastInputsTwoBit = TwoBitIn;
+        TPack = Since();
         seqa_params Prm{};
         Prm.algo = Algo;
         Prm.gap = Scoring.getGapPenalty();
@@ -484,6 +527,7 @@ class SequenceAligner {
                            R.OpsOff.data(), R.OpsLen.data(), (uint64_t)OpsCap, 0};
         if (seqa_cuda_align_batch(&Prm, &In, &Out) != SEQA_OK)
             throw std::runtime_error(std::string("seqa_cuda_align_batch: ") + seqa_cuda_last_error());
+        TGpu = Since();
         // (large batches are processed in waves whose op strings sit at each wave's own base offset inside Ops)
         LastScores.resize(N);
         LastUnsupported.clear();
@@ -494,6 +538,9 @@ class SequenceAligner {
                 if (R.OpsLen[P] == SEQA_PAIR_UNSUPPORTED) Rejected[T].push_back(P);
         });
         for (const std::vector<size_t> &V : Rejected) LastUnsupported.insert(LastUnsupported.end(), V.begin(), V.end());
+        if (Timing)
+            std::fprintf(stderr, "[seqa api] %zu pairs, %zu threads: lengths %.2f ms, pack (%s) %.2f ms, seqa_cuda_align_batch %.2f ms, scores %.2f ms\n",
+                         N, Threads, TLen, TwoBitIn ? "2-bit" : "8-bit", TPack - TLen, TGpu - TPack, Since() - TGpu);
         return R;
     }
 

@@ -103,6 +103,19 @@ template <class T> struct HBuf {
     }
 };
 
+// Which packed fills rebuild the column profile from 2-bit column codes instead of reading 8 bytes per column, pair and
+// strip (seqa_packed.cuh: pk_colprof): the affine fills, which are bound by HBM writes (+6-7 %: 2,601 -> 2,756 GCUPS
+// GlobalGotoh, 2,616 -> 2,792 LocalGotoh).  The linear fills keep the precomputed profile: the short-pair ones are
+// ALU-bound, and the long-pair ones measured slightly slower with codes.  DESIGN.md 4.
+#ifndef PKG_CODES
+#define PKG_CODES 1
+#endif
+#ifndef PK_GB_CODES_NW
+#define PK_GB_CODES_NW 0 /* measured: 4,655 vs 4,752 GCUPS fill on the 50-1000 bp mix: the profile stays */
+#endif
+#ifndef PK_GB_CODES_SW
+#define PK_GB_CODES_SW 0 /* 5,236 vs 5,375 */
+#endif
 constexpr int GEN_R = 4;          // rows per lane of the generic wavefront
 constexpr int PK_R = 16;          // rows per register strip of the packed kernel
 constexpr uint32_t PK_MAX_LEN = 320; // longest side the thread-per-pair kernel takes (shared-memory column)
@@ -761,6 +774,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
         A.bound = c->pk_bound.p;
         A.bound_stride = bound_stride;
         A.ticket = reinterpret_cast<uint32_t *>(c->flags.p + 1);
+        A.colcodes = affine ? (PKG_CODES != 0) : (gb && (local ? PK_GB_CODES_SW != 0 : PK_GB_CODES_NW != 0));
         CK(cudaMemsetAsync(c->flags.p + 1, 0, sizeof(int), c->stream));
         const unsigned wpb = PK_BLOCK / 32;
         const unsigned full = (nj + wpb - 1) / wpb;
@@ -768,29 +782,29 @@ int run_packed(seqa_ctx *c, bool want_walk)
         LAUNCH(c, (pk_prep_kernel), full, PK_BLOCK, 0, A, PK_R); // one job per warp
         cudaEventRecord(next_event(c), c->stream);
         if (affine && local && tb == 4)
-            LAUNCH(c, (pkg_fill_kernel<true, PK_R, 4>), grid, PK_BLOCK, 0, A);
+            LAUNCH(c, (pkg_fill_kernel<true, PK_R, 4, PKG_CODES != 0>), grid, PK_BLOCK, 0, A);
         else if (affine && local)
-            LAUNCH(c, (pkg_fill_kernel<true, PK_R, 8>), grid, PK_BLOCK, 0, A);
+            LAUNCH(c, (pkg_fill_kernel<true, PK_R, 8, PKG_CODES != 0>), grid, PK_BLOCK, 0, A);
         else if (affine && tb == 4)
-            LAUNCH(c, (pkg_fill_kernel<false, PK_R, 4>), grid, PK_BLOCK, 0, A);
+            LAUNCH(c, (pkg_fill_kernel<false, PK_R, 4, PKG_CODES != 0>), grid, PK_BLOCK, 0, A);
         else if (affine)
-            LAUNCH(c, (pkg_fill_kernel<false, PK_R, 8>), grid, PK_BLOCK, 0, A);
+            LAUNCH(c, (pkg_fill_kernel<false, PK_R, 8, PKG_CODES != 0>), grid, PK_BLOCK, 0, A);
         else if (gb && local && tb == 2)
-            LAUNCH(c, (pk_fill_kernel<true, PK_R, 2, true>), grid, PK_BLOCK, 0, A);
+            LAUNCH(c, (pk_fill_kernel<true, PK_R, 2, true, PK_GB_CODES_SW != 0>), grid, PK_BLOCK, 0, A);
         else if (gb && tb == 2)
-            LAUNCH(c, (pk_fill_kernel<false, PK_R, 2, true>), grid, PK_BLOCK, 0, A);
+            LAUNCH(c, (pk_fill_kernel<false, PK_R, 2, true, PK_GB_CODES_NW != 0>), grid, PK_BLOCK, 0, A);
         else if (local && tb == 2)
             LAUNCH(c, (pk_fill_kernel<true, PK_R, 2, false>), grid, PK_BLOCK, smem, A);
         else if (tb == 2)
             LAUNCH(c, (pk_fill_kernel<false, PK_R, 2, false>), grid, PK_BLOCK, smem, A);
         else if (gb && local && tb == 4)
-            LAUNCH(c, (pk_fill_kernel<true, PK_R, 4, true>), grid, PK_BLOCK, 0, A);
+            LAUNCH(c, (pk_fill_kernel<true, PK_R, 4, true, PK_GB_CODES_SW != 0>), grid, PK_BLOCK, 0, A);
         else if (gb && local)
-            LAUNCH(c, (pk_fill_kernel<true, PK_R, 8, true>), grid, PK_BLOCK, 0, A);
+            LAUNCH(c, (pk_fill_kernel<true, PK_R, 8, true, PK_GB_CODES_SW != 0>), grid, PK_BLOCK, 0, A);
         else if (gb && tb == 4)
-            LAUNCH(c, (pk_fill_kernel<false, PK_R, 4, true>), grid, PK_BLOCK, 0, A);
+            LAUNCH(c, (pk_fill_kernel<false, PK_R, 4, true, PK_GB_CODES_NW != 0>), grid, PK_BLOCK, 0, A);
         else if (gb)
-            LAUNCH(c, (pk_fill_kernel<false, PK_R, 8, true>), grid, PK_BLOCK, 0, A);
+            LAUNCH(c, (pk_fill_kernel<false, PK_R, 8, true, PK_GB_CODES_NW != 0>), grid, PK_BLOCK, 0, A);
         else if (local && tb == 4)
             LAUNCH(c, (pk_fill_kernel<true, PK_R, 4, false>), grid, PK_BLOCK, smem, A);
         else if (local)

@@ -70,6 +70,8 @@ struct PkArgs {
     uint4 *bound;          // per-warp strip boundary rows (kernels that keep them in global memory)
     uint64_t bound_stride; // uint4 per warp
     uint32_t *ticket;      // job counter: warps draw jobs (largest first) instead of striding over them
+    int colcodes;          // != 0: prep writes 2-bit COLUMN CODES (uint16 [Ng][32] per job, at the job's profile offset) instead of
+                           // the column profiles, and the fill builds the profile words itself (kernels that are HBM-bound)
 };
 
 // next job of this warp: dynamic (ticket) so that ragged batches, sorted largest-first, balance across warps
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
             bad |= (letters ^ w) & vmask;
         };
         uint4 *pout = reinterpret_cast<uint4 *>(A.prof + J.prof_off) + lane; // [cg][half][lane]: every warp store / load is 512 contiguous bytes
+        uint16_t *cout = reinterpret_cast<uint16_t *>(A.prof + J.prof_off) + lane; // colcodes: [cg][lane], byte k = pair k, 2 bits per column
         for (uint32_t cg = 0; cg < Ng; cg++) {
             const uint32_t j0 = cg * 4;
             const uint32_t h0 = j0 < N0 ? N0 - j0 : 0u, h1 = j0 < N1 ? N1 - j0 : 0u; // real columns left in this group
@@ -147,6 +150,13 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
             const uint32_t k0 = (w0 >> 1) & 0x03030303u, k1 = (w1 >> 1) & 0x03030303u;
             check4(w0, k0, valid_mask(h0), bad0);
             check4(w1, k1, valid_mask(h1), bad1);
+            if (A.colcodes) { // four 2-bit codes per byte (pk_colprof rebuilds the profile words; padding is masked there)
+                uint32_t y0 = (k0 | (k0 >> 6)) & 0x000f000fu, y1 = (k1 | (k1 >> 6)) & 0x000f000fu;
+                y0 = (y0 | (y0 >> 12)) & 0xffu;
+                y1 = (y1 | (y1 >> 12)) & 0xffu;
+                cout[(uint64_t)cg * 32] = (uint16_t)(y0 | (y1 << 8));
+                continue;
+            }
             const uint32_t s0 = k0 << 3, s1 = k1 << 3; // 8 * code: the byte position of the matching row base in the profile
             unsigned t[8];
 #pragma unroll
@@ -193,6 +203,20 @@ __device__ __forceinline__ unsigned pk_insert(unsigned w, unsigned x, unsigned m
 #endif
 __device__ __forceinline__ unsigned pk_dup(int v) { return ((unsigned)v & 0xffffu) * 0x00010001u; }
 __device__ __forceinline__ int pk_half(unsigned v, int k) { return (int)(int16_t)(k ? (v >> 16) : (v & 0xffffu)); }
+
+// Column profile words of one 4-column group rebuilt from the 2-bit column codes (PkArgs.colcodes): T[2c + k] = the four
+// int8 scores of column c of pair k against row bases A/C/T/G = mm4 ^ (mx << 8*code); padded columns score -128 everywhere.
+// ~4 ALU instructions per column and pair, once per 16 rows -- for the kernels that are HBM-bound, where re-reading 8 bytes
+// of profile per column, pair and strip costs more than rebuilding it (profiles/r02_ncu_pkg_fill*.txt).
+__device__ __forceinline__ void pk_colprof(unsigned codes, int left0, int left1, unsigned mm4, unsigned mx, unsigned *T)
+{
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const unsigned s0 = ((codes >> (2 * c)) & 3u) * 8u, s1 = ((codes >> (8 + 2 * c)) & 3u) * 8u;
+        T[2 * c] = c < left0 ? mm4 ^ (mx << s0) : 0x80808080u;
+        T[2 * c + 1] = c < left1 ? mm4 ^ (mx << s1) : 0x80808080u;
+    }
+}
 
 // ---- fill -------------------------------------------------------------------------------------------------
 // Trace: the low TB bits (TB = 8, or 4 when Match + |Mismatch| + 2|Gap| <= 7) of every H value.  Layout of a warp
@@ -246,7 +270,7 @@ __device__ __forceinline__ void pk_store_stream(uint2 *p, uint2 v) { __stcs(p, v
 
 // GB = false: the strip boundary row lives in shared memory (pairs up to 320 columns); GB = true: in a per-warp
 // global (L2-resident) row, read one column group ahead -- any length whose scores fit 16 bits.
-template <bool LOCAL, int R, int TB, bool GB>
+template <bool LOCAL, int R, int TB, bool GB, bool CODES = false>
 __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
 {
     static_assert(R % 2 == 0, "R must be even");
@@ -256,6 +280,8 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned gap2 = pk_dup(A.gap);
+    const unsigned mmb = A.allow ? ((unsigned)(A.mismatch - A.prof_bias) & 0xffu) : 0x80u; // CODES: as pk_prep_kernel
+    const unsigned mm4 = mmb * 0x01010101u, mx = ((unsigned)(A.match - A.prof_bias) & 0xffu) ^ mmb;
     uint4 *__restrict__ bnd = A.bound + (uint64_t)gw * A.bound_stride + lane; // GB: [cg][lane] x 4 columns
     for (;;) {
         const uint32_t w = pk_next_job(A, lane);
@@ -266,6 +292,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
         const int M1 = p1 == PK_NULL ? 0 : (int)A.len1[p1], N1 = p1 == PK_NULL ? 0 : (int)A.len2[p1];
         const int Ng = ((int)J.Nw + 3) >> 2, Nw = (int)J.Nw;
         const uint4 *__restrict__ prof = reinterpret_cast<const uint4 *>(A.prof + J.prof_off) + lane;
+        const uint16_t *__restrict__ ccode = reinterpret_cast<const uint16_t *>(A.prof + J.prof_off) + lane;
         const uint32_t *__restrict__ rowsel = A.rowsel + J.rowsel_off + lane;
         uint8_t *__restrict__ trace = A.trace + J.trace_off + (uint64_t)lane * 16;
         int best0 = 0, best1 = 0, bi0 = 0, bi1 = 0; // SW: running (max, last row holding it)
@@ -285,14 +312,32 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
             }
             unsigned diag = LOCAL ? 0u : pk_dup(i0 * A.gap);
             uint8_t *__restrict__ tr = trace + (uint64_t)s * ((PK_PAIR_PIECES == 1 && TB == 4) ? (Ng + 1) / 2 * 2 : Ng) * (R * TB / 16 * 512);
-            uint4 na = prof[0], nb = prof[32]; // profile of the next group: {T0,T1} x 4 columns
+            uint4 na = make_uint4(0, 0, 0, 0), nb = na; // profile of the next group: {T0,T1} x 4 columns
+            unsigned ncode = 0;                          // CODES: column codes of the next group
+            if (CODES) {
+                ncode = ccode[0];
+            } else {
+                na = prof[0];
+                nb = prof[32];
+            }
             uint4 nu = make_uint4(0, 0, 0, 0);  // GB: boundary of the next group
             if (GB && !first) nu = bnd[0];
             for (int cg = 0; cg < Ng; cg++) {
-                const uint4 ca = na, cb = nb, cu = nu;
+                uint4 ca = na, cb = nb;
+                const uint4 cu = nu;
+                if (CODES) {
+                    unsigned T[8];
+                    pk_colprof(ncode, N0 - cg * 4, N1 - cg * 4, mm4, mx, T);
+                    ca = make_uint4(T[0], T[1], T[2], T[3]);
+                    cb = make_uint4(T[4], T[5], T[6], T[7]);
+                }
                 if (cg + 1 < Ng) {
-                    na = prof[(uint64_t)(cg + 1) * 64];
-                    nb = prof[(uint64_t)(cg + 1) * 64 + 32];
+                    if (CODES) {
+                        ncode = ccode[(uint64_t)(cg + 1) * 32];
+                    } else {
+                        na = prof[(uint64_t)(cg + 1) * 64];
+                        nb = prof[(uint64_t)(cg + 1) * 64 + 32];
+                    }
                     if (GB && !first) nu = bnd[(uint64_t)(cg + 1) * 32];
                 }
                 // long pairs: the boundary rows of all resident warps outgrow the L2; pull mine back in well ahead

@@ -33,7 +33,7 @@ __host__ __device__ inline uint64_t pkg_trace_bytes(uint32_t nstrips, uint32_t N
 //   word (r%8)/2, byte (r%2)*2 + k      (r = row inside the strip, hf = r/8, k = pair half)
 // TB == 4 halves the HBM write stream that bounds the 8-bit variant; the host admits it when every difference the
 // walk tests stays below 16 (packed_affine_trace_bits in seqa_cuda.cu).
-template <bool LOCAL, int R, int TB>
+template <bool LOCAL, int R, int TB, bool CODES = true>
 __global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
 {
     static_assert(TB == 4 || TB == 8, "trace bits");
@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int gogo = A.go + A.ge;
     const unsigned ge2 = pk_dup(A.ge), gogo2 = pk_dup(gogo), neg2 = pk_dup(PKG_NEG);
+    const unsigned mmb = A.allow ? ((unsigned)(A.mismatch - A.prof_bias) & 0xffu) : 0x80u; // CODES: as pk_prep_kernel
+    const unsigned mm4 = mmb * 0x01010101u, mx = ((unsigned)(A.match - A.prof_bias) & 0xffu) ^ mmb;
     uint4 *__restrict__ bnd = A.bound + (uint64_t)gw * A.bound_stride + lane * 2; // [cg][lane][{G,Ix} x 4 columns]
     for (;;) {
         const uint32_t w = pk_next_job(A, lane);
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
         const int M1 = p1 == PK_NULL ? 0 : (int)A.len1[p1], N1 = p1 == PK_NULL ? 0 : (int)A.len2[p1];
         const int Ng = ((int)J.Nw + 3) >> 2, Nw = (int)J.Nw;
         const uint4 *__restrict__ prof = reinterpret_cast<const uint4 *>(A.prof + J.prof_off) + lane;
+        const uint16_t *__restrict__ ccode = reinterpret_cast<const uint16_t *>(A.prof + J.prof_off) + lane;
         const uint32_t *__restrict__ rowsel = A.rowsel + J.rowsel_off + lane;
         uint4 *__restrict__ trace = reinterpret_cast<uint4 *>(A.trace + J.trace_off) + lane;
         int best0 = 0, best1 = 0, bi0 = 0, bi1 = 0; // local: running (max, last row holding it)
@@ -73,17 +76,35 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
             unsigned diag = pk_dup((LOCAL || i0 == 0 ? 0 : A.go + i0 * A.ge) + gogo); // G(i0, 0)
             const int NC = TB == 8 ? Nw : (Nw + 1) >> 1;
             uint4 *__restrict__ tr = trace + (uint64_t)s * NC * (3 * RH * 32);
-            uint4 na = prof[0], nb = prof[32];
+            uint4 na = make_uint4(0, 0, 0, 0), nb = na;
+            unsigned ncode = 0; // CODES: column codes of the next group (the profile words are rebuilt here, seqa_packed.cuh)
+            if (CODES) {
+                ncode = ccode[0];
+            } else {
+                na = prof[0];
+                nb = prof[32];
+            }
             uint4 nu0 = make_uint4(0, 0, 0, 0), nu1 = nu0;
             if (!first) {
                 nu0 = bnd[0];
                 nu1 = bnd[1];
             }
             for (int cg = 0; cg < Ng; cg++) {
-                const uint4 ca = na, cb = nb, cu0 = nu0, cu1 = nu1;
+                uint4 ca = na, cb = nb;
+                const uint4 cu0 = nu0, cu1 = nu1;
+                if (CODES) {
+                    unsigned T[8];
+                    pk_colprof(ncode, N0 - cg * 4, N1 - cg * 4, mm4, mx, T);
+                    ca = make_uint4(T[0], T[1], T[2], T[3]);
+                    cb = make_uint4(T[4], T[5], T[6], T[7]);
+                }
                 if (cg + 1 < Ng) {
-                    na = prof[(uint64_t)(cg + 1) * 64];
-                    nb = prof[(uint64_t)(cg + 1) * 64 + 32];
+                    if (CODES) {
+                        ncode = ccode[(uint64_t)(cg + 1) * 32];
+                    } else {
+                        na = prof[(uint64_t)(cg + 1) * 64];
+                        nb = prof[(uint64_t)(cg + 1) * 64 + 32];
+                    }
                     if (!first) {
                         nu0 = bnd[(uint64_t)(cg + 1) * 64];
                         nu1 = bnd[(uint64_t)(cg + 1) * 64 + 1];
