@@ -33,7 +33,9 @@
 #include <functional>
 #include <limits>
 #include <list>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <stdexcept>
 #include <string>
@@ -418,7 +420,13 @@ class SequenceAligner {
                                         "include/SequenceAlignment.h)");
     }
 
-    // First(P) / Second(P) return the two sequences of pair P (no pointer vectors are built for a million pairs)
+    // First(P) / Second(P) return the two sequences of pair P (no pointer vectors are built for a million pairs).
+    //
+    // Large batches are PIPELINED in a few chunks: while the library aligns chunk k (upload, kernels and download of its
+    // own waves), the host threads pack chunk k+1 -- reading a million std::strings out of the heap costs about as much as
+    // the GPU work on them (tests/cpp/bench_header.cpp, SEQA_API_TIMING=1).  Every chunk is one seqa_cuda_align_batch
+    // call into sub-ranges of the same result arrays; a chunk that holds a symbol outside ACGT goes out as 8-bit symbols,
+    // the others 2-bit packed.
     template <typename FirstFn, typename SecondFn> seqa::PackedAlignments runBatch(int Algo, size_t N, FirstFn First, SecondFn Second)
     {
         static_assert(sizeof(Ty) == 1, "seqalib_b200: the GPU path aligns 8-bit symbols (char); wider types are reference-only");
@@ -427,15 +435,14 @@ class SequenceAligner {
         R.TwoBit = true;
         if (N == 0) {
             LastScores.clear();
+            LastUnsupported.clear();
             return R;
         }
         auto Up = [](size_t X) { return (X + 63) / 64 * 64; };
         const bool Timing = std::getenv("SEQA_API_TIMING") != nullptr; // phase times of this call on stderr
         const auto T0 = std::chrono::steady_clock::now();
         auto Since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count(); };
-        double TLen = 0, TPack = 0, TGpu = 0;
-        // ---- inputs: lengths / offsets and symbols packed into page-locked memory by the host threads.  Symbols go out
-        // 2-bit packed (SEQA_FLAG_BASES_2BIT: a quarter of the PCIe bytes) when every symbol is one of ACGT, else 8-bit ----
+        // ---- lengths and their prefix sums (threaded) ----
         if (!IdxBlock) IdxBlock = std::make_shared<seqa::PinnedBlock>();
         if (!BasesBlock) BasesBlock = std::make_shared<seqa::PinnedBlock>();
         IdxBlock->reserve(Up(8 * N) * 2 + Up(4 * N) * 2);
@@ -444,73 +451,33 @@ class SequenceAligner {
         uint32_t *Len1 = reinterpret_cast<uint32_t *>(IdxBlock->P + 2 * Up(8 * N));
         uint32_t *Len2 = reinterpret_cast<uint32_t *>(IdxBlock->P + 2 * Up(8 * N) + Up(4 * N));
         const size_t Threads = seqa::detail::hostThreads(N, 8192);
-        std::vector<uint64_t> PartSyms(Threads + 1, 0), PartBytes(Threads + 1, 0);
-        seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) { // lengths + per-thread totals
-            uint64_t Syms = 0, Bytes = 0;
-            for (size_t P = Lo; P < Hi; P++) {
-                const uint32_t A = (uint32_t)First(P).size(), B = (uint32_t)Second(P).size();
-                Len1[P] = A;
-                Len2[P] = B;
-                Syms += (uint64_t)A + B;
-                Bytes += (uint64_t)((A + 3) >> 2) + ((B + 3) >> 2);
-            }
-            PartSyms[T + 1] = Syms;
-            PartBytes[T + 1] = Bytes;
-        });
-        for (size_t T = 0; T < Threads; T++) {
-            PartSyms[T + 1] += PartSyms[T];
-            PartBytes[T + 1] += PartBytes[T];
-        }
-        const uint64_t Total = PartSyms[Threads], TotalPacked = PartBytes[Threads];
-        TLen = Since();
-        BasesBlock->reserve(Total + 64); // large enough for either wire format
+        // chunks of the pipeline: ranges of pairs, each cut into one slice per host thread
+        const char *ChunkEnv = std::getenv("SEQA_API_CHUNK_PAIRS"); // batches of at least this many pairs are pipelined (tests lower it)
+        const size_t Chunks = N >= (ChunkEnv ? (size_t)std::max(1L, std::atol(ChunkEnv)) : (size_t)200000) && N >= 4 ? 4 : 1;
+        std::vector<size_t> ChunkLo(Chunks + 1);
+        for (size_t K = 0; K <= Chunks; K++) ChunkLo[K] = N * K / Chunks;
+        auto SliceLo = [&](size_t K, size_t T) { return ChunkLo[K] + (ChunkLo[K + 1] - ChunkLo[K]) * T / Threads; };
+        std::vector<uint64_t> SliceSyms(Chunks * Threads + 1, 0); // symbols before slice (K, T); filled below
+        for (size_t K = 0; K < Chunks; K++)
+            seqa::detail::parallelFor(Threads, Threads, [&](size_t TLo, size_t THi, size_t) {
+                for (size_t T = TLo; T < THi; T++) {
+                    uint64_t Syms = 0;
+                    for (size_t P = SliceLo(K, T); P < SliceLo(K, T + 1); P++) {
+                        const uint32_t A = (uint32_t)First(P).size(), B = (uint32_t)Second(P).size();
+                        Len1[P] = A;
+                        Len2[P] = B;
+                        Syms += (uint64_t)A + B;
+                    }
+                    SliceSyms[K * Threads + T + 1] = Syms;
+                }
+            });
+        for (size_t I = 0; I < Chunks * Threads; I++) SliceSyms[I + 1] += SliceSyms[I];
+        const uint64_t Total = SliceSyms[Chunks * Threads];
+        BasesBlock->reserve(Total + 64); // chunk K owns bytes [SymsBefore(K), SymsBefore(K+1)): room for either wire format
         char *Bases = BasesBlock->P;
-        std::vector<char> ThreadOk(Threads, 1);
-        bool TwoBitIn = !ForceByteInputs && EqualityChecked != 2; // a class table is applied to 8-bit symbols
-        if (TwoBitIn) {
-            seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) { // byte offsets + packed symbols
-                uint64_t Run = PartBytes[T];
-                bool Ok = true;
-                for (size_t P = Lo; P < Hi && Ok; P++) {
-                    Off1[P] = Run;
-                    Off2[P] = Run + ((Len1[P] + 3) >> 2);
-                    Ok = seqa::detail::pack2bit(seqa::detail::bytes_of(First(P)), Len1[P], reinterpret_cast<uint8_t *>(Bases) + Off1[P]) &&
-                         seqa::detail::pack2bit(seqa::detail::bytes_of(Second(P)), Len2[P], reinterpret_cast<uint8_t *>(Bases) + Off2[P]);
-                    Run = Off2[P] + ((Len2[P] + 3) >> 2);
-                }
-                ThreadOk[T] = Ok ? 1 : 0;
-            });
-            for (char Ok : ThreadOk) TwoBitIn = TwoBitIn && Ok != 0;
-        }
-        if (!TwoBitIn) {
-            seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) { // symbol offsets + 8-bit symbols
-                uint64_t Run = PartSyms[T];
-                for (size_t P = Lo; P < Hi; P++) {
-                    Off1[P] = Run;
-                    Off2[P] = Run + Len1[P];
-                    if (Len1[P]) std::memcpy(Bases + Off1[P], seqa::detail::bytes_of(First(P)), Len1[P]);
-                    if (Len2[P]) std::memcpy(Bases + Off2[P], seqa::detail::bytes_of(Second(P)), Len2[P]);
-                    Run = Off2[P] + Len2[P];
-                }
-            });
-        }
-        LastInputsTwoBit = TwoBitIn;
-        TPack = Since();
-        seqa_params Prm{};
-        Prm.algo = Algo;
-        Prm.gap = Scoring.getGapPenalty();
-        Prm.gap_open = Scoring.getGapOpenPenalty();
-        Prm.gap_extend = Scoring.getGapExtendPenalty();
-        Prm.match = Scoring.getMatchProfit();
-        Prm.allow_mismatch = Scoring.getAllowMismatch() ? 1 : 0;
-        Prm.mismatch = Scoring.getAllowMismatch() ? Scoring.getMismatchPenalty() : 0;
-        Prm.device_first = 0;
-        Prm.device_count = 0; // every visible device
-        Prm.flags = SEQA_FLAG_OPS_2BIT | (TwoBitIn ? SEQA_FLAG_BASES_2BIT : 0u); // a quarter of the bytes over PCIe, both ways
-        seqa_batch_in In{Bases, Off1, Off2, Len1, Len2, (uint64_t)N, TwoBitIn ? TotalPacked : Total,
-                         EqualityChecked == 2 ? ClassTable.data() : nullptr};
+        const double TLen = Since();
         // ---- results: one page-locked block; the previous one is reused once nobody else holds it ----
-        const size_t OpsCap = (size_t)(Total / 4 + N + 1);
+        const size_t OpsCap = (size_t)(Total / 4 + N + 1 + 8 * Chunks);
         if (!OutBlock || OutBlock.use_count() > 1) OutBlock = std::make_shared<seqa::PinnedBlock>();
         OutBlock->reserve(Up(4 * N) * 6 + Up(8 * N) + Up(OpsCap));
         char *O = OutBlock->P;
@@ -523,24 +490,130 @@ class SequenceAligner {
         R.OpsOff = {reinterpret_cast<uint64_t *>(O + 6 * Up(4 * N)), N};
         R.Ops = {reinterpret_cast<uint8_t *>(O + 6 * Up(4 * N) + Up(8 * N)), OpsCap};
         R.Store = OutBlock;
-        seqa_batch_out Out{R.Score.data(), R.StartI.data(), R.StartJ.data(), R.EndI.data(), R.EndJ.data(), R.Ops.data(),
-                           R.OpsOff.data(), R.OpsLen.data(), (uint64_t)OpsCap, 0};
-        if (seqa_cuda_align_batch(&Prm, &In, &Out) != SEQA_OK)
-            throw std::runtime_error(std::string("seqa_cuda_align_batch: ") + seqa_cuda_last_error());
-        TGpu = Since();
-        // (large batches are processed in waves whose op strings sit at each wave's own base offset inside Ops)
+        seqa_params Prm{};
+        Prm.algo = Algo;
+        Prm.gap = Scoring.getGapPenalty();
+        Prm.gap_open = Scoring.getGapOpenPenalty();
+        Prm.gap_extend = Scoring.getGapExtendPenalty();
+        Prm.match = Scoring.getMatchProfit();
+        Prm.allow_mismatch = Scoring.getAllowMismatch() ? 1 : 0;
+        Prm.mismatch = Scoring.getAllowMismatch() ? Scoring.getMismatchPenalty() : 0;
+        Prm.device_first = 0;
+        Prm.device_count = 0; // every visible device
+        // ---- the pipeline: this thread (+ helpers) packs chunk after chunk, one worker thread hands packed chunks to the GPU ----
+        std::vector<char> ChunkTwoBit(Chunks, 0);
+        std::vector<uint64_t> OpsBase(Chunks + 1, 0); // where chunk K's op strings start inside R.Ops
+        for (size_t K = 0; K < Chunks; K++)
+            OpsBase[K + 1] = OpsBase[K] + (SliceSyms[(K + 1) * Threads] - SliceSyms[K * Threads]) / 4 + (ChunkLo[K + 1] - ChunkLo[K]) + 8;
+        std::mutex Mu;
+        std::condition_variable Cv;
+        size_t Packed = 0;
+        std::string Error;
+        double TPackBusy = 0, TGpuBusy = 0;
+        auto AlignChunk = [&](size_t K) -> bool {
+            const size_t Lo = ChunkLo[K], Cnt = ChunkLo[K + 1] - Lo;
+            if (Cnt == 0) return true;
+            seqa_params P = Prm;
+            // a quarter of the bytes over PCIe, both ways (symbols only when the whole chunk is ACGT)
+            P.flags = SEQA_FLAG_OPS_2BIT | (ChunkTwoBit[K] ? SEQA_FLAG_BASES_2BIT : 0u);
+            seqa_batch_in In{Bases, Off1 + Lo, Off2 + Lo, Len1 + Lo, Len2 + Lo, (uint64_t)Cnt, (uint64_t)(Total + 64),
+                             EqualityChecked == 2 ? ClassTable.data() : nullptr};
+            seqa_batch_out Out{R.Score.data() + Lo, R.StartI.data() + Lo, R.StartJ.data() + Lo, R.EndI.data() + Lo, R.EndJ.data() + Lo,
+                               R.Ops.data() + OpsBase[K], R.OpsOff.data() + Lo, R.OpsLen.data() + Lo, OpsBase[K + 1] - OpsBase[K], 0};
+            if (seqa_cuda_align_batch(&P, &In, &Out) != SEQA_OK) {
+                Error = std::string("seqa_cuda_align_batch: ") + seqa_cuda_last_error();
+                return false;
+            }
+            return true;
+        };
+        std::thread Gpu;
+        if (Chunks > 1)
+            Gpu = std::thread([&]() {
+                for (size_t K = 0; K < Chunks; K++) {
+                    {
+                        std::unique_lock<std::mutex> Lk(Mu);
+                        Cv.wait(Lk, [&] { return Packed > K; });
+                    }
+                    const double A = Since();
+                    const bool Ok = AlignChunk(K);
+                    TGpuBusy += Since() - A;
+                    if (!Ok) return;
+                }
+            });
+        const bool TryTwoBit = !ForceByteInputs && EqualityChecked != 2; // a class table is applied to 8-bit symbols
+        for (size_t K = 0; K < Chunks; K++) {
+            const double A = Since();
+            std::vector<char> SliceOk(Threads, 1);
+            if (TryTwoBit) {
+                // every slice packs into the byte range its symbols own: 2-bit sequences never need more bytes than 8-bit ones
+                seqa::detail::parallelFor(Threads, Threads, [&](size_t TLo, size_t THi, size_t) {
+                    for (size_t T = TLo; T < THi; T++) {
+                        uint64_t Run = SliceSyms[K * Threads + T];
+                        bool Ok = true;
+                        for (size_t P = SliceLo(K, T); P < SliceLo(K, T + 1) && Ok; P++) {
+                            Off1[P] = Run;
+                            Off2[P] = Run + ((Len1[P] + 3) >> 2);
+                            Ok = seqa::detail::pack2bit(seqa::detail::bytes_of(First(P)), Len1[P], reinterpret_cast<uint8_t *>(Bases) + Off1[P]) &&
+                                 seqa::detail::pack2bit(seqa::detail::bytes_of(Second(P)), Len2[P], reinterpret_cast<uint8_t *>(Bases) + Off2[P]);
+                            Run = Off2[P] + ((Len2[P] + 3) >> 2);
+                        }
+                        SliceOk[T] = Ok ? 1 : 0;
+                    }
+                });
+            }
+            bool Two = TryTwoBit;
+            for (char Ok : SliceOk) Two = Two && Ok != 0;
+            if (!Two) {
+                seqa::detail::parallelFor(Threads, Threads, [&](size_t TLo, size_t THi, size_t) {
+                    for (size_t T = TLo; T < THi; T++) {
+                        uint64_t Run = SliceSyms[K * Threads + T];
+                        for (size_t P = SliceLo(K, T); P < SliceLo(K, T + 1); P++) {
+                            Off1[P] = Run;
+                            Off2[P] = Run + Len1[P];
+                            if (Len1[P]) std::memcpy(Bases + Off1[P], seqa::detail::bytes_of(First(P)), Len1[P]);
+                            if (Len2[P]) std::memcpy(Bases + Off2[P], seqa::detail::bytes_of(Second(P)), Len2[P]);
+                            Run = Off2[P] + Len2[P];
+                        }
+                    }
+                });
+            }
+            ChunkTwoBit[K] = Two ? 1 : 0;
+            TPackBusy += Since() - A;
+            if (Chunks > 1) {
+                std::lock_guard<std::mutex> Lk(Mu);
+                Packed = K + 1;
+                Cv.notify_all();
+            } else {
+                const double B = Since();
+                AlignChunk(K);
+                TGpuBusy += Since() - B;
+            }
+        }
+        if (Gpu.joinable()) Gpu.join();
+        if (!Error.empty()) throw std::runtime_error(Error);
+        LastInputsTwoBit = true;
+        for (char Tb : ChunkTwoBit) LastInputsTwoBit = LastInputsTwoBit && Tb != 0;
+        const double TDone = Since();
+        // ---- scores, rejected pairs, op offsets relative to R.Ops (threaded) ----
         LastScores.resize(N);
         LastUnsupported.clear();
-        std::vector<std::vector<size_t>> Rejected(Threads);
-        seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) {
-            std::memcpy(LastScores.data() + Lo, R.Score.data() + Lo, (Hi - Lo) * sizeof(int));
-            for (size_t P = Lo; P < Hi; P++)
-                if (R.OpsLen[P] == SEQA_PAIR_UNSUPPORTED) Rejected[T].push_back(P);
-        });
+        std::vector<std::vector<size_t>> Rejected(Chunks * Threads);
+        for (size_t K = 0; K < Chunks; K++)
+            seqa::detail::parallelFor(Threads, Threads, [&](size_t TLo, size_t THi, size_t) {
+                for (size_t T = TLo; T < THi; T++) {
+                    const size_t Lo = SliceLo(K, T), Hi = SliceLo(K, T + 1);
+                    std::memcpy(LastScores.data() + Lo, R.Score.data() + Lo, (Hi - Lo) * sizeof(int));
+                    for (size_t P = Lo; P < Hi; P++) {
+                        R.OpsOff[P] += OpsBase[K];
+                        if (R.OpsLen[P] == SEQA_PAIR_UNSUPPORTED) Rejected[K * Threads + T].push_back(P);
+                    }
+                }
+            });
         for (const std::vector<size_t> &V : Rejected) LastUnsupported.insert(LastUnsupported.end(), V.begin(), V.end());
         if (Timing)
-            std::fprintf(stderr, "[seqa api] %zu pairs, %zu threads: lengths %.2f ms, pack (%s) %.2f ms, seqa_cuda_align_batch %.2f ms, scores %.2f ms\n",
-                         N, Threads, TLen, TwoBitIn ? "2-bit" : "8-bit", TPack - TLen, TGpu - TPack, Since() - TGpu);
+            std::fprintf(stderr, "[seqa api] %zu pairs, %zu threads, %zu chunk(s): lengths %.2f ms, packing busy %.2f ms (%s), GPU calls busy %.2f ms, "
+                                 "pipeline %.2f ms, scores %.2f ms\n", N, Threads, Chunks, TLen, TPackBusy, LastInputsTwoBit ? "2-bit" : "8-bit",
+                         TGpuBusy, TDone - TLen, Since() - TDone);
         return R;
     }
 
