@@ -422,11 +422,10 @@ class SequenceAligner {
 
     // First(P) / Second(P) return the two sequences of pair P (no pointer vectors are built for a million pairs).
     //
-    // Large batches are PIPELINED in a few chunks: while the library aligns chunk k (upload, kernels and download of its
-    // own waves), the host threads pack chunk k+1 -- reading a million std::strings out of the heap costs about as much as
-    // the GPU work on them (tests/cpp/bench_header.cpp, SEQA_API_TIMING=1).  Every chunk is one seqa_cuda_align_batch
-    // call into sub-ranges of the same result arrays; a chunk that holds a symbol outside ACGT goes out as 8-bit symbols,
-    // the others 2-bit packed.
+    // The symbols are packed LAZILY, wave by wave, from the library's own pipeline (seqa_cuda_align_batch_lazy): while the
+    // GPU works on wave k the host threads pack wave k+1 -- reading a million std::strings out of the heap costs about as
+    // much as the GPU work on them (tests/cpp/bench_header.cpp, SEQA_API_TIMING=1).  Lengths and offsets are laid out up
+    // front for the 2-bit wire format; if a symbol outside ACGT turns up, the call is repeated with 8-bit symbols.
     template <typename FirstFn, typename SecondFn> seqa::PackedAlignments runBatch(int Algo, size_t N, FirstFn First, SecondFn Second)
     {
         static_assert(sizeof(Ty) == 1, "seqalib_b200: the GPU path aligns 8-bit symbols (char); wider types are reference-only");
@@ -442,7 +441,7 @@ class SequenceAligner {
         const bool Timing = std::getenv("SEQA_API_TIMING") != nullptr; // phase times of this call on stderr
         const auto T0 = std::chrono::steady_clock::now();
         auto Since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count(); };
-        // ---- lengths and their prefix sums (threaded) ----
+        // ---- lengths, then offsets for the chosen wire format (threaded two-pass prefix sums) ----
         if (!IdxBlock) IdxBlock = std::make_shared<seqa::PinnedBlock>();
         if (!BasesBlock) BasesBlock = std::make_shared<seqa::PinnedBlock>();
         IdxBlock->reserve(Up(8 * N) * 2 + Up(4 * N) * 2);
@@ -451,33 +450,39 @@ class SequenceAligner {
         uint32_t *Len1 = reinterpret_cast<uint32_t *>(IdxBlock->P + 2 * Up(8 * N));
         uint32_t *Len2 = reinterpret_cast<uint32_t *>(IdxBlock->P + 2 * Up(8 * N) + Up(4 * N));
         const size_t Threads = seqa::detail::hostThreads(N, 8192);
-        // chunks of the pipeline: ranges of pairs, each cut into one slice per host thread
-        const char *ChunkEnv = std::getenv("SEQA_API_CHUNK_PAIRS"); // batches of at least this many pairs are pipelined (tests lower it)
-        const size_t Chunks = N >= (ChunkEnv ? (size_t)std::max(1L, std::atol(ChunkEnv)) : (size_t)200000) && N >= 4 ? 4 : 1;
-        std::vector<size_t> ChunkLo(Chunks + 1);
-        for (size_t K = 0; K <= Chunks; K++) ChunkLo[K] = N * K / Chunks;
-        auto SliceLo = [&](size_t K, size_t T) { return ChunkLo[K] + (ChunkLo[K + 1] - ChunkLo[K]) * T / Threads; };
-        std::vector<uint64_t> SliceSyms(Chunks * Threads + 1, 0); // symbols before slice (K, T); filled below
-        for (size_t K = 0; K < Chunks; K++)
-            seqa::detail::parallelFor(Threads, Threads, [&](size_t TLo, size_t THi, size_t) {
-                for (size_t T = TLo; T < THi; T++) {
-                    uint64_t Syms = 0;
-                    for (size_t P = SliceLo(K, T); P < SliceLo(K, T + 1); P++) {
-                        const uint32_t A = (uint32_t)First(P).size(), B = (uint32_t)Second(P).size();
-                        Len1[P] = A;
-                        Len2[P] = B;
-                        Syms += (uint64_t)A + B;
-                    }
-                    SliceSyms[K * Threads + T + 1] = Syms;
+        std::vector<uint64_t> PartSyms(Threads + 1, 0), PartBytes(Threads + 1, 0);
+        seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) {
+            uint64_t Syms = 0, Bytes = 0;
+            for (size_t P = Lo; P < Hi; P++) {
+                const uint32_t A = (uint32_t)First(P).size(), B = (uint32_t)Second(P).size();
+                Len1[P] = A;
+                Len2[P] = B;
+                Syms += (uint64_t)A + B;
+                Bytes += (uint64_t)((A + 3) >> 2) + ((B + 3) >> 2);
+            }
+            PartSyms[T + 1] = Syms;
+            PartBytes[T + 1] = Bytes;
+        });
+        for (size_t T = 0; T < Threads; T++) {
+            PartSyms[T + 1] += PartSyms[T];
+            PartBytes[T + 1] += PartBytes[T];
+        }
+        const uint64_t Total = PartSyms[Threads], TotalPacked = PartBytes[Threads];
+        BasesBlock->reserve(Total + 64); // large enough for either wire format
+        char *Bases = BasesBlock->P;
+        auto LayOut = [&](bool TwoBit) { // Off1 / Off2 of every pair: sequences back to back (byte-aligned ones in the 2-bit format)
+            seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) {
+                uint64_t Run = TwoBit ? PartBytes[T] : PartSyms[T];
+                for (size_t P = Lo; P < Hi; P++) {
+                    const uint64_t B1 = TwoBit ? (Len1[P] + 3) >> 2 : Len1[P], B2 = TwoBit ? (Len2[P] + 3) >> 2 : Len2[P];
+                    Off1[P] = Run;
+                    Off2[P] = Run + B1;
+                    Run += B1 + B2;
                 }
             });
-        for (size_t I = 0; I < Chunks * Threads; I++) SliceSyms[I + 1] += SliceSyms[I];
-        const uint64_t Total = SliceSyms[Chunks * Threads];
-        BasesBlock->reserve(Total + 64); // chunk K owns bytes [SymsBefore(K), SymsBefore(K+1)): room for either wire format
-        char *Bases = BasesBlock->P;
-        const double TLen = Since();
+        };
         // ---- results: one page-locked block; the previous one is reused once nobody else holds it ----
-        const size_t OpsCap = (size_t)(Total / 4 + N + 1 + 8 * Chunks);
+        const size_t OpsCap = (size_t)(Total / 4 + N + 1);
         if (!OutBlock || OutBlock.use_count() > 1) OutBlock = std::make_shared<seqa::PinnedBlock>();
         OutBlock->reserve(Up(4 * N) * 6 + Up(8 * N) + Up(OpsCap));
         char *O = OutBlock->P;
@@ -500,120 +505,78 @@ class SequenceAligner {
         Prm.mismatch = Scoring.getAllowMismatch() ? Scoring.getMismatchPenalty() : 0;
         Prm.device_first = 0;
         Prm.device_count = 0; // every visible device
-        // ---- the pipeline: this thread (+ helpers) packs chunk after chunk, one worker thread hands packed chunks to the GPU ----
-        std::vector<char> ChunkTwoBit(Chunks, 0);
-        std::vector<uint64_t> OpsBase(Chunks + 1, 0); // where chunk K's op strings start inside R.Ops
-        for (size_t K = 0; K < Chunks; K++)
-            OpsBase[K + 1] = OpsBase[K] + (SliceSyms[(K + 1) * Threads] - SliceSyms[K * Threads]) / 4 + (ChunkLo[K + 1] - ChunkLo[K]) + 8;
-        std::mutex Mu;
-        std::condition_variable Cv;
-        size_t Packed = 0;
-        std::string Error;
-        double TPackBusy = 0, TGpuBusy = 0;
-        auto AlignChunk = [&](size_t K) -> bool {
-            const size_t Lo = ChunkLo[K], Cnt = ChunkLo[K + 1] - Lo;
-            if (Cnt == 0) return true;
-            seqa_params P = Prm;
-            // a quarter of the bytes over PCIe, both ways (symbols only when the whole chunk is ACGT)
-            P.flags = SEQA_FLAG_OPS_2BIT | (ChunkTwoBit[K] ? SEQA_FLAG_BASES_2BIT : 0u);
-            seqa_batch_in In{Bases, Off1 + Lo, Off2 + Lo, Len1 + Lo, Len2 + Lo, (uint64_t)Cnt, (uint64_t)(Total + 64),
-                             EqualityChecked == 2 ? ClassTable.data() : nullptr};
-            seqa_batch_out Out{R.Score.data() + Lo, R.StartI.data() + Lo, R.StartJ.data() + Lo, R.EndI.data() + Lo, R.EndJ.data() + Lo,
-                               R.Ops.data() + OpsBase[K], R.OpsOff.data() + Lo, R.OpsLen.data() + Lo, OpsBase[K + 1] - OpsBase[K], 0};
-            if (seqa_cuda_align_batch(&P, &In, &Out) != SEQA_OK) {
-                Error = std::string("seqa_cuda_align_batch: ") + seqa_cuda_last_error();
-                return false;
+        // ---- the call: the library asks for the symbols of one wave at a time (from its producer threads) ----
+        struct Filler {
+            bool TwoBit;
+            char *Bases;
+            const uint64_t *Off1, *Off2;
+            const uint32_t *Len1, *Len2;
+            FirstFn *First;
+            SecondFn *Second;
+            size_t Threads;
+            double Busy = 0; // ms spent packing (one device: no concurrent callbacks)
+            static int fill(void *User, uint64_t Lo, uint64_t Cnt)
+            {
+                Filler &F = *static_cast<Filler *>(User);
+                const auto A = std::chrono::steady_clock::now();
+                std::vector<char> Ok(F.Threads, 1);
+                // two threads stay free for the library's own producer / consumer, which feed the GPU meanwhile
+                const size_t Use = std::max<size_t>(1, std::min<size_t>(F.Threads > 3 ? F.Threads - 2 : F.Threads, (size_t)Cnt / 2048 + 1));
+                seqa::detail::parallelFor((size_t)Cnt, Use, [&](size_t L, size_t H, size_t T) {
+                    bool Good = true;
+                    for (size_t P = (size_t)Lo + L; P < (size_t)Lo + H && Good; P++) {
+                        const char *S1 = seqa::detail::bytes_of((*F.First)(P)), *S2 = seqa::detail::bytes_of((*F.Second)(P));
+                        if (F.TwoBit) {
+                            Good = seqa::detail::pack2bit(S1, F.Len1[P], reinterpret_cast<uint8_t *>(F.Bases) + F.Off1[P]) &&
+                                   seqa::detail::pack2bit(S2, F.Len2[P], reinterpret_cast<uint8_t *>(F.Bases) + F.Off2[P]);
+                        } else {
+                            if (F.Len1[P]) std::memcpy(F.Bases + F.Off1[P], S1, F.Len1[P]);
+                            if (F.Len2[P]) std::memcpy(F.Bases + F.Off2[P], S2, F.Len2[P]);
+                        }
+                    }
+                    Ok[T] = Good ? 1 : 0;
+                });
+                F.Busy += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - A).count();
+                for (char G : Ok)
+                    if (!G) return 1; // a symbol outside ACGT: this batch cannot go out 2-bit packed
+                return 0;
             }
-            return true;
         };
-        std::thread Gpu;
-        if (Chunks > 1)
-            Gpu = std::thread([&]() {
-                for (size_t K = 0; K < Chunks; K++) {
-                    {
-                        std::unique_lock<std::mutex> Lk(Mu);
-                        Cv.wait(Lk, [&] { return Packed > K; });
-                    }
-                    const double A = Since();
-                    const bool Ok = AlignChunk(K);
-                    TGpuBusy += Since() - A;
-                    if (!Ok) return;
-                }
-            });
-        const bool TryTwoBit = !ForceByteInputs && EqualityChecked != 2; // a class table is applied to 8-bit symbols
-        for (size_t K = 0; K < Chunks; K++) {
-            const double A = Since();
-            std::vector<char> SliceOk(Threads, 1);
-            if (TryTwoBit) {
-                // every slice packs into the byte range its symbols own: 2-bit sequences never need more bytes than 8-bit ones
-                seqa::detail::parallelFor(Threads, Threads, [&](size_t TLo, size_t THi, size_t) {
-                    for (size_t T = TLo; T < THi; T++) {
-                        uint64_t Run = SliceSyms[K * Threads + T];
-                        bool Ok = true;
-                        for (size_t P = SliceLo(K, T); P < SliceLo(K, T + 1) && Ok; P++) {
-                            Off1[P] = Run;
-                            Off2[P] = Run + ((Len1[P] + 3) >> 2);
-                            Ok = seqa::detail::pack2bit(seqa::detail::bytes_of(First(P)), Len1[P], reinterpret_cast<uint8_t *>(Bases) + Off1[P]) &&
-                                 seqa::detail::pack2bit(seqa::detail::bytes_of(Second(P)), Len2[P], reinterpret_cast<uint8_t *>(Bases) + Off2[P]);
-                            Run = Off2[P] + ((Len2[P] + 3) >> 2);
-                        }
-                        SliceOk[T] = Ok ? 1 : 0;
-                    }
-                });
+        bool TwoBitIn = !ForceByteInputs && EqualityChecked != 2; // a class table is applied to 8-bit symbols
+        double TLay = 0, TCall = 0, TPackBusy = 0;
+        for (;;) {
+            LayOut(TwoBitIn);
+            TLay = Since();
+            Filler F{TwoBitIn, Bases, Off1, Off2, Len1, Len2, &First, &Second, Threads};
+            Prm.flags = SEQA_FLAG_OPS_2BIT | (TwoBitIn ? SEQA_FLAG_BASES_2BIT : 0u); // a quarter of the bytes over PCIe, both ways
+            seqa_batch_in In{Bases, Off1, Off2, Len1, Len2, (uint64_t)N, TwoBitIn ? TotalPacked : Total,
+                             EqualityChecked == 2 ? ClassTable.data() : nullptr};
+            seqa_batch_out Out{R.Score.data(), R.StartI.data(), R.StartJ.data(), R.EndI.data(), R.EndJ.data(), R.Ops.data(),
+                               R.OpsOff.data(), R.OpsLen.data(), (uint64_t)OpsCap, 0};
+            const int Rc = seqa_cuda_align_batch_lazy(&Prm, &In, &Out, &Filler::fill, &F);
+            TPackBusy = F.Busy;
+            if (Rc == SEQA_OK) break;
+            if (TwoBitIn && Rc == SEQA_ERR_INVALID) { // the filler met a symbol outside ACGT: once more, as 8-bit symbols
+                TwoBitIn = false;
+                continue;
             }
-            bool Two = TryTwoBit;
-            for (char Ok : SliceOk) Two = Two && Ok != 0;
-            if (!Two) {
-                seqa::detail::parallelFor(Threads, Threads, [&](size_t TLo, size_t THi, size_t) {
-                    for (size_t T = TLo; T < THi; T++) {
-                        uint64_t Run = SliceSyms[K * Threads + T];
-                        for (size_t P = SliceLo(K, T); P < SliceLo(K, T + 1); P++) {
-                            Off1[P] = Run;
-                            Off2[P] = Run + Len1[P];
-                            if (Len1[P]) std::memcpy(Bases + Off1[P], seqa::detail::bytes_of(First(P)), Len1[P]);
-                            if (Len2[P]) std::memcpy(Bases + Off2[P], seqa::detail::bytes_of(Second(P)), Len2[P]);
-                            Run = Off2[P] + Len2[P];
-                        }
-                    }
-                });
-            }
-            ChunkTwoBit[K] = Two ? 1 : 0;
-            TPackBusy += Since() - A;
-            if (Chunks > 1) {
-                std::lock_guard<std::mutex> Lk(Mu);
-                Packed = K + 1;
-                Cv.notify_all();
-            } else {
-                const double B = Since();
-                AlignChunk(K);
-                TGpuBusy += Since() - B;
-            }
+            throw std::runtime_error(std::string("seqa_cuda_align_batch: ") + seqa_cuda_last_error());
         }
-        if (Gpu.joinable()) Gpu.join();
-        if (!Error.empty()) throw std::runtime_error(Error);
-        LastInputsTwoBit = true;
-        for (char Tb : ChunkTwoBit) LastInputsTwoBit = LastInputsTwoBit && Tb != 0;
-        const double TDone = Since();
-        // ---- scores, rejected pairs, op offsets relative to R.Ops (threaded) ----
+        LastInputsTwoBit = TwoBitIn;
+        TCall = Since();
+        // (large batches are processed in waves whose op strings sit at each wave's own base offset inside Ops)
         LastScores.resize(N);
         LastUnsupported.clear();
-        std::vector<std::vector<size_t>> Rejected(Chunks * Threads);
-        for (size_t K = 0; K < Chunks; K++)
-            seqa::detail::parallelFor(Threads, Threads, [&](size_t TLo, size_t THi, size_t) {
-                for (size_t T = TLo; T < THi; T++) {
-                    const size_t Lo = SliceLo(K, T), Hi = SliceLo(K, T + 1);
-                    std::memcpy(LastScores.data() + Lo, R.Score.data() + Lo, (Hi - Lo) * sizeof(int));
-                    for (size_t P = Lo; P < Hi; P++) {
-                        R.OpsOff[P] += OpsBase[K];
-                        if (R.OpsLen[P] == SEQA_PAIR_UNSUPPORTED) Rejected[K * Threads + T].push_back(P);
-                    }
-                }
-            });
+        std::vector<std::vector<size_t>> Rejected(Threads);
+        seqa::detail::parallelFor(N, Threads, [&](size_t Lo, size_t Hi, size_t T) {
+            std::memcpy(LastScores.data() + Lo, R.Score.data() + Lo, (Hi - Lo) * sizeof(int));
+            for (size_t P = Lo; P < Hi; P++)
+                if (R.OpsLen[P] == SEQA_PAIR_UNSUPPORTED) Rejected[T].push_back(P);
+        });
         for (const std::vector<size_t> &V : Rejected) LastUnsupported.insert(LastUnsupported.end(), V.begin(), V.end());
         if (Timing)
-            std::fprintf(stderr, "[seqa api] %zu pairs, %zu threads, %zu chunk(s): lengths %.2f ms, packing busy %.2f ms (%s), GPU calls busy %.2f ms, "
-                                 "pipeline %.2f ms, scores %.2f ms\n", N, Threads, Chunks, TLen, TPackBusy, LastInputsTwoBit ? "2-bit" : "8-bit",
-                         TGpuBusy, TDone - TLen, Since() - TDone);
+            std::fprintf(stderr, "[seqa api] %zu pairs, %zu threads: lengths + layout %.2f ms, seqa_cuda_align_batch_lazy %.2f ms (packing %s inside: "
+                                 "%.2f ms busy), scores %.2f ms\n", N, Threads, TLay, TCall - TLay, TwoBitIn ? "2-bit" : "8-bit", TPackBusy, Since() - TCall);
         return R;
     }
 

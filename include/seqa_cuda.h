@@ -156,6 +156,16 @@ typedef struct seqa_batch_out {
  * inter-device communication.  Re-entrant for disjoint device sets. */
 int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, seqa_batch_out *out);
 
+/* The same call for a caller that PACKS its batch while the GPU works: `len1` / `len2` / `off1` / `off2` must be complete
+ * when the call starts (they plan the waves), but the symbols in `bases` may be produced lazily -- right before the library
+ * reads the symbols of pairs [first_pair, first_pair + n_pairs) it calls fill(user, first_pair, n_pairs) from one of its own
+ * threads (every pair exactly once, increasing order per device, concurrently for different devices).  The caller's packing of
+ * wave k+1 then overlaps the upload, kernels and download of wave k inside ONE call.  fill returns 0, or a non-zero value to
+ * abort the call (SEQA_ERR_INVALID; e.g. a symbol the chosen wire format cannot hold).  include/SequenceAlignment.h packs its
+ * std::string pairs this way. */
+typedef int (*seqa_fill_fn)(void *user, uint64_t first_pair, uint64_t n_pairs);
+int seqa_cuda_align_batch_lazy(const seqa_params *params, const seqa_batch_in *in, seqa_batch_out *out, seqa_fill_fn fill, void *user);
+
 /* Frees the per-device contexts (device buffers) that seqa_cuda_align_batch creates lazily and keeps between
  * calls -- the only hidden state of the library. */
 void seqa_cuda_trim(void);

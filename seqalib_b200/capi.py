@@ -29,7 +29,7 @@ EXPORTS = ["seqa_cuda_align_batch", "seqa_cuda_last_error", "seqa_cuda_device_co
            "seqa_ctx_create", "seqa_ctx_destroy", "seqa_ctx_upload", "seqa_ctx_generate", "seqa_ctx_run",
            "seqa_ctx_download", "seqa_ctx_device_results", "seqa_ctx_sync", "seqa_ctx_launch_count", "seqa_ctx_cells", "seqa_ctx_last_fill_ms",
            "seqa_ctx_last_kernel", "seqa_ctx_download_inputs", "seqa_cuda_int_peak", "seqa_cuda_trim",
-           "seqa_cuda_host_alloc", "seqa_cuda_host_free", "seqa_ctx_download_range", "seqa_cuda_last_split"]
+           "seqa_cuda_host_alloc", "seqa_cuda_host_free", "seqa_ctx_download_range", "seqa_cuda_last_split", "seqa_cuda_align_batch_lazy"]
 
 
 def pack_bases_2bit(bases, off1, off2, len1, len2, out=None):

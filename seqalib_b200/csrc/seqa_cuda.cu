@@ -1639,7 +1639,19 @@ void seqa_cuda_trim(void)
 // copy of a third overlap.  A wave's ops land in the caller's buffer at the prefix sum of (len1+len2) of the
 // pairs before it (the ABI lets ops_off point anywhere), which needs no ordering between waves; when
 // ops_capacity is smaller than sum(len1+len2) the waves are packed densely in order instead.
+static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, seqa_batch_out *out, seqa_fill_fn fill, void *fill_user);
+
 int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, seqa_batch_out *out)
+{
+    return align_batch_impl(params, in, out, nullptr, nullptr);
+}
+
+int seqa_cuda_align_batch_lazy(const seqa_params *params, const seqa_batch_in *in, seqa_batch_out *out, seqa_fill_fn fill, void *user)
+{
+    return align_batch_impl(params, in, out, fill, user);
+}
+
+static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, seqa_batch_out *out, seqa_fill_fn fill, void *fill_user)
 {
     CKS(validate_params(params));
     if (!in || !out) return fail(SEQA_ERR_INVALID, "NULL argument");
@@ -1838,6 +1850,9 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
                 }
                 cudaEventRecord(wev[w].e[0], P.c[slot]->up);
             }
+            if (s == SEQA_OK && fill && fill(fill_user, wave_lo[w], wave_lo[w + 1] - wave_lo[w]) != 0)
+                s = fail(SEQA_ERR_INVALID, "the caller's fill callback refused pairs [%llu, %llu)", (unsigned long long)wave_lo[w],
+                         (unsigned long long)wave_lo[w + 1]);
             if (s == SEQA_OK) s = ctx_upload_range(P.c[slot], params, in, wave_lo[w], wave_lo[w + 1], &facts);
             if (dbg && s == SEQA_OK) {
                 cudaEventRecord(wev[w].e[1], P.c[slot]->up);
@@ -1958,6 +1973,10 @@ int seqa_cuda_align_batch(const seqa_params *params, const seqa_batch_in *in, se
             rc = cache_acquire(first + d, &c, &cached);
             for (size_t w = dev_lo[d]; w < dev_lo[d + 1] && rc == SEQA_OK; w++) {
                 uint64_t u = 0;
+                if (fill && fill(fill_user, wave_lo[w], wave_lo[w + 1] - wave_lo[w]) != 0)
+                    rc = fail(SEQA_ERR_INVALID, "the caller's fill callback refused pairs [%llu, %llu)", (unsigned long long)wave_lo[w],
+                              (unsigned long long)wave_lo[w + 1]);
+                if (rc != SEQA_OK) break;
                 rc = ctx_upload_range(c, params, in, wave_lo[w], wave_lo[w + 1], &facts);
                 if (rc == SEQA_OK) rc = ctx_run(c);
                 if (rc == SEQA_OK) rc = ctx_download_into(c, out, wave_lo[w], used, &u);

@@ -194,26 +194,7 @@ int main()
             expect("2-bit vs 8-bit inputs row2", R2, Q2);
             expect("2-bit vs 8-bit inputs flags", Fl, QF);
         }
-        // the pipelined path of large batches (4 chunks packed while the previous one is on the GPU), forced onto this small
-        // batch: one chunk holds the 'N' pair and goes out as 8-bit symbols, the others 2-bit -- same alignments
-        setenv("SEQA_API_CHUNK_PAIRS", "8", 1);
-        auto OneShot = NW.getAlignments(Dirty);
-        SmithWatermanSA<std::string, char, '-'> SWp(ScoringSystem(-1, 1, -1));
-        seqa::PackedAlignments Pk = SWp.getAlignmentsPacked(Clean);
-        unsetenv("SEQA_API_CHUNK_PAIRS");
-        auto Plain = NW.getAlignments(Dirty);
-        seqa::PackedAlignments Pk1 = SWp.getAlignmentsPacked(Clean);
-        for (size_t K = 0; K < Dirty.size(); K++) {
-            std::string Q1, Q2, QF;
-            rows(OneShot[K], R1, R2, Fl);
-            rows(Plain[K], Q1, Q2, QF);
-            expect("pipelined chunks row1", R1, Q1);
-            expect("pipelined chunks row2", R2, Q2);
-            if (Pk.Score[K] != Pk1.Score[K] || Pk.runs(K) != Pk1.runs(K) || Pk.OpsLen[K] != Pk1.OpsLen[K]) {
-                std::printf("FAIL pipelined chunks: packed result of pair %zu\n", K);
-                Failures++;
-            }
-        }
+
     }
     { // table-driven equality: functors that are an equivalence on bytes run on the GPU path
         std::string L1 = "aaagaATGCat", L2 = "AAACtcAT", U1 = "AAAGAATGCAT", U2 = "AAACTCAT";
