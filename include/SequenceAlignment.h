@@ -25,6 +25,7 @@
 #define SEQA_SEQUENCE_ALIGNMENT_H
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -247,22 +248,32 @@ template <typename BodyTy> inline void parallelFor(size_t N, size_t Threads, Bod
 #ifdef SEQA_HAVE_AVX2_DISPATCH
 // 32 symbols per step where the CPU has AVX2 (checked at run time; the header itself needs no -mavx2): codes by shift + and,
 // validity by a byte shuffle through "ACTG", four codes per byte by two multiply-adds (1,4 then 1,16).  Packs the first
-// Len / 32 * 32 symbols and returns how many it packed; *Bad collects symbol ^ letter-of-its-code.
-__attribute__((target("avx2"))) inline size_t pack2bit_avx2(const char *S, size_t Len, uint8_t *Dst, uint64_t *Bad)
+// whole sequence (the last partial step from a padded stack copy); *Bad is set when a symbol is not one of ACGT.
+__attribute__((target("avx2"))) inline uint64_t pack2bit_step_avx2(const __m256i X, __m256i *Acc) // 32 symbols -> 8 packed bytes
 {
     const __m256i Lut = _mm256_setr_epi8('A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 'A', 'C', 'T', 'G', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
     const __m256i Three = _mm256_set1_epi8(3), W1 = _mm256_set1_epi16(0x0401), W2 = _mm256_set1_epi32(0x00100001);
     const __m256i Pick = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i C = _mm256_and_si256(_mm256_srli_epi16(X, 1), Three);
+    *Acc = _mm256_or_si256(*Acc, _mm256_xor_si256(_mm256_shuffle_epi8(Lut, C), X));
+    const __m256i P = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(C, W1), W2), Pick);
+    return (uint64_t)(uint32_t)_mm256_extract_epi32(P, 0) | ((uint64_t)(uint32_t)_mm256_extract_epi32(P, 4) << 32);
+}
+__attribute__((target("avx2"))) inline size_t pack2bit_avx2(const char *S, size_t Len, uint8_t *Dst, uint64_t *Bad)
+{
     __m256i Acc = _mm256_setzero_si256();
     size_t K = 0;
     for (; K + 32 <= Len; K += 32) {
-        const __m256i X = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(S + K));
-        const __m256i C = _mm256_and_si256(_mm256_srli_epi16(X, 1), Three);
-        Acc = _mm256_or_si256(Acc, _mm256_xor_si256(_mm256_shuffle_epi8(Lut, C), X));
-        const __m256i P = _mm256_shuffle_epi8(_mm256_madd_epi16(_mm256_maddubs_epi16(C, W1), W2), Pick);
-        const uint32_t Lo = (uint32_t)_mm256_extract_epi32(P, 0), Hi = (uint32_t)_mm256_extract_epi32(P, 4);
-        std::memcpy(Dst + (K >> 2), &Lo, 4);
-        std::memcpy(Dst + (K >> 2) + 4, &Hi, 4);
+        const uint64_t V = pack2bit_step_avx2(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(S + K)), &Acc);
+        std::memcpy(Dst + (K >> 2), &V, 8);
+    }
+    if (K < Len) { // the last 1..31 symbols, padded with 'A' (code 0) in a stack buffer: one more step
+        alignas(32) char Tail[32];
+        std::memset(Tail, 'A', 32);
+        std::memcpy(Tail, S + K, Len - K);
+        const uint64_t V = pack2bit_step_avx2(_mm256_load_si256(reinterpret_cast<const __m256i *>(Tail)), &Acc);
+        std::memcpy(Dst + (K >> 2), &V, (Len - K + 3) >> 2);
+        K = Len;
     }
     if (!_mm256_testz_si256(Acc, Acc)) *Bad |= 1;
     return K;
@@ -277,7 +288,10 @@ inline bool pack2bit(const char *S, size_t Len, uint8_t *Dst)
     size_t K = 0;
 #ifdef SEQA_HAVE_AVX2_DISPATCH
     static const bool HasAvx2 = __builtin_cpu_supports("avx2");
-    if (HasAvx2 && Len >= 32) K = pack2bit_avx2(S, Len, Dst, &Bad);
+    if (HasAvx2 && Len >= 8) {
+        pack2bit_avx2(S, Len, Dst, &Bad);
+        return Bad == 0;
+    }
 #endif
     for (; K + 8 <= Len; K += 8) {
         uint64_t X;
@@ -514,7 +528,7 @@ class SequenceAligner {
             FirstFn *First;
             SecondFn *Second;
             size_t Threads;
-            double Busy = 0; // ms spent packing (one device: no concurrent callbacks)
+            std::atomic<long long> BusyUs{0}; // time spent packing (callbacks of several devices may run concurrently)
             static int fill(void *User, uint64_t Lo, uint64_t Cnt)
             {
                 Filler &F = *static_cast<Filler *>(User);
@@ -536,7 +550,7 @@ class SequenceAligner {
                     }
                     Ok[T] = Good ? 1 : 0;
                 });
-                F.Busy += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - A).count();
+                F.BusyUs += (long long)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - A).count();
                 for (char G : Ok)
                     if (!G) return 1; // a symbol outside ACGT: this batch cannot go out 2-bit packed
                 return 0;
@@ -547,14 +561,23 @@ class SequenceAligner {
         for (;;) {
             LayOut(TwoBitIn);
             TLay = Since();
-            Filler F{TwoBitIn, Bases, Off1, Off2, Len1, Len2, &First, &Second, Threads};
+            Filler F;
+            F.TwoBit = TwoBitIn;
+            F.Bases = Bases;
+            F.Off1 = Off1;
+            F.Off2 = Off2;
+            F.Len1 = Len1;
+            F.Len2 = Len2;
+            F.First = &First;
+            F.Second = &Second;
+            F.Threads = Threads;
             Prm.flags = SEQA_FLAG_OPS_2BIT | (TwoBitIn ? SEQA_FLAG_BASES_2BIT : 0u); // a quarter of the bytes over PCIe, both ways
             seqa_batch_in In{Bases, Off1, Off2, Len1, Len2, (uint64_t)N, TwoBitIn ? TotalPacked : Total,
                              EqualityChecked == 2 ? ClassTable.data() : nullptr};
             seqa_batch_out Out{R.Score.data(), R.StartI.data(), R.StartJ.data(), R.EndI.data(), R.EndJ.data(), R.Ops.data(),
                                R.OpsOff.data(), R.OpsLen.data(), (uint64_t)OpsCap, 0};
             const int Rc = seqa_cuda_align_batch_lazy(&Prm, &In, &Out, &Filler::fill, &F);
-            TPackBusy = F.Busy;
+            TPackBusy = (double)F.BusyUs.load() / 1e3;
             if (Rc == SEQA_OK) break;
             if (TwoBitIn && Rc == SEQA_ERR_INVALID) { // the filler met a symbol outside ACGT: once more, as 8-bit symbols
                 TwoBitIn = false;

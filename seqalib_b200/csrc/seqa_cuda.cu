@@ -1804,7 +1804,7 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
     struct DevPipe {
         std::mutex mu;
         std::condition_variable cv;
-        long produced = 0, consumed = 0;
+        long produced = 0, consumed = 0, filled = 0; // waves launched / downloaded / filled by the caller's callback
         bool stop = false;
         seqa_ctx *c[SEQA_CACHE_SLOTS] = {};
         int cached[SEQA_CACHE_SLOTS];
@@ -1850,9 +1850,11 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
                 }
                 cudaEventRecord(wev[w].e[0], P.c[slot]->up);
             }
-            if (s == SEQA_OK && fill && fill(fill_user, wave_lo[w], wave_lo[w + 1] - wave_lo[w]) != 0)
-                s = fail(SEQA_ERR_INVALID, "the caller's fill callback refused pairs [%llu, %llu)", (unsigned long long)wave_lo[w],
-                         (unsigned long long)wave_lo[w + 1]);
+            if (fill) { // the filler thread runs ahead of this one: wait until it has produced this wave's symbols
+                std::unique_lock<std::mutex> lk(P.mu);
+                P.cv.wait(lk, [&] { return P.filled > k || P.stop; });
+                if (P.stop) break;
+            }
             if (s == SEQA_OK) s = ctx_upload_range(P.c[slot], params, in, wave_lo[w], wave_lo[w + 1], &facts);
             if (dbg && s == SEQA_OK) {
                 cudaEventRecord(wev[w].e[1], P.c[slot]->up);
@@ -1877,6 +1879,31 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
         std::lock_guard<std::mutex> lk(P.mu);
         P.stop = true;
         P.cv.notify_all();
+    };
+    // seqa_cuda_align_batch_lazy: a third thread per device calls the caller's fill callback wave after wave, ahead of the
+    // producer, so that packing wave k+1, uploading / launching wave k and downloading wave k-1 all overlap
+    auto filler = [&](int d) {
+        DevPipe &P = pipes[d];
+        const long nw = (long)(dev_lo[d + 1] - dev_lo[d]);
+        for (long k = 0; k < nw; k++) {
+            const size_t w = dev_lo[d] + (size_t)k;
+            {
+                std::lock_guard<std::mutex> lk(P.mu);
+                if (P.stop) break;
+            }
+            const int rc = fill(fill_user, wave_lo[w], wave_lo[w + 1] - wave_lo[w]);
+            std::lock_guard<std::mutex> lk(P.mu);
+            if (rc != 0) {
+                wstatus[w] = fail(SEQA_ERR_INVALID, "the caller's fill callback refused pairs [%llu, %llu)", (unsigned long long)wave_lo[w],
+                                  (unsigned long long)wave_lo[w + 1]);
+                werr[w] = g_err;
+                P.stop = true;
+                P.cv.notify_all();
+                break;
+            }
+            P.filled = k + 1;
+            P.cv.notify_all();
+        }
     };
     auto consumer = [&](int d) {
         DevPipe &P = pipes[d];
@@ -1924,6 +1951,7 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
                     for (int q = 0; q < 4; q++) pipes[d].st[q] = g_pipe_stream[first + d][q];
                 (void)cudaGetLastError();
             }
+            if (fill) th.emplace_back(filler, d);
             th.emplace_back(producer, d);
             th.emplace_back(consumer, d);
         }
