@@ -1720,6 +1720,12 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
                         sched.push_back(take);
                         left -= take;
                     }
+                    // lazy fill: the caller's packing, not the GPU, paces the pipeline, and the GPU work on the LAST wave is
+                    // what remains once the packing is done: keep it to one round
+                    if (fill && sched.back() > round + round / 2) {
+                        sched.back() -= round;
+                        sched.push_back(round);
+                    }
                 }
             }
         }
