@@ -1031,7 +1031,7 @@ int ctx_upload_range_2bit(seqa_ctx *c, const seqa_params *params, const seqa_bat
     c->st_uniform = st_uni;
     if (n == 0 || hi < lo) lo = hi = 0;
     c->bases_len = st_slots; // the unpacked copy is dense whatever the layout of the packed bytes
-    CKS(c->bases.ensure(c->bases_len + 16));
+    CKS(c->bases.ensure(c->bases_len + 64));
     CKS(c->packed_in.ensure(hi - lo + 16));
     if (hi > lo) CK(cudaMemcpyAsync(c->packed_in.p, in->bases + lo, hi - lo, cudaMemcpyHostToDevice, c->up));
     if (n) {
@@ -1146,7 +1146,7 @@ int ctx_upload_range(seqa_ctx *c, const seqa_params *params, const seqa_batch_in
     c->st_uniform = st_uni;
     if (n == 0 || hi < lo) lo = hi = 0;
     c->bases_len = hi - lo;
-    CKS(c->bases.ensure(c->bases_len + 16));
+    CKS(c->bases.ensure(c->bases_len + 64));
     if (hi > lo) CK(cudaMemcpyAsync(c->bases.p, in->bases + lo, hi - lo, cudaMemcpyHostToDevice, c->up));
     const bool dev_lengths = dense && st_uni; // uniform: the device fills the length arrays itself
     if (n) {
@@ -1414,7 +1414,7 @@ int seqa_ctx_generate(seqa_ctx *c, const seqa_params *params, uint64_t seed, uin
         run += (uint64_t)a + b;
     }
     c->bases_len = run;
-    CKS(c->bases.ensure(run + 16));
+    CKS(c->bases.ensure(run + 64));
     if (n_pairs) {
         CK(cudaMemcpyAsync(c->off1.p, o1.data(), n_pairs * 8, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(c->off2.p, o2.data(), n_pairs * 8, cudaMemcpyHostToDevice, c->stream));

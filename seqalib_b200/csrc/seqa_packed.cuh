@@ -90,22 +90,28 @@ __device__ __forceinline__ bool pk_is_acgt(unsigned c) { return c == 'A' || c ==
 // Sequences are read as ALIGNED 32-bit words (one load per 4 symbols; a funnel shift restores the pair's own
 // alignment): a warp's lanes read 32 different sequences, so the number of load instructions, not bytes, is the
 // cost.  Words may reach 3 bytes before / 11 bytes after a sequence; `bases` is 4-byte aligned with 16 bytes of slack.
+// The loads run PK_PREP_AHEAD words ahead of their use (a ring of registers, indexed at compile time by the unrolled
+// loops of pk_prep_kernel): with one word ahead every iteration waited a full HBM round trip (ncu: 45 % of the stall
+// samples on the four moves behind the loads, profiles/r02_ncu_pk_prep_fill_walk_sw150_1M.txt); reads reach at most
+// 4 * (PK_PREP_AHEAD + 1) bytes behind a sequence (`bases` is allocated with 64 bytes of slack).
+#define PK_PREP_AHEAD 4
 struct PkSeqReader {
     const uint32_t *w; // aligned word pointer
     unsigned sh;       // bit shift of the first symbol inside *w
-    uint32_t carry, ahead; // `ahead` is loaded one call early: the load of call k+1 overlaps the work of call k
+    uint32_t carry, ahead[PK_PREP_AHEAD];
     __device__ __forceinline__ void init(const uint8_t *base, const uint8_t *p)
     {
         const uint64_t o = (uint64_t)(p - base);
         w = reinterpret_cast<const uint32_t *>(base) + (o >> 2);
         sh = (unsigned)(o & 3u) * 8u;
         carry = __ldg(w++);
-        ahead = __ldg(w++);
+#pragma unroll
+        for (int k = 0; k < PK_PREP_AHEAD; k++) ahead[k] = __ldg(w++);
     }
-    __device__ __forceinline__ uint32_t next4() // the next 4 symbols, first in the low byte
+    template <int K> __device__ __forceinline__ uint32_t next4() // the next 4 symbols, first in the low byte; K = call index % PK_PREP_AHEAD
     {
-        const uint32_t hi = ahead;
-        ahead = __ldg(w++);
+        const uint32_t hi = ahead[K];
+        ahead[K] = __ldg(w++);
         const uint32_t v = sh ? ((carry >> sh) | (hi << (32u - sh))) : carry;
         carry = hi;
         return v;
@@ -143,10 +149,11 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
         };
         uint4 *pout = reinterpret_cast<uint4 *>(A.prof + J.prof_off) + lane; // [cg][half][lane]: every warp store / load is 512 contiguous bytes
         uint16_t *cout = reinterpret_cast<uint16_t *>(A.prof + J.prof_off) + lane; // colcodes: [cg][lane], byte k = pair k, 2 bits per column
-        for (uint32_t cg = 0; cg < Ng; cg++) {
+        auto colstep = [&](uint32_t cg, auto kk) {
+            constexpr int K = decltype(kk)::value;
             const uint32_t j0 = cg * 4;
             const uint32_t h0 = j0 < N0 ? N0 - j0 : 0u, h1 = j0 < N1 ? N1 - j0 : 0u; // real columns left in this group
-            const uint32_t w0 = h0 ? b0.next4() : 0u, w1 = h1 ? b1.next4() : 0u;
+            const uint32_t w0 = h0 ? b0.template next4<K>() : 0u, w1 = h1 ? b1.template next4<K>() : 0u;
             const uint32_t k0 = (w0 >> 1) & 0x03030303u, k1 = (w1 >> 1) & 0x03030303u;
             check4(w0, k0, valid_mask(h0), bad0);
             check4(w1, k1, valid_mask(h1), bad1);
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
                 y0 = (y0 | (y0 >> 12)) & 0xffu;
                 y1 = (y1 | (y1 >> 12)) & 0xffu;
                 cout[(uint64_t)cg * 32] = (uint16_t)(y0 | (y1 << 8));
-                continue;
+                return;
             }
             const uint32_t s0 = k0 << 3, s1 = k1 << 3; // 8 * code: the byte position of the matching row base in the profile
             unsigned t[8];
@@ -167,12 +174,19 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
             }
             pout[(uint64_t)cg * 64] = make_uint4(t[0], t[1], t[2], t[3]);
             pout[(uint64_t)cg * 64 + 32] = make_uint4(t[4], t[5], t[6], t[7]);
+        };
+        for (uint32_t cg = 0; cg < Ng; cg += PK_PREP_AHEAD) { // unrolled by the ring depth: the ring index is a compile-time constant
+            colstep(cg, std::integral_constant<int, 0>());
+            if (cg + 1 < Ng) colstep(cg + 1, std::integral_constant<int, 1>());
+            if (cg + 2 < Ng) colstep(cg + 2, std::integral_constant<int, 2>());
+            if (cg + 3 < Ng) colstep(cg + 3, std::integral_constant<int, 3>());
         }
         const uint32_t rows = J.nstrips * (uint32_t)R;
         uint32_t *rout = A.rowsel + J.rowsel_off + lane;
-        for (uint32_t i0 = 0; i0 < rows; i0 += 4) {
+        auto rowstep = [&](uint32_t i0, auto kk) {
+            constexpr int K = decltype(kk)::value;
             const uint32_t h0 = i0 < M0 ? M0 - i0 : 0u, h1 = i0 < M1 ? M1 - i0 : 0u;
-            const uint32_t w0 = h0 ? a0.next4() : 0u, w1 = h1 ? a1.next4() : 0u;
+            const uint32_t w0 = h0 ? a0.template next4<K>() : 0u, w1 = h1 ? a1.template next4<K>() : 0u;
             const uint32_t v0 = valid_mask(h0), v1 = valid_mask(h1);
             const uint32_t k0 = (w0 >> 1) & 0x03030303u & v0, k1 = (w1 >> 1) & 0x03030303u & v1; // rows behind the end: code 0
             check4(w0, k0, v0, bad0);
@@ -183,6 +197,12 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
                 // nibble0: byte c0 of T0; nibble1: its sign (8 | c0); nibble2: byte 4 + c1 (= T1); nibble3: its sign (12 | c1)
                 rout[(uint64_t)(i0 + c) * 32] = 0xC480u + c0 * 0x11u + c1 * 0x1100u;
             }
+        };
+        for (uint32_t i0 = 0; i0 < rows; i0 += 4 * PK_PREP_AHEAD) {
+            rowstep(i0, std::integral_constant<int, 0>());
+            if (i0 + 4 < rows) rowstep(i0 + 4, std::integral_constant<int, 1>());
+            if (i0 + 8 < rows) rowstep(i0 + 8, std::integral_constant<int, 2>());
+            if (i0 + 12 < rows) rowstep(i0 + 12, std::integral_constant<int, 3>());
         }
         if (bad0 | bad1) *A.bad = 1;
         if (bad0 && p0 != PK_NULL) A.badpair[p0] = 1;
