@@ -178,7 +178,7 @@ def cpu_reference_gcups(n_pairs, threads):
     return cells / sec / 1e9, kind, sec
 
 
-def header_api_bench(pairs):
+def header_api_bench(pairs, device_index=0):
     """e2e.api_packed / e2e.api_list: tests/cpp/bench_header.cpp (the reference's own class templates from
     include/SequenceAlignment.h, std::string pairs in pageable memory) compiled against the in-tree library and run as a
     separate process on this GPU.  -> {"packed": {...}, "list": {...}, "note": ...} or {"note": why not}"""
@@ -189,7 +189,11 @@ def header_api_bench(pairs):
         subprocess.check_call(["g++", "-std=c++14", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"),
                                os.path.join(ROOT, "tests", "cpp", "bench_header.cpp"), "-o", exe, "-L", libdir, "-lseqa_cuda",
                                "-Wl,-rpath," + libdir], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=300)
-        out = subprocess.run([exe, str(pairs), "3", str(min(pairs, 200000))], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        # the header uses every VISIBLE device: show it this rank's GPU only, so that the figure belongs to the N = 1 line
+        env = dict(os.environ)
+        vis = [v for v in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        env["CUDA_VISIBLE_DEVICES"] = vis[device_index] if device_index < len(vis) else str(device_index)
+        out = subprocess.run([exe, str(pairs), "3", str(min(pairs, 200000))], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=env)
         line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
         d = json.loads(line)
         d["note"] = ("getAlignmentsPacked on %d and getAlignments on %d std::string pairs of %d bp, best of 3 / 2 calls after a warm-up call, "
@@ -595,7 +599,7 @@ def run_ours(args):
     # ---- the template API itself (include/SequenceAlignment.h), rank 0 at N=1: compiled here, run as its own process ----
     api = None
     if world == 1 and not args.no_api:
-        api = header_api_bench(n)
+        api = header_api_bench(n, local)
 
     # ---- the other BASELINE configs, sharded over the same ranks (strong scaling) ----
     configs = None
