@@ -20,6 +20,7 @@
 #include "seqa_util.cuh"
 #include "seqa_wavefront.cuh"
 #include "seqa_packed.cuh"
+#include "seqa_packed_walk2.cuh"
 #include "seqa_packed_affine.cuh"
 #include "seqa_linspace.cuh"
 #include "seqa_linspace_packed.cuh"
@@ -559,7 +560,7 @@ int build_plan(seqa_ctx *c)
             J.nstrips = (Mw + PK_R - 1) / PK_R;
             const uint64_t tbytes = packed_affine(prm) ? pkg_trace_bytes(J.nstrips, Nw, PK_R, packed_affine_trace_bits(prm))
                                                        : pk_trace_bytes(J.nstrips, Nw, PK_R, packed_trace_bits(prm));
-            const uint64_t pelems = (uint64_t)((Nw + 3) / 4) * 128, relems = (uint64_t)J.nstrips * PK_R * 32;
+            const uint64_t pelems = (uint64_t)((Nw + 3) / 4) * 128, relems = pk_rowsel_elems(J.nstrips, Nw, PK_R);
             const uint64_t lelems = (uint64_t)J.nstrips * (PK_R / 4) * 32; // last-column values (SW walk), uint4
             if (ch.hi > ch.lo && chunk_bytes(tr + tbytes, pf + pelems, rs + relems, lc + lelems) > budget) {
                 ch.scratch_bytes = chunk_bytes(tr, pf, rs, lc);
@@ -692,6 +693,9 @@ static int env_int(const char *name, int dflt, int lo, int hi)
     return (int)std::min<long>(hi, std::max<long>(lo, x));
 }
 // resident CTAs per SM of the packed affine fill (168 registers x 128 threads: 3 fit); SEQA_PKG_BPS overrides for A/B runs
+// round-synchronous walk of the packed linear path (seqa_packed_walk2.cuh); SEQA_WALK2=0 selects pk_walk_kernel for A/B runs
+static int use_walk2() { static const int v = PK_PAIR_PIECES != 0 ? 0 : env_int("SEQA_WALK2", PK_WALK2, 0, 1); return v; }
+static int walk2_tune() { static const int v = env_int("SEQA_WALK2_T", 4, 0, 8); return v; }
 static int pkg_ctas_per_sm() { static const int v = env_int("SEQA_PKG_BPS", 3, 1, 3); return v; }
 
 // resident CTAs per SM of the packed linear fill: its dynamic shared memory (one strip-boundary column per thread)
@@ -735,7 +739,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
             const PkWarpJob &L = c->jobs[ch.hi - 1];
             tr = L.trace_off + (affine ? pkg_trace_bytes(L.nstrips, L.Nw, PK_R, tb) : pk_trace_bytes(L.nstrips, L.Nw, PK_R, tb));
             pf = L.prof_off + (uint64_t)((L.Nw + 3) / 4) * 128;
-            rs = L.rowsel_off + (uint64_t)L.nstrips * PK_R * 32;
+            rs = L.rowsel_off + pk_rowsel_elems(L.nstrips, L.Nw, PK_R);
         }
         PkArgs A{};
         A.bases = c->bases.p;
@@ -774,6 +778,7 @@ int run_packed(seqa_ctx *c, bool want_walk)
         A.bound = c->pk_bound.p;
         A.bound_stride = bound_stride;
         A.ticket = reinterpret_cast<uint32_t *>(c->flags.p + 1);
+        A.walk_tune = walk2_tune();
         A.colcodes = affine ? (PKG_CODES != 0) : (gb && (local ? PK_GB_CODES_SW != 0 : PK_GB_CODES_NW != 0));
         CK(cudaMemsetAsync(c->flags.p + 1, 0, sizeof(int), c->stream));
         const unsigned wpb = PK_BLOCK / 32;
@@ -828,6 +833,14 @@ int run_packed(seqa_ctx *c, bool want_walk)
                 LAUNCH(c, (pkg_walk_kernel<false, PK_R, 4>), wgrid, 256, 0, Wk);
             else if (affine)
                 LAUNCH(c, (pkg_walk_kernel<false, PK_R, 8>), wgrid, 256, 0, Wk);
+            else if (local && tb == 2 && use_walk2())
+                LAUNCH(c, (pk_walk2_kernel<true, 2, PK_R>), wgrid, 256, 0, Wk);
+            else if (tb == 2 && use_walk2())
+                LAUNCH(c, (pk_walk2_kernel<false, 2, PK_R>), wgrid, 256, 0, Wk);
+            else if (local && tb == 4 && use_walk2())
+                LAUNCH(c, (pk_walk2_kernel<true, 4, PK_R>), wgrid, 256, 0, Wk);
+            else if (tb == 4 && use_walk2())
+                LAUNCH(c, (pk_walk2_kernel<false, 4, PK_R>), wgrid, 256, 0, Wk);
             else if (local && tb == 2)
                 LAUNCH(c, (pk_walk_kernel<true, 2, PK_R>), wgrid, 256, 0, Wk);
             else if (tb == 2)

@@ -39,9 +39,18 @@ struct PkWarpJob {
     uint32_t nstrips; // ceil(Mw / R)
     uint64_t trace_off;  // byte offset of the warp's trace region
     uint64_t prof_off;   // uint2 index of the column profile: uint4 [ceil(Nw/4)][2][32] = {T0,T1} of columns (0,1) / (2,3) per lane
-    uint64_t rowsel_off; // uint32 index of the row selectors  [nstrips*R][32]
+    uint64_t rowsel_off; // uint32 index of the row selectors  [nstrips*R][32], followed by the walk's 2-bit symbol codes (pk_rowsel_elems)
     uint64_t last_off;   // uint4 index of the last-column values (SmithWaterman) [nstrips][R/4][32]
 };
+
+// uint32 elements of a job's row-selector region: the selectors [nstrips*R][32], then the 2-bit symbol codes pk_walk2_kernel
+// compares instead of the 8-bit symbols -- ROW codes [nstrips][2][32] (16 rows of one pair per word: strip s, pair half k,
+// lane) and COLUMN codes [ceil(Ng/4)][2][32] (16 columns per word), both written by pk_prep_kernel (R = 16).
+__host__ __device__ inline uint64_t pk_rowsel_elems(uint32_t nstrips, uint32_t Nw, int R)
+{
+    const uint32_t Ng = (Nw + 3) / 4;
+    return (uint64_t)nstrips * (uint64_t)R * 32ull + (uint64_t)nstrips * 64ull + (uint64_t)((Ng + 3) / 4) * 64ull;
+}
 
 struct PkArgs {
     const uint8_t *bases;
@@ -70,6 +79,7 @@ struct PkArgs {
     uint4 *bound;          // per-warp strip boundary rows (kernels that keep them in global memory)
     uint64_t bound_stride; // uint4 per warp
     uint32_t *ticket;      // job counter: warps draw jobs (largest first) instead of striding over them
+    int walk_tune;         // pk_walk2_kernel: leave a STEP phase when fewer than walk_tune/8 of the unfinished lanes can step (0: when none can)
     int colcodes;          // != 0: prep writes 2-bit COLUMN CODES (uint16 [Ng][32] per job, at the job's profile offset) instead of
                            // the column profiles, and the fill builds the profile words itself (kernels that are HBM-bound)
 };
@@ -147,6 +157,8 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
             const unsigned letters = seqa_prmt(0x47544341u, 0u, seqa_prmt(x, 0u, 0x4420)); // "ACTG"[c0..c3]
             bad |= (letters ^ w) & vmask;
         };
+        uint32_t cacc0 = 0, cacc1 = 0; // 2-bit codes of the 16 columns / rows in flight (pair 0 / pair 1)
+        uint32_t *wcode = A.rowsel + J.rowsel_off + (uint64_t)J.nstrips * (uint32_t)R * 32 + lane; // [nstrips][2][32], then [ceil(Ng/4)][2][32]
         uint4 *pout = reinterpret_cast<uint4 *>(A.prof + J.prof_off) + lane; // [cg][half][lane]: every warp store / load is 512 contiguous bytes
         uint16_t *cout = reinterpret_cast<uint16_t *>(A.prof + J.prof_off) + lane; // colcodes: [cg][lane], byte k = pair k, 2 bits per column
         auto colstep = [&](uint32_t cg, auto kk) {
@@ -157,10 +169,13 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
             const uint32_t k0 = (w0 >> 1) & 0x03030303u, k1 = (w1 >> 1) & 0x03030303u;
             check4(w0, k0, valid_mask(h0), bad0);
             check4(w1, k1, valid_mask(h1), bad1);
-            if (A.colcodes) { // four 2-bit codes per byte (pk_colprof rebuilds the profile words; padding is masked there)
-                uint32_t y0 = (k0 | (k0 >> 6)) & 0x000f000fu, y1 = (k1 | (k1 >> 6)) & 0x000f000fu;
-                y0 = (y0 | (y0 >> 12)) & 0xffu;
-                y1 = (y1 | (y1 >> 12)) & 0xffu;
+            // four 2-bit codes per byte: the walk's column codes (16 columns per word), and the fills' with A.colcodes
+            uint32_t y0 = (k0 | (k0 >> 6)) & 0x000f000fu, y1 = (k1 | (k1 >> 6)) & 0x000f000fu;
+            y0 = (y0 | (y0 >> 12)) & 0xffu;
+            y1 = (y1 | (y1 >> 12)) & 0xffu;
+            cacc0 |= y0 << (8 * K);
+            cacc1 |= y1 << (8 * K);
+            if (A.colcodes) { // pk_colprof rebuilds the profile words; padding is masked there
                 cout[(uint64_t)cg * 32] = (uint16_t)(y0 | (y1 << 8));
                 return;
             }
@@ -180,6 +195,10 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
             if (cg + 1 < Ng) colstep(cg + 1, std::integral_constant<int, 1>());
             if (cg + 2 < Ng) colstep(cg + 2, std::integral_constant<int, 2>());
             if (cg + 3 < Ng) colstep(cg + 3, std::integral_constant<int, 3>());
+            uint32_t *o = wcode + (uint64_t)J.nstrips * 64 + (uint64_t)(cg >> 2) * 64;
+            o[0] = cacc0;
+            o[32] = cacc1;
+            cacc0 = cacc1 = 0;
         }
         const uint32_t rows = J.nstrips * (uint32_t)R;
         uint32_t *rout = A.rowsel + J.rowsel_off + lane;
@@ -191,6 +210,11 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
             const uint32_t k0 = (w0 >> 1) & 0x03030303u & v0, k1 = (w1 >> 1) & 0x03030303u & v1; // rows behind the end: code 0
             check4(w0, k0, v0, bad0);
             check4(w1, k1, v1, bad1);
+            {
+                uint32_t y0 = (k0 | (k0 >> 6)) & 0x000f000fu, y1 = (k1 | (k1 >> 6)) & 0x000f000fu;
+                cacc0 |= ((y0 | (y0 >> 12)) & 0xffu) << (8 * K);
+                cacc1 |= ((y1 | (y1 >> 12)) & 0xffu) << (8 * K);
+            }
 #pragma unroll
             for (uint32_t c = 0; c < 4; c++) {
                 const unsigned c0 = (k0 >> (8 * c)) & 3u, c1 = (k1 >> (8 * c)) & 3u;
@@ -203,6 +227,10 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
             if (i0 + 4 < rows) rowstep(i0 + 4, std::integral_constant<int, 1>());
             if (i0 + 8 < rows) rowstep(i0 + 8, std::integral_constant<int, 2>());
             if (i0 + 12 < rows) rowstep(i0 + 12, std::integral_constant<int, 3>());
+            uint32_t *o = wcode + (uint64_t)(i0 >> 4) * 64; // rows is a multiple of 16 (R = 16)
+            o[0] = cacc0;
+            o[32] = cacc1;
+            cacc0 = cacc1 = 0;
         }
         if (bad0 | bad1) *A.bad = 1;
         if (bad0 && p0 != PK_NULL) A.badpair[p0] = 1;
