@@ -695,7 +695,7 @@ static int env_int(const char *name, int dflt, int lo, int hi)
 // resident CTAs per SM of the packed affine fill (168 registers x 128 threads: 3 fit); SEQA_PKG_BPS overrides for A/B runs
 // round-synchronous walk of the packed linear path (seqa_packed_walk2.cuh); SEQA_WALK2=0 selects pk_walk_kernel for A/B runs
 static int use_walk2() { static const int v = PK_PAIR_PIECES != 0 ? 0 : env_int("SEQA_WALK2", PK_WALK2, 0, 1); return v; }
-static int walk2_tune() { static const int v = env_int("SEQA_WALK2_T", 4, 0, 8); return v; }
+static int walk2_tune() { static const int v = env_int("SEQA_WALK2_T", 4, 1, 16); return v; }
 static int pkg_ctas_per_sm() { static const int v = env_int("SEQA_PKG_BPS", 3, 1, 3); return v; }
 
 // resident CTAs per SM of the packed linear fill: its dynamic shared memory (one strip-boundary column per thread)

@@ -206,37 +206,51 @@ __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK2_MINB) pk_walk2_kernel(Pk
     int ci = i - 1, cj = j - 1;  // the current cell, 0-based (>= 0 while st < 8)
     uint32_t need = 0xffffffffu; // blocked: tag (row band << 16 | column group) of the piece to load; 0xffffffff: symbol codes only
     uint32_t ka = 0xffffffffu, kb = 0xffffffffu, aw = 0, bw = 0; // symbol codes held: strip / column block and their words
-    const int tune = A.walk_tune; // leave the STEP phase when fewer than tune/8 of the unfinished lanes can step
+    const int steps = A.walk_tune; // neighbour tests per STEP phase
+    constexpr uint32_t NONE = 0xffffffffu;
+    auto piece_of = [&](uint32_t tagv) -> uint64_t { // 16-byte piece index of a tag (relative to `pieces`)
+        const uint32_t band = tagv >> 16, cg = tagv & 0xffffu;
+        return (uint64_t)(((band >> (4 - PRSH)) * Ng + cg) * RG + (band & (RG - 1u))) * 64;
+    };
+    auto slot_row = [&](uint32_t tagv) -> uint32_t { return ((tagv & 1u) << 3) | ((tagv >> 14) & 4u); }; // first row of the tag's slot
+    auto put_piece = [&](uint32_t tagv, const uint4 &v) {
+        const uint32_t srow = slot_row(tagv);
+        S.st((srow + 0) * ROWB, v.x);
+        S.st((srow + 1) * ROWB, v.y);
+        S.st((srow + 2) * ROWB, v.z);
+        S.st((srow + 3) * ROWB, v.w);
+        S.st(16 * ROWB + srow * (ROWB / 4), tagv);
+    };
     for (;;) {
-        // ---- LOAD: everything the blocked lanes wait for, in flight together
+        // ---- LOAD: the piece a blocked lane waits for, the piece its path is about to enter, and the symbol codes of a new
+        //      strip / column block -- all lanes' loads in flight together
         if (st < 8) {
             const uint32_t sa = (uint32_t)ci >> 4, sb = (uint32_t)cj >> 4;
             uint32_t na = aw, nb = bw;
-            uint4 v = make_uint4(0, 0, 0, 0);
             if (sa != ka) na = rcode[(uint64_t)sa * 64];
             if (sb != kb) nb = ccode[(uint64_t)sb * 64];
-            const bool ld = st >= 4 && need != 0xffffffffu;
-            const uint32_t band = need >> 16, cg = need & 0xffffu;
-            if (ld) v = pieces[(uint64_t)(((band >> (4 - PRSH)) * Ng + cg) * RG + (band & (RG - 1u))) * 64];
+            const uint32_t t1 = st >= 4 ? need : NONE;
+            // prefetch: the left neighbour of the current cell's piece when a diagonal from the cell leaves the piece through
+            // its left edge (row inside the piece > column inside the group); skipped when the slot already holds it
+            const uint32_t band = (uint32_t)ci >> PRSH, cg = (uint32_t)cj >> 2;
+            uint32_t t2 = seqa_prmt(cg - 1u, band, 0x5410);
+            if (cg == 0u || ((uint32_t)ci & ((1u << PRSH) - 1u)) <= ((uint32_t)cj & 3u) || t2 == t1 ||
+                S.ld(16 * ROWB + slot_row(t2) * (ROWB / 4)) == t2)
+                t2 = NONE;
+            uint4 v1 = make_uint4(0, 0, 0, 0), v2 = v1;
+            if (t1 != NONE) v1 = pieces[piece_of(t1)];
+            if (t2 != NONE) v2 = pieces[piece_of(t2)];
             aw = na;
             bw = nb;
             ka = sa;
             kb = sb;
-            if (ld) {
-                const uint32_t srow = ((cg & 1u) << 3) | ((band & 1u) << 2);
-                S.st((srow + 0) * ROWB, v.x);
-                S.st((srow + 1) * ROWB, v.y);
-                S.st((srow + 2) * ROWB, v.z);
-                S.st((srow + 3) * ROWB, v.w);
-                S.st(16 * ROWB + srow * (ROWB / 4), need);
-            }
+            if (t1 != NONE) put_piece(t1, v1);
+            if (t2 != NONE) put_piece(t2, v2);
             st &= 3;
         }
         // ---- STEP: one neighbour test per iteration and lane, shared memory and registers only
-        for (int k = 0; k < PK_WALK2_KMAX; k++) {
-            const unsigned can = __ballot_sync(SEQA_FULL, st < 4);
-            if (can == 0u) break;
-            if (tune > 0 && __popc(can) * 8 < __popc(__ballot_sync(SEQA_FULL, st < 8)) * tune) break;
+#pragma unroll 1
+        for (int k = 0; k < steps; k++) {
             if (st < 4) {
                 const int dd = 3 - st;                             // 3 diagonal, 2 up, 1 left: bit 1 = row - 1, bit 0 = column - 1
                 const int ni = ci - (dd >> 1), nj = cj - (dd & 1); // the neighbour under test (0-based; -1: border)
@@ -265,7 +279,7 @@ __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK2_MINB) pk_walk2_kernel(Pk
                         cj = nj;
                         nc = v;
                         h -= expect;
-                        need = 0xffffffffu;
+                        need = NONE;
                         st = (border || (LOCAL && h == 0)) ? 8 : (cross ? 4 : 0);
                     } else {
                         st++;
