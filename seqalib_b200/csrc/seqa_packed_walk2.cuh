@@ -29,10 +29,10 @@
 #define PK_WALK2 0
 #endif
 #ifndef PK_WALK2_MINB
-#define PK_WALK2_MINB 6
+#define PK_WALK2_MINB 5 /* 48 registers: 6 CTAs (40 registers) spill inside the STEP loop -- 1.57 vs 1.19 ms per 1 M x 150 bp pairs */
 #endif
-#ifndef PK_WALK2_KMAX
-#define PK_WALK2_KMAX 12 /* neighbour tests per STEP phase at most */
+#ifndef PK_WALK2_STEPS
+#define PK_WALK2_STEPS 4 /* neighbour tests per STEP phase: 3 / 4 / 6 / 8 measured 1.34 / 1.28 / 1.31 / 1.52 ms per 1 M x 150 bp pairs */
 #endif
 
 // MaxCol of SmithWaterman: the last column of row MaxRow holding MaxScore (include/SASmithWaterman.h:177-182), found from
@@ -84,46 +84,63 @@ __device__ __forceinline__ int pk_maxcol_scan(const PkArgs &A, const PkWarpJob &
     return bj;
 }
 
-// ops leave back to front as 32-bit words: a shift register collects 4 ops (one IMAD per op), positions are 32-bit offsets
-// from the 4-byte aligned start of the pair's slot; the first and the last word of a slot share their other bytes with the
-// neighbouring pairs' slots and go out as single bytes.
-struct PkOpWriter32 {
-    uint8_t *base;    // A.slots + (slot begin rounded down to 4)
-    uint32_t rel;     // offset of the last op written (starts at end)
-    uint32_t end, acc;
+// ops leave back to front as 32-bit words.  put() only shifts the op into a 64-bit shift register (2 instructions); the
+// stores happen in flush(), once per LOAD phase for all lanes together (at most 4 ops arrive between two flushes, at most 3
+// stay pending after one): a walk step never branches into a store.  Positions are 32-bit offsets from the 4-byte aligned
+// start of the pair's slot; the first and the last word of a slot share their other bytes with the neighbouring pairs' slots
+// and go out as single bytes.
+#ifdef SEQA_EMU
+static inline uint32_t pk_funnel_l(uint32_t lo, uint32_t hi, uint32_t n) { return n ? (hi << n) | (lo >> (32u - n)) : hi; } // n < 32
+static inline uint32_t pk_funnel_r(uint32_t lo, uint32_t hi, uint32_t n) { return n ? (lo >> n) | (hi << (32u - n)) : lo; }
+#else
+__device__ __forceinline__ uint32_t pk_funnel_l(uint32_t lo, uint32_t hi, uint32_t n) { return __funnelshift_l(lo, hi, n); }
+__device__ __forceinline__ uint32_t pk_funnel_r(uint32_t lo, uint32_t hi, uint32_t n) { return __funnelshift_r(lo, hi, n); }
+#endif
+struct PkOpWriter64 {
+    uint8_t *base;       // A.slots + (slot begin rounded down to 4)
+    uint32_t rel;        // offset of the last op taken (ops go back to front; starts at end)
+    uint32_t srel;       // offset of the last op stored: ops [rel, srel) are pending in (hi:lo), byte k = offset rel + k
+    uint32_t lo, hi;
     __device__ __forceinline__ void init(uint8_t *slots, uint64_t begin, uint32_t len)
     {
         const uint64_t a0 = begin & ~(uint64_t)3;
         base = slots + a0;
-        rel = end = (uint32_t)(begin - a0) + len;
-        acc = 0;
-    }
-    __device__ __forceinline__ void bytes(uint32_t n) // the n pending ops: byte k of acc -> base[rel + k]
-    {
-#pragma unroll 1
-        for (uint32_t k = 0; k < n; k++) base[rel + k] = (uint8_t)(acc >> (8u * k));
+        rel = srel = (uint32_t)(begin - a0) + len;
+        lo = hi = 0;
     }
     __device__ __forceinline__ void put(unsigned op)
     {
+        hi = pk_funnel_l(lo, hi, 8);
+        lo = lo * 256u + op;
         rel--;
-        acc = acc * 256u + op;
-        if ((rel & 3u) == 0u) {
-            if (rel + 4u <= end)
-                *reinterpret_cast<uint32_t *>(base + rel) = acc;
-            else
-                bytes(end - rel);
-            acc = 0;
+    }
+    __device__ __forceinline__ uint32_t pending_byte(uint32_t k) const { return (k < 4u ? lo >> (8u * k) : hi >> (8u * (k - 4u))) & 0xffu; }
+    __device__ __forceinline__ void flush()
+    {
+        if (srel & 3u) { // the slot's top word (shared with the next pair's slot): single bytes, once the word's ops are all taken
+            const uint32_t a = srel & ~3u;
+            if (rel > a) return;
+#pragma unroll 1
+            for (uint32_t o = a; o < srel; o++) base[o] = (uint8_t)pending_byte(o - rel);
+            srel = a;
+        }
+#pragma unroll 1
+        while (srel - rel >= 4u) {
+            const uint32_t a = srel - 4u, k0 = a - rel; // k0 <= 3 in the steady state
+            const uint32_t w = k0 < 4u ? pk_funnel_r(lo, hi, 8u * k0) : hi >> (8u * (k0 - 4u));
+            *reinterpret_cast<uint32_t *>(base + a) = w;
+            srel = a;
         }
     }
-    __device__ __forceinline__ void finish()
+    __device__ __forceinline__ void finish() // everything still pending, byte by byte (the slot's lowest word is shared too)
     {
-        const uint32_t top = min((rel + 3u) & ~3u, end);
-        bytes(top - rel);
+        flush();
+#pragma unroll 1
+        for (uint32_t o = rel; o < srel; o++) base[o] = (uint8_t)pending_byte(o - rel);
+        srel = rel;
     }
 };
 
-// this thread's column of the walk's shared array [20][PK_WALK_TPB]: rows 0-15 piece words, 16-19 the slots' tags.  On the
-// device the column is a raw shared-space address (one register; the compiler otherwise rebuilds the window base per access).
 #ifdef SEQA_EMU
 static inline uint32_t pk_shr_wrap(uint32_t x, uint32_t n) { return x >> (n & 31u); }
 #else
@@ -156,8 +173,10 @@ template <bool LOCAL, int TB, int R>
 __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK2_MINB) pk_walk2_kernel(PkArgs A)
 {
     static_assert(R == 16 && (TB == 2 || TB == 4), "pk_walk2_kernel: 16-row strips, one-pair pieces");
-    // rows 0-15: 4 piece slots x 4 words, row = [cg parity, row-band parity, word(2 bits)]; rows 16-19: tag of slot row >> 2
-    __shared__ uint32_t sm[20][PK_WALK_TPB];
+    static_assert(PK_WALK2_STEPS <= 4, "PkOpWriter64: 3 pending + 4 new ops + 1");
+    // rows 0-15: 4 piece slots x 4 words, row = [cg parity, row-band parity, word(2 bits)]; row 16 + r: the tag of row r's slot
+    // (each slot's tag four times: a lookup reads word and tag at one computed address)
+    __shared__ uint32_t sm[32][PK_WALK_TPB];
     constexpr uint32_t ROWB = PK_WALK_TPB * 4; // bytes per row
     const int tid = threadIdx.x;
     const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,9 +198,9 @@ __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK2_MINB) pk_walk2_kernel(Pk
     PkSmemCol S;
     S.init(&sm[0][tid]);
 #pragma unroll
-    for (int q = 0; q < 4; q++) S.st((16 + q) * ROWB, 0xffffffffu);
+    for (int q = 0; q < 16; q++) S.st((16 + q) * ROWB, 0xffffffffu);
     const uint64_t slot_begin = have ? A.slot_off[p] : 0;
-    PkOpWriter32 out;
+    PkOpWriter64 out;
     out.init(A.slots, slot_begin, (uint32_t)(M + N));
     int i = 0, j = 0, h = 0;
     if (have) {
@@ -205,8 +224,11 @@ __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK2_MINB) pk_walk2_kernel(Pk
     int st = (!have || i <= 0 || j <= 0 || (LOCAL && h == 0)) ? 8 : 0; // include/SASmithWaterman.h:281-284
     int ci = i - 1, cj = j - 1;  // the current cell, 0-based (>= 0 while st < 8)
     uint32_t need = 0xffffffffu; // blocked: tag (row band << 16 | column group) of the piece to load; 0xffffffff: symbol codes only
-    uint32_t ka = 0xffffffffu, kb = 0xffffffffu, aw = 0, bw = 0; // symbol codes held: strip / column block and their words
-    const int steps = A.walk_tune; // neighbour tests per STEP phase
+    // 2-bit symbol codes of the current cell's 16-row strip / 16-column block (aw, bw) and of the next ones towards the origin
+    // (aw2, bw2: loaded one LOAD phase after a crossing, long before the path can cross again); cf: which of them are loaded
+    uint32_t aw = 0, bw = 0, aw2 = 0, bw2 = 0;
+    int cf = 0; // bit 0 aw, 1 aw2, 2 bw, 3 bw2
+    constexpr int steps = PK_WALK2_STEPS; // neighbour tests per STEP phase (PkOpWriter64 holds what they can emit)
     constexpr uint32_t NONE = 0xffffffffu;
     auto piece_of = [&](uint32_t tagv) -> uint64_t { // 16-byte piece index of a tag (relative to `pieces`)
         const uint32_t band = tagv >> 16, cg = tagv & 0xffffu;
@@ -219,31 +241,38 @@ __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK2_MINB) pk_walk2_kernel(Pk
         S.st((srow + 1) * ROWB, v.y);
         S.st((srow + 2) * ROWB, v.z);
         S.st((srow + 3) * ROWB, v.w);
-        S.st(16 * ROWB + srow * (ROWB / 4), tagv);
+#pragma unroll
+        for (int q = 0; q < 4; q++) S.st((16 + srow + q) * ROWB, tagv);
     };
     for (;;) {
         // ---- LOAD: the piece a blocked lane waits for, the piece its path is about to enter, and the symbol codes of a new
         //      strip / column block -- all lanes' loads in flight together
         if (st < 8) {
             const uint32_t sa = (uint32_t)ci >> 4, sb = (uint32_t)cj >> 4;
-            uint32_t na = aw, nb = bw;
-            if (sa != ka) na = rcode[(uint64_t)sa * 64];
-            if (sb != kb) nb = ccode[(uint64_t)sb * 64];
+            uint32_t na = aw, nb = bw, na2 = aw2, nb2 = bw2;
+            if (cf != 15) {
+                if (!(cf & 1)) na = rcode[(uint64_t)sa * 64];
+                if (!(cf & 2) && sa > 0u) na2 = rcode[(uint64_t)(sa - 1u) * 64];
+                if (!(cf & 4)) nb = ccode[(uint64_t)sb * 64];
+                if (!(cf & 8) && sb > 0u) nb2 = ccode[(uint64_t)(sb - 1u) * 64];
+            }
             const uint32_t t1 = st >= 4 ? need : NONE;
             // prefetch: the left neighbour of the current cell's piece when a diagonal from the cell leaves the piece through
             // its left edge (row inside the piece > column inside the group); skipped when the slot already holds it
             const uint32_t band = (uint32_t)ci >> PRSH, cg = (uint32_t)cj >> 2;
             uint32_t t2 = seqa_prmt(cg - 1u, band, 0x5410);
             if (cg == 0u || ((uint32_t)ci & ((1u << PRSH) - 1u)) <= ((uint32_t)cj & 3u) || t2 == t1 ||
-                S.ld(16 * ROWB + slot_row(t2) * (ROWB / 4)) == t2)
+                S.ld((16 + slot_row(t2)) * ROWB) == t2)
                 t2 = NONE;
             uint4 v1 = make_uint4(0, 0, 0, 0), v2 = v1;
             if (t1 != NONE) v1 = pieces[piece_of(t1)];
             if (t2 != NONE) v2 = pieces[piece_of(t2)];
             aw = na;
             bw = nb;
-            ka = sa;
-            kb = sb;
+            aw2 = na2;
+            bw2 = nb2;
+            cf = 15;
+            out.flush();
             if (t1 != NONE) put_piece(t1, v1);
             if (t2 != NONE) put_piece(t2, v2);
             st &= 3;
@@ -258,8 +287,8 @@ __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK2_MINB) pk_walk2_kernel(Pk
                                              : ((((uint32_t)ni >> 2) & 7u) + (((uint32_t)nj & 4u) << 1));
                 const uint32_t sh = TB == 4 ? ((uint32_t)ni * 8u + ((uint32_t)nj & 1u) * 4u) : ((uint32_t)ni * 8u + ((uint32_t)nj & 3u) * 2u); // mod 32
                 const uint32_t tagv = seqa_prmt((uint32_t)nj >> 2, (uint32_t)ni >> PRSH, 0x5410); // row band << 16 | column group
-                const uint32_t tg = S.ld(16 * ROWB + ((row * (ROWB / 4)) & (3u * ROWB)));
                 const uint32_t wv = S.ld(row * ROWB);
+                const uint32_t tg = S.ld(row * ROWB + 16 * ROWB);
                 const bool border = (ni | nj) < 0; // H(0,j) / H(i,0): SW 0; NW K(0,j) = 0, K(i,0) = i*gap
                 const unsigned v = border ? (LOCAL ? 0u : (unsigned)((ni + 1) * gap) & MASK) : (pk_shr_wrap(wv, sh) & MASK);
                 if (!border && tg != tagv) { // the piece is not held: wait for the LOAD phase, then repeat this test
@@ -273,14 +302,20 @@ __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK2_MINB) pk_walk2_kernel(Pk
                     if (st == 2) ok = true; // :223
                     if (ok) {
                         out.put((unsigned)st);
-                        // the cell leaves the strip / column block whose symbol codes are held: LOAD fetches the next words
-                        const bool cross = ((((uint32_t)ni ^ (uint32_t)ci) | ((uint32_t)nj ^ (uint32_t)cj)) & ~15u) != 0u;
+                        // the cell leaves the strip / column block of aw / bw: the next words move up, LOAD refills them
+                        if ((((uint32_t)ni ^ (uint32_t)ci) & ~15u) != 0u) {
+                            aw = aw2;
+                            cf &= ~2;
+                        }
+                        if ((((uint32_t)nj ^ (uint32_t)cj) & ~15u) != 0u) {
+                            bw = bw2;
+                            cf &= ~8;
+                        }
                         ci = ni;
                         cj = nj;
                         nc = v;
                         h -= expect;
-                        need = NONE;
-                        st = (border || (LOCAL && h == 0)) ? 8 : (cross ? 4 : 0);
+                        st = (border || (LOCAL && h == 0)) ? 8 : 0;
                     } else {
                         st++;
                     }
@@ -293,8 +328,9 @@ __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK2_MINB) pk_walk2_kernel(Pk
     j = cj + 1;
     if (!have) return;
     if (!LOCAL) { // borders: column 0 -> up, row 0 -> left
-        while (i > 0) { out.put(1); i--; }
-        while (j > 0) { out.put(2); j--; }
+        out.flush();
+        while (i > 0) { out.put(1); i--; if ((i & 3) == 0) out.flush(); }
+        while (j > 0) { out.put(2); j--; if ((j & 3) == 0) out.flush(); }
     }
     out.finish();
     const uint32_t k = out.rel - (uint32_t)(slot_begin & 3u);
