@@ -173,7 +173,7 @@ template <bool LOCAL, int TB, int R>
 __global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK2_MINB) pk_walk2_kernel(PkArgs A)
 {
     static_assert(R == 16 && (TB == 2 || TB == 4), "pk_walk2_kernel: 16-row strips, one-pair pieces");
-    static_assert(PK_WALK2_STEPS <= 4, "PkOpWriter64: 3 pending + 4 new ops + 1");
+    static_assert(PK_WALK2_STEPS <= 5, "PkOpWriter64 holds 8 ops: 3 pending + the new ones");
     // rows 0-15: 4 piece slots x 4 words, row = [cg parity, row-band parity, word(2 bits)]; row 16 + r: the tag of row r's slot
     // (each slot's tag four times: a lookup reads word and tag at one computed address)
     __shared__ uint32_t sm[32][PK_WALK_TPB];

@@ -1,5 +1,5 @@
-for lib in seqalib_b200/libseqa_cuda.so build_ab/libseqa_minb5.so; do
+for lib in build_ab/libseqa_p3.so build_ab/libseqa_p5.so; do
 echo "=== $lib"
-export SEQA_LIB=$PWD/$lib
-SWEEP="4" bash tests/gpu_sweep_walk.sh
+SEQA_LIB=$PWD/$lib SWEEP="4" bash tests/gpu_sweep_walk.sh 2>&1 | grep -v passed
 done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
