@@ -330,7 +330,13 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
     const unsigned gap2 = pk_dup(A.gap);
     const unsigned mmb = A.allow ? ((unsigned)(A.mismatch - A.prof_bias) & 0xffu) : 0x80u; // CODES: as pk_prep_kernel
     const unsigned mm4 = mmb * 0x01010101u, mx = ((unsigned)(A.match - A.prof_bias) & 0xffu) ^ mmb;
-    uint4 *__restrict__ bnd = A.bound + (uint64_t)gw * A.bound_stride + lane; // GB: [cg][lane] x 4 columns
+    // GB: the strip's bottom row, [cg][lane] x 4 columns x 2 pairs, as 8-BIT DIFFERENCES along the row (PK_BND_DELTA): the row is
+    // written in strip s and read in strip s+1, ~100 us and hundreds of MB of trace later, so it makes the round trip through
+    // HBM (the resident warps' rows outgrow the L2) -- a third on top of a 2-bit trace.  Neighbouring columns of a row differ by
+    // [gap, match - gap] (column-normalised NW: [0, match - 2 gap]), inside int8 for every packed scoring (host check
+    // match + |mismatch| + 2|gap| <= 120), so 8 bytes per group instead of 16 carry the row exactly; 14 more ALU instructions
+    // per group and strip (128 cells).
+    uint2 *__restrict__ bnd = reinterpret_cast<uint2 *>(A.bound + (uint64_t)gw * A.bound_stride) + lane;
     for (;;) {
         const uint32_t w = pk_next_job(A, lane);
         if (w >= A.njobs) break;
@@ -368,11 +374,13 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                 na = prof[0];
                 nb = prof[32];
             }
-            uint4 nu = make_uint4(0, 0, 0, 0);  // GB: boundary of the next group
+            uint2 nu = make_uint2(0, 0);  // GB: boundary of the next group (differences)
             if (GB && !first) nu = bnd[0];
+            unsigned uprev = diag;                                       // GB: upper boundary value left of the group (column 0: the corner)
+            unsigned bprev = LOCAL ? 0u : pk_dup((i0 + R) * A.gap);      // GB: bottom row value left of the group (column 0 of row i0 + R)
             for (int cg = 0; cg < Ng; cg++) {
                 uint4 ca = na, cb = nb;
-                const uint4 cu = nu;
+                const uint2 cu = nu;
                 if (CODES) {
                     unsigned T[8];
                     pk_colprof(ncode, N0 - cg * 4, N1 - cg * 4, mm4, mx, T);
@@ -389,14 +397,18 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                     if (GB && !first) nu = bnd[(uint64_t)(cg + 1) * 32];
                 }
                 // long pairs: the boundary rows of all resident warps outgrow the L2; pull mine back in well ahead
-                if (GB && !first && (lane & 7) == 0 && cg + PK_BND_AHEAD < Ng) pk_prefetch_l2_line(&bnd[(uint64_t)(cg + PK_BND_AHEAD) * 32]);
+                if (GB && !first && (lane & 15) == 0 && cg + PK_BND_AHEAD < Ng) pk_prefetch_l2_line(&bnd[(uint64_t)(cg + PK_BND_AHEAD) * 32]);
                 unsigned up[4];
                 if (GB) {
                     if (first) { // matrix row 0 (SW 0; NW H(0,j) = j*gap, include/SANeedlemanWunsch.h:61-62, i.e. K(0,j) = 0)
 #pragma unroll
                         for (int c = 0; c < 4; c++) up[c] = 0u;
-                    } else {
-                        up[0] = cu.x; up[1] = cu.y; up[2] = cu.z; up[3] = cu.w;
+                    } else { // byte (2c + k) = difference of column c, pair k: sign-extend into the halves, add up along the row
+                        up[0] = __vadd2(uprev, seqa_prmt(cu.x, 0u, 0x9180));
+                        up[1] = __vadd2(up[0], seqa_prmt(cu.x, 0u, 0xB3A2));
+                        up[2] = __vadd2(up[1], seqa_prmt(cu.y, 0u, 0x9180));
+                        up[3] = __vadd2(up[2], seqa_prmt(cu.y, 0u, 0xB3A2));
+                        uprev = up[3];
                     }
                 } else {
 #pragma unroll
@@ -462,7 +474,11 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pk_fill_kernel(PkArgs A)
                     else
                         cols(std::false_type());
                 }
-                if (GB && keep) bnd[(uint64_t)cg * 32] = make_uint4(bot[0], bot[1], bot[2], bot[3]);
+                if (GB && keep) {
+                    const unsigned d0 = __vsub2(bot[0], bprev), d1 = __vsub2(bot[1], bot[0]), d2 = __vsub2(bot[2], bot[1]), d3 = __vsub2(bot[3], bot[2]);
+                    bprev = bot[3];
+                    bnd[(uint64_t)cg * 32] = make_uint2(seqa_prmt(d0, d1, 0x6420), seqa_prmt(d2, d3, 0x6420));
+                }
                 if (TB == 8) {
                     uint4 *dst = reinterpret_cast<uint4 *>(tr + (uint64_t)cg * (RP * 32 * 16));
 #pragma unroll

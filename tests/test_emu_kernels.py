@@ -287,3 +287,16 @@ def test_table_driven_symbol_equality(emu_lib, algo, sc):
     bad[65] = 254
     with pytest.raises(capi.SeqaError):
         emu_lib.align_batch(scoring_to_params(algo, sc), *orc.batch_arrays([("ACGT", "ACGA")]), sym_class=bad)
+
+
+@pytest.mark.parametrize("algo,sc", [
+    ("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("nw", S.linear(-1, 116, -2)), ("sw", S.linear(-29, 30, -30)),
+    ("nw", S.linear(-2, 3, -1, False)),
+])
+def test_long_pairs_global_strip_boundaries(emu_lib, algo, sc):
+    """Pairs above 320 columns: the packed fill keeps its strip-boundary rows in global memory as 8-bit differences along
+    the row (pk_fill_kernel<GB>); scorings at both ends of the difference window, AllowMismatch off, related pairs."""
+    rng = np.random.default_rng(17)
+    pairs = random_pairs(rng, 5, 321, 420) + random_pairs(rng, 3, 330, 400, related=0.2) + random_pairs(rng, 3, 40, 350, "AC") + \
+        [("ACGT" * 90, "ACGT" * 90), ("A" * 340, "C" * 330), ("A" * 25, "ACGT" * 85)]
+    check_batch_against_oracle(emu_lib, algo, sc, pairs)
