@@ -45,7 +45,12 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
     const unsigned ge2 = pk_dup(A.ge), gogo2 = pk_dup(gogo), neg2 = pk_dup(PKG_NEG);
     const unsigned mmb = A.allow ? ((unsigned)(A.mismatch - A.prof_bias) & 0xffu) : 0x80u; // CODES: as pk_prep_kernel
     const unsigned mm4 = mmb * 0x01010101u, mx = ((unsigned)(A.match - A.prof_bias) & 0xffu) ^ mmb;
-    uint4 *__restrict__ bnd = A.bound + (uint64_t)gw * A.bound_stride + lane * 2; // [cg][lane][{G,Ix} x 4 columns]
+    // The strip's bottom row (G and Ix of 4 columns x 2 pairs per group and lane) crosses to the next strip through global
+    // memory; the rows of the resident warps (116 MB at 250 bp) outgrow the L2 and make the round trip through HBM, a quarter
+    // of this HBM-bound kernel's traffic as 16-bit values.  They travel as 8-BIT fields instead, one uint4 per group and lane:
+    //   x, y: G(j) - G(j-1) along the row, int8 (inside [go+ge, match - go - ge]: packed_scoring_ok, m + g <= 120)
+    //   z, w: H - Ix, uint8: Ix(i,j) >= H(i-1,j) + go + ge and H(i,j) - H(i-1,j) <= match - go - ge, so 0 <= H - Ix <= m + 2g <= 170
+    uint4 *__restrict__ bnd = A.bound + (uint64_t)gw * A.bound_stride + lane; // [cg][lane]
     for (;;) {
         const uint32_t w = pk_next_job(A, lane);
         if (w >= A.njobs) break;
@@ -84,14 +89,13 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
                 na = prof[0];
                 nb = prof[32];
             }
-            uint4 nu0 = make_uint4(0, 0, 0, 0), nu1 = nu0;
-            if (!first) {
-                nu0 = bnd[0];
-                nu1 = bnd[1];
-            }
+            uint4 nu = make_uint4(0, 0, 0, 0);
+            if (!first) nu = bnd[0];
+            unsigned gprev = diag;                                                                  // G(i0, 0): the upper row left of the group
+            unsigned bprev = pk_dup((LOCAL ? 0 : A.go + (i0 + R) * A.ge) + gogo);                   // G(i0 + R, 0): the bottom row left of the group
             for (int cg = 0; cg < Ng; cg++) {
                 uint4 ca = na, cb = nb;
-                const uint4 cu0 = nu0, cu1 = nu1;
+                const uint4 cu = nu;
                 if (CODES) {
                     unsigned T[8];
                     pk_colprof(ncode, N0 - cg * 4, N1 - cg * 4, mm4, mx, T);
@@ -105,12 +109,21 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
                         na = prof[(uint64_t)(cg + 1) * 64];
                         nb = prof[(uint64_t)(cg + 1) * 64 + 32];
                     }
-                    if (!first) {
-                        nu0 = bnd[(uint64_t)(cg + 1) * 64];
-                        nu1 = bnd[(uint64_t)(cg + 1) * 64 + 1];
-                    }
+                    if (!first) nu = bnd[(uint64_t)(cg + 1) * 32];
                 }
-                if (!first && (lane & 3) == 0 && cg + PK_BND_AHEAD < Ng) pk_prefetch_l2_line(&bnd[(uint64_t)(cg + PK_BND_AHEAD) * 64]);
+                if (!first && (lane & 7) == 0 && cg + PK_BND_AHEAD < Ng) pk_prefetch_l2_line(&bnd[(uint64_t)(cg + PK_BND_AHEAD) * 32]);
+                unsigned upG[4] = {0, 0, 0, 0}, upX[4] = {0, 0, 0, 0}; // G and Ix of the row above the strip
+                if (!first) {
+                    upG[0] = __vadd2(gprev, seqa_prmt(cu.x, 0u, 0x9180));
+                    upG[1] = __vadd2(upG[0], seqa_prmt(cu.x, 0u, 0xB3A2));
+                    upG[2] = __vadd2(upG[1], seqa_prmt(cu.y, 0u, 0x9180));
+                    upG[3] = __vadd2(upG[2], seqa_prmt(cu.y, 0u, 0xB3A2));
+                    gprev = upG[3];
+                    upX[0] = __vsub2(__vsub2(upG[0], gogo2), seqa_prmt(cu.z, 0u, 0x4140)); // Ix = H - (H - Ix)
+                    upX[1] = __vsub2(__vsub2(upG[1], gogo2), seqa_prmt(cu.z, 0u, 0x4342));
+                    upX[2] = __vsub2(__vsub2(upG[2], gogo2), seqa_prmt(cu.w, 0u, 0x4140));
+                    upX[3] = __vsub2(__vsub2(upG[3], gogo2), seqa_prmt(cu.w, 0u, 0x4342));
+                }
                 unsigned outG[4], outX[4];
                 unsigned Wg[RP], Wx[RP], Wy[RP];
                 // CAP = this group holds the corner column of one of my global alignments: only that rare variant carries
@@ -127,8 +140,8 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
                         gu = pk_dup((LOCAL ? 0 : A.go + j * A.ge) + gogo);
                         xu = neg2;
                     } else {
-                        gu = c == 0 ? cu0.x : c == 1 ? cu0.z : c == 2 ? cu1.x : cu1.z;
-                        xu = c == 0 ? cu0.y : c == 1 ? cu0.w : c == 2 ? cu1.y : cu1.w;
+                        gu = upG[c];
+                        xu = upX[c];
                     }
                     unsigned gd = diag;
                     diag = gu;
@@ -197,8 +210,15 @@ __global__ void __launch_bounds__(PK_BLOCK, 3) pkg_fill_kernel(PkArgs A)
                         cols(std::false_type());
                 }
                 if (keep) {
-                    bnd[(uint64_t)cg * 64] = make_uint4(outG[0], outX[0], outG[1], outX[1]);
-                    bnd[(uint64_t)cg * 64 + 1] = make_uint4(outG[2], outX[2], outG[3], outX[3]);
+                    unsigned d[4], e[4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        d[c] = __vsub2(outG[c], c ? outG[c - 1] : bprev);
+                        e[c] = __vsub2(__vsub2(outG[c], gogo2), outX[c]);
+                    }
+                    bprev = outG[3];
+                    bnd[(uint64_t)cg * 32] = make_uint4(seqa_prmt(d[0], d[1], 0x6420), seqa_prmt(d[2], d[3], 0x6420),
+                                                        seqa_prmt(e[0], e[1], 0x6420), seqa_prmt(e[2], e[3], 0x6420));
                 }
             }
             if (LOCAL) {
