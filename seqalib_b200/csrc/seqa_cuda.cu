@@ -22,6 +22,7 @@
 #include "seqa_packed.cuh"
 #include "seqa_packed_walk2.cuh"
 #include "seqa_packed_affine.cuh"
+#include "seqa_packed_affine_walk2.cuh"
 #include "seqa_linspace.cuh"
 #include "seqa_linspace_packed.cuh"
 #include "../../include/seqa_cuda.h"
@@ -694,7 +695,7 @@ static int env_int(const char *name, int dflt, int lo, int hi)
 }
 // resident CTAs per SM of the packed affine fill (168 registers x 128 threads: 3 fit); SEQA_PKG_BPS overrides for A/B runs
 // round-synchronous walk of the packed linear path (seqa_packed_walk2.cuh); SEQA_WALK2=0 selects pk_walk_kernel for A/B runs
-static int use_walk2() { static const int v = PK_PAIR_PIECES != 0 ? 0 : env_int("SEQA_WALK2", PK_WALK2, 0, 1); return v; }
+static int use_walk2() { static const int v = PK_PAIR_PIECES != 0 ? 0 : env_int("SEQA_WALK2", PK_WALK2, 0, 2); return v; }
 static int walk2_tune() { static const int v = env_int("SEQA_WALK2_T", 4, 1, 16); return v; }
 static int pkg_ctas_per_sm() { static const int v = env_int("SEQA_PKG_BPS", 3, 1, 3); return v; }
 
@@ -825,7 +826,13 @@ int run_packed(seqa_ctx *c, bool want_walk)
             Wk.perm = c->d_perm.p + (uint64_t)ch.lo * 64;
             // jobs' `first` fields are absolute; the walk indexes perm by position, so rebase via pointer only
             const unsigned wgrid = (unsigned)((Wk.npos + 255) / 256);
-            if (affine && local && tb == 4)
+            // LocalGotoh stays on pkg_walk_kernel: its walk is the MaxCol row scan (125 pieces per 250 bp pair, at the HBM
+            // roofline in both kernels: 0.57 ms per 200 k pairs there, 0.81 ms here), the alignments of the log regime are short
+            if (affine && local && tb == 4 && use_walk2() > 1)
+                LAUNCH(c, (pkg_walk2_kernel<true, PK_R>), wgrid, 256, 0, Wk);
+            else if (affine && !local && tb == 4 && use_walk2())
+                LAUNCH(c, (pkg_walk2_kernel<false, PK_R>), wgrid, 256, 0, Wk);
+            else if (affine && local && tb == 4)
                 LAUNCH(c, (pkg_walk_kernel<true, PK_R, 4>), wgrid, 256, 0, Wk);
             else if (affine && local)
                 LAUNCH(c, (pkg_walk_kernel<true, PK_R, 8>), wgrid, 256, 0, Wk);
