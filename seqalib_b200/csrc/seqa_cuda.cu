@@ -1726,12 +1726,12 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
                 if (round * rounds * 2 * (uint64_t)nd <= n) maxcnt = std::min<uint64_t>(n, round * rounds);
                 else if (nd > 1 && maxcnt > round) maxcnt = maxcnt / round * round;
                 // One device, several rounds, no explicit SEQA_WAVE_MCELLS: a ONE-round first wave (its upload is all that
-                // delays the first kernel), then waves of SEQA_WAVE_ROUNDS rounds (default 2: two rounds of the fill are exactly
-                // one full wave of walk CTAs -- three leave the walk a half-empty second wave, measured 8.6 against 8.35 ms per
-                // 1 M x 150 bp) -- per-wave costs and the half-empty walk of one-round waves shrink; the last wave's walk,
-                // gather and download are the tail.
+                // delays the first kernel), then waves of SEQA_WAVE_ROUNDS rounds -- per-wave costs shrink; the last wave's walk,
+                // gather and download are the tail.  Default 3 with pk_walk2_kernel (7.5-7.7 ms per 1 M x 150 bp against 7.6-7.9
+                // with 2 and 7.8-8.1 with 4; pk_walk_kernel's 6 CTAs per SM preferred 2: two rounds of the fill were exactly one
+                // full wave of its CTAs).
                 if (nd == 1 && !getenv("SEQA_WAVE_MCELLS") && n > 2 * round) {
-                    const uint64_t mid = (uint64_t)env_int("SEQA_WAVE_ROUNDS", 2, 1, 64);
+                    const uint64_t mid = (uint64_t)env_int("SEQA_WAVE_ROUNDS", 3, 1, 64);
                     uint64_t left = n - std::min(n, round);
                     sched.push_back(std::min(n, round));
                     while (left > 0) {
