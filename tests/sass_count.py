@@ -22,16 +22,16 @@ SO = os.path.join(ROOT, "seqalib_b200", "libseqa_cuda.so")
 
 # bench.py's kernel names -> mangled functions, cells per hot-loop iteration
 KERNELS = {
-    "pk_fill_sw_s16x2_t2": ("_Z14pk_fill_kernelILb1ELi16ELi2ELb0EEv6PkArgs", 128),
-    "pk_fill_nw_s16x2_t2": ("_Z14pk_fill_kernelILb0ELi16ELi2ELb0EEv6PkArgs", 128),
-    "pk_fill_sw_s16x2_t4": ("_Z14pk_fill_kernelILb1ELi16ELi4ELb0EEv6PkArgs", 128),
-    "pk_fill_nw_s16x2_t4": ("_Z14pk_fill_kernelILb0ELi16ELi4ELb0EEv6PkArgs", 128),
-    "pk_fill_sw_s16x2_t8": ("_Z14pk_fill_kernelILb1ELi16ELi8ELb0EEv6PkArgs", 128),
-    "pk_fill_nw_s16x2_t8": ("_Z14pk_fill_kernelILb0ELi16ELi8ELb0EEv6PkArgs", 128),
-    "pk_fill_sw_s16x2_t4_gb": ("_Z14pk_fill_kernelILb1ELi16ELi4ELb1EEv6PkArgs", 128),
-    "pk_fill_nw_s16x2_t4_gb": ("_Z14pk_fill_kernelILb0ELi16ELi4ELb1EEv6PkArgs", 128),
-    "pkg_fill_ggotoh_s16x2_t4": ("_Z15pkg_fill_kernelILb0ELi16ELi4EEv6PkArgs", 128),
-    "pkg_fill_lgotoh_s16x2_t4": ("_Z15pkg_fill_kernelILb1ELi16ELi4EEv6PkArgs", 128),
+    "pk_fill_sw_s16x2_t2": ("_Z14pk_fill_kernelILb1ELi16ELi2ELb0ELb0EEv6PkArgs", 128),
+    "pk_fill_nw_s16x2_t2": ("_Z14pk_fill_kernelILb0ELi16ELi2ELb0ELb0EEv6PkArgs", 128),
+    "pk_fill_sw_s16x2_t4": ("_Z14pk_fill_kernelILb1ELi16ELi4ELb0ELb0EEv6PkArgs", 128),
+    "pk_fill_nw_s16x2_t4": ("_Z14pk_fill_kernelILb0ELi16ELi4ELb0ELb0EEv6PkArgs", 128),
+    "pk_fill_sw_s16x2_t8": ("_Z14pk_fill_kernelILb1ELi16ELi8ELb0ELb0EEv6PkArgs", 128),
+    "pk_fill_nw_s16x2_t8": ("_Z14pk_fill_kernelILb0ELi16ELi8ELb0ELb0EEv6PkArgs", 128),
+    "pk_fill_sw_s16x2_t4_gb": ("_Z14pk_fill_kernelILb1ELi16ELi4ELb1ELb0EEv6PkArgs", 128),
+    "pk_fill_nw_s16x2_t4_gb": ("_Z14pk_fill_kernelILb0ELi16ELi4ELb1ELb0EEv6PkArgs", 128),
+    "pkg_fill_ggotoh_s16x2_t4": ("_Z15pkg_fill_kernelILb0ELi16ELi4ELb1EEv6PkArgs", 128),
+    "pkg_fill_lgotoh_s16x2_t4": ("_Z15pkg_fill_kernelILb1ELi16ELi4ELb1EEv6PkArgs", 128),
 }
 
 ALU = ("VIADDMNMX", "VIADD", "VIMNMX", "VIMNMX3", "PRMT", "LOP3", "SHF", "SEL", "ISETP", "IABS", "BMSK", "SGXT", "LEA", "PLOP3", "POPC", "FLO")
