@@ -972,18 +972,19 @@ struct BatchFacts {
     bool uniform = false, dense = false, in_bounds = false;
 };
 
-BatchFacts scan_batch_facts(const seqa_batch_in *in, bool two_bit)
+// pairs [lo, hi) against the closed form anchored at pair 0 (the shape of pair 0, back to back from its offset on)
+BatchFacts scan_batch_facts(const seqa_batch_in *in, bool two_bit, uint64_t lo0, uint64_t hi0, int max_threads = 8)
 {
     BatchFacts f;
     const uint64_t n = in->n_pairs;
-    if (n == 0 || !in->off1 || !in->off2 || !in->len1 || !in->len2) return f;
+    if (n == 0 || hi0 <= lo0 || !in->off1 || !in->off2 || !in->len1 || !in->len2) return f;
     const uint32_t M0 = in->len1[0], N0 = in->len2[0];
     const uint64_t s1 = two_bit ? (uint64_t)((M0 + 3) >> 2) : (uint64_t)M0, s2 = two_bit ? (uint64_t)((N0 + 3) >> 2) : (uint64_t)N0;
-    const uint64_t first = in->off1[0], stride = s1 + s2;
-    const int threads = (int)std::min<uint64_t>(8, std::max<uint64_t>(1, n / 131072));
+    const uint64_t first = in->off1[0], stride = s1 + s2, cnt = hi0 - lo0;
+    const int threads = (int)std::min<uint64_t>((uint64_t)max_threads, std::max<uint64_t>(1, cnt / 131072));
     std::vector<char> ok((size_t)threads, 1);
     auto part = [&](int t) {
-        const uint64_t lo = n * t / threads, hi = n * (t + 1) / threads;
+        const uint64_t lo = lo0 + cnt * t / threads, hi = lo0 + cnt * (t + 1) / threads;
         unsigned diff = 0;
         uint64_t bad = 0;
         for (uint64_t p = lo; p < hi; p++) {
@@ -1006,9 +1007,10 @@ BatchFacts scan_batch_facts(const seqa_batch_in *in, bool two_bit)
         f.dense &= (v & 2) != 0;
     }
     f.dense &= f.uniform; // the closed form above only describes a uniform batch
-    f.in_bounds = first <= in->bases_len && n * stride <= in->bases_len - first;
+    f.in_bounds = first <= in->bases_len && n * stride <= in->bases_len - first; // of the WHOLE batch, if it is uniform and dense
     return f;
 }
+BatchFacts scan_batch_facts(const seqa_batch_in *in, bool two_bit) { return scan_batch_facts(in, two_bit, 0, in->n_pairs); }
 
 // SEQA_FLAG_BASES_2BIT: `in->bases` holds 2-bit symbols (4 per byte, A0 C1 T2 G3, every sequence on a byte boundary;
 // off1 / off2 are BYTE offsets into it, len1 / len2 count symbols).  A quarter of the bytes cross PCIe; the device
@@ -1688,13 +1690,31 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
     if ((uint64_t)nd > n) nd = (int)n;
 
     // one (threaded) pass over the index arrays: uniform shape? dense layout? inside `bases`?  The waves then skip their own loops
-    const BatchFacts facts = scan_batch_facts(in, (params->flags & SEQA_FLAG_BASES_2BIT) != 0);
+    const auto t_entry = std::chrono::steady_clock::now();
+    const bool dbg_call = getenv("SEQA_DEBUG_TIMING") != nullptr;
+    // A large batch on one device does not wait for that pass (0.4 ms per 1 M pairs, in front of everything): the waves are
+    // planned as if the batch were uniform and dense like its first pair, the first wave's pairs are checked (a tenth of the
+    // pass), and while that wave uploads and runs a helper thread checks the rest.  No later wave starts before the helper
+    // agrees; if it does not, the first wave's results stand and the remaining pairs go through a second, ordinary call.
+    const bool two_bit_in = (params->flags & SEQA_FLAG_BASES_2BIT) != 0;
+    bool spec = n >= (uint64_t)env_int("SEQA_SPEC_MIN_PAIRS", 524288, 1, 1 << 30) && nd == 1 && in->off1 && in->off2 && !getenv("SEQA_NO_SPECULATIVE_FACTS");
+    BatchFacts facts;
+    if (spec) {
+        facts = scan_batch_facts(in, two_bit_in, 0, 1, 1); // closed-form bounds of the whole batch from pair 0
+        spec = facts.in_bounds;
+    }
+    if (!spec) facts = scan_batch_facts(in, two_bit_in);
+    const double t_facts = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count();
     // waves: contiguous, ~3e9 cells or 256k pairs each; linear-space pairs (huge sweeps) go one wave per 4e10 cells
     const bool linspace = params->algo == SEQA_HIRSCHBERG || params->algo == SEQA_MYERS_MILLER;
     const uint64_t wave_cells = linspace ? 40000000000ull : (uint64_t)env_int("SEQA_WAVE_MCELLS", 3000, 10, 100000) * 1000000ull;
     std::vector<uint64_t> wave_lo, wave_slots, wave_cellsum; // first pair; (len1+len2) before the wave; cells of the wave
     uint64_t tot = 0;
-    {
+    auto plan_waves = [&]() {
+        wave_lo.clear();
+        wave_slots.clear();
+        wave_cellsum.clear();
+        tot = 0;
         uint64_t acc = 0, slots = 0, cnt = 0;
         std::vector<uint64_t> sched; // explicit wave sizes (uniform packed batch on one device), else empty
         // several devices: at least two waves per device even for small batches
@@ -1785,7 +1805,40 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
         }
         wave_lo.push_back(n);
         wave_slots.push_back(slots);
+    };
+    plan_waves();
+    std::thread spec_thread;       // checks the pairs behind the first wave
+    BatchFacts spec_rest;          // its verdict
+    std::mutex spec_mu;
+    std::condition_variable spec_cv;
+    bool spec_done = false, spec_failed = false;
+    if (spec) {
+        bool ok = wave_lo.size() >= 3; // a single wave: nothing to overlap
+        const bool ops2_ = (params->flags & SEQA_FLAG_OPS_2BIT) != 0;
+        // the pipelined (sparse) layout only: the wave-after-wave path for small caller buffers plans with the full pass
+        ok = ok && (out->ops_capacity >= (ops2_ ? wave_slots.back() / 4 + n : wave_slots.back()) || (params->flags & SEQA_FLAG_SCORE_ONLY));
+        if (ok) {
+            const BatchFacts f0 = scan_batch_facts(in, two_bit_in, 0, wave_lo[1], 1);
+            ok = f0.uniform && f0.dense;
+        }
+        if (!ok) { // the ordinary full pass, and the waves planned from what it finds
+            spec = false;
+            facts = scan_batch_facts(in, two_bit_in);
+            plan_waves();
+        }
     }
+    if (spec)
+        spec_thread = std::thread([&]() {
+            const BatchFacts r = scan_batch_facts(in, two_bit_in, wave_lo[1], n);
+            std::lock_guard<std::mutex> lk(spec_mu);
+            spec_rest = r;
+            spec_done = true;
+            spec_cv.notify_all();
+        });
+    struct SpecJoin { // the helper never outlives the call
+        std::thread &t;
+        ~SpecJoin() { if (t.joinable()) t.join(); }
+    } spec_join{spec_thread};
     const size_t nwaves = wave_lo.size() - 1;
     const uint64_t slots_total = wave_slots.back();
     // where a wave's ops start in the caller's buffer: behind the slots of all earlier pairs (one byte per op), or, in the
@@ -1817,6 +1870,8 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
     std::vector<WaveEv> wev(dbg ? nwaves : 0);
     std::vector<cudaEvent_t> dbg_base(dbg ? nd : 0, nullptr);
     const auto t_start = std::chrono::steady_clock::now();
+    if (dbg) fprintf(stderr, "[seqa] host before the pipeline: batch facts %.3f ms, wave schedule ..%.3f ms\n", t_facts,
+                     std::chrono::duration<double, std::milli>(t_start - t_entry).count());
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     // Per device a PRODUCER thread uploads, plans and launches wave after wave into a ring of contexts (each with its
     // own stream) and a CONSUMER thread, in the same order, waits for a wave and copies its results out: the host
@@ -1849,6 +1904,14 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
                 std::unique_lock<std::mutex> lk(P.mu);
                 P.cv.wait(lk, [&] { return P.consumed > k - ring || P.stop; });
                 if (P.stop) break;
+            }
+            if (spec && w > 0) { // the pairs behind the first wave must have been checked, and found as assumed
+                std::unique_lock<std::mutex> lk(spec_mu);
+                spec_cv.wait(lk, [&] { return spec_done; });
+                if (!(spec_rest.uniform && spec_rest.dense)) {
+                    spec_failed = true;
+                    break;
+                }
             }
             int s = SEQA_OK;
             const double t0 = since();
@@ -1982,6 +2045,7 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
             th.emplace_back(consumer, d);
         }
         for (auto &t : th) t.join();
+        if (dbg) fprintf(stderr, "[seqa] threads joined at %.3f ms\n", since());
         for (int d = 0; d < nd; d++)
             for (int q = 0; q < SEQA_CACHE_SLOTS; q++)
                 if (pipes[d].c[q]) {
@@ -2000,6 +2064,43 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
                 g_err = werr[w];
             }
             used += wused[w];
+        }
+        if (spec_thread.joinable()) spec_thread.join();
+        if (spec_failed && rc == SEQA_OK) {
+            // the pairs behind the first wave are not like pair 0: they go through an ordinary call of their own (own pass
+            // over the index arrays, own waves); their ops follow the first wave's slots in the caller's buffer
+            const uint64_t pb = wave_lo[1], base = wave_ops_base(1);
+            seqa_batch_in in2 = *in;
+            in2.n_pairs = n - pb;
+            in2.off1 += pb;
+            in2.off2 += pb;
+            in2.len1 += pb;
+            in2.len2 += pb;
+            seqa_batch_out out2 = *out;
+            out2.score += pb;
+            if (out2.start_i) out2.start_i += pb;
+            if (out2.start_j) out2.start_j += pb;
+            if (out2.end_i) out2.end_i += pb;
+            if (out2.end_j) out2.end_j += pb;
+            if (out2.ops_off) out2.ops_off += pb;
+            if (out2.ops_len) out2.ops_len += pb;
+            if (out2.ops) out2.ops += base;
+            out2.ops_capacity = out->ops_capacity >= base ? out->ops_capacity - base : 0;
+            out2.ops_used = 0;
+            struct Shim {
+                seqa_fill_fn fn;
+                void *user;
+                uint64_t off;
+                static int call(void *u, uint64_t first_pair, uint64_t cnt)
+                {
+                    Shim *s = static_cast<Shim *>(u);
+                    return s->fn(s->user, first_pair + s->off, cnt);
+                }
+            } shim{fill, fill_user, pb};
+            rc = align_batch_impl(params, &in2, &out2, fill ? &Shim::call : nullptr, fill ? &shim : nullptr);
+            if (rc == SEQA_OK && out->ops_off && !(params->flags & SEQA_FLAG_SCORE_ONLY))
+                for (uint64_t q = pb; q < n; q++) out->ops_off[q] += base;
+            used += out2.ops_used;
         }
         if (dbg) { // every stream was synchronised above: the events are complete
             fprintf(stderr, "[seqa] device timeline (ms after the first upload was queued): wave pairs | H2D start..done | kernels start..done | D2H done\n");
@@ -2040,6 +2141,7 @@ static int align_batch_impl(const seqa_params *params, const seqa_batch_in *in, 
         }
     }
     out->ops_used = used;
+    if (dbg_call) fprintf(stderr, "[seqa] call returns %.3f ms after entry\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count());
     return rc;
 }
 

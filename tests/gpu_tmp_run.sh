@@ -1,4 +1,5 @@
-for w in 0 1; do
-SEQA_WALK2=$w ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:walk -c 1 --csv --log-file gpurun_out/lgw_$w.csv python tests/bench_configs.py 1 "config3 Local" > /dev/null 2>&1
-grep -o 'pkg_walk[2]*_kernel<[^>]*>\|"gpu__time_duration.sum","ns","[0-9,]*"\|"dram__bytes_read.sum","[A-Za-z]*","[0-9.,]*"\|"smsp__inst_executed.sum","inst","[0-9,]*"\|"smsp__issue_active[^"]*","%","[0-9.]*"' gpurun_out/lgw_$w.csv | tr '\n' ' '; echo
-done
+python tests/e2e_probe.py 2>&1 | sed -n '/2-bit symbols in, 2-bit ops out/,$p' | grep -v "upload+plan\|wait "
+python bench.py --no-cpu --no-configs --no-api --steps 10 --warmup 3 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); e=d['e2e']; print('value %.0f ms %.3f e2e %.3f bytebases %.3f byteops %.3f' % (d['value'], d['ms_per_step'], e['ms_per_step'], e['byte_bases']['ms_per_step'], e['byte_ops']['ms_per_step']))"
+python -m pytest tests -m gpu -x -q -k "wire or two_bit or 2bit or full_size or layout or wave" 2>&1 | tail -3

@@ -300,3 +300,29 @@ def test_long_pairs_global_strip_boundaries(emu_lib, algo, sc):
     pairs = random_pairs(rng, 5, 321, 420) + random_pairs(rng, 3, 330, 400, related=0.2) + random_pairs(rng, 3, 40, 350, "AC") + \
         [("ACGT" * 90, "ACGT" * 90), ("A" * 340, "C" * 330), ("A" * 25, "ACGT" * 85)]
     check_batch_against_oracle(emu_lib, algo, sc, pairs)
+
+
+def test_speculative_batch_facts(emu_lib, monkeypatch):
+    """Large one-device batches start their first wave before the pass over the index arrays has finished (planned as if
+    every pair were like pair 0); a batch that stops being uniform behind the first wave keeps that wave's results and sends
+    the rest through an ordinary second call.  Both outcomes against the oracle, then every wire format against that."""
+    monkeypatch.setenv("SEQA_SPEC_MIN_PAIRS", "1000")
+    rng = np.random.default_rng(23)
+    uniform = random_pairs(rng, 4200, 12, 12)
+    # same slots per pair (len1 + len2 = 24), other shapes: the caller's ops buffer still fits the assumed layout, so the first
+    # wave really starts on the assumption and the helper thread is the one that refutes it
+    odd = [(a[:10], b + a[10:]) for a, b in random_pairs(rng, 900, 12, 12)]
+    ragged = uniform[:2500] + odd + uniform[2500:3000]  # fails behind the first wave
+    early = uniform[:700] + random_pairs(rng, 10, 3, 20) + uniform[700:3500]      # fails inside the first wave: full pass
+    for algo, sc, pairs in (("sw", S.linear(-1, 1, -1), uniform), ("sw", S.linear(-1, 1, -1), ragged), ("nw", S.linear(-1, 2, -1), ragged[1000:]),
+                            ("sw", S.linear(-1, 1, -1), early)):
+        check_batch_against_oracle(emu_lib, algo, sc, pairs)
+        bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+        ref = emu_lib.align_batch(scoring_to_params(algo, sc), bases, off1, off2, len1, len2)
+        pk, p1, p2 = capi.pack_bases_2bit(bases, off1, off2, len1, len2)
+        for flags, ins in ((capi.FLAG_OPS_2BIT, (bases, off1, off2)), (capi.FLAG_OPS_2BIT | capi.FLAG_BASES_2BIT, (pk, p1, p2))):
+            got = emu_lib.align_batch(scoring_to_params(algo, sc, flags=flags), ins[0], ins[1], ins[2], len1, len2)
+            for f in ("score", "start_i", "start_j", "end_i", "end_j", "ops_len"):
+                assert np.array_equal(getattr(got, f), getattr(ref, f)), (algo, flags, f)
+            for q in range(0, len(pairs), 7):
+                assert np.array_equal(got.pair_ops(q), ref.pair_ops(q)), (algo, flags, q)
