@@ -290,8 +290,8 @@ def test_table_driven_symbol_equality(emu_lib, algo, sc):
 
 
 @pytest.mark.parametrize("algo,sc", [
-    ("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("nw", S.linear(-1, 116, -2)), ("sw", S.linear(-29, 30, -30)),
-    ("nw", S.linear(-2, 3, -1, False)),
+    ("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("nw", S.linear(-14, 75, -1)), ("sw", S.linear(-29, 30, -30)),
+    ("nw", S.linear(-2, 3, -1, False)), ("ggotoh", S.affine(-10, -40, 20, -30)), ("lgotoh", S.affine(-5, -5, 12, -9)),
 ])
 def test_long_pairs_global_strip_boundaries(emu_lib, algo, sc):
     """Pairs above 320 columns: the packed fill keeps its strip-boundary rows in global memory as 8-bit differences along

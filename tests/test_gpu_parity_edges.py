@@ -132,6 +132,22 @@ def test_strip_boundary_storage_switch_320_321(gpu_lib):
         check_batch_against_oracle(gpu_lib, algo, sc, more, label="321")
 
 
+def test_strip_boundary_rows_as_8_bit_differences(gpu_lib):
+    """The strip-boundary rows in global memory travel as 8-bit fields (differences along the row; affine: + H - Ix): scorings
+    that push the differences to both ends of their windows, identical / disjoint / related long pairs, AllowMismatch off."""
+    rng = np.random.default_rng(29)
+    a = _seq(rng, 330)
+    pairs = random_pairs(rng, 60, 321, 420) + random_pairs(rng, 20, 330, 400, related=0.15) + random_pairs(rng, 20, 40, 350, "AC") + \
+        [(a, a), ("ACGT" * 90, "ACGT" * 90), ("A" * 340, "C" * 330), ("A" * 25, "ACGT" * 85), ("ACGT" * 85, "A" * 25), (a, a[::-1])]
+    for algo, sc in (("nw", S.linear(-14, 75, -1)), ("nw", S.linear(-1, 70, -40)), ("sw", S.linear(-29, 30, -30)), ("sw", S.linear(-1, 1, -1)),
+                     ("nw", S.linear(-2, 3, -1, False)), ("sw", S.linear(-50, 19, -1))):
+        check_batch_against_oracle(gpu_lib, algo, sc, pairs, label="gb-rows")
+    short = [(x[:260], y[:250]) for x, y in pairs]
+    for algo, sc in (("ggotoh", S.affine(-3, -1, 1, -1)), ("ggotoh", S.affine(-10, -40, 20, -30)), ("lgotoh", S.affine(-5, -5, 12, -9)),
+                     ("ggotoh", S.affine(0, -1, 7, -5)), ("lgotoh", S.affine(-3, -1, 1, -1, False)), ("ggotoh", S.affine(-40, -10, 30, -1))):
+        check_batch_against_oracle(gpu_lib, algo, sc, _defined(algo, short), label="affine-rows")
+
+
 def test_packed_length_cap_2048_2049(gpu_lib):
     """PKG_MAX_LEN: a side of 2,048 still runs on the s16x2 kernels, 2,049 goes to the int32 wavefront -- in one batch."""
     rng = np.random.default_rng(6)
@@ -366,3 +382,30 @@ def test_table_driven_symbol_equality(gpu_lib, algo, sc):
         ctx.sync()
         assert ctx.last_kernel().startswith("pk"), ctx.last_kernel()
         ctx.close()
+
+
+def test_one_shot_call_speculative_first_wave(gpu_lib):
+    """Batches above 524,288 pairs on one device start their first wave before the pass over the index arrays is complete
+    (planned on pair 0's shape).  600,000 x 40 bp: (1) really uniform; (2) 50,000 pairs of another shape with the same slot
+    size behind the first wave -- the helper thread refutes the assumption, the first wave stands, the rest goes through a
+    second call; every pair of both against the threaded oracle, 8-bit and 2-bit symbols in."""
+    n = 600_000
+    sc = S.linear(-1, 1, -1)
+    rng = np.random.default_rng(41)
+    codes = rng.integers(0, 4, n * 80, dtype=np.uint8)
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    for odd in (False, True):
+        len1 = np.full(n, 40, np.uint32)
+        len2 = np.full(n, 40, np.uint32)
+        if odd:
+            len1[400_000:450_000] = 33
+            len2[400_000:450_000] = 47
+        off1 = np.arange(n, dtype=np.uint64) * 80
+        off2 = off1 + len1
+        res = gpu_lib.align_batch(scoring_to_params("sw", sc), bases, off1, off2, len1, len2)
+        compare_with_oracle_batch(res, "sw", sc, bases, off1, off2, len1, len2, label="speculative odd=%s" % odd)
+        pk, p1, p2 = capi.pack_bases_2bit(bases, off1, off2, len1, len2)
+        got = gpu_lib.align_batch(scoring_to_params("sw", sc, flags=capi.FLAG_BASES_2BIT), pk, p1, p2, len1, len2)
+        for name in ("score", "start_i", "start_j", "end_i", "end_j", "ops_len", "ops_off"):
+            assert np.array_equal(getattr(res, name), getattr(got, name)), (odd, name)
+        assert np.array_equal(res.ops[:res.c.ops_used], got.ops[:got.c.ops_used])
