@@ -696,7 +696,6 @@ static int env_int(const char *name, int dflt, int lo, int hi)
 // resident CTAs per SM of the packed affine fill (168 registers x 128 threads: 3 fit); SEQA_PKG_BPS overrides for A/B runs
 // round-synchronous walk of the packed linear path (seqa_packed_walk2.cuh); SEQA_WALK2=0 selects pk_walk_kernel for A/B runs
 static int use_walk2() { static const int v = PK_PAIR_PIECES != 0 ? 0 : env_int("SEQA_WALK2", PK_WALK2, 0, 2); return v; }
-static int walk2_tune() { static const int v = env_int("SEQA_WALK2_T", 4, 1, 16); return v; }
 static int pkg_ctas_per_sm() { static const int v = env_int("SEQA_PKG_BPS", 3, 1, 3); return v; }
 
 // resident CTAs per SM of the packed linear fill: its dynamic shared memory (one strip-boundary column per thread)
@@ -779,7 +778,6 @@ int run_packed(seqa_ctx *c, bool want_walk)
         A.bound = c->pk_bound.p;
         A.bound_stride = bound_stride;
         A.ticket = reinterpret_cast<uint32_t *>(c->flags.p + 1);
-        A.walk_tune = walk2_tune();
         A.colcodes = affine ? (PKG_CODES != 0) : (gb && (local ? PK_GB_CODES_SW != 0 : PK_GB_CODES_NW != 0));
         CK(cudaMemsetAsync(c->flags.p + 1, 0, sizeof(int), c->stream));
         const unsigned wpb = PK_BLOCK / 32;

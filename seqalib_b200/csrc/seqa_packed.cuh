@@ -79,7 +79,6 @@ struct PkArgs {
     uint4 *bound;          // per-warp strip boundary rows (kernels that keep them in global memory)
     uint64_t bound_stride; // uint4 per warp
     uint32_t *ticket;      // job counter: warps draw jobs (largest first) instead of striding over them
-    int walk_tune;         // pk_walk2_kernel: neighbour tests per STEP phase (between two LOAD phases)
     int colcodes;          // != 0: prep writes 2-bit COLUMN CODES (uint16 [Ng][32] per job, at the job's profile offset) instead of
                            // the column profiles, and the fill builds the profile words itself (kernels that are HBM-bound)
 };
