@@ -16,6 +16,10 @@
 #include "seqa_packed_affine.cuh"
 #include "seqa_packed_walk2.cuh"
 
+#ifndef PKG_WALK2_STEPS
+#define PKG_WALK2_STEPS PK_WALK2_STEPS /* lookups per STEP phase (PkOpWriter64: at most 5) */
+#endif
+
 template <bool LOCAL, int R>
 __device__ __forceinline__ void pkg_walk2_pairs(const PkArgs &A, const uint64_t pos, const PkSmemCol S)
 {
@@ -139,7 +143,7 @@ __device__ __forceinline__ void pkg_walk2_pairs(const PkArgs &A, const uint64_t 
         }
         // ---- STEP
 #pragma unroll 1
-        for (int k = 0; k < PK_WALK2_STEPS; k++) {
+        for (int k = 0; k < PKG_WALK2_STEPS; k++) {
             if (st < 4) {
                 const bool eq = ((pk_shr_wrap(aw, (uint32_t)ci * 2u) ^ pk_shr_wrap(bw, (uint32_t)cj * 2u)) & 3u) == 0u;
                 const int t = val - (eq ? A.match : A.mismatch); // state 0: H(i-1,j-1) if this cell came from the diagonal

@@ -1,8 +1,6 @@
-nproc; free -g | head -2
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 6 --warmup 2 --no-configs --no-api --no-cpu 2>gpurun_out/e8_$1.err | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); e=d['e2e']; print('$1 value %.0f ms %.3f e2e %.0f ms %.3f bytebases %.3f' % (d['value'], d['ms_per_step'], e['value'], e['ms_per_step'], e['byte_bases']['ms_per_step']))"; }
-run default
-SEQA_NO_SPECULATIVE_FACTS=1 run nospec
-SEQA_DEBUG_TIMING=1 run debug
-grep "dev 0 wave\|host before\|call returns\|threads joined" gpurun_out/e8_debug.err | tail -40
+for lib in seqalib_b200/libseqa_cuda.so build_ab/libseqa_g2.so build_ab/libseqa_g3.so build_ab/libseqa_g5.so; do
+echo "=== $lib"
+SEQA_LIB=$PWD/$lib python tests/bench_configs.py 1 "config3 Global" | grep -o '"gcups_step": [0-9.]*\|"gcups_fill": [0-9.]*' | paste - -
+SEQA_LIB=$PWD/$lib ncu --metrics gpu__time_duration.sum --clock-control none -k regex:walk -c 1 --csv --log-file gpurun_out/gx.csv python tests/bench_configs.py 1 "config3 Global" > /dev/null 2>&1
+grep -o '"gpu__time_duration.sum","ns","[0-9,]*"' gpurun_out/gx.csv
+done
