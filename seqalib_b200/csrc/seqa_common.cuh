@@ -35,6 +35,41 @@ __device__ __forceinline__ unsigned seqa_prmt(unsigned a, unsigned b, unsigned s
 }
 #endif
 
+// ---- TMA bulk copy global -> shared (cp.async.bulk, SASS UBLKCP) and the mbarrier its bytes arrive on ----
+// One barrier per warp (arrival count 1): the issuing lane arms it with the byte count and issues the copy, every
+// lane of the warp polls the phase parity.  Source and destination 16-byte aligned, size a multiple of 16.
+#ifdef SEQA_EMU
+static inline void seqa_mbar_init(uint64_t *bar) { *bar = 0; }
+static inline void seqa_bulk_load(void *dst, const void *src, unsigned bytes, uint64_t *) { memcpy(dst, src, bytes); }
+static inline void seqa_mbar_wait(uint64_t *, unsigned) { __syncwarp(); } // the emulated copy is lane 0's memcpy
+#else
+__device__ __forceinline__ unsigned seqa_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void seqa_mbar_init(uint64_t *bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(seqa_smem_addr(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void seqa_bulk_load(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    const unsigned b = seqa_smem_addr(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(seqa_smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void seqa_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    const unsigned b = seqa_smem_addr(bar);
+    unsigned done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(b), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+#endif
+
 #define SEQA_WARP 32
 #define SEQA_FULL 0xffffffffu
 #define SEQA_GOTOH_NEG (-10000) /* the reference's literal "-infinity", include/SAGlobalGotoh.h:78-79 */

@@ -783,7 +783,23 @@ int run_packed(seqa_ctx *c, bool want_walk)
         const unsigned wpb = PK_BLOCK / 32;
         const unsigned full = (nj + wpb - 1) / wpb;
         const unsigned grid = std::min<unsigned>(full, (unsigned)(c->sms * bps));
-        LAUNCH(c, (pk_prep_kernel), full, PK_BLOCK, 0, A, PK_R); // one job per warp
+        // pk_prep_kernel: a uniform batch is dense in `bases` (both upload paths lay it out back to back), so the 128 sequences of
+        // a job are one span of it -- staged in shared memory by one TMA bulk copy per job (two-warp CTAs: 5 per SM at 150 bp)
+        unsigned prep_block = PK_BLOCK;
+        size_t prep_smem = 0;
+        A.prep_stage = 0;
+        if (c->st_uniform && c->n > 0 && env_int("SEQA_PREP_TMA", 1, 0, 1)) {
+            const uint64_t span = 64ull * ((uint64_t)c->hlen1[0] + c->hlen2[0]) + 32; // + 16-byte alignment at both ends
+            if (span <= 48u * 1024u) {
+                A.prep_stage = (uint32_t)((span + 15) & ~15ull);
+                prep_block = 64;
+                prep_smem = (size_t)(prep_block / 32) * (A.prep_stage + 64 + sizeof(uint64_t));
+                if (prep_smem > 48u * 1024u)
+                    CK(cudaFuncSetAttribute(pk_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+            }
+        }
+        const unsigned prep_wpb = prep_block / 32;
+        LAUNCH(c, (pk_prep_kernel), (nj + prep_wpb - 1) / prep_wpb, prep_block, prep_smem, A, PK_R); // one job per warp
         cudaEventRecord(next_event(c), c->stream);
         if (affine && local && tb == 4)
             LAUNCH(c, (pkg_fill_kernel<true, PK_R, 4, PKG_CODES != 0>), grid, PK_BLOCK, 0, A);

@@ -79,6 +79,7 @@ struct PkArgs {
     uint4 *bound;          // per-warp strip boundary rows (kernels that keep them in global memory)
     uint64_t bound_stride; // uint4 per warp
     uint32_t *ticket;      // job counter: warps draw jobs (largest first) instead of striding over them
+    uint32_t prep_stage;   // pk_prep_kernel: bytes of shared staging per warp (multiple of 16; 0 = read global memory directly)
     int colcodes;          // != 0: prep writes 2-bit COLUMN CODES (uint16 [Ng][32] per job, at the job's profile offset) instead of
                            // the column profiles, and the fill builds the profile words itself (kernels that are HBM-bound)
 };
@@ -104,6 +105,7 @@ __device__ __forceinline__ bool pk_is_acgt(unsigned c) { return c == 'A' || c ==
 // samples on the four moves behind the loads, profiles/r02_ncu_pk_prep_fill_walk_sw150_1M.txt); reads reach at most
 // 4 * (PK_PREP_AHEAD + 1) bytes behind a sequence (`bases` is allocated with 64 bytes of slack).
 #define PK_PREP_AHEAD 4
+template <bool SM> // SM: the words come from the warp's TMA-staged copy in shared memory (pk_prep_kernel), else from global memory
 struct PkSeqReader {
     const uint32_t *w; // aligned word pointer
     unsigned sh;       // bit shift of the first symbol inside *w
@@ -113,38 +115,38 @@ struct PkSeqReader {
         const uint64_t o = (uint64_t)(p - base);
         w = reinterpret_cast<const uint32_t *>(base) + (o >> 2);
         sh = (unsigned)(o & 3u) * 8u;
-        carry = __ldg(w++);
+        carry = ld(w++);
 #pragma unroll
-        for (int k = 0; k < PK_PREP_AHEAD; k++) ahead[k] = __ldg(w++);
+        for (int k = 0; k < PK_PREP_AHEAD; k++) ahead[k] = ld(w++);
     }
+    static __device__ __forceinline__ uint32_t ld(const uint32_t *q) { return SM ? *q : __ldg(q); }
     template <int K> __device__ __forceinline__ uint32_t next4() // the next 4 symbols, first in the low byte; K = call index % PK_PREP_AHEAD
     {
         const uint32_t hi = ahead[K];
-        ahead[K] = __ldg(w++);
+        ahead[K] = ld(w++);
         const uint32_t v = sh ? ((carry >> sh) | (hi << (32u - sh))) : carry;
         carry = hi;
         return v;
     }
 };
 
-__global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
+// One job (64 pairs, two per lane).  `base` is the 4-byte aligned start of the memory the four sequences s* live in: `bases`
+// itself, or the warp's staged copy of the job's span of it (SM).
+template <bool SM>
+__device__ __forceinline__ void pk_prep_job(const PkArgs &A, const int R, const PkWarpJob &J, const int lane, const uint32_t p0,
+                                            const uint32_t p1, const uint32_t M0, const uint32_t N0, const uint32_t M1, const uint32_t N1,
+                                            const uint8_t *base, const uint8_t *sa0, const uint8_t *sb0, const uint8_t *sa1,
+                                            const uint8_t *sb1)
 {
-    const int lane = threadIdx.x & 31;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
     const unsigned mm = A.allow ? ((unsigned)(A.mismatch - A.prof_bias) & 0xffu) : 0x80u; // -128 marks "never" (see header)
     const unsigned mt = (unsigned)(A.match - A.prof_bias) & 0xffu;
     const unsigned mm4 = mm * 0x01010101u, mx = mt ^ mm;
-    for (uint32_t w = gw; w < A.njobs; w += nw) {
-        const PkWarpJob J = A.jobs[w];
-        const uint32_t p0 = A.perm[J.first + 2 * lane], p1 = A.perm[J.first + 2 * lane + 1];
-        const uint32_t M0 = p0 == PK_NULL ? 0u : A.len1[p0], N0 = p0 == PK_NULL ? 0u : A.len2[p0];
-        const uint32_t M1 = p1 == PK_NULL ? 0u : A.len1[p1], N1 = p1 == PK_NULL ? 0u : A.len2[p1];
-        PkSeqReader a0, b0, a1, b1;
-        a0.init(A.bases, p0 == PK_NULL ? A.bases : A.bases + A.off1[p0]);
-        b0.init(A.bases, p0 == PK_NULL ? A.bases : A.bases + A.off2[p0]);
-        a1.init(A.bases, p1 == PK_NULL ? A.bases : A.bases + A.off1[p1]);
-        b1.init(A.bases, p1 == PK_NULL ? A.bases : A.bases + A.off2[p1]);
+    {
+        PkSeqReader<SM> a0, b0, a1, b1;
+        a0.init(base, sa0);
+        b0.init(base, sb0);
+        a1.init(base, sa1);
+        b1.init(base, sb1);
         // Four symbols per 32-bit word are handled together: codes4 = (w >> 1) & 0x03030303 (A0 C1 T2 G3 in every byte); the
         // word is valid iff "ACTG"[code] gives back every byte (one PRMT table look-up + XOR); bytes behind the end of
         // the sequence are masked out.
@@ -234,6 +236,59 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
         if (bad0 | bad1) *A.bad = 1;
         if (bad0 && p0 != PK_NULL) A.badpair[p0] = 1;
         if (bad1 && p1 != PK_NULL) A.badpair[p1] = 1;
+    }
+}
+
+// A.prep_stage != 0 (dynamic shared memory: per warp [A.prep_stage + 64] bytes of staging, then one mbarrier per warp): a job
+// whose 128 sequences lie within A.prep_stage bytes of `bases` (64 pairs of a dense batch do) is brought in by ONE TMA bulk
+// copy of that span and read from shared memory; the per-lane 4-byte global loads of the other form -- 32 different sequences
+// per warp load, every one a sector of its own -- were the kernel's whole cost (long-scoreboard stalls, ncu round 2).
+__global__ void __launch_bounds__(PK_BLOCK) pk_prep_kernel(PkArgs A, int R)
+{
+    SEQA_DYN_SMEM(unsigned char, stage_raw);
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    unsigned char *stage = stage_raw + (size_t)wib * (A.prep_stage + 64u);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(stage_raw + (size_t)wpb * (A.prep_stage + 64u)) + wib;
+    const bool can_stage = A.prep_stage != 0 && (reinterpret_cast<uintptr_t>(A.bases) & 15u) == 0;
+    unsigned phase = 0;
+    if (can_stage) {
+        if (lane == 0) seqa_mbar_init(bar);
+        __syncwarp();
+    }
+    for (uint32_t w = gw; w < A.njobs; w += nw) {
+        const PkWarpJob J = A.jobs[w];
+        const uint32_t p0 = A.perm[J.first + 2 * lane], p1 = A.perm[J.first + 2 * lane + 1];
+        const uint32_t M0 = p0 == PK_NULL ? 0u : A.len1[p0], N0 = p0 == PK_NULL ? 0u : A.len2[p0];
+        const uint32_t M1 = p1 == PK_NULL ? 0u : A.len1[p1], N1 = p1 == PK_NULL ? 0u : A.len2[p1];
+        const uint64_t oa0 = p0 == PK_NULL ? 0ull : A.off1[p0], ob0 = p0 == PK_NULL ? 0ull : A.off2[p0];
+        const uint64_t oa1 = p1 == PK_NULL ? 0ull : A.off1[p1], ob1 = p1 == PK_NULL ? 0ull : A.off2[p1];
+        if (can_stage) {
+            // the span of `bases` the job reads: [lo, hi)
+            uint64_t lo = ~0ull, hi = 0;
+            if (p0 != PK_NULL) lo = min(oa0, ob0), hi = max(oa0 + M0, ob0 + N0);
+            if (p1 != PK_NULL) lo = min(lo, min(oa1, ob1)), hi = max(hi, max(oa1 + M1, ob1 + N1));
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                lo = min(lo, __shfl_xor_sync(SEQA_FULL, lo, d));
+                hi = max(hi, __shfl_xor_sync(SEQA_FULL, hi, d));
+            }
+            lo &= ~15ull;
+            if (hi > lo && hi - lo <= (uint64_t)A.prep_stage) { // warp-uniform
+                const unsigned bytes = (unsigned)((hi - lo + 15ull) & ~15ull); // <= 15 bytes behind hi: inside the slack of `bases`
+                if (lane == 0) seqa_bulk_load(stage, A.bases + lo, bytes, bar);
+                seqa_mbar_wait(bar, phase);
+                phase ^= 1u;
+                pk_prep_job<true>(A, R, J, lane, p0, p1, M0, N0, M1, N1, stage, p0 == PK_NULL ? stage : stage + (oa0 - lo),
+                                  p0 == PK_NULL ? stage : stage + (ob0 - lo), p1 == PK_NULL ? stage : stage + (oa1 - lo),
+                                  p1 == PK_NULL ? stage : stage + (ob1 - lo));
+                __syncwarp(); // every lane is done with the staged copy before the next job's bytes land in it
+                continue;
+            }
+        }
+        pk_prep_job<false>(A, R, J, lane, p0, p1, M0, N0, M1, N1, A.bases, A.bases + oa0, A.bases + ob0, A.bases + oa1, A.bases + ob1);
     }
 }
 
