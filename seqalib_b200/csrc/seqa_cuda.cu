@@ -405,6 +405,10 @@ int plan_generic(seqa_ctx *c)
     return SEQA_OK;
 }
 
+static int env_int(const char *name, int dflt, int lo, int hi);
+static int pkg_ctas_per_sm();
+static int pk_ctas_per_sm(size_t smem_optin, uint32_t cols);
+
 int build_plan(seqa_ctx *c)
 {
     const uint64_t n = c->n;
@@ -518,6 +522,7 @@ int build_plan(seqa_ctx *c)
         }
     }
     if (!c->budget) c->budget = free_budget();
+    if (const int kb = env_int("SEQA_SCRATCH_BUDGET_KB", 0, 0, 1 << 30)) c->budget = (size_t)kb << 10; // tests: many chunks from a small batch
     const size_t budget = c->budget;
 
     // ---- packed jobs: 64 pairs per warp, similar shapes together ----
@@ -541,6 +546,19 @@ int build_plan(seqa_ctx *c)
         Chunk ch{0, 0, 0};
         uint64_t tr = 0, pf = 0, rs = 0, lc = 0; // running offsets inside the chunk
         auto chunk_bytes = [&](uint64_t t, uint64_t q, uint64_t r, uint64_t l) { return t + q * 8 + r * 4 + l * 16 + 4096; };
+        // A uniform batch larger than the scratch budget (10 M x 250 bp Gotoh: 98 KB of trace per pair) is cut at WHOLE ROUNDS of
+        // the fill -- one job per resident warp: every warp then runs the same number of equal jobs and they end together.  Cut
+        // at the budget alone (5,800 jobs = 3.27 rounds of 1,776) the last round ran with a quarter of the warps and took as
+        // long as a full one.
+        uint64_t cap_jobs = ~0ull;
+        if (fast && c->sms > 0 && env_int("SEQA_ROUND_CHUNKS", 1, 0, 1)) {
+            const uint32_t M = c->hlen1[0], N = c->hlen2[0], ns = (M + PK_R - 1) / PK_R;
+            const uint64_t tb1 = packed_affine(prm) ? pkg_trace_bytes(ns, N, PK_R, packed_affine_trace_bits(prm)) : pk_trace_bytes(ns, N, PK_R, packed_trace_bits(prm));
+            const uint64_t per_job = chunk_bytes(tb1, (uint64_t)((N + 3) / 4) * 128, pk_rowsel_elems(ns, N, PK_R), (uint64_t)ns * (PK_R / 4) * 32) - 4096;
+            const uint64_t max_jobs = budget > 4096 ? (budget - 4096) / std::max<uint64_t>(per_job, 1) : 0;
+            const uint64_t round = (uint64_t)c->sms * (uint64_t)(packed_affine(prm) ? pkg_ctas_per_sm() : pk_ctas_per_sm(c->smem_optin, N)) * (PK_BLOCK / 32);
+            if (njobs > max_jobs && max_jobs >= round) cap_jobs = max_jobs / round * round;
+        }
         for (size_t w = 0; w < njobs; w++) {
             uint32_t Mw = 0, Nw = 0;
             if (fast) {
@@ -563,7 +581,7 @@ int build_plan(seqa_ctx *c)
                                                        : pk_trace_bytes(J.nstrips, Nw, PK_R, packed_trace_bits(prm));
             const uint64_t pelems = (uint64_t)((Nw + 3) / 4) * 128, relems = pk_rowsel_elems(J.nstrips, Nw, PK_R);
             const uint64_t lelems = (uint64_t)J.nstrips * (PK_R / 4) * 32; // last-column values (SW walk), uint4
-            if (ch.hi > ch.lo && chunk_bytes(tr + tbytes, pf + pelems, rs + relems, lc + lelems) > budget) {
+            if (ch.hi > ch.lo && (chunk_bytes(tr + tbytes, pf + pelems, rs + relems, lc + lelems) > budget || ch.hi - ch.lo >= cap_jobs)) {
                 ch.scratch_bytes = chunk_bytes(tr, pf, rs, lc);
                 c->pk_chunks.push_back(ch);
                 ch.lo = ch.hi;

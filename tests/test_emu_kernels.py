@@ -147,6 +147,21 @@ def test_measured_trace_layout_variants_stay_correct(oracle_built, tmp_path, var
         check_batch_against_oracle(lib, algo, sc, pairs)
 
 
+def test_uniform_batch_cut_at_whole_rounds(emu_lib, monkeypatch):
+    """A uniform batch that outgrows the scratch budget is cut into chunks of whole fill rounds (one job per resident warp:
+    2 SMs x 3 CTAs x 4 warps = 24 jobs on the emulated device); results do not depend on where the cuts fall."""
+    rng = np.random.default_rng(77)
+    pairs = random_pairs(rng, 64 * 58 + 5, 18, 18)  # 59 jobs of 64 pairs
+    monkeypatch.setenv("SEQA_SCRATCH_BUDGET_KB", "2200")  # ~30 jobs of this shape per chunk -> cut at 24
+    sc = S.affine(-3, -1, 1, -1)
+    bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
+    want = orc.oracle_align_batch("ggotoh", sc, bases, off1, off2, len1, len2)
+    for rounds in ("1", "0"):
+        monkeypatch.setenv("SEQA_ROUND_CHUNKS", rounds)
+        got = emu_lib.align_batch(scoring_to_params("ggotoh", sc), bases, off1, off2, len1, len2)
+        _same_results(want, got, len(pairs))
+
+
 def test_batch_layouts_dense_and_scattered(emu_lib):
     """A dense batch (seq1, seq2, next pair ... back to back) sends no offset arrays -- the device derives them from the
     op-slot scan -- and a uniform one no length arrays either; any other layout (gaps, reordered or shared sequences,
