@@ -858,12 +858,13 @@ int run_packed(seqa_ctx *c, bool want_walk)
             Wk.perm = c->d_perm.p + (uint64_t)ch.lo * 64;
             // jobs' `first` fields are absolute; the walk indexes perm by position, so rebase via pointer only
             const unsigned wgrid = (unsigned)((Wk.npos + 255) / 256);
+            const unsigned wgrid2 = (unsigned)((Wk.npos + PK_WALK2_TPB - 1) / PK_WALK2_TPB); // the round-synchronous walks
             // LocalGotoh stays on pkg_walk_kernel: its walk is the MaxCol row scan (125 pieces per 250 bp pair, at the HBM
             // roofline in both kernels: 0.57 ms per 200 k pairs there, 0.81 ms here), the alignments of the log regime are short
             if (affine && local && tb == 4 && use_walk2() > 1)
-                LAUNCH(c, (pkg_walk2_kernel<true, PK_R>), wgrid, 256, 0, Wk);
+                LAUNCH(c, (pkg_walk2_kernel<true, PK_R>), wgrid2, PK_WALK2_TPB, 0, Wk);
             else if (affine && !local && tb == 4 && use_walk2())
-                LAUNCH(c, (pkg_walk2_kernel<false, PK_R>), wgrid, 256, 0, Wk);
+                LAUNCH(c, (pkg_walk2_kernel<false, PK_R>), wgrid2, PK_WALK2_TPB, 0, Wk);
             else if (affine && local && tb == 4)
                 LAUNCH(c, (pkg_walk_kernel<true, PK_R, 4>), wgrid, 256, 0, Wk);
             else if (affine && local)
@@ -873,13 +874,13 @@ int run_packed(seqa_ctx *c, bool want_walk)
             else if (affine)
                 LAUNCH(c, (pkg_walk_kernel<false, PK_R, 8>), wgrid, 256, 0, Wk);
             else if (local && tb == 2 && use_walk2())
-                LAUNCH(c, (pk_walk2_kernel<true, 2, PK_R>), wgrid, 256, 0, Wk);
+                LAUNCH(c, (pk_walk2_kernel<true, 2, PK_R>), wgrid2, PK_WALK2_TPB, 0, Wk);
             else if (tb == 2 && use_walk2())
-                LAUNCH(c, (pk_walk2_kernel<false, 2, PK_R>), wgrid, 256, 0, Wk);
+                LAUNCH(c, (pk_walk2_kernel<false, 2, PK_R>), wgrid2, PK_WALK2_TPB, 0, Wk);
             else if (local && tb == 4 && use_walk2())
-                LAUNCH(c, (pk_walk2_kernel<true, 4, PK_R>), wgrid, 256, 0, Wk);
+                LAUNCH(c, (pk_walk2_kernel<true, 4, PK_R>), wgrid2, PK_WALK2_TPB, 0, Wk);
             else if (tb == 4 && use_walk2())
-                LAUNCH(c, (pk_walk2_kernel<false, 4, PK_R>), wgrid, 256, 0, Wk);
+                LAUNCH(c, (pk_walk2_kernel<false, 4, PK_R>), wgrid2, PK_WALK2_TPB, 0, Wk);
             else if (local && tb == 2)
                 LAUNCH(c, (pk_walk_kernel<true, 2, PK_R>), wgrid, 256, 0, Wk);
             else if (tb == 2)

@@ -24,7 +24,7 @@ template <bool LOCAL, int R>
 __device__ __forceinline__ void pkg_walk2_pairs(const PkArgs &A, const uint64_t pos, const PkSmemCol S)
 {
     static_assert(R == 16, "16-row strips");
-    constexpr uint32_t ROWB = PK_WALK_TPB * 4; // bytes per row of the shared array: rows 0-31 piece words (slot*4 + word), 32-39 tags
+    constexpr uint32_t ROWB = PK_WALK2_TPB * 4; // bytes per row of the shared array: rows 0-31 piece words (slot*4 + word), 32-39 tags
     constexpr unsigned MASK = 0xfu;
     constexpr uint32_t NONE = 0xffffffffu;
     const uint32_t p = A.perm[pos];
@@ -207,9 +207,9 @@ __device__ __forceinline__ void pkg_walk2_pairs(const PkArgs &A, const uint64_t 
 }
 
 template <bool LOCAL, int R>
-__global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK2_MINB) pkg_walk2_kernel(PkArgs A)
+__global__ void __launch_bounds__(PK_WALK2_TPB, PK_WALK2_MINB) pkg_walk2_kernel(PkArgs A)
 {
-    __shared__ uint32_t sm[40][PK_WALK_TPB];
+    __shared__ uint32_t sm[40][PK_WALK2_TPB];
     const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= A.npos) return; // npos is a multiple of 64: whole warps leave
     PkSmemCol S;

@@ -28,6 +28,9 @@
 #undef PK_WALK2
 #define PK_WALK2 0
 #endif
+#ifndef PK_WALK2_TPB
+#define PK_WALK2_TPB 256 /* threads per CTA of the round-synchronous walks (pk_walk2_kernel, pkg_walk2_kernel) */
+#endif
 #ifndef PK_WALK2_MINB
 #define PK_WALK2_MINB 5 /* 48 registers: 6 CTAs (40 registers) spill inside the STEP loop -- 1.57 vs 1.19 ms per 1 M x 150 bp pairs */
 #endif
@@ -170,14 +173,14 @@ struct PkSmemCol {
 };
 
 template <bool LOCAL, int TB, int R>
-__global__ void __launch_bounds__(PK_WALK_TPB, PK_WALK2_MINB) pk_walk2_kernel(PkArgs A)
+__global__ void __launch_bounds__(PK_WALK2_TPB, PK_WALK2_MINB) pk_walk2_kernel(PkArgs A)
 {
     static_assert(R == 16 && (TB == 2 || TB == 4), "pk_walk2_kernel: 16-row strips, one-pair pieces");
     static_assert(PK_WALK2_STEPS <= 5, "PkOpWriter64 holds 8 ops: 3 pending + the new ones");
     // rows 0-15: 4 piece slots x 4 words, row = [cg parity, row-band parity, word(2 bits)]; row 16 + r: the tag of row r's slot
     // (each slot's tag four times: a lookup reads word and tag at one computed address)
-    __shared__ uint32_t sm[32][PK_WALK_TPB];
-    constexpr uint32_t ROWB = PK_WALK_TPB * 4; // bytes per row
+    __shared__ uint32_t sm[32][PK_WALK2_TPB];
+    constexpr uint32_t ROWB = PK_WALK2_TPB * 4; // bytes per row
     const int tid = threadIdx.x;
     const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= A.npos) return; // npos is a multiple of 64: whole warps leave
