@@ -96,7 +96,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "25"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -106,6 +106,12 @@ class ClockSampler(object):
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout=8.0):
+        """block until nvidia-smi has delivered its first sample (its start-up can outlast a 50 ms timed region)"""
+        t_end = time.time() + timeout
+        while self.proc and not self.rows and time.time() < t_end:
+            time.sleep(0.01)
 
     def mark(self):
         return time.time()
@@ -514,6 +520,7 @@ def run_ours(args):
     sampler.start()
     for _ in range(args.warmup):
         ctx.run()
+    sampler.wait_first()
     ctx.sync()
     barrier()
     torch.cuda.synchronize()

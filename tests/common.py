@@ -92,3 +92,24 @@ def compare_with_oracle_batch(res, algo, sc, bases, off1, off2, len1, len2, labe
     assert p < 0, "%s %s %r: ops of pair %d differ: got %s, oracle %s" % (
         label, algo, sc, p, res.pair_ops(p).tolist(), o.pair_ops(p).tolist())
     return n
+
+
+def prep_staging_layouts(rng, n_pairs, length):
+    """Uniform pairs in three layouts: dense; every sequence 1,000 bytes from the next (a job's span outgrows the staging
+    buffer of pk_prep_kernel: global loads); the first 64 pairs dense and the rest spread out (both forms in one launch)."""
+    pairs = random_pairs(rng, n_pairs, length, length)
+    out = [orc.batch_arrays(pairs) + (pairs,)]
+    for dense_head in (0, 64):
+        chunks, o1, o2, pos = [], np.zeros(n_pairs, np.uint64), np.zeros(n_pairs, np.uint64), 3
+        chunks.append(b"NNN")
+        for p, (a, b) in enumerate(pairs):
+            gap = b"" if p < dense_head else b"N" * 1000
+            o1[p] = pos
+            chunks += [a.encode(), gap]
+            pos += len(a) + len(gap)
+            o2[p] = pos
+            chunks += [b.encode(), gap]
+            pos += len(b) + len(gap)
+        l = np.full(n_pairs, length, np.uint32)
+        out.append((np.frombuffer(b"".join(chunks), dtype=np.uint8).copy(), o1, o2, l, l.copy(), pairs))
+    return out

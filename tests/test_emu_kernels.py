@@ -4,7 +4,7 @@ index arithmetic, tie-breaks and the packed-integer tricks checked where no GPU 
 import numpy as np
 import pytest
 
-from common import capi, check_batch_against_oracle, orc, random_pairs, scoring_to_params
+from common import capi, check_batch_against_oracle, orc, prep_staging_layouts, random_pairs, scoring_to_params
 from test_oracle_golden import sc_from
 
 S = orc.Scoring
@@ -145,6 +145,19 @@ def test_measured_trace_layout_variants_stay_correct(oracle_built, tmp_path, var
         [("", ""), ("A", "C"), ("ACGT", "")]
     for algo, sc in (("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("sw", S.linear(-2, 1, -1, False))):
         check_batch_against_oracle(lib, algo, sc, pairs)
+
+
+@pytest.mark.parametrize("algo,sc", [("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("ggotoh", S.affine(-3, -1, 1, -1))])
+def test_prep_staging_and_global_loads_agree(emu_lib, algo, sc, monkeypatch):
+    """pk_prep_kernel stages a job's span of `bases` in shared memory by one TMA bulk copy when it fits and reads global
+    memory otherwise; SEQA_PREP_TMA=0 never stages.  All of them give the oracle's alignments."""
+    rng = np.random.default_rng(91)
+    for bases, off1, off2, len1, len2, pairs in prep_staging_layouts(rng, 64 * 2 + 9, 33):
+        want = orc.oracle_align_batch(algo, sc, bases, off1, off2, len1, len2)
+        for tma in ("1", "0"):
+            monkeypatch.setenv("SEQA_PREP_TMA", tma)
+            got = emu_lib.align_batch(scoring_to_params(algo, sc), bases, off1, off2, len1, len2)
+            _same_results(want, got, len(pairs))
 
 
 def test_uniform_batch_cut_at_whole_rounds(emu_lib, monkeypatch):

@@ -9,7 +9,7 @@ import zlib
 import numpy as np
 import pytest
 
-from common import ROOT, capi, check_batch_against_oracle, compare_with_oracle_batch, orc, random_pairs, scoring_to_params
+from common import ROOT, capi, check_batch_against_oracle, compare_with_oracle_batch, orc, prep_staging_layouts, random_pairs, scoring_to_params
 from seqalib_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -409,3 +409,19 @@ def test_one_shot_call_speculative_first_wave(gpu_lib):
         for name in ("score", "start_i", "start_j", "end_i", "end_j", "ops_len", "ops_off"):
             assert np.array_equal(getattr(res, name), getattr(got, name)), (odd, name)
         assert np.array_equal(res.ops[:res.c.ops_used], got.ops[:got.c.ops_used])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo,sc", [("sw", S.linear(-1, 1, -1)), ("nw", S.linear(-1, 2, -1)), ("ggotoh", S.affine(-3, -1, 1, -1)),
+                                     ("lgotoh", S.affine(-3, -1, 1, -1))])
+def test_prep_tma_staging_and_global_loads(gpu_lib, algo, sc, monkeypatch):
+    """pk_prep_kernel: a job's 128 sequences come in by one TMA bulk copy (cp.async.bulk + mbarrier) when they lie in one
+    span of `bases` that fits the staging buffer, else by per-lane global loads -- dense, spread-out and mixed layouts of a
+    uniform batch, with staging on and off, against the oracle."""
+    rng = np.random.default_rng(92)
+    for length in (150, 250):
+        for bases, off1, off2, len1, len2, pairs in prep_staging_layouts(rng, 64 * 40 + 17, length):
+            for tma in ("1", "0"):
+                monkeypatch.setenv("SEQA_PREP_TMA", tma)
+                res = gpu_lib.align_batch(scoring_to_params(algo, sc), bases, off1, off2, len1, len2)
+                compare_with_oracle_batch(res, algo, sc, bases, off1, off2, len1, len2, label="%s len %d tma %s" % (algo, length, tma))
