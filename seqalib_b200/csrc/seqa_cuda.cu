@@ -443,7 +443,7 @@ int build_plan(seqa_ctx *c)
         const uint64_t run = c->st_slots;
         c->slots_total = run;
         CKS(c->slot_off.ensure(n));
-        CKS(c->slots.ensure(run));
+        CKS(c->slots.ensure(run + 32)); // gather_ops_kernel reads whole aligned (16-byte) words around a string
         CKS(c->ops_len.ensure(n));
         CKS(c->tile_sum.ensure((n + SEQA_SCAN_TILE - 1) / SEQA_SCAN_TILE + 1));
         CKS(c->total.ensure(1));

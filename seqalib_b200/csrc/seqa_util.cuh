@@ -286,8 +286,12 @@ __global__ void __launch_bounds__(256) gather_ops_kernel(GatherArgs A)
         }
         return;
     }
-    // Many short pairs: 8 lanes per pair, every lane's loads of a 64-byte round issued before the first store, so a warp
-    // has four pairs and eight bytes per lane in flight (the kernel is bound by dependent-load latency, not by bytes).
+    // Many short pairs: 8 lanes per pair.  The op strings sit at arbitrary byte offsets on both sides; copied byte by byte the
+    // kernel was bound by its load / store instructions (a warp instruction moved 32 bytes).  It now works on the 32-bit words of
+    // the DESTINATION grid: every interior word is built from aligned source words by a funnel shift (2-bit output: from two
+    // aligned 16-byte loads, 16 ops -> one word) and leaves as one 32-bit store; only the first and the last word of a string,
+    // which are shared with the neighbouring strings, go byte by byte.  Aligned words that hold a byte of the string lie inside
+    // the buffers (256-byte aligned allocations, 32 bytes of slack behind `slots`).
     const uint32_t sub = threadIdx.x & 7;
     const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const uint64_t ng = ((uint64_t)gridDim.x * blockDim.x) >> 3;
@@ -295,37 +299,69 @@ __global__ void __launch_bounds__(256) gather_ops_kernel(GatherArgs A)
         const uint8_t *src = A.slots + A.slot_off[p] + A.slot_start[p];
         uint8_t *dst = A.dense + A.ops_off[p];
         const uint32_t len = A.ops_len[p];
-        if (A.pack) {
-            const uint32_t nb = (len + 3u) >> 2; // output bytes
-            for (uint32_t base = 0; base < nb; base += 32) {
-                unsigned v[4];
+        const uint32_t nb = A.pack ? (len + 3u) >> 2 : len; // output bytes
+        if (nb == 0) continue;
+        const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u);
+        uint32_t *d0 = reinterpret_cast<uint32_t *>(dst - head); // word j holds output bytes [4j - head, 4j - head + 4)
+        const uint32_t W = (head + nb + 3u) >> 2;
+        auto out_byte = [&](uint32_t b) -> uint8_t { // one output byte the slow way (edge words)
+            if (!A.pack) return src[b];
+            unsigned v = 0;
 #pragma unroll
-                for (uint32_t q = 0; q < 4; q++) {
-                    const uint32_t b = base + sub + 8u * q;
-                    v[q] = 0;
-#pragma unroll
-                    for (uint32_t t = 0; t < 4; t++)
-                        if (b * 4 + t < len) v[q] |= (unsigned)(src[b * 4 + t] & 3u) << (2 * t);
+            for (uint32_t t = 0; t < 4; t++)
+                if (b * 4 + t < len) v |= (unsigned)(src[b * 4 + t] & 3u) << (2 * t);
+            return (uint8_t)v;
+        };
+        // edge words: lanes 0-3 the first word's bytes, lanes 4-7 the last word's
+        {
+            const uint32_t b = sub < 4 ? sub : 4u * (W - 1u) - head + (sub - 4u);
+            const bool mine = sub < 4 ? (b + head < 4u) : (W > 1u && b >= 4u * (W - 1u) - head);
+            if (mine && b < nb) dst[b] = out_byte(b);
+        }
+        if (!A.pack) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(src) - head; // source address of word 0's first byte
+            const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+            const uint32_t *aw = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+            for (uint32_t j0 = 1; j0 + 1 < W; j0 += 16) { // two words per lane in flight
+                const uint32_t j1 = j0 + sub, j2 = j1 + 8u;
+                uint32_t lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0;
+                if (j1 + 1 < W) {
+                    lo1 = aw[j1];
+                    if (sh) hi1 = aw[j1 + 1];
                 }
-#pragma unroll
-                for (uint32_t q = 0; q < 4; q++) {
-                    const uint32_t b = base + sub + 8u * q;
-                    if (b < nb) dst[b] = (uint8_t)v[q];
+                if (j2 + 1 < W) {
+                    lo2 = aw[j2];
+                    if (sh) hi2 = aw[j2 + 1];
                 }
+                if (j1 + 1 < W) d0[j1] = sh ? (lo1 >> sh) | (hi1 << (32u - sh)) : lo1;
+                if (j2 + 1 < W) d0[j2] = sh ? (lo2 >> sh) | (hi2 << (32u - sh)) : lo2;
             }
         } else {
-            for (uint32_t base = 0; base < len; base += 64) {
-                uint8_t v[8];
-#pragma unroll
-                for (uint32_t q = 0; q < 8; q++) {
-                    const uint32_t k = base + sub + 8u * q;
-                    v[q] = k < len ? src[k] : (uint8_t)0;
+            auto pack4 = [](uint32_t w) -> uint32_t { // four ops, one per byte -> 8 bits
+                w &= 0x03030303u;
+                w |= w >> 6;
+                w |= w >> 12;
+                return w & 0xffu;
+            };
+            const uintptr_t a = reinterpret_cast<uintptr_t>(src) - 4u * head; // source address of word 0's first op
+            const uint32_t ws = (uint32_t)(a >> 2) & 3u, sh = (uint32_t)(a & 3u) * 8u;
+            const uint4 *aq = reinterpret_cast<const uint4 *>(a & ~(uintptr_t)15);
+            for (uint32_t j = 1 + sub; j + 1 < W; j += 8) {
+                const uint4 c0 = aq[j];
+                uint4 c1 = make_uint4(0, 0, 0, 0);
+                if (ws | sh) c1 = aq[j + 1];
+                // y[0..4] = the five words from word offset ws on
+                uint32_t y0 = c0.x, y1 = c0.y, y2 = c0.z, y3 = c0.w, y4 = c1.x;
+                if (ws == 1) y0 = c0.y, y1 = c0.z, y2 = c0.w, y3 = c1.x, y4 = c1.y;
+                if (ws == 2) y0 = c0.z, y1 = c0.w, y2 = c1.x, y3 = c1.y, y4 = c1.z;
+                if (ws == 3) y0 = c0.w, y1 = c1.x, y2 = c1.y, y3 = c1.z, y4 = c1.w;
+                if (sh) {
+                    y0 = (y0 >> sh) | (y1 << (32u - sh));
+                    y1 = (y1 >> sh) | (y2 << (32u - sh));
+                    y2 = (y2 >> sh) | (y3 << (32u - sh));
+                    y3 = (y3 >> sh) | (y4 << (32u - sh));
                 }
-#pragma unroll
-                for (uint32_t q = 0; q < 8; q++) {
-                    const uint32_t k = base + sub + 8u * q;
-                    if (k < len) dst[k] = v[q];
-                }
+                d0[j] = pack4(y0) | (pack4(y1) << 8) | (pack4(y2) << 16) | (pack4(y3) << 24);
             }
         }
     }

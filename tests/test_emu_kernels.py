@@ -160,6 +160,16 @@ def test_prep_staging_and_global_loads_agree(emu_lib, algo, sc, monkeypatch):
             _same_results(want, got, len(pairs))
 
 
+@pytest.mark.parametrize("flags", [0, capi.FLAG_OPS_2BIT])
+def test_gather_ops_word_path(emu_lib, flags):
+    """gather_ops_kernel with more pairs than warps (8 lanes per pair): op strings of every length and alignment, copied as
+    words of the destination grid (byte ops) or packed 16 ops per word (2-bit ops), first / last word byte by byte."""
+    rng = np.random.default_rng(55)
+    pairs = random_pairs(rng, 1500, 0, 45) + random_pairs(rng, 40, 60, 120, related=0.2)
+    for algo, sc in (("nw", S.linear(-1, 2, -1)), ("sw", S.linear(-1, 1, -1))):
+        check_batch_against_oracle(emu_lib, algo, sc, pairs, flags=flags)
+
+
 def test_uniform_batch_cut_at_whole_rounds(emu_lib, monkeypatch):
     """A uniform batch that outgrows the scratch budget is cut into chunks of whole fill rounds (one job per resident warp:
     2 SMs x 3 CTAs x 4 warps = 24 jobs on the emulated device); results do not depend on where the cuts fall."""
