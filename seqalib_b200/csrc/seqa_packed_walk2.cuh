@@ -29,10 +29,13 @@
 #define PK_WALK2 0
 #endif
 #ifndef PK_WALK2_TPB
-#define PK_WALK2_TPB 256 /* threads per CTA of the round-synchronous walks (pk_walk2_kernel, pkg_walk2_kernel) */
+#define PK_WALK2_TPB 128 /* threads per CTA of the round-synchronous walks (pk_walk2_kernel, pkg_walk2_kernel): a CTA ends with its
+                            longest path, and 128-thread CTAs free their slots sooner -- headline 4,378 / 4,418 / 4,417 GCUPS with 256,
+                            4,401 / 4,443 / 4,440 with 128 (three A/B runs), 64: like 128 */
 #endif
 #ifndef PK_WALK2_MINB
-#define PK_WALK2_MINB 5 /* 48 registers: 6 CTAs (40 registers) spill inside the STEP loop -- 1.57 vs 1.19 ms per 1 M x 150 bp pairs */
+#define PK_WALK2_MINB (1280 / PK_WALK2_TPB) /* 1,280 threads per SM at 48 registers (5 CTAs of 256, 10 of 128): 1,536 threads (40 registers)
+                                                spill inside the STEP loop -- 1.57 vs 1.19 ms per 1 M x 150 bp pairs */
 #endif
 #ifndef PK_WALK2_STEPS
 #define PK_WALK2_STEPS 4 /* neighbour tests per STEP phase: 3 / 4 / 6 / 8 measured 1.34 / 1.28 / 1.31 / 1.52 ms per 1 M x 150 bp pairs */
