@@ -175,14 +175,15 @@ def test_uniform_batch_cut_at_whole_rounds(emu_lib, monkeypatch):
     2 SMs x 3 CTAs x 4 warps = 24 jobs on the emulated device); results do not depend on where the cuts fall."""
     rng = np.random.default_rng(77)
     pairs = random_pairs(rng, 64 * 58 + 5, 18, 18)  # 59 jobs of 64 pairs
-    monkeypatch.setenv("SEQA_SCRATCH_BUDGET_KB", "2200")  # ~30 jobs of this shape per chunk -> cut at 24
-    sc = S.affine(-3, -1, 1, -1)
+    # budgets of ~30 jobs of this shape per chunk -> cut at 24 (GlobalGotoh: 3 x 4-bit planes; SW: 2-bit trace; NW: 4-bit)
     bases, off1, off2, len1, len2 = orc.batch_arrays(pairs)
-    want = orc.oracle_align_batch("ggotoh", sc, bases, off1, off2, len1, len2)
-    for rounds in ("1", "0"):
-        monkeypatch.setenv("SEQA_ROUND_CHUNKS", rounds)
-        got = emu_lib.align_batch(scoring_to_params("ggotoh", sc), bases, off1, off2, len1, len2)
-        _same_results(want, got, len(pairs))
+    for algo, sc, kb in (("ggotoh", S.affine(-3, -1, 1, -1), "2200"), ("sw", S.linear(-1, 1, -1), "850"), ("nw", S.linear(-1, 2, -1), "1150")):
+        monkeypatch.setenv("SEQA_SCRATCH_BUDGET_KB", kb)
+        want = orc.oracle_align_batch(algo, sc, bases, off1, off2, len1, len2)
+        for rounds in ("1", "0"):
+            monkeypatch.setenv("SEQA_ROUND_CHUNKS", rounds)
+            got = emu_lib.align_batch(scoring_to_params(algo, sc), bases, off1, off2, len1, len2)
+            _same_results(want, got, len(pairs))
 
 
 def test_batch_layouts_dense_and_scattered(emu_lib):
